@@ -1,0 +1,150 @@
+/*
+ * ra_b200.h -- C-ABI of the B200-native RelightableAvatar inference renderer.
+ *
+ * Drop-in boundary: the reference selects its renderer with
+ *   importlib.import_module(cfg.renderer_module).Renderer(network)      lib/networks/renderer/make_renderer.py:5-8
+ * and calls `renderer.render(batch) -> dotdict` once per frame             run.py:45,80
+ * The Python plugin `relightableavatar_b200.renderer.Renderer` mirrors that surface and forwards
+ * to the entry points below through ctypes.  No torch types cross this boundary: plain pointers
+ * and sizes only.  All tensors are fp32, row-major, with the reference's batch dimension B=1
+ * squeezed away.  Pointers are DEVICE pointers unless the parameter says "host or device".
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (message via ra_last_error);
+ * no exceptions cross the ABI; the caller allocates every output; the library owns only its
+ * workspace and its packed weight copies; all work is enqueued on the passed cudaStream_t
+ * (void*), no internal device synchronisation on the product path; one handle per device.
+ */
+#ifndef RA_B200_H
+#define RA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ra_handle ra_handle;
+
+enum { RA_PRECISION_FP32 = 0,   /* CUDA-core fp32 MLPs everywhere (reference precision) */
+       RA_PRECISION_TC = 1 };   /* distance-query MLPs on tcgen05 (fp16 operands, fp32 accumulate) */
+
+/* Values the reference reads from its global `cfg` (lib/config/config.py; SURVEY.md 8 notation). */
+typedef struct ra_config {
+    int32_t relight;            /* 1: relight_network (raw 17 ch), 0: AniSDF base_network (raw 16 ch) */
+    int32_t precision;          /* RA_PRECISION_* */
+    int32_t max_rays;           /* capacity: max P of any render call */
+    int32_t n_verts, n_bones;   /* 6890, 52 */
+    float dist_th;              /* net.dist_th: 0.125 relight / 0.1 AniSDF      base_network.py:177 */
+    float blend_radius;         /* 0.075                                        config.py:191 */
+    float resd_limit;           /* 0.05                                         config.py:224 */
+    int32_t st_iter;            /* 16    cfg.sphere_tracing.*                   config.py:116-124 */
+    float st_tan_i, st_relax, st_offset, st_eps;
+    int32_t st_skip;
+    int32_t lv_iter;            /* 4     cfg.obj_lvis.*                         config.py:127-132 */
+    float lv_offset, lv_relax, lv_near, lv_dist_th;
+    float env_r;                /* 10: far of shadow rays                        config.py:113 */
+    float bbox_margin;          /* 0.25, applied per pixel chunk                 sphere_tracing_renderer.py:1020-1022 */
+    int32_t render_chunk;       /* 65536                                         base.yaml:170 */
+    int32_t n_samples;          /* 3 surface samples                             base.yaml:169 */
+    float surf_sample_range;    /* 0.005                                         config.py:76 */
+    float fresnel_f0;           /* 0.02 */
+    float albedo_slope, albedo_bias, rough_slope, rough_bias, albedo_multiplier, shading_albedo;
+    int32_t env_h, env_w;       /* 16, 32 */
+    int32_t vol_samples;        /* 128: base_renderer uniform samples            base.yaml:78 */
+    float clip_near, clip_far;  /* 0.02, 10                                      config.py:79-80 */
+} ra_config;
+
+/* Network tensors in torch layout (out_features x in_features), weight-norm already folded
+ * (w = g * v / ||v||_row) by the caller.  "host or device" pointers; the library copies them.
+ * State-dict keys: SURVEY.md 8b. */
+typedef struct ra_weights {
+    const float* resd_w[9]; const float* resd_b[9];     /* residual_deformation_network.mlp.linears.{l} */
+    const float* sdf_w[9];  const float* sdf_b[9];      /* signed_distance_network.mlp.lin{l} (folded)  */
+    float sdf_beta;                                     /* clamp(_beta, 1e-9, 1e6) */
+    const float* render_w[5]; const float* render_b[5]; /* render_network.l{l} (folded); NULL if absent  */
+    const float* albedo_w[3]; const float* albedo_b[3]; /* albedo_network.linears.{l}; NULL for AniSDF   */
+    const float* rough_w[3];  const float* rough_b[3];  /* roughness_network.linears.{l}                 */
+    const float* env_main;  int32_t env_main_h, env_main_w;  /* softplus(global_env_map_) expanded to 3 ch */
+    const float* light_xyz;   /* (env_h, env_w, 3) */
+    const float* light_area;  /* (env_h, env_w)    */
+    const float* light_sharp; /* (env_h, env_w)    */
+} ra_weights;
+
+/* Per-frame tensors of `batch` (lib/datasets/pose_dataset.py:45-113, base_dataset.py:337-397).
+ * Device pointers, borrowed until the next ra_set_frame. */
+typedef struct ra_frame {
+    const float* R;        /* (3,3)    */
+    const float* Th;       /* (3)      */
+    const float* poses;    /* (156)    */
+    const float* A;        /* (52,4,4) */
+    const float* big_A;    /* (52,4,4) */
+    const float* weights;  /* (N,52)   */
+    const float* pverts;   /* (N,3)    */
+    const float* pnorm;    /* (N,3)    */
+    const float* tverts;   /* (N,3) big-pose vertices */
+    const float* wbounds;  /* (2,3)  world AABB of the posed body (+-0.05); read, not modified */
+    const float* mat_cond; /* (156) train_motion.poses[fix_material]; may be NULL for relight */
+} ra_frame;
+
+/* Per-ray output maps, each (P, C) fp32, premultiplied by acc like the reference's alpha_output_
+ * (sphere_tracing_renderer.py:454-460,1113).  NULL pointers are skipped. */
+typedef struct ra_outputs {
+    float* rgb_map;        /* (P,3) */
+    float* acc_map;        /* (P)   */
+    float* depth_map;      /* (P)   */
+    float* surf_map;       /* (P,3) */
+    float* norm_map;       /* (P,3) */
+    float* cpts_map;       /* (P,3) */
+    float* bpts_map;       /* (P,3) */
+    float* resd_map;       /* (P,3) */
+    float* albedo_map;     /* (P,3) relight only */
+    float* roughness_map;  /* (P)   relight only */
+    float* shade_map;      /* (P,3) relight only */
+    float* lvis_map;       /* (P,512) optional */
+    float* ldot_map;       /* (P,512) optional */
+} ra_outputs;
+
+/* Work counters of the last render call (device-side counts read back on request; forces a sync). */
+typedef struct ra_stats {
+    int64_t n_rays;            /* P */
+    int64_t n_fg;              /* S_fg: pixels with acc > 0 */
+    int64_t n_shadow_rays;     /* traced (pixel, light) pairs */
+    int64_t n_queries;         /* HDQ distance queries issued (all iterations) */
+    int64_t n_queries_in_shell;/* ... of which went through the MLPs */
+    int64_t n_attr_samples;    /* in-shell surface/volume samples (fwd + input-gradient) */
+} ra_stats;
+
+int  ra_create(ra_handle** out, const ra_config* cfg);
+void ra_destroy(ra_handle* h);
+const char* ra_last_error(ra_handle* h);
+
+int ra_upload_weights(ra_handle* h, const ra_weights* w, void* stream);
+int ra_set_frame(ra_handle* h, const ra_frame* f, void* stream);
+
+/* sphere_tracing_renderer.Renderer.render for the relight network (a1-a18, a21). */
+int ra_render_relight(ra_handle* h, const float* ray_o, const float* ray_d, const float* near, const float* far,
+                      int64_t P, const ra_outputs* out, void* stream);
+/* novel_light_sphere_tracing per-env-map re-shade (a19): probes (n_env,16,32,3); rgb/shade/spec (n_env,P,3).
+ * Uses the maps of the preceding ra_render_relight call (kept in the workspace). */
+int ra_relight_envmaps(ra_handle* h, const float* probes, int32_t n_env, float* rgb, float* shade, float* spec,
+                       void* stream);
+/* sphere_tracing_renderer.Renderer.render for the AniSDF network (config 1; raw 16-ch branch :634-635). */
+int ra_render_anisdf_trace(ra_handle* h, const float* ray_o, const float* ray_d, const float* near, const float* far,
+                           int64_t P, const ra_outputs* out, void* stream);
+/* base_renderer.Renderer.render (config 2): 128 uniform samples per ray. */
+int ra_render_anisdf_volume(ra_handle* h, const float* ray_o, const float* ray_d, const float* near, const float* far,
+                            int64_t P, const ra_outputs* out, void* stream);
+
+/* Building blocks exposed for parity tests (same kernels the render calls use). */
+/* net.inference_world_distance_field(x, batch, smooth_transition, dist_th): x (n,3) -> sdf (n) */
+int ra_query_sdf(ra_handle* h, const float* x, int64_t n, float dist_th, int32_t smooth, float* sdf, void* stream);
+/* net(x, v, d, batch).raw (eval): x,v (n,3) -> raw (n, 17 | 16), zero rows out of shell */
+int ra_query_raw(ra_handle* h, const float* x, const float* v, int64_t n, float* raw, void* stream);
+
+int ra_get_stats(ra_handle* h, ra_stats* out);   /* synchronises the device */
+/* number of kernels the library launched since creation (bench.py's gpu_launches) */
+int64_t ra_launch_count(ra_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RA_B200_H */

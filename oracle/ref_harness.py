@@ -1,0 +1,212 @@
+"""TEST INFRASTRUCTURE -- runs the UNMODIFIED reference renderer from the read-only tree under
+import shims on a synthetic scene and dumps its outputs as golden vectors.
+
+The reference cannot be imported as-is here (easymocap / pytorch3d / smplx / termcolor / pdbr ...
+are not installed, no network).  A `sys.meta_path` finder hands out permissive stub modules for
+those names; the only third-party *arithmetic* on the path, `pytorch3d.ops.knn_points`, is
+restated as an exact squared-L2 K-NN.  Nothing is copied from the reference: it is imported from
+where it lies (`$RA_REFERENCE`, /root/reference or baseline/_ref).
+
+One process per config (hot-path parameters are bound as default args at import time):
+
+    python oracle/ref_harness.py --mode relight|anisdf_trace|anisdf_volume --H 48 --out x.npz
+
+Never imported by the product; used by tests/golden/make_golden.py only.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import types
+
+import numpy as np
+
+STUB_ROOTS = ('easymocap', 'pytorch3d', 'smplx', 'termcolor', 'pdbr', 'trimesh', 'mcubes', 'imageio', 'skimage',
+              'lpips', 'torch_scatter', 'h5py', 'ujson', 'matplotlib', 'cupy', 'cupy_knn', 'open3d', 'sympy_stub',
+              'bvh_distance_queries', 'nvdiffrast', 'largesteps', 'spconv', 'rich_stub', 'tensorboardX', 'plyfile',
+              'pymeshlab', 'pyrender', 'OpenGL', 'glfw')
+
+
+class _Anything:
+    """Callable, attribute-able, subclass-able placeholder."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return _Anything()
+
+    def __getattr__(self, name):
+        if name.startswith('__') and name.endswith('__'):
+            raise AttributeError(name)
+        return _Anything()
+
+    def __iter__(self):
+        return iter(())
+
+    def __mro_entries__(self, bases):
+        return (object,)
+
+
+class _StubModule(types.ModuleType):
+    __path__: list = []
+
+    def __getattr__(self, name):
+        if name.startswith('__') and name.endswith('__'):
+            raise AttributeError(name)
+        cls = type(name, (_Anything,), {})
+        setattr(self, name, cls)
+        return cls
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.split('.')[0] in STUB_ROOTS:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = _StubModule(spec.name)
+        m.__path__ = []
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+def find_reference() -> str:
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for c in (os.environ.get('RA_REFERENCE'), '/root/reference', os.path.join(here, 'baseline', '_ref')):
+        if c and os.path.exists(os.path.join(c, 'lib', 'networks', 'renderer', 'sphere_tracing_renderer.py')):
+            return c
+    raise FileNotFoundError('reference tree not found')
+
+
+def install_shims():
+    import torch
+    sys.meta_path.insert(0, _StubFinder())
+    import termcolor
+    termcolor.colored = lambda s, *a, **k: s
+    import pytorch3d.ops as p3o
+
+    def knn_points(p1, p2, K=1, return_nn=False, return_sorted=True, **kw):
+        outs_d, outs_i = [], []
+        for s in range(0, p1.shape[1], 8192):
+            q = p1[:, s:s + 8192]
+            d = (q[:, :, None, 0] - p2[:, None, :, 0]) ** 2
+            d = d + (q[:, :, None, 1] - p2[:, None, :, 1]) ** 2
+            d = d + (q[:, :, None, 2] - p2[:, None, :, 2]) ** 2
+            v, i = torch.topk(d, K, dim=-1, largest=False, sorted=True)
+            outs_d.append(v); outs_i.append(i)
+        if not outs_d:
+            return p1.new_zeros(p1.shape[0], 0, K), torch.zeros(p1.shape[0], 0, K, dtype=torch.long), None
+        return torch.cat(outs_d, 1), torch.cat(outs_i, 1), None
+
+    p3o.knn_points = knn_points
+    torch.cuda.synchronize = lambda *a, **k: None
+
+
+def setup_reference(mode: str):
+    """Import the reference config and replay the cascade of lib/config/config.py:498-517 by hand."""
+    root = find_reference()
+    install_shims()
+    sys.path.insert(0, root)
+    sys.argv = ['oracle']
+    os.chdir(root)
+    from lib.config import cfg, yacs
+    cfg.merge_strain(yacs.load_cfg(open('configs/mobile_stage/xuzhen_12v_geo.yaml', 'r')))
+    if mode == 'relight':
+        cfg.relighting = True; cfg.vis_novel_light = True; cfg.vis_pose_sequence = True
+        cfg.merge_from_other_cfg(cfg.relighting_cfg)
+        cfg.merge_from_other_cfg(cfg.pose_seq_cfg)
+        cfg.merge_from_other_cfg(cfg.novel_light_cfg)
+    elif mode == 'anisdf_trace':
+        cfg.vis_pose_sequence = True; cfg.vis_sphere_tracing = True
+        cfg.merge_from_other_cfg(cfg.pose_seq_cfg)
+        cfg.merge_from_other_cfg(cfg.sphere_tracing_cfg)
+    elif mode == 'anisdf_volume':
+        cfg.vis_pose_sequence = True
+        cfg.merge_from_other_cfg(cfg.pose_seq_cfg)
+    else:
+        raise ValueError(mode)
+    cfg.n_bones = 52
+    cfg.cond_dim = 156
+    cfg.vis_rendering_map = True
+    cfg.probe_size_ratio = 0.0
+    cfg.geometry_pretrain = '/nonexistent'
+    return cfg
+
+
+def to_ref_batch(b: dict, device='cpu'):
+    import torch
+    from lib.utils.base_utils import dotdict
+    out = dotdict()
+    for k, v in b.items():
+        if k == 'novel_lights':
+            out.novel_lights = dotdict({n: dotdict(probe=torch.from_numpy(p).to(device)) for n, p in v.items()})
+        elif k == 'train_poses':
+            out.train_motion = dotdict(poses=torch.from_numpy(v).to(device))
+        elif isinstance(v, np.ndarray) and v.ndim > 0:
+            out[k] = torch.from_numpy(v.copy()).to(device)
+    out.meta = dotdict(H=torch.tensor([int(b['H'])]), W=torch.tensor([int(b['W'])]))
+    return out
+
+
+def run(mode: str, H: int, seed: int, n_env: int, fitted: bool, threads: int = 0):
+    import torch
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, here)
+    cfg = setup_reference(mode)
+    from relightableavatar_b200 import scene
+    if threads:
+        torch.set_num_threads(threads)
+    if mode == 'relight':
+        cfg.test_light = ['main'] + list(scene.make_envmaps(n_env, 10 + seed).keys()) if n_env else ['main']
+    from lib.networks.make_network import make_network
+    from lib.networks.renderer.make_renderer import make_renderer
+    net = make_network(cfg)
+    sd = scene.make_state_dict(seed, relight=(mode == 'relight'), fitted=fitted)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    missing = [m for m in missing if 'freq_bands' not in m and 'embedder' not in m]
+    assert not unexpected, unexpected
+    assert not missing, missing
+    net.eval()
+    renderer = make_renderer(cfg, net)
+    b = scene.make_batch(H, H, seed=seed, n_env=n_env if mode == 'relight' else 0)
+    batch = to_ref_batch(b)
+    with torch.no_grad():
+        out = renderer.render(batch)
+    flat = {}
+
+    def put(prefix, d):
+        for k, v in d.items():
+            if isinstance(v, torch.Tensor):
+                flat[prefix + k] = v.detach().cpu().numpy()
+            elif isinstance(v, dict):
+                put(prefix + k + '.', v)
+
+    put('', out)
+    flat['wbounds_after'] = batch.wbounds.cpu().numpy()
+    return flat, b
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--mode', required=True)
+    ap.add_argument('--H', type=int, default=48)
+    ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--n_env', type=int, default=2)
+    ap.add_argument('--raw_init', action='store_true', help='geometric-init SDF instead of the fitted one')
+    ap.add_argument('--out', required=True)
+    a = ap.parse_args()
+    out_path = os.path.abspath(a.out)
+    flat, _ = run(a.mode, a.H, a.seed, a.n_env, not a.raw_init)
+    np.savez_compressed(out_path, **flat)
+    print('wrote', out_path, {k: v.shape for k, v in flat.items()})
+
+
+if __name__ == '__main__':
+    main()

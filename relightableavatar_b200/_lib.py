@@ -1,0 +1,82 @@
+"""ctypes binding of include/ra_b200.h.  Fails loudly when the CUDA library is missing or a call
+returns an error -- there is no CPU fallback anywhere in the product path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libra_b200.so')
+
+EXPORTS = ['ra_create', 'ra_destroy', 'ra_last_error', 'ra_upload_weights', 'ra_set_frame', 'ra_render_relight',
+           'ra_relight_envmaps', 'ra_render_anisdf_trace', 'ra_render_anisdf_volume', 'ra_query_sdf', 'ra_query_raw',
+           'ra_get_stats', 'ra_launch_count']
+
+fp = C.POINTER(C.c_float)
+
+
+class ra_config(C.Structure):
+    _fields_ = [('relight', C.c_int32), ('precision', C.c_int32), ('max_rays', C.c_int32), ('n_verts', C.c_int32),
+                ('n_bones', C.c_int32), ('dist_th', C.c_float), ('blend_radius', C.c_float), ('resd_limit', C.c_float),
+                ('st_iter', C.c_int32), ('st_tan_i', C.c_float), ('st_relax', C.c_float), ('st_offset', C.c_float),
+                ('st_eps', C.c_float), ('st_skip', C.c_int32), ('lv_iter', C.c_int32), ('lv_offset', C.c_float),
+                ('lv_relax', C.c_float), ('lv_near', C.c_float), ('lv_dist_th', C.c_float), ('env_r', C.c_float),
+                ('bbox_margin', C.c_float), ('render_chunk', C.c_int32), ('n_samples', C.c_int32),
+                ('surf_sample_range', C.c_float), ('fresnel_f0', C.c_float), ('albedo_slope', C.c_float),
+                ('albedo_bias', C.c_float), ('rough_slope', C.c_float), ('rough_bias', C.c_float),
+                ('albedo_multiplier', C.c_float), ('shading_albedo', C.c_float), ('env_h', C.c_int32), ('env_w', C.c_int32),
+                ('vol_samples', C.c_int32), ('clip_near', C.c_float), ('clip_far', C.c_float)]
+
+
+class ra_weights(C.Structure):
+    _fields_ = [('resd_w', fp * 9), ('resd_b', fp * 9), ('sdf_w', fp * 9), ('sdf_b', fp * 9), ('sdf_beta', C.c_float),
+                ('render_w', fp * 5), ('render_b', fp * 5), ('albedo_w', fp * 3), ('albedo_b', fp * 3),
+                ('rough_w', fp * 3), ('rough_b', fp * 3), ('env_main', fp), ('env_main_h', C.c_int32),
+                ('env_main_w', C.c_int32), ('light_xyz', fp), ('light_area', fp), ('light_sharp', fp)]
+
+
+class ra_frame(C.Structure):
+    _fields_ = [(n, fp) for n in ('R', 'Th', 'poses', 'A', 'big_A', 'weights', 'pverts', 'pnorm', 'tverts', 'wbounds', 'mat_cond')]
+
+
+OUTPUT_MAPS = ('rgb_map', 'acc_map', 'depth_map', 'surf_map', 'norm_map', 'cpts_map', 'bpts_map', 'resd_map', 'albedo_map',
+               'roughness_map', 'shade_map', 'lvis_map', 'ldot_map')
+
+
+class ra_outputs(C.Structure):
+    _fields_ = [(n, fp) for n in OUTPUT_MAPS]
+
+
+class ra_stats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ('n_rays', 'n_fg', 'n_shadow_rays', 'n_queries', 'n_queries_in_shell', 'n_attr_samples')]
+
+
+_lib = None
+
+
+def load():
+    """Load libra_b200.so; raises (never falls back) if it is absent or lacks a declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f'{LIB_PATH} not built: run `python -m relightableavatar_b200.build` (no CPU fallback exists)')
+    lib = C.CDLL(LIB_PATH)
+    for s in EXPORTS:
+        if not hasattr(lib, s):
+            raise RuntimeError(f'{LIB_PATH} does not export {s}')
+    vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+    lib.ra_create.argtypes = [C.POINTER(vp), C.POINTER(ra_config)]
+    lib.ra_destroy.argtypes = [vp]; lib.ra_destroy.restype = None
+    lib.ra_last_error.argtypes = [vp]; lib.ra_last_error.restype = C.c_char_p
+    lib.ra_upload_weights.argtypes = [vp, C.POINTER(ra_weights), vp]
+    lib.ra_set_frame.argtypes = [vp, C.POINTER(ra_frame), vp]
+    for n in ('ra_render_relight', 'ra_render_anisdf_trace', 'ra_render_anisdf_volume'):
+        getattr(lib, n).argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(ra_outputs), vp]
+    lib.ra_relight_envmaps.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    lib.ra_query_sdf.argtypes = [vp, vp, i64, f32, i32, vp, vp]
+    lib.ra_query_raw.argtypes = [vp, vp, vp, i64, vp, vp]
+    lib.ra_get_stats.argtypes = [vp, C.POINTER(ra_stats)]
+    lib.ra_launch_count.argtypes = [vp]; lib.ra_launch_count.restype = i64
+    _lib = lib
+    return lib

@@ -1,0 +1,77 @@
+// Shared declarations for the ra_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <math.h>
+
+#define RA_MAX_GRID_DIM 64
+#define RA_MAX_CELLS (RA_MAX_GRID_DIM * RA_MAX_GRID_DIM * RA_MAX_GRID_DIM)
+#define RA_NLIGHT_MAX 512
+#define RA_KNN_RMAX 3
+
+// Per-frame constants living in device memory (written by k_frame_prep, read by every kernel).
+struct FrameConst {
+    float R[9];            // pose->world rotation (batch.R), row-major
+    float Th[3];
+    float g_org[3];        // uniform grid over the posed vertices (pose space)
+    float g_h, g_inv_h;
+    int g_dim[3];
+    int g_cells;
+    float wb[6];           // wbounds (2,3) as given (unpadded)
+    float resd_b0[256];    // layer-0 bias + W0[:,63:219] . poses      (cond folded, base_network.py:34-40)
+    float resd_b4[256];    // layer-4 bias + W4[:,256+63:475] . poses
+    float rend_b3[256];    // render l3 bias + W3[:,256:412] . mat_cond (base_network.py:166-167,501-504)
+};
+
+// Per-vertex data sorted by grid cell.
+struct SortedVerts {
+    float4* pos;    // xyz (pose space), w = original vertex index (int bits)
+    float4* nrm;    // pnorm xyz
+    float4* tv;     // big-pose vertex xyz
+    float* T;       // [N][24]: A_v (3x4 row-major) then bigA_v (3x4): sum_j weights[v][j] * A_j
+    int* cell_start;  // [cells+1]
+};
+
+struct KnnOut {
+    float d2[3];
+    int id[3];      // sorted-vertex ids
+};
+
+__device__ __forceinline__ float3 make3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return make3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return make3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return make3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float signf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+// reference normalize(): x / (||x|| + 1e-8)   net_utils.py:1626-1628
+__device__ __forceinline__ float3 normalize_ref(float3 v) {
+    float n = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z) + 1e-8f;
+    return make3(v.x / n, v.y / n, v.z / n);
+}
+// F.normalize(x, eps=1e-7): x / max(||x||, 1e-7)   relight_utils.py:534-536
+__device__ __forceinline__ float3 normalize_f(float3 v) {
+    float n = fmaxf(sqrtf(v.x * v.x + v.y * v.y + v.z * v.z), 1e-7f);
+    return make3(v.x / n, v.y / n, v.z / n);
+}
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// torch.nn.Softplus(beta=100, threshold=20)
+__device__ __forceinline__ float softplus100(float z) {
+    float t = 100.f * z;
+    return (t > 20.f) ? z : log1pf(expf(t)) * 0.01f;
+}
+// d softplus / dz expressed from the activation value a = softplus100(z): sigmoid(100 z) = 1 - exp(-100 a)
+__device__ __forceinline__ float dsoftplus100_from_act(float a) { return 1.f - expf(-100.f * a); }
+
+// warp-aggregated append: returns the slot for lanes with pred, -1 otherwise
+__device__ __forceinline__ int warp_append(int* counter, bool pred) {
+    unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return -1;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return pred ? base + __popc(mask & ((1u << lane) - 1u)) : -1;
+}

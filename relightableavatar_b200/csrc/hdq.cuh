@@ -1,0 +1,338 @@
+// Hierarchical distance query front-end: world->pose, exact 3-NN to the posed SMPL-H vertices,
+// signed vertex distances, geodesic filter, shell test, Gaussian-blended inverse LBS to big pose.
+// Reference: base_network.py:238-336,365-383; sample_utils.py:103-162; blend_utils.py:125-165,212-329.
+#pragma once
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------ frame prep
+// One block: pose-space bounds of the vertices -> uniform grid; fold the per-frame condition vectors
+// into layer biases; copy R / Th / wbounds.
+__global__ void k_frame_prep(FrameConst* fc, const float* __restrict__ R, const float* __restrict__ Th,
+                             const float* __restrict__ pverts, int nverts, const float* __restrict__ wbounds,
+                             const float* __restrict__ poses, const float* __restrict__ mat_cond,
+                             const float* __restrict__ resd_w0, const float* __restrict__ resd_b0,   // (256,219)
+                             const float* __restrict__ resd_w4, const float* __restrict__ resd_b4,   // (256,475)
+                             const float* __restrict__ rend_w3, const float* __restrict__ rend_b3,   // (256,412) or null
+                             int* cell_count, float cell_h) {
+    __shared__ float smin[3][32], smax[3][32];
+    int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+    for (int i = tid; i < nverts; i += blockDim.x)
+        for (int a = 0; a < 3; a++) {
+            float v = pverts[i * 3 + a];
+            mn[a] = fminf(mn[a], v);
+            mx[a] = fmaxf(mx[a], v);
+        }
+    for (int a = 0; a < 3; a++) {
+        for (int o = 16; o; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+        if (lane == 0) { smin[a][wid] = mn[a]; smax[a][wid] = mx[a]; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nw = blockDim.x >> 5;
+        float h = cell_h;
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; a++) {
+            lo[a] = 1e30f; hi[a] = -1e30f;
+            for (int w = 0; w < nw; w++) { lo[a] = fminf(lo[a], smin[a][w]); hi[a] = fmaxf(hi[a], smax[a][w]); }
+            h = fmaxf(h, (hi[a] - lo[a]) * (1.0f / (RA_MAX_GRID_DIM - 1)));
+        }
+        int cells = 1;
+        for (int a = 0; a < 3; a++) {
+            fc->g_org[a] = lo[a] - 0.5f * h;
+            int d = (int)floorf((hi[a] - lo[a] + h) / h) + 1;
+            d = min(max(d, 1), RA_MAX_GRID_DIM);
+            fc->g_dim[a] = d;
+            cells *= d;
+        }
+        fc->g_h = h;
+        fc->g_inv_h = 1.0f / h;
+        fc->g_cells = cells;
+        for (int i = 0; i < 9; i++) fc->R[i] = R[i];
+        for (int i = 0; i < 3; i++) fc->Th[i] = Th[i];
+        for (int i = 0; i < 6; i++) fc->wb[i] = wbounds ? wbounds[i] : 0.f;
+    }
+    // zero the cell counters (max size) for the counting sort that follows
+    for (int i = tid; i < RA_MAX_CELLS + 1; i += blockDim.x) cell_count[i] = 0;
+    // folded biases: one output row per thread
+    for (int o = tid; o < 256; o += blockDim.x) {
+        float s0 = resd_b0[o], s4 = resd_b4[o];
+        const float* w0 = resd_w0 + (size_t)o * 219 + 63;
+        const float* w4 = resd_w4 + (size_t)o * 475 + 256 + 63;
+        for (int k = 0; k < 156; k++) {
+            float c = poses[k];
+            s0 += w0[k] * c;
+            s4 += w4[k] * c;
+        }
+        fc->resd_b0[o] = s0;
+        fc->resd_b4[o] = s4;
+        if (rend_w3 != nullptr && mat_cond != nullptr) {
+            float s3 = rend_b3[o];
+            const float* w3 = rend_w3 + (size_t)o * 412 + 256;
+            for (int k = 0; k < 156; k++) s3 += w3[k] * mat_cond[k];
+            fc->rend_b3[o] = s3;
+        }
+    }
+}
+
+__device__ __forceinline__ int cell_of(const FrameConst* fc, float3 p, int& cx, int& cy, int& cz) {
+    cx = min(max((int)floorf((p.x - fc->g_org[0]) * fc->g_inv_h), 0), fc->g_dim[0] - 1);
+    cy = min(max((int)floorf((p.y - fc->g_org[1]) * fc->g_inv_h), 0), fc->g_dim[1] - 1);
+    cz = min(max((int)floorf((p.z - fc->g_org[2]) * fc->g_inv_h), 0), fc->g_dim[2] - 1);
+    return (cz * fc->g_dim[1] + cy) * fc->g_dim[0] + cx;
+}
+
+__global__ void k_grid_count(const FrameConst* fc, const float* __restrict__ pverts, int nverts, int* cell_count,
+                             int* vert_cell) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nverts) return;
+    int cx, cy, cz;
+    int c = cell_of(fc, make3(pverts[i * 3], pverts[i * 3 + 1], pverts[i * 3 + 2]), cx, cy, cz);
+    vert_cell[i] = c;
+    atomicAdd(&cell_count[c], 1);
+}
+
+// single block exclusive scan over g_cells (+1) entries; also resets the fill cursors
+__global__ void k_grid_scan(const FrameConst* fc, const int* __restrict__ cell_count, int* cell_start, int* cell_fill) {
+    __shared__ int carry;
+    __shared__ int wsum[32];
+    int n = fc->g_cells;
+    int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        int i = base + tid;
+        int v = (i < n) ? cell_count[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int s = (lane < (blockDim.x >> 5)) ? wsum[lane] : 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += y;
+            }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        int excl = carry + (wid ? wsum[wid - 1] : 0) + x - v;
+        if (i < n) { cell_start[i] = excl; cell_fill[i] = 0; }
+        __syncthreads();
+        if (tid == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) cell_start[n] = carry;
+}
+
+// scatter vertices into cell order and pre-blend the per-vertex skinning transforms:
+// T_v = sum_j weights[v][j] * A_j (and big_A_j).  sum_k w_k T_{nn_k} == sum_j (sum_k w_k W[nn_k][j]) A_j
+// (blend_transform, blend_utils.py:212-218) up to fp32 re-association.
+__global__ void k_grid_fill(const FrameConst* fc, const float* __restrict__ pverts, const float* __restrict__ pnorm,
+                            const float* __restrict__ tverts, const float* __restrict__ weights,
+                            const float* __restrict__ A, const float* __restrict__ bigA, int nverts, int nbones,
+                            const int* __restrict__ vert_cell, const int* __restrict__ cell_start, int* cell_fill,
+                            SortedVerts sv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nverts) return;
+    int c = vert_cell[i];
+    int dst = cell_start[c] + atomicAdd(&cell_fill[c], 1);
+    sv.pos[dst] = make_float4(pverts[i * 3], pverts[i * 3 + 1], pverts[i * 3 + 2], __int_as_float(i));
+    sv.nrm[dst] = make_float4(pnorm[i * 3], pnorm[i * 3 + 1], pnorm[i * 3 + 2], 0.f);
+    sv.tv[dst] = make_float4(tverts[i * 3], tverts[i * 3 + 1], tverts[i * 3 + 2], 0.f);
+    float T[24];
+#pragma unroll
+    for (int k = 0; k < 24; k++) T[k] = 0.f;
+    for (int j = 0; j < nbones; j++) {
+        float w = weights[(size_t)i * nbones + j];
+        if (w != 0.f) {
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                T[k] += w * A[j * 16 + k];
+                T[12 + k] += w * bigA[j * 16 + k];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 24; k++) sv.T[(size_t)dst * 24 + k] = T[k];
+}
+
+// ------------------------------------------------------------------------------------------ exact 3-NN
+__device__ __forceinline__ void knn_insert(KnnOut& o, float d2, int id) {
+    if (d2 < o.d2[2]) {
+        if (d2 < o.d2[1]) {
+            o.d2[2] = o.d2[1]; o.id[2] = o.id[1];
+            if (d2 < o.d2[0]) {
+                o.d2[1] = o.d2[0]; o.id[1] = o.id[0];
+                o.d2[0] = d2; o.id[0] = id;
+            } else { o.d2[1] = d2; o.id[1] = id; }
+        } else { o.d2[2] = d2; o.id[2] = id; }
+    }
+}
+
+// squared L2 as (dx^2 + dy^2) + dz^2 with separately rounded products (matches the oracle's elementwise form)
+__device__ __forceinline__ float dist2_ref(float3 p, float4 v) {
+    float dx = p.x - v.x, dy = p.y - v.y, dz = p.z - v.z;
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ void knn_range(KnnOut& o, float3 p, const float4* __restrict__ pos, int s, int e) {
+    for (int v = s; v < e; v++) knn_insert(o, dist2_ref(p, __ldg(&pos[v])), v);
+}
+
+// Exact 3 nearest vertices (K=3 of pytorch3d.ops.knn_points at sample_utils.py:122): expanding cube
+// shells over the uniform grid until the 3rd best distance is within the explored block; brute force
+// over all vertices beyond RA_KNN_RMAX rings (points far from the body).
+__device__ void knn3_query(const FrameConst* __restrict__ fc, const SortedVerts& sv, int nverts, float3 p, KnnOut& o) {
+    o.d2[0] = o.d2[1] = o.d2[2] = 3.0e38f;
+    o.id[0] = o.id[1] = o.id[2] = 0;
+    int cx, cy, cz;
+    cell_of(fc, p, cx, cy, cz);
+    const int dx_ = fc->g_dim[0], dy_ = fc->g_dim[1], dz_ = fc->g_dim[2];
+    const float h = fc->g_h;
+    bool done = false;
+    for (int r = 0; r <= RA_KNN_RMAX && !done; r++) {
+        int z0 = max(cz - r, 0), z1 = min(cz + r, dz_ - 1);
+        int y0 = max(cy - r, 0), y1 = min(cy + r, dy_ - 1);
+        int x0 = max(cx - r, 0), x1 = min(cx + r, dx_ - 1);
+        for (int z = z0; z <= z1; z++) {
+            bool zf = (z == cz - r) || (z == cz + r);
+            for (int y = y0; y <= y1; y++) {
+                bool yf = zf || (y == cy - r) || (y == cy + r);
+                int row = (z * dy_ + y) * dx_;
+                if (yf) {
+                    knn_range(o, p, sv.pos, __ldg(&sv.cell_start[row + x0]), __ldg(&sv.cell_start[row + x1 + 1]));
+                } else {
+                    if (cx - r >= 0) knn_range(o, p, sv.pos, __ldg(&sv.cell_start[row + cx - r]), __ldg(&sv.cell_start[row + cx - r + 1]));
+                    if (cx + r < dx_ && r > 0) knn_range(o, p, sv.pos, __ldg(&sv.cell_start[row + cx + r]), __ldg(&sv.cell_start[row + cx + r + 1]));
+                }
+            }
+        }
+        // distance from p to the nearest face of the explored block that still has unexplored cells behind it
+        float bound = 3.0e38f;
+        if (cx - r > 0) bound = fminf(bound, p.x - (fc->g_org[0] + (cx - r) * h));
+        if (cx + r < dx_ - 1) bound = fminf(bound, (fc->g_org[0] + (cx + r + 1) * h) - p.x);
+        if (cy - r > 0) bound = fminf(bound, p.y - (fc->g_org[1] + (cy - r) * h));
+        if (cy + r < dy_ - 1) bound = fminf(bound, (fc->g_org[1] + (cy + r + 1) * h) - p.y);
+        if (cz - r > 0) bound = fminf(bound, p.z - (fc->g_org[2] + (cz - r) * h));
+        if (cz + r < dz_ - 1) bound = fminf(bound, (fc->g_org[2] + (cz + r + 1) * h) - p.z);
+        // safety margin of one part in 1e5 against fp32 rounding of the face coordinates
+        if (bound > 0.f && o.d2[2] <= bound * bound * 0.9999f) done = true;
+        if (bound == 3.0e38f) done = true;   // whole grid explored
+    }
+    if (!done) {
+        o.d2[0] = o.d2[1] = o.d2[2] = 3.0e38f;
+        knn_range(o, p, sv.pos, 0, nverts);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ front-end
+struct HdqFront {
+    float smpl;       // mean signed vertex distance after the |.| rule (base_network.py:374-375)
+    bool in_shell;
+    float3 bpts;      // big-pose point (valid if in_shell)
+    float Ar[9];      // blended A[:3,:3]       (valid if in_shell and want_mats)
+    float Rinv[9];    // inverse_3x3 of it
+    float bigAr[9];   // blended big_A[:3,:3]
+    float bigRinv[9];
+};
+
+__device__ __forceinline__ void inverse3x3_ref(const float* R, float* M) {
+    // adjugate / (det + 1e-8)   blend_utils.py:125-165
+    float r00 = R[0], r01 = R[1], r02 = R[2], r10 = R[3], r11 = R[4], r12 = R[5], r20 = R[6], r21 = R[7], r22 = R[8];
+    float m00 = r11 * r22 - r21 * r12, m10 = -r10 * r22 + r20 * r12, m20 = r10 * r21 - r20 * r11;
+    float m01 = -r01 * r22 + r21 * r02, m11 = r00 * r22 - r20 * r02, m21 = -r00 * r21 + r20 * r01;
+    float m02 = r01 * r12 - r11 * r02, m12 = -r00 * r12 + r10 * r02, m22 = r00 * r11 - r10 * r01;
+    float D = r00 * m00 + r01 * m10 + r02 * m20;
+    float inv = D + 1e-8f;
+    M[0] = m00 / inv; M[1] = m01 / inv; M[2] = m02 / inv;
+    M[3] = m10 / inv; M[4] = m11 / inv; M[5] = m12 / inv;
+    M[6] = m20 / inv; M[7] = m21 / inv; M[8] = m22 / inv;
+}
+
+template <bool WANT_MATS>
+__device__ void hdq_front(const FrameConst* __restrict__ fc, const SortedVerts& sv, int nverts, float3 x, float th,
+                          float blend_radius, HdqFront& out) {
+    // world -> pose: (x - Th) @ R      blend_utils.py:252-261
+    float3 q = make3(x.x - fc->Th[0], x.y - fc->Th[1], x.z - fc->Th[2]);
+    float3 p = make3(q.x * fc->R[0] + q.y * fc->R[3] + q.z * fc->R[6],
+                     q.x * fc->R[1] + q.y * fc->R[4] + q.z * fc->R[7],
+                     q.x * fc->R[2] + q.y * fc->R[5] + q.z * fc->R[8]);
+    KnnOut nn;
+    knn3_query(fc, sv, nverts, p, nn);
+    float th2 = th * th;
+    float sdfk[3];
+    float4 tv0 = __ldg(&sv.tv[nn.id[0]]);
+    float d2f[3];
+    int idf[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float4 v = __ldg(&sv.pos[nn.id[k]]);
+        float4 n = __ldg(&sv.nrm[nn.id[k]]);
+        float dt = (p.x - v.x) * n.x + (p.y - v.y) * n.y + (p.z - v.z) * n.z;
+        sdfk[k] = sqrtf(nn.d2[k]) * signf(dt);
+        d2f[k] = nn.d2[k];
+        idf[k] = nn.id[k];
+    }
+    // geodesic filter: neighbours whose canonical vertex is >= th from the closest one's -> closest  (:148-160)
+#pragma unroll
+    for (int k = 1; k < 3; k++) {
+        float4 t = __ldg(&sv.tv[nn.id[k]]);
+        float ex = t.x - tv0.x, ey = t.y - tv0.y, ez = t.z - tv0.z;
+        float g2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+        if (!(g2 < th2)) { sdfk[k] = sdfk[0]; d2f[k] = d2f[0]; idf[k] = idf[0]; }
+    }
+    float smpl = (sdfk[0] + sdfk[1] + sdfk[2]) / 3.0f;
+    out.smpl = (smpl < -th) ? smpl : fabsf(smpl);
+    out.in_shell = nn.d2[0] < th2;
+    if (!out.in_shell) return;
+    // gaussian blend of the 3 neighbours' skinning transforms   base_network.py:287-296
+    float inv2r2 = 1.0f / (2.0f * blend_radius * blend_radius);
+    float w[3], ws = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { w[k] = expf(-d2f[k] * inv2r2); ws += w[k]; }
+    ws += 1.1920929e-07f;   // torch.finfo(float32).eps
+    float T[24];
+#pragma unroll
+    for (int i = 0; i < 24; i++) T[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float wk = w[k] / ws;
+        const float4* Tp = reinterpret_cast<const float4*>(sv.T + (size_t)idf[k] * 24);
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            float4 t = __ldg(&Tp[i]);
+            T[i * 4 + 0] += wk * t.x; T[i * 4 + 1] += wk * t.y; T[i * 4 + 2] += wk * t.z; T[i * 4 + 3] += wk * t.w;
+        }
+    }
+    float Ar[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+    float Rinv[9];
+    inverse3x3_ref(Ar, Rinv);
+    float3 dlt = make3(p.x - T[3], p.y - T[7], p.z - T[11]);
+    float3 tp = make3(Rinv[0] * dlt.x + Rinv[1] * dlt.y + Rinv[2] * dlt.z,
+                      Rinv[3] * dlt.x + Rinv[4] * dlt.y + Rinv[5] * dlt.z,
+                      Rinv[6] * dlt.x + Rinv[7] * dlt.y + Rinv[8] * dlt.z);
+    const float* B = T + 12;
+    out.bpts = make3(B[0] * tp.x + B[1] * tp.y + B[2] * tp.z + B[3],
+                     B[4] * tp.x + B[5] * tp.y + B[6] * tp.z + B[7],
+                     B[8] * tp.x + B[9] * tp.y + B[10] * tp.z + B[11]);
+    if (WANT_MATS) {
+        float Br[9] = {B[0], B[1], B[2], B[4], B[5], B[6], B[8], B[9], B[10]};
+#pragma unroll
+        for (int i = 0; i < 9; i++) { out.Ar[i] = Ar[i]; out.Rinv[i] = Rinv[i]; out.bigAr[i] = Br[i]; }
+        inverse3x3_ref(Br, out.bigRinv);
+    }
+}
+
+// smooth transition of the network distance with the SMPL distance  (base_network.py:377-381)
+__device__ __forceinline__ float hdq_blend(float net, float smpl, float th, bool smooth) {
+    if (!smooth) return net;
+    float r = clampf(fabsf(net) / th, 0.f, 1.f);
+    return smpl * r + net * (1.f - r);
+}

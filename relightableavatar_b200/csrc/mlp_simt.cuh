@@ -1,0 +1,243 @@
+// fp32 CUDA-core MLP path: per-layer tiled SGEMM with fused bias/activation (forward) and fused
+// activation-derivative (input-gradient backward), plus the small element-wise kernels around them.
+// This is the reference-precision path (RA_PRECISION_FP32) and the surface-attribute path (forward +
+// analytic d sdf / d bpts, base_network.py:456-475 via autograd in the reference).
+#pragma once
+#include "common.cuh"
+
+enum { EPI_NONE = 0, EPI_RELU = 1, EPI_SOFTPLUS = 2, EPI_MUL_DRELU = 3, EPI_MUL_DSOFTPLUS = 4 };
+
+struct GemmArgs {
+    const float* X; int ldx;      // (M, K) row-major, K % 8 == 0, rows readable up to M
+    const float* W; int ldw;      // (N, K) row-major (torch Linear layout), zero padded to K
+    const float* bias;            // (N) or null
+    float* Y; int ldy;            // (M, N) written at column offset 0 of Y
+    const float* aux; int ldaux;  // activation values for the derivative epilogues
+    const int* count;             // device row count (total); rows [row0, row0 + M) processed
+    int row0, rows_cap;
+    int N, K;
+};
+
+#define GBM 128
+#define GBN 128
+#define GBK 8
+
+template <int EPI>
+__global__ void __launch_bounds__(256) k_gemm(GemmArgs a) {
+    int total = *a.count;
+    int M = min(total - a.row0, a.rows_cap);
+    int m0 = blockIdx.x * GBM;
+    if (m0 >= M) return;
+    int n0 = blockIdx.y * GBN;
+    __shared__ __align__(16) float As[2][GBK][GBM + 4];
+    __shared__ __align__(16) float Bs[2][GBK][GBN + 4];
+    int tid = threadIdx.x;
+    int tx = tid & 15, ty = tid >> 4;
+    int lrow = tid >> 1, lk = (tid & 1) * 4;
+    const float* Xp = a.X + (size_t)(m0 + lrow) * a.ldx + lk;
+    const float* Wp = a.W + (size_t)(n0 + lrow) * a.ldw + lk;
+    bool xok = (m0 + lrow) < M, wok = (n0 + lrow) < a.N;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+    float4 xa = xok ? *reinterpret_cast<const float4*>(Xp) : make_float4(0, 0, 0, 0);
+    float4 wa = wok ? __ldg(reinterpret_cast<const float4*>(Wp)) : make_float4(0, 0, 0, 0);
+    As[0][lk + 0][lrow] = xa.x; As[0][lk + 1][lrow] = xa.y; As[0][lk + 2][lrow] = xa.z; As[0][lk + 3][lrow] = xa.w;
+    Bs[0][lk + 0][lrow] = wa.x; Bs[0][lk + 1][lrow] = wa.y; Bs[0][lk + 2][lrow] = wa.z; Bs[0][lk + 3][lrow] = wa.w;
+    __syncthreads();
+    int nk = a.K / GBK;
+    for (int kt = 0; kt < nk; kt++) {
+        int cur = kt & 1;
+        if (kt + 1 < nk) {
+            xa = xok ? *reinterpret_cast<const float4*>(Xp + (kt + 1) * GBK) : make_float4(0, 0, 0, 0);
+            wa = wok ? __ldg(reinterpret_cast<const float4*>(Wp + (kt + 1) * GBK)) : make_float4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < GBK; k++) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+            float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
+            float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            int nx = cur ^ 1;
+            As[nx][lk + 0][lrow] = xa.x; As[nx][lk + 1][lrow] = xa.y; As[nx][lk + 2][lrow] = xa.z; As[nx][lk + 3][lrow] = xa.w;
+            Bs[nx][lk + 0][lrow] = wa.x; Bs[nx][lk + 1][lrow] = wa.y; Bs[nx][lk + 2][lrow] = wa.z; Bs[nx][lk + 3][lrow] = wa.w;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= M) continue;
+        size_t grow = (size_t)m;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (n >= a.N) continue;
+            float v = acc[i][j];
+            if (a.bias) v += __ldg(&a.bias[n]);
+            if (EPI == EPI_RELU) v = fmaxf(v, 0.f);
+            if (EPI == EPI_SOFTPLUS) v = softplus100(v);
+            if (EPI == EPI_MUL_DRELU) v = (a.aux[grow * a.ldaux + n] > 0.f) ? v : 0.f;
+            if (EPI == EPI_MUL_DSOFTPLUS) v *= dsoftplus100_from_act(a.aux[grow * a.ldaux + n]);
+            a.Y[grow * a.ldy + n] = v;
+        }
+    }
+}
+// All pointers are CHUNK-LOCAL: the host offsets per-point arrays by row0; row0 only bounds M.
+
+// Y[m, n] for n < N <= 4: one warp per row.
+__global__ void k_skinny(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
+                         const float* __restrict__ bias, float* Y, int ldy, const int* count, int row0, int rows_cap,
+                         int N, int K) {
+    int total = *count;
+    int M = min(total - row0, rows_cap);
+    int warps_per_block = blockDim.x >> 5;
+    int lane = threadIdx.x & 31;
+    for (int m = blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < M; m += gridDim.x * warps_per_block) {
+        const float* x = X + (size_t)m * ldx;
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = lane; k < K; k += 32) {
+            float xv = x[k];
+#pragma unroll
+            for (int n = 0; n < 4; n++)
+                if (n < N) s[n] = fmaf(xv, __ldg(&W[(size_t)n * ldw + k]), s[n]);
+        }
+#pragma unroll
+        for (int n = 0; n < 4; n++)
+            for (int o = 16; o; o >>= 1) s[n] += __shfl_xor_sync(0xffffffffu, s[n], o);
+        if (lane == 0)
+            for (int n = 0; n < N; n++) Y[(size_t)m * ldy + n] = s[n] + (bias ? bias[n] : 0.f);
+    }
+}
+
+// D[m, k] = (sum_{n<N} U[m, n] * W[n, k]) * dact(aux[m, k]);  U == null means N == 1 and U = 1 (start of the
+// SDF backward: d a_7 = W8[0, :]).  N <= 4.
+template <int EPI>
+__global__ void k_outer_small(const float* __restrict__ U, int ldu, const float* __restrict__ W, int ldw, int N, int K,
+                              const float* __restrict__ aux, int ldaux, float* D, int ldd, const int* count, int row0,
+                              int rows_cap) {
+    int total = *count;
+    int M = min(total - row0, rows_cap);
+    size_t n_el = (size_t)M * K;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (size_t)gridDim.x * blockDim.x) {
+        int m = (int)(i / K), k = (int)(i % K);
+        size_t g = (size_t)m;
+        float v = 0.f;
+        if (U == nullptr) v = __ldg(&W[k]);
+        else
+            for (int n = 0; n < N; n++) v = fmaf(U[g * ldu + n], __ldg(&W[(size_t)n * ldw + k]), v);
+        float a = aux[g * ldaux + k];
+        if (EPI == EPI_MUL_DRELU) v = (a > 0.f) ? v : 0.f;
+        if (EPI == EPI_MUL_DSOFTPLUS) v *= dsoftplus100_from_act(a);
+        D[g * ldd + k] = v;
+    }
+}
+
+// positional encoding of x (3) into dst[0 .. 3+6L), zero padding up to `width`   embedder.py:26-37
+__device__ __forceinline__ void pe_write(float3 x, int L, float* dst, int width) {
+    dst[0] = x.x; dst[1] = x.y; dst[2] = x.z;
+    float f = 1.f;
+    for (int l = 0; l < L; l++) {
+        float* d = dst + 3 + l * 6;
+        d[0] = sinf(x.x * f); d[1] = sinf(x.y * f); d[2] = sinf(x.z * f);
+        d[3] = cosf(x.x * f); d[4] = cosf(x.y * f); d[5] = cosf(x.z * f);
+        f *= 2.f;
+    }
+    for (int k = 3 + 6 * L; k < width; k++) dst[k] = 0.f;
+}
+
+// X0[m, 0:64] = PE_L(p[m]);  optionally the same into a second buffer at a column offset (skip input)
+__global__ void k_encode(const float* __restrict__ pts, int L, float* X0, int ld0, int w0, float* X1, int ld1, int off1,
+                         int w1, const int* count, int row0, int rows_cap) {
+    int total = *count;
+    int M = min(total - row0, rows_cap);
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
+        size_t g = (size_t)m;
+        float3 x = make3(pts[g * 3], pts[g * 3 + 1], pts[g * 3 + 2]);
+        float buf[64];
+        pe_write(x, L, buf, 64);
+        for (int k = 0; k < w0; k++) X0[g * ld0 + k] = buf[k];
+        if (X1)
+            for (int k = 0; k < w1; k++) X1[g * ld1 + off1 + k] = buf[k];
+    }
+}
+
+// resd = resd_limit * tanh(z8);  cpts = bpts + resd   (base_network.py:41,466)
+__global__ void k_resd_finish(const float* __restrict__ z8, int ldz, const float* __restrict__ bpts, float limit,
+                              float* resd, float* cpts, const int* count, int row0, int rows_cap) {
+    int total = *count;
+    int M = min(total - row0, rows_cap);
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
+        size_t g = (size_t)m;
+        for (int c = 0; c < 3; c++) {
+            float r = tanhf(z8[g * ldz + c]) * limit;
+            resd[g * 3 + c] = r;
+            cpts[g * 3 + c] = bpts[g * 3 + c] + r;
+        }
+    }
+}
+
+// Gradient of a PE input: g_x = d[0:3] + sum_l 2^l (cos(2^l x) d_sin[l] - sin(2^l x) d_cos[l]),
+// where d = dA (cols offA..) + dB (cols offB..)
+__device__ __forceinline__ float3 pe_backward(float3 x, int L, const float* dA, const float* dB) {
+    float g[3];
+    float xs[3] = {x.x, x.y, x.z};
+    for (int c = 0; c < 3; c++) g[c] = dA[c] + (dB ? dB[c] : 0.f);
+    float f = 1.f;
+    for (int l = 0; l < L; l++) {
+        for (int c = 0; c < 3; c++) {
+            float ds = dA[3 + l * 6 + c] + (dB ? dB[3 + l * 6 + c] : 0.f);
+            float dc = dA[3 + l * 6 + 3 + c] + (dB ? dB[3 + l * 6 + 3 + c] : 0.f);
+            float s, co;
+            sincosf(xs[c] * f, &s, &co);
+            g[c] += f * (co * ds - s * dc);
+        }
+        f *= 2.f;
+    }
+    return make3(g[0], g[1], g[2]);
+}
+
+// g_cp = PE8-backward(cp; d_pe(layer0) + d_pe(skip));  u = g_cp * limit * (1 - tanh(z8)^2)  (upstream of the resd MLP)
+__global__ void k_sdf_grad_to_cp(const float* __restrict__ cpts, const float* __restrict__ dA, int lda,
+                                 const float* __restrict__ dB, int ldb, int offB, const float* __restrict__ z8, int ldz,
+                                 float limit, float* gcp, float* u, int ldu, const int* count, int row0, int rows_cap) {
+    int total = *count;
+    int M = min(total - row0, rows_cap);
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
+        size_t g = (size_t)m;
+        float3 x = make3(cpts[g * 3], cpts[g * 3 + 1], cpts[g * 3 + 2]);
+        float3 gr = pe_backward(x, 8, dA + g * lda, dB + g * ldb + offB);
+        gcp[g * 3] = gr.x; gcp[g * 3 + 1] = gr.y; gcp[g * 3 + 2] = gr.z;
+        float gv[3] = {gr.x, gr.y, gr.z};
+        for (int c = 0; c < 3; c++) {
+            float t = tanhf(z8[g * ldz + c]);
+            u[g * ldu + c] = gv[c] * limit * (1.f - t * t);
+        }
+    }
+}
+
+// g_bp = g_cp + PE10-backward(bp; d_pe(layer0) + d_pe(skip))
+__global__ void k_resd_grad_to_bp(const float* __restrict__ bpts, const float* __restrict__ dA, int lda,
+                                  const float* __restrict__ dB, int ldb, int offB, const float* __restrict__ gcp,
+                                  float* gbp, const int* count, int row0, int rows_cap) {
+    int total = *count;
+    int M = min(total - row0, rows_cap);
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
+        size_t g = (size_t)m;
+        float3 x = make3(bpts[g * 3], bpts[g * 3 + 1], bpts[g * 3 + 2]);
+        float3 gr = pe_backward(x, 10, dA + g * lda, dB + g * ldb + offB);
+        gbp[g * 3] = gcp[g * 3] + gr.x;
+        gbp[g * 3 + 1] = gcp[g * 3 + 1] + gr.y;
+        gbp[g * 3 + 2] = gcp[g * 3 + 2] + gr.z;
+    }
+}

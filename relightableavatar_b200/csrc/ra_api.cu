@@ -1,0 +1,602 @@
+// C-ABI entry points (include/ra_b200.h) and host-side orchestration of the kernels.
+// One handle per device.  The product path enqueues a fixed sequence of kernels on the caller's
+// stream; every data-dependent size stays in device counters (no host sync) except in the
+// RA_PRECISION_FP32 debug/reference-precision mode and the 128-sample volume renderer, which chunk
+// their MLP work by a counter read back from the device.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cmath>
+
+#include "../../include/ra_b200.h"
+#include "common.cuh"
+#include "hdq.cuh"
+#include "mlp_simt.cuh"
+#include "render.cuh"
+#include "mlp_tc.cuh"
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + std::to_string(__LINE__); \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+#define LAUNCH(h, kern, grid, block, smem, stream, ...)          \
+    do {                                                         \
+        kern<<<grid, block, smem, stream>>>(__VA_ARGS__);        \
+        (h)->launches++;                                         \
+    } while (0)
+
+static const int ATTR_CH = 262144;   // rows per fp32 MLP chunk
+
+struct Lin {            // one fp32 linear layer, K zero-padded to a multiple of 8
+    float* w = nullptr; float* b = nullptr; int N = 0, K = 0;     // (N, K) row-major
+    float* wt = nullptr; int Nt = 0, Kt = 0;                      // transposed (K_in rows, N padded to 8) for backward
+};
+
+struct ra_handle {
+    ra_config cfg;
+    std::string err;
+    int64_t launches = 0;
+    int dev = 0, sms = 148;
+    bool have_weights = false, have_frame = false;
+    // ---- weights
+    Lin resd[9], sdf[9], rend[5], alb[3], rgh[3];
+    float *resd_w0_raw = nullptr, *resd_b0_raw = nullptr, *resd_w4_raw = nullptr, *resd_b4_raw = nullptr;
+    float *rend_w3_raw = nullptr, *rend_b3_raw = nullptr;
+    float* w4_skipT = nullptr;       // resd WT4 rows 256..319 live inside resd[4].wt; helper pointers below
+    float beta = 0.1f;
+    float *env_main = nullptr; int emh = 0, emw = 0;
+    float *lxyz = nullptr, *larea = nullptr, *lsharp = nullptr, *ldir = nullptr;
+    TcWeights tc;                    // fp16 UMMA images for the tcgen05 path
+    // ---- frame
+    FrameConst* fc = nullptr;
+    SortedVerts sv{};
+    int *cell_count = nullptr, *cell_fill = nullptr, *vert_cell = nullptr;
+    ra_frame frame{};
+    // ---- per-render workspace
+    int64_t P_cap = 0, q_cap = 0, attr_cap = 0, vol_rays = 8192;
+    SurfState ss{};
+    float *surf = nullptr, *acc = nullptr, *depth = nullptr;
+    int* fg_ray = nullptr;
+    FgMaps fm{};
+    float *lvis = nullptr, *ldot = nullptr;
+    ShadowRays sr{};
+    QueryList q{};
+    AttrList al{};
+    float* raw = nullptr;
+    Counters cnt{};
+    int* counters_blk = nullptr;     // n_fg, n_shadow, n_attr, q.count, (pad), n_queries(ull), n_inshell(ull)
+    float *pt_smpl = nullptr; int* pt_slot = nullptr;     // ra_query_sdf scratch
+    float* bg_spec = nullptr;
+    // ---- fp32 MLP chunk buffers
+    float *Xr0, *ra_[8], *Xr4, *z8, *resd_o, *cpts_o, *Xs0, *sb_[8], *Xs4, *out257, *GA, *GB, *dpe0, *dpes, *gcp, *u4, *gbp, *nrm_o;
+    float *hd1, *hd2, *head_a, *head_r, *Xrn, *rn1, *rn2;
+    // last render
+    int64_t last_P = 0; const float* last_ray_o = nullptr; int chunk_actual = 1;
+};
+
+// ---------------------------------------------------------------------------------------------- helpers
+static int grid_for(ra_handle* h, long long n, int block = 256, int per_sm = 8) {
+    long long g = (n + block - 1) / block;
+    long long cap = (long long)h->sms * per_sm;
+    return (int)std::max(1LL, std::min(g, cap));
+}
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(T));
+    return e;
+}
+
+// copy a (N, K) fp32 matrix (host or device) into a zero-padded (N, Kp) device buffer, optionally selecting columns
+static int upload_lin(ra_handle* h, Lin& L, const float* w, const float* b, int N, int K_src, int col0, int K_use, int Kp,
+                      float scale, const int* row_perm, cudaStream_t st) {
+    std::vector<float> hw((size_t)N * K_src), hb(N);
+    CK(cudaMemcpyAsync(hw.data(), w, hw.size() * sizeof(float), cudaMemcpyDefault, st));
+    if (b) CK(cudaMemcpyAsync(hb.data(), b, hb.size() * sizeof(float), cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<float> pw((size_t)N * Kp, 0.f), pb(N, 0.f);
+    for (int n = 0; n < N; n++) {
+        int sn = row_perm ? row_perm[n] : n;
+        for (int k = 0; k < K_use; k++) pw[(size_t)n * Kp + k] = hw[(size_t)sn * K_src + col0 + k] * scale;
+        pb[n] = b ? hb[sn] : 0.f;
+    }
+    int Np8 = (N + 7) / 8 * 8;
+    std::vector<float> pt((size_t)Kp * Np8, 0.f);
+    for (int n = 0; n < N; n++)
+        for (int k = 0; k < Kp; k++) pt[(size_t)k * Np8 + n] = pw[(size_t)n * Kp + k];
+    if (L.w) { cudaFree(L.w); cudaFree(L.b); cudaFree(L.wt); }
+    CK(dalloc(&L.w, pw.size())); CK(dalloc(&L.b, pb.size())); CK(dalloc(&L.wt, pt.size()));
+    CK(cudaMemcpy(L.w, pw.data(), pw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(L.b, pb.data(), pb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(L.wt, pt.data(), pt.size() * sizeof(float), cudaMemcpyHostToDevice));
+    L.N = N; L.K = Kp; L.Nt = Kp; L.Kt = Np8;
+    return 0;
+}
+
+static int upload_raw(ra_handle* h, float** dst, const float* src, size_t n, cudaStream_t st) {
+    if (*dst) cudaFree(*dst);
+    CK(dalloc(dst, n));
+    CK(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+template <int EPI>
+static void gemm(ra_handle* h, cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias, float* Y,
+                 int ldy, const float* aux, int ldaux, const int* count, int row0, int rows_cap, int N, int K) {
+    GemmArgs a{X, ldx, W, ldw, bias, Y, ldy, aux, ldaux, count, row0, rows_cap, N, K};
+    dim3 grid((rows_cap + GBM - 1) / GBM, (N + GBN - 1) / GBN);
+    LAUNCH(h, k_gemm<EPI>, grid, 256, 0, st, a);
+}
+
+// ---------------------------------------------------------------------------------------------- create / destroy
+extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
+    if (!out || !cfg) return 1;
+    ra_handle* h = new ra_handle();
+    *out = h;
+    h->cfg = *cfg;
+    if (cfg->n_verts <= 0 || cfg->n_bones <= 0 || cfg->max_rays <= 0) { h->err = "bad config"; return 1; }
+    if (cfg->env_h * cfg->env_w > RA_NLIGHT_MAX) { h->err = "env_h*env_w > 512"; return 1; }
+    CK(cudaGetDevice(&h->dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->dev));
+    h->sms = prop.multiProcessorCount;
+    if (prop.major != 10) { h->err = "ra_b200 requires an sm_100 (B200) device"; return 1; }
+    int64_t P = cfg->max_rays;
+    int L = cfg->env_h * cfg->env_w;
+    h->P_cap = P;
+    h->q_cap = std::max<int64_t>(256 * P, 1 << 20);
+    h->attr_cap = std::max<int64_t>((int64_t)cfg->n_samples * P, h->vol_rays * cfg->vol_samples);
+    int N = cfg->n_verts;
+    CK(dalloc(&h->fc, 1));
+    CK(dalloc(&h->sv.pos, N)); CK(dalloc(&h->sv.nrm, N)); CK(dalloc(&h->sv.tv, N)); CK(dalloc(&h->sv.T, (size_t)N * 24));
+    CK(dalloc(&h->sv.cell_start, RA_MAX_CELLS + 1));
+    CK(dalloc(&h->cell_count, RA_MAX_CELLS + 1)); CK(dalloc(&h->cell_fill, RA_MAX_CELLS + 1)); CK(dalloc(&h->vert_cell, N));
+    float** ssp[] = {&h->ss.t, &h->ss.occ, &h->ss.d0, &h->ss.cd, &h->ss.dt, &h->ss.st, &h->ss.off, &h->ss.rlx, &h->ss.q_smpl};
+    for (auto p : ssp) CK(dalloc(p, P));
+    CK(dalloc(&h->ss.q_slot, P));
+    CK(dalloc(&h->surf, 3 * P)); CK(dalloc(&h->acc, P)); CK(dalloc(&h->depth, P)); CK(dalloc(&h->fg_ray, P));
+    CK(dalloc(&h->fm.norm, 3 * P)); CK(dalloc(&h->fm.albedo, 3 * P)); CK(dalloc(&h->fm.rough, P));
+    if (cfg->relight) {
+        CK(dalloc(&h->lvis, (size_t)P * L)); CK(dalloc(&h->ldot, (size_t)P * L));
+        int64_t S = 256 * P;
+        CK(dalloc(&h->sr.fg, S)); CK(dalloc(&h->sr.light, S)); CK(dalloc(&h->sr.near_, S)); CK(dalloc(&h->sr.far_, S));
+        CK(dalloc(&h->sr.t, S)); CK(dalloc(&h->sr.occ, S)); CK(dalloc(&h->sr.d0, S)); CK(dalloc(&h->sr.q_smpl, S)); CK(dalloc(&h->sr.q_slot, S));
+    }
+    CK(dalloc(&h->q.bpts, (size_t)h->q_cap * 3)); CK(dalloc(&h->q.net, (size_t)h->q_cap));
+    CK(dalloc(&h->al.bpts, (size_t)h->attr_cap * 3)); CK(dalloc(&h->al.mats, (size_t)h->attr_cap * 18));
+    CK(dalloc(&h->al.bvds, (size_t)h->attr_cap * 3)); CK(dalloc(&h->al.src, (size_t)h->attr_cap));
+    CK(dalloc(&h->raw, (size_t)h->attr_cap * 17));
+    CK(dalloc(&h->counters_blk, 16));
+    h->cnt.n_fg = h->counters_blk; h->cnt.n_shadow = h->counters_blk + 1; h->cnt.n_attr = h->counters_blk + 2;
+    h->q.count = h->counters_blk + 3; h->al.count = h->cnt.n_attr;
+    h->cnt.n_queries = (unsigned long long*)(h->counters_blk + 8); h->cnt.n_inshell = (unsigned long long*)(h->counters_blk + 10);
+    CK(dalloc(&h->pt_smpl, (size_t)h->q_cap)); CK(dalloc(&h->pt_slot, (size_t)h->q_cap));
+    CK(dalloc(&h->bg_spec, 4));
+    size_t R = ATTR_CH;
+    CK(dalloc(&h->Xr0, R * 64)); for (int i = 0; i < 8; i++) CK(dalloc(&h->ra_[i], R * 256));
+    CK(dalloc(&h->Xr4, R * 320)); CK(dalloc(&h->z8, R * 4)); CK(dalloc(&h->resd_o, R * 3)); CK(dalloc(&h->cpts_o, R * 3));
+    CK(dalloc(&h->Xs0, R * 64)); for (int i = 0; i < 8; i++) CK(dalloc(&h->sb_[i], R * 256));
+    CK(dalloc(&h->Xs4, R * 256)); CK(dalloc(&h->out257, R * 264));
+    CK(dalloc(&h->GA, R * 256)); CK(dalloc(&h->GB, R * 256)); CK(dalloc(&h->dpe0, R * 64)); CK(dalloc(&h->dpes, R * 64));
+    CK(dalloc(&h->gcp, R * 3)); CK(dalloc(&h->u4, R * 4)); CK(dalloc(&h->gbp, R * 3)); CK(dalloc(&h->nrm_o, R * 3));
+    CK(dalloc(&h->hd1, R * 128)); CK(dalloc(&h->hd2, R * 128)); CK(dalloc(&h->head_a, R * 4)); CK(dalloc(&h->head_r, R * 4));
+    CK(dalloc(&h->Xrn, R * 288)); CK(dalloc(&h->rn1, R * 256)); CK(dalloc(&h->rn2, R * 256));
+    if (tc_init(h->tc, h->err)) return 1;
+    return 0;
+}
+
+extern "C" void ra_destroy(ra_handle* h) {
+    if (!h) return;
+    // device memory is released with the context; explicit frees of the big blocks keep long-lived processes tidy
+    float* bufs[] = {h->lvis, h->ldot, h->q.bpts, h->q.net, h->raw, h->al.bpts, h->al.mats, h->al.bvds, h->Xr4, h->out257};
+    for (float* b : bufs) if (b) cudaFree(b);
+    for (int i = 0; i < 8; i++) { if (h->ra_[i]) cudaFree(h->ra_[i]); if (h->sb_[i]) cudaFree(h->sb_[i]); }
+    tc_free(h->tc);
+    delete h;
+}
+
+extern "C" const char* ra_last_error(ra_handle* h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" int64_t ra_launch_count(ra_handle* h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------- weights
+extern "C" int ra_upload_weights(ra_handle* h, const ra_weights* w, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const float rs2 = (float)(1.0 / std::sqrt(2.0));
+    // residual deformation MLP: 219 -> 256 x4 -> (256+219) -> 256 x3 -> 3; the 156-d pose condition is folded into biases per frame
+    static const int rK[9] = {219, 256, 256, 256, 475, 256, 256, 256, 256};
+    for (int l = 0; l < 9; l++) {
+        int N = (l == 8) ? 3 : 256;
+        if (l == 0) { if (upload_lin(h, h->resd[l], w->resd_w[l], w->resd_b[l], N, rK[l], 0, 63, 64, 1.f, nullptr, st)) return 1; }
+        else if (l == 4) {
+            // columns [h3 (256) | PE10 (63)] -> (256, 320)
+            if (upload_lin(h, h->resd[l], w->resd_w[l], w->resd_b[l], N, rK[l], 0, 256 + 63, 320, 1.f, nullptr, st)) return 1;
+        } else if (upload_lin(h, h->resd[l], w->resd_w[l], w->resd_b[l], N, rK[l], 0, rK[l], 256, 1.f, nullptr, st)) return 1;
+    }
+    if (upload_raw(h, &h->resd_w0_raw, w->resd_w[0], 256 * 219, st)) return 1;
+    if (upload_raw(h, &h->resd_b0_raw, w->resd_b[0], 256, st)) return 1;
+    if (upload_raw(h, &h->resd_w4_raw, w->resd_w[4], 256 * 475, st)) return 1;
+    if (upload_raw(h, &h->resd_b4_raw, w->resd_b[4], 256, st)) return 1;
+    // SDF MLP: 51 -> 256,256,256,205 -> cat(205,51)/sqrt2 -> 256 x3 -> 257 ; rows of the last layer permuted to [feat(256), sdf]
+    static const int sN[9] = {256, 256, 256, 205, 256, 256, 256, 256, 257};
+    static const int sK[9] = {51, 256, 256, 256, 256, 256, 256, 256, 256};
+    std::vector<int> perm(257);
+    for (int i = 0; i < 256; i++) perm[i] = i + 1;
+    perm[256] = 0;
+    for (int l = 0; l < 9; l++) {
+        int Kp = (l == 0) ? 64 : 256;
+        if (upload_lin(h, h->sdf[l], w->sdf_w[l], w->sdf_b[l], sN[l], sK[l], 0, sK[l], Kp, l == 4 ? rs2 : 1.f,
+                       l == 8 ? perm.data() : nullptr, st)) return 1;
+    }
+    h->beta = w->sdf_beta;
+    if (w->render_w[0]) {
+        static const int nK[5] = {286, 256, 256, 412, 256};
+        for (int l = 0; l < 5; l++) {
+            int N = (l == 4) ? 3 : 256;
+            int use = (l == 3) ? 256 : nK[l];
+            int Kp = (l == 0) ? 288 : 256;
+            if (upload_lin(h, h->rend[l], w->render_w[l], w->render_b[l], N, nK[l], 0, use, Kp, 1.f, nullptr, st)) return 1;
+        }
+        if (upload_raw(h, &h->rend_w3_raw, w->render_w[3], 256 * 412, st)) return 1;
+        if (upload_raw(h, &h->rend_b3_raw, w->render_b[3], 256, st)) return 1;
+    }
+    if (h->cfg.relight) {
+        if (!w->albedo_w[0] || !w->rough_w[0] || !w->env_main || !w->light_xyz) { h->err = "relight weights missing"; return 1; }
+        static const int aK[3] = {256, 128, 128};
+        for (int l = 0; l < 3; l++) {
+            if (upload_lin(h, h->alb[l], w->albedo_w[l], w->albedo_b[l], l == 2 ? 3 : 128, aK[l], 0, aK[l], aK[l], 1.f, nullptr, st)) return 1;
+            if (upload_lin(h, h->rgh[l], w->rough_w[l], w->rough_b[l], l == 2 ? 1 : 128, aK[l], 0, aK[l], aK[l], 1.f, nullptr, st)) return 1;
+        }
+        h->emh = w->env_main_h; h->emw = w->env_main_w;
+        if (upload_raw(h, &h->env_main, w->env_main, (size_t)h->emh * h->emw * 3, st)) return 1;
+        int L = h->cfg.env_h * h->cfg.env_w;
+        if (upload_raw(h, &h->lxyz, w->light_xyz, (size_t)L * 3, st)) return 1;
+        if (upload_raw(h, &h->larea, w->light_area, L, st)) return 1;
+        if (upload_raw(h, &h->lsharp, w->light_sharp, L, st)) return 1;
+        // shadow ray directions: normalize(xyz) with the reference's normalize (x / (|x| + 1e-8))
+        std::vector<float> xyz((size_t)L * 3), dir((size_t)L * 3);
+        CK(cudaMemcpy(xyz.data(), h->lxyz, xyz.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (int l = 0; l < L; l++) {
+            float x = xyz[l * 3], y = xyz[l * 3 + 1], z = xyz[l * 3 + 2];
+            float n = sqrtf(x * x + y * y + z * z) + 1e-8f;
+            dir[l * 3] = x / n; dir[l * 3 + 1] = y / n; dir[l * 3 + 2] = z / n;
+        }
+        if (upload_raw(h, &h->ldir, dir.data(), dir.size(), st)) return 1;
+    }
+    if (tc_upload(h->tc, w, h->err, st)) return 1;
+    h->have_weights = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- frame
+extern "C" int ra_set_frame(ra_handle* h, const ra_frame* f, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!h->have_weights) { h->err = "ra_set_frame before ra_upload_weights"; return 1; }
+    h->frame = *f;
+    int N = h->cfg.n_verts;
+    LAUNCH(h, k_frame_prep, 1, 1024, 0, st, h->fc, f->R, f->Th, f->pverts, N, f->wbounds, f->poses, f->mat_cond,
+           h->resd_w0_raw, h->resd_b0_raw, h->resd_w4_raw, h->resd_b4_raw, h->rend_w3_raw, h->rend_b3_raw, h->cell_count, 0.04f);
+    LAUNCH(h, k_grid_count, (N + 255) / 256, 256, 0, st, h->fc, f->pverts, N, h->cell_count, h->vert_cell);
+    LAUNCH(h, k_grid_scan, 1, 1024, 0, st, h->fc, h->cell_count, h->sv.cell_start, h->cell_fill);
+    LAUNCH(h, k_grid_fill, (N + 127) / 128, 128, 0, st, h->fc, f->pverts, f->pnorm, f->tverts, f->weights, f->A, f->big_A, N,
+           h->cfg.n_bones, h->vert_cell, h->sv.cell_start, h->cell_fill, h->sv);
+    if (h->cfg.precision == RA_PRECISION_TC) tc_set_frame(h->tc, h->fc, st, h->launches);
+    CK(cudaGetLastError());
+    h->have_frame = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- fp32 MLP passes
+// forward of both MLPs on rows [0, rows_cap) of a chunk whose points are `bpts` (chunk-local pointer).
+// full == false: distance only (sdf written to net_out).
+static void mlp_forward_fp32(ra_handle* h, cudaStream_t st, const float* bpts, const int* count, int row0, int rows, bool full,
+                             float* net_out) {
+    int g = grid_for(h, rows);
+    const float* b0 = &h->fc->resd_b0[0];
+    const float* b4 = &h->fc->resd_b4[0];
+    LAUNCH(h, k_encode, g, 256, 0, st, bpts, 10, h->Xr0, 64, 64, h->Xr4, 320, 256, 64, count, row0, rows);
+    gemm<EPI_RELU>(h, st, h->Xr0, 64, h->resd[0].w, 64, b0, h->ra_[0], 256, nullptr, 0, count, row0, rows, 256, 64);
+    gemm<EPI_RELU>(h, st, h->ra_[0], 256, h->resd[1].w, 256, h->resd[1].b, h->ra_[1], 256, nullptr, 0, count, row0, rows, 256, 256);
+    gemm<EPI_RELU>(h, st, h->ra_[1], 256, h->resd[2].w, 256, h->resd[2].b, h->ra_[2], 256, nullptr, 0, count, row0, rows, 256, 256);
+    gemm<EPI_RELU>(h, st, h->ra_[2], 256, h->resd[3].w, 256, h->resd[3].b, h->Xr4, 320, nullptr, 0, count, row0, rows, 256, 256);
+    gemm<EPI_RELU>(h, st, h->Xr4, 320, h->resd[4].w, 320, b4, h->ra_[4], 256, nullptr, 0, count, row0, rows, 256, 320);
+    for (int l = 5; l < 8; l++)
+        gemm<EPI_RELU>(h, st, h->ra_[l - 1], 256, h->resd[l].w, 256, h->resd[l].b, h->ra_[l], 256, nullptr, 0, count, row0, rows, 256, 256);
+    LAUNCH(h, k_skinny, grid_for(h, (long long)rows * 32), 256, 0, st, h->ra_[7], 256, h->resd[8].w, 256, h->resd[8].b, h->z8, 4, count, row0, rows, 3, 256);
+    LAUNCH(h, k_resd_finish, g, 256, 0, st, h->z8, 4, bpts, h->cfg.resd_limit, h->resd_o, h->cpts_o, count, row0, rows);
+    LAUNCH(h, k_encode, g, 256, 0, st, h->cpts_o, 8, h->Xs0, 64, 64, h->Xs4, 256, 205, 51, count, row0, rows);
+    gemm<EPI_SOFTPLUS>(h, st, h->Xs0, 64, h->sdf[0].w, 64, h->sdf[0].b, h->sb_[0], 256, nullptr, 0, count, row0, rows, 256, 64);
+    gemm<EPI_SOFTPLUS>(h, st, h->sb_[0], 256, h->sdf[1].w, 256, h->sdf[1].b, h->sb_[1], 256, nullptr, 0, count, row0, rows, 256, 256);
+    gemm<EPI_SOFTPLUS>(h, st, h->sb_[1], 256, h->sdf[2].w, 256, h->sdf[2].b, h->sb_[2], 256, nullptr, 0, count, row0, rows, 256, 256);
+    gemm<EPI_SOFTPLUS>(h, st, h->sb_[2], 256, h->sdf[3].w, 256, h->sdf[3].b, h->Xs4, 256, nullptr, 0, count, row0, rows, 205, 256);
+    gemm<EPI_SOFTPLUS>(h, st, h->Xs4, 256, h->sdf[4].w, 256, h->sdf[4].b, h->sb_[4], 256, nullptr, 0, count, row0, rows, 256, 256);
+    for (int l = 5; l < 8; l++)
+        gemm<EPI_SOFTPLUS>(h, st, h->sb_[l - 1], 256, h->sdf[l].w, 256, h->sdf[l].b, h->sb_[l], 256, nullptr, 0, count, row0, rows, 256, 256);
+    if (full)
+        gemm<EPI_NONE>(h, st, h->sb_[7], 256, h->sdf[8].w, 256, h->sdf[8].b, h->out257, 264, nullptr, 0, count, row0, rows, 257, 256);
+    else
+        LAUNCH(h, k_skinny, grid_for(h, (long long)rows * 32), 256, 0, st, h->sb_[7], 256, h->sdf[8].w + 256 * 256, 256, h->sdf[8].b + 256,
+               net_out, 1, count, row0, rows, 1, 256);
+}
+
+// analytic d sdf / d bpts through both MLPs (what autograd does at base_network.py:463-468)
+static void mlp_backward_fp32(ra_handle* h, cudaStream_t st, const float* bpts, const int* count, int row0, int rows) {
+    int g = grid_for(h, rows);
+    int ge = grid_for(h, (long long)rows * 256);
+    // ---- SDF net
+    LAUNCH(h, k_outer_small<EPI_MUL_DSOFTPLUS>, ge, 256, 0, st, (const float*)nullptr, 0, h->sdf[8].w + 256 * 256, 256, 1, 256,
+           h->sb_[7], 256, h->GA, 256, count, row0, rows);
+    float *cur = h->GA, *nxt = h->GB;
+    for (int l = 7; l >= 5; l--) {   // dZ_{l-1} = (dZ_l W_l) * dsp(a_{l-1})
+        gemm<EPI_MUL_DSOFTPLUS>(h, st, cur, 256, h->sdf[l].wt, h->sdf[l].Kt, nullptr, nxt, 256, h->sb_[l - 1], 256, count, row0, rows, 256, 256);
+        std::swap(cur, nxt);
+    }
+    // layer 4 input = [a3 (205) | PE8 (51)]
+    gemm<EPI_MUL_DSOFTPLUS>(h, st, cur, 256, h->sdf[4].wt, h->sdf[4].Kt, nullptr, nxt, 256, h->Xs4, 256, count, row0, rows, 205, 256);
+    gemm<EPI_NONE>(h, st, cur, 256, h->sdf[4].wt + (size_t)205 * h->sdf[4].Kt, h->sdf[4].Kt, nullptr, h->dpes, 64, nullptr, 0, count, row0, rows, 51, 256);
+    std::swap(cur, nxt);
+    // dZ_2 = (dZ_3 W_3) * dsp(a_2): K = 205 padded to 208 (zero weight columns)
+    gemm<EPI_MUL_DSOFTPLUS>(h, st, cur, 256, h->sdf[3].wt, h->sdf[3].Kt, nullptr, nxt, 256, h->sb_[2], 256, count, row0, rows, 256, 208);
+    std::swap(cur, nxt);
+    for (int l = 2; l >= 1; l--) {
+        gemm<EPI_MUL_DSOFTPLUS>(h, st, cur, 256, h->sdf[l].wt, h->sdf[l].Kt, nullptr, nxt, 256, h->sb_[l - 1], 256, count, row0, rows, 256, 256);
+        std::swap(cur, nxt);
+    }
+    gemm<EPI_NONE>(h, st, cur, 256, h->sdf[0].wt, h->sdf[0].Kt, nullptr, h->dpe0, 64, nullptr, 0, count, row0, rows, 51, 256);
+    LAUNCH(h, k_sdf_grad_to_cp, g, 256, 0, st, h->cpts_o, h->dpe0, 64, h->dpes, 64, 0, h->z8, 4, h->cfg.resd_limit, h->gcp, h->u4, 4, count, row0, rows);
+    // ---- residual net
+    LAUNCH(h, k_outer_small<EPI_MUL_DRELU>, ge, 256, 0, st, h->u4, 4, h->resd[8].w, 256, 3, 256, h->ra_[7], 256, h->GA, 256, count, row0, rows);
+    cur = h->GA; nxt = h->GB;
+    for (int l = 7; l >= 5; l--) {
+        gemm<EPI_MUL_DRELU>(h, st, cur, 256, h->resd[l].wt, h->resd[l].Kt, nullptr, nxt, 256, h->ra_[l - 1], 256, count, row0, rows, 256, 256);
+        std::swap(cur, nxt);
+    }
+    gemm<EPI_MUL_DRELU>(h, st, cur, 256, h->resd[4].wt, h->resd[4].Kt, nullptr, nxt, 256, h->Xr4, 320, count, row0, rows, 256, 256);
+    gemm<EPI_NONE>(h, st, cur, 256, h->resd[4].wt + (size_t)256 * h->resd[4].Kt, h->resd[4].Kt, nullptr, h->dpes, 64, nullptr, 0, count, row0, rows, 63, 256);
+    std::swap(cur, nxt);
+    for (int l = 3; l >= 1; l--) {
+        gemm<EPI_MUL_DRELU>(h, st, cur, 256, h->resd[l].wt, h->resd[l].Kt, nullptr, nxt, 256, h->ra_[l - 1], 256, count, row0, rows, 256, 256);
+        std::swap(cur, nxt);
+    }
+    gemm<EPI_NONE>(h, st, cur, 256, h->resd[0].wt, h->resd[0].Kt, nullptr, h->dpe0, 64, nullptr, 0, count, row0, rows, 63, 256);
+    LAUNCH(h, k_resd_grad_to_bp, g, 256, 0, st, bpts, h->dpe0, 64, h->dpes, 64, 0, h->gcp, h->gbp, count, row0, rows);
+}
+
+// a3 of the residual net lives in Xr4[:, :256] (ld 320); a3 of the SDF net in Xs4[:, :205] (ld 256).
+// ra_[3] / sb_[3] are unused placeholders.
+
+// forward + gradient + heads + raw assembly for the attribute list, chunk by chunk
+static int attr_pass(ra_handle* h, cudaStream_t st, int64_t max_rows, bool sync_count) {
+    int64_t rows_total = max_rows;
+    if (sync_count) {
+        int c = 0;
+        CK(cudaMemcpyAsync(&c, h->al.count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        rows_total = c;
+    }
+    const int* count = h->al.count;
+    for (int64_t row0 = 0; row0 < rows_total; row0 += ATTR_CH) {
+        int rows = (int)std::min<int64_t>(ATTR_CH, rows_total - row0);
+        const float* bp = h->al.bpts + row0 * 3;
+        int g = grid_for(h, rows);
+        mlp_forward_fp32(h, st, bp, count, (int)row0, rows, true, nullptr);
+        mlp_backward_fp32(h, st, bp, count, (int)row0, rows);
+        LAUNCH(h, k_attr_normals, g, 256, 0, st, h->fc, h->gbp, h->al.mats + row0 * 18, h->nrm_o, count, (int)row0, rows);
+        if (h->cfg.relight) {
+            gemm<EPI_SOFTPLUS>(h, st, h->out257, 264, h->alb[0].w, 256, h->alb[0].b, h->hd1, 128, nullptr, 0, count, (int)row0, rows, 128, 256);
+            gemm<EPI_SOFTPLUS>(h, st, h->hd1, 128, h->alb[1].w, 128, h->alb[1].b, h->hd2, 128, nullptr, 0, count, (int)row0, rows, 128, 128);
+            LAUNCH(h, k_skinny, grid_for(h, (long long)rows * 32), 256, 0, st, h->hd2, 128, h->alb[2].w, 128, h->alb[2].b, h->head_a, 4, count, (int)row0, rows, 3, 128);
+            gemm<EPI_SOFTPLUS>(h, st, h->out257, 264, h->rgh[0].w, 256, h->rgh[0].b, h->hd1, 128, nullptr, 0, count, (int)row0, rows, 128, 256);
+            gemm<EPI_SOFTPLUS>(h, st, h->hd1, 128, h->rgh[1].w, 128, h->rgh[1].b, h->hd2, 128, nullptr, 0, count, (int)row0, rows, 128, 128);
+            LAUNCH(h, k_skinny, grid_for(h, (long long)rows * 32), 256, 0, st, h->hd2, 128, h->rgh[2].w, 128, h->rgh[2].b, h->head_r, 4, count, (int)row0, rows, 1, 128);
+        } else {
+            if (!h->rend[0].w) { h->err = "render_network weights missing for AniSDF"; return 1; }
+            LAUNCH(h, k_render_input, g, 256, 0, st, h->al.bvds + row0 * 3, h->nrm_o, h->out257, 264, h->Xrn, 288, count, (int)row0, rows);
+            gemm<EPI_RELU>(h, st, h->Xrn, 288, h->rend[0].w, 288, h->rend[0].b, h->rn1, 256, nullptr, 0, count, (int)row0, rows, 256, 288);
+            gemm<EPI_RELU>(h, st, h->rn1, 256, h->rend[1].w, 256, h->rend[1].b, h->rn2, 256, nullptr, 0, count, (int)row0, rows, 256, 256);
+            gemm<EPI_RELU>(h, st, h->rn2, 256, h->rend[2].w, 256, h->rend[2].b, h->rn1, 256, nullptr, 0, count, (int)row0, rows, 256, 256);
+            gemm<EPI_RELU>(h, st, h->rn1, 256, h->rend[3].w, 256, &h->fc->rend_b3[0], h->rn2, 256, nullptr, 0, count, (int)row0, rows, 256, 256);
+            LAUNCH(h, k_skinny, grid_for(h, (long long)rows * 32), 256, 0, st, h->rn2, 256, h->rend[4].w, 256, h->rend[4].b, h->head_a, 4, count, (int)row0, rows, 3, 256);
+        }
+        LAUNCH(h, k_attr_finish, g, 256, 0, st, h->cfg.relight, bp, h->cpts_o, h->resd_o, h->out257 + 256, 264, h->nrm_o, h->head_a, h->head_r,
+               h->beta, h->cfg.albedo_slope, h->cfg.albedo_bias, h->cfg.rough_slope, h->cfg.rough_bias, h->al.src + row0, h->raw, count, (int)row0, rows);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// distance MLPs over the query list (net sdf into q.net)
+static int distance_pass(ra_handle* h, cudaStream_t st) {
+    if (h->cfg.precision == RA_PRECISION_TC) {
+        tc_distance(h->tc, h->q.bpts, h->q.net, h->q.count, h->cfg.resd_limit, h->sms, st, h->launches);
+        return 0;
+    }
+    int c = 0;
+    CK(cudaMemcpyAsync(&c, h->q.count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int64_t row0 = 0; row0 < c; row0 += ATTR_CH) {
+        int rows = (int)std::min<int64_t>(ATTR_CH, c - row0);
+        mlp_forward_fp32(h, st, h->q.bpts + row0 * 3, h->q.count, (int)row0, rows, false, h->q.net + row0);
+    }
+    return 0;
+}
+
+static Counters no_count(ra_handle* h) { return h->cnt; }
+
+// ---------------------------------------------------------------------------------------------- render: sphere tracing
+static int zero_outputs(ra_handle* h, const ra_outputs* o, int64_t P, cudaStream_t st) {
+    int L = h->cfg.env_h * h->cfg.env_w;
+    struct { float* p; size_t n; } m[] = {{o->rgb_map, 3}, {o->acc_map, 1}, {o->depth_map, 1}, {o->surf_map, 3}, {o->norm_map, 3},
+                                          {o->cpts_map, 3}, {o->bpts_map, 3}, {o->resd_map, 3}, {o->albedo_map, 3}, {o->roughness_map, 1},
+                                          {o->shade_map, 3}, {o->lvis_map, (size_t)L}, {o->ldot_map, (size_t)L}};
+    for (auto& e : m)
+        if (e.p) CK(cudaMemsetAsync(e.p, 0, e.n * P * sizeof(float), st));
+    return 0;
+}
+
+static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, const float* near_, const float* far_, int64_t P,
+                        const ra_outputs* out, cudaStream_t st) {
+    if (!h->have_frame) { h->err = "render before ra_set_frame"; return 1; }
+    if (P > h->P_cap) { h->err = "P exceeds ra_config.max_rays"; return 1; }
+    const ra_config& c = h->cfg;
+    if (zero_outputs(h, out, P, st)) return 1;
+    CK(cudaMemsetAsync(h->counters_blk, 0, 16 * sizeof(int), st));
+    h->last_P = P; h->last_ray_o = ray_o;
+    int n_chunks = std::max<int64_t>((P + c.render_chunk - 1) / c.render_chunk, 1);
+    h->chunk_actual = P ? (int)((P + n_chunks - 1) / n_chunks) : 1;        // chunkify's equalised size, net_utils.py:323
+    if (P == 0) return 0;
+    TraceCfg tc{c.st_iter, c.st_tan_i, c.st_relax, c.st_offset, c.st_eps, c.st_skip, c.dist_th, c.blend_radius};
+    int N = c.n_verts;
+    int g = grid_for(h, P, 128, 16);
+    for (int it = 0; it <= c.st_iter; it++) {
+        CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
+        LAUNCH(h, k_trace_surface, g, 128, 0, st, it, tc, h->fc, h->sv, N, ray_o, ray_d, near_, far_, (int)P, h->ss, h->q, h->cnt,
+               h->surf, h->acc, h->depth, h->fg_ray);
+        if (it < c.st_iter && distance_pass(h, st)) return 1;
+    }
+    // surface samples -> attributes
+    int C = c.relight ? 17 : 16;
+    CK(cudaMemsetAsync(h->raw, 0, (size_t)P * c.n_samples * C * sizeof(float), st));
+    LAUNCH(h, k_attr_front, grid_for(h, P * c.n_samples, 128, 16), 128, 0, st, 1, h->fc, h->sv, N, c.dist_th, c.blend_radius,
+           (const float*)nullptr, (const float*)nullptr, 0LL, h->cnt.n_fg, h->fg_ray, h->surf, ray_o, ray_d, near_, far_, c.n_samples,
+           c.surf_sample_range, c.clip_near, c.clip_far, 0LL, 0LL, h->al, h->cnt);
+    if (attr_pass(h, st, P * c.n_samples, h->cfg.precision == RA_PRECISION_FP32)) return 1;
+    OutMaps om{out->rgb_map, out->acc_map, out->depth_map, out->surf_map, out->norm_map, out->cpts_map, out->bpts_map, out->resd_map,
+               out->albedo_map, out->roughness_map, out->shade_map};
+    LAUNCH(h, k_surface_blend, grid_for(h, P), 256, 0, st, c.relight, h->cnt.n_fg, h->fg_ray, h->raw, c.n_samples, h->acc, h->surf, h->depth,
+           c.albedo_slope, c.albedo_bias, c.rough_slope, c.rough_bias, c.albedo_multiplier, h->fm, om);
+    if (!c.relight) { CK(cudaGetLastError()); return 0; }
+    // light visibility (DFSS)
+    int L = c.env_h * c.env_w;
+    LAUNCH(h, k_shadow_gen, grid_for(h, P * L / 4, 256, 16), 256, 0, st, h->fc, h->cnt.n_fg, h->fg_ray, h->surf, h->fm.norm, h->ldir, L,
+           c.lv_near, c.bbox_margin, h->chunk_actual, h->lvis, h->ldot, h->sr, h->cnt.n_shadow);
+    TraceCfg sc{c.lv_iter, 1.f, c.lv_relax, c.lv_offset, c.st_eps, c.st_skip, c.lv_dist_th, c.blend_radius};
+    int gs = grid_for(h, P * 64, 128, 16);
+    for (int it = 0; it <= c.lv_iter; it++) {
+        CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
+        LAUNCH(h, k_trace_shadow, gs, 128, 0, st, it, sc, h->fc, h->sv, N, h->cnt.n_shadow, h->fg_ray, h->surf, h->ldir, h->lsharp, L, h->sr,
+               h->q, h->cnt, h->lvis);
+        if (it < c.lv_iter && distance_pass(h, st)) return 1;
+    }
+    LAUNCH(h, k_shade, grid_for(h, P * 32, 256, 8), 256, 0, st, h->cnt.n_fg, h->fg_ray, ray_o, h->surf, h->acc, h->fm, h->lvis, h->ldot,
+           h->lxyz, h->larea, L, h->env_main, h->emh, h->emw, c.fresnel_f0, c.shading_albedo, 0, 1, out->rgb_map, out->shade_map,
+           (float*)nullptr);
+    if (out->lvis_map || out->ldot_map)
+        LAUNCH(h, k_scatter_lmaps, grid_for(h, P * L / 4), 256, 0, st, h->cnt.n_fg, h->fg_ray, h->acc, h->lvis, h->ldot, L, out->lvis_map, out->ldot_map);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ra_render_relight(ra_handle* h, const float* ray_o, const float* ray_d, const float* near_, const float* far_,
+                                 int64_t P, const ra_outputs* out, void* stream) {
+    if (!h->cfg.relight) { h->err = "handle was created with relight=0"; return 1; }
+    return render_trace(h, ray_o, ray_d, near_, far_, P, out, (cudaStream_t)stream);
+}
+
+extern "C" int ra_render_anisdf_trace(ra_handle* h, const float* ray_o, const float* ray_d, const float* near_, const float* far_,
+                                      int64_t P, const ra_outputs* out, void* stream) {
+    if (h->cfg.relight) { h->err = "handle was created with relight=1"; return 1; }
+    return render_trace(h, ray_o, ray_d, near_, far_, P, out, (cudaStream_t)stream);
+}
+
+extern "C" int ra_relight_envmaps(ra_handle* h, const float* probes, int32_t n_env, float* rgb, float* shade, float* spec, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const ra_config& c = h->cfg;
+    if (!c.relight || h->last_ray_o == nullptr) { h->err = "ra_relight_envmaps needs a preceding ra_render_relight"; return 1; }
+    int64_t P = h->last_P;
+    int L = c.env_h * c.env_w;
+    for (int e = 0; e < n_env; e++) {
+        const float* probe = probes + (size_t)e * L * 3;
+        float* r = rgb ? rgb + (size_t)e * P * 3 : nullptr;
+        float* s = shade ? shade + (size_t)e * P * 3 : nullptr;
+        float* p = spec ? spec + (size_t)e * P * 3 : nullptr;
+        if (r) CK(cudaMemsetAsync(r, 0, (size_t)P * 3 * sizeof(float), st));
+        if (s) CK(cudaMemsetAsync(s, 0, (size_t)P * 3 * sizeof(float), st));
+        if (p && P) {
+            LAUNCH(h, k_bg_spec, 1, 32, 0, st, h->lxyz, h->larea, L, probe, c.env_h, c.env_w, c.fresnel_f0, h->bg_spec);
+            LAUNCH(h, k_fill3, grid_for(h, P * 3), 256, 0, st, p, h->bg_spec, (long long)P);
+        }
+        if (P)
+            LAUNCH(h, k_shade, grid_for(h, P * 32, 256, 8), 256, 0, st, h->cnt.n_fg, h->fg_ray, h->last_ray_o, h->surf, h->acc, h->fm, h->lvis,
+                   h->ldot, h->lxyz, h->larea, L, probe, c.env_h, c.env_w, c.fresnel_f0, c.shading_albedo, 1, 0, r, s, p);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- render: volume (config 2)
+extern "C" int ra_render_anisdf_volume(ra_handle* h, const float* ray_o, const float* ray_d, const float* near_, const float* far_,
+                                       int64_t P, const ra_outputs* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const ra_config& c = h->cfg;
+    if (c.relight) { h->err = "volume renderer is the AniSDF path (relight=0)"; return 1; }
+    if (!h->have_frame) { h->err = "render before ra_set_frame"; return 1; }
+    if (zero_outputs(h, out, P, st)) return 1;
+    CK(cudaMemsetAsync(h->counters_blk, 0, 16 * sizeof(int), st));
+    OutMaps om{out->rgb_map, out->acc_map, out->depth_map, nullptr, out->norm_map, out->cpts_map, out->bpts_map, out->resd_map, nullptr, nullptr, nullptr};
+    int S = c.vol_samples;
+    for (int64_t r0 = 0; r0 < P; r0 += h->vol_rays) {
+        int64_t nr = std::min<int64_t>(h->vol_rays, P - r0);
+        CK(cudaMemsetAsync(h->al.count, 0, sizeof(int), st));
+        CK(cudaMemsetAsync(h->raw, 0, (size_t)nr * S * 16 * sizeof(float), st));
+        LAUNCH(h, k_attr_front, grid_for(h, nr * S, 128, 16), 128, 0, st, 2, h->fc, h->sv, c.n_verts, c.dist_th, c.blend_radius,
+               (const float*)nullptr, (const float*)nullptr, 0LL, h->cnt.n_fg, h->fg_ray, h->surf, ray_o, ray_d, near_, far_, S,
+               c.surf_sample_range, c.clip_near, c.clip_far, (long long)r0, (long long)nr, h->al, h->cnt);
+        if (attr_pass(h, st, nr * S, true)) return 1;
+        LAUNCH(h, k_volume_blend, grid_for(h, nr), 128, 0, st, h->raw, 16, S, near_, far_, c.clip_near, c.clip_far, (long long)r0, (long long)nr, om);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- point queries
+extern "C" int ra_query_sdf(ra_handle* h, const float* x, int64_t n, float dist_th, int32_t smooth, float* sdf, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!h->have_frame) { h->err = "query before ra_set_frame"; return 1; }
+    if (n > h->q_cap) { h->err = "too many query points"; return 1; }
+    if (n == 0) return 0;
+    CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
+    LAUNCH(h, k_points_front, grid_for(h, n, 128, 16), 128, 0, st, h->fc, h->sv, h->cfg.n_verts, x, (int)n, dist_th, h->cfg.blend_radius,
+           h->pt_smpl, h->pt_slot, h->q, h->cnt);
+    if (distance_pass(h, st)) return 1;
+    LAUNCH(h, k_points_finish, grid_for(h, n), 256, 0, st, h->pt_smpl, h->pt_slot, h->q.net, (int)n, dist_th, smooth, sdf);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ra_query_raw(ra_handle* h, const float* x, const float* v, int64_t n, float* raw, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!h->have_frame) { h->err = "query before ra_set_frame"; return 1; }
+    if (n > h->attr_cap) { h->err = "too many query points"; return 1; }
+    int C = h->cfg.relight ? 17 : 16;
+    if (n == 0) return 0;
+    CK(cudaMemsetAsync(h->al.count, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(h->raw, 0, (size_t)n * C * sizeof(float), st));
+    LAUNCH(h, k_attr_front, grid_for(h, n, 128, 16), 128, 0, st, 0, h->fc, h->sv, h->cfg.n_verts, h->cfg.dist_th, h->cfg.blend_radius, x, v,
+           (long long)n, h->cnt.n_fg, h->fg_ray, h->surf, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr,
+           (const float*)nullptr, 1, 0.f, 0.f, 0.f, 0LL, 0LL, h->al, h->cnt);
+    if (attr_pass(h, st, n, true)) return 1;
+    CK(cudaMemcpyAsync(raw, h->raw, (size_t)n * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int ra_get_stats(ra_handle* h, ra_stats* out) {
+    CK(cudaDeviceSynchronize());
+    int c[16];
+    CK(cudaMemcpy(c, h->counters_blk, sizeof(c), cudaMemcpyDeviceToHost));
+    out->n_rays = h->last_P;
+    out->n_fg = c[0]; out->n_shadow_rays = c[1]; out->n_attr_samples = c[2];
+    unsigned long long q[2];
+    memcpy(q, &c[8], 16);
+    out->n_queries = (int64_t)q[0]; out->n_queries_in_shell = (int64_t)q[1];
+    return 0;
+}

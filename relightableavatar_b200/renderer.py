@@ -1,0 +1,314 @@
+"""Host-side mirror of the reference renderer plugin surface.
+
+The reference builds its renderer with
+    importlib.import_module(cfg.renderer_module).Renderer(network)     lib/networks/renderer/make_renderer.py:5-8
+and calls `renderer.render(batch) -> dotdict` under no_grad with `net.eval()` (run.py:68-85).  This
+module offers the same surface -- `Renderer(net).render(batch)` -- and forwards the whole per-pixel
+path to the CUDA library through the C-ABI of include/ra_b200.h:
+
+    relightableavatar_b200.renderer            <->  reference module
+    Renderer(net, mode='relight')               lib.networks.renderer.novel_light_sphere_tracing.Renderer
+    Renderer(net, mode='anisdf_trace')          lib.networks.renderer.sphere_tracing_renderer.Renderer (AniSDF net)
+    Renderer(net, mode='anisdf_volume')         lib.networks.renderer.base_renderer.Renderer
+
+PyTorch is used for device memory, streams and (in parallel.py) torch.distributed only.  There is no
+CPU fallback: a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import OUTPUT_MAPS, ra_config, ra_frame, ra_outputs, ra_stats, ra_weights
+
+PRECISION = {'fp32': 0, 'tc': 1}
+
+
+class dotdict(dict):
+    """Attribute-access dict, like the reference's lib.utils.base_utils.dotdict."""
+    __getattr__ = dict.get
+    __setattr__ = dict.__setitem__
+    __delattr__ = dict.__delitem__
+
+
+def default_config(relight: bool = True, **over) -> Dict:
+    """Effective cfg values of xuzhen_12v_geo(_fix_mat) (notation paragraph)."""
+    c = dict(relight=int(relight), precision=1, max_rays=1 << 17, n_verts=6890, n_bones=52,
+             dist_th=0.125 if relight else 0.1, blend_radius=0.075, resd_limit=0.05,
+             st_iter=16, st_tan_i=1000.0, st_relax=0.0, st_offset=0.02, st_eps=1e-8, st_skip=1,
+             lv_iter=4, lv_offset=0.01, lv_relax=0.0, lv_near=0.02, lv_dist_th=0.125,
+             env_r=10.0, bbox_margin=0.25, render_chunk=65536, n_samples=3, surf_sample_range=0.005,
+             fresnel_f0=0.02, albedo_slope=1.0, albedo_bias=0.0, rough_slope=0.9, rough_bias=0.09,
+             albedo_multiplier=1.0, shading_albedo=0.8, env_h=16, env_w=32, vol_samples=128, clip_near=0.02, clip_far=10.0)
+    c.update(over)
+    return c
+
+
+def config_from_reference_cfg(cfg, relight: bool) -> Dict:
+    """Read the same keys the reference renderer reads from its global `cfg` (once, at construction)."""
+    st, lv = cfg.sphere_tracing, cfg.obj_lvis
+    return default_config(
+        relight, dist_th=cfg.dist_th, blend_radius=cfg.blend_radius, resd_limit=cfg.resd_limit,
+        st_iter=st.iter, st_tan_i=st.tan_i, st_relax=st.relax, st_offset=st.offset, st_eps=st.eps, st_skip=st.shadow_skip_iter,
+        lv_iter=lv.iter, lv_offset=lv.offset, lv_relax=lv.relax, lv_near=lv.near_offset, lv_dist_th=lv.dist_th,
+        env_r=cfg.env_r, bbox_margin=cfg.env_lvis.bbox_margin, render_chunk=cfg.render_chunk_size, n_samples=cfg.n_samples,
+        surf_sample_range=cfg.surf_sample_range, fresnel_f0=cfg.fresnel_f0, albedo_slope=cfg.albedo_slope,
+        albedo_bias=cfg.albedo_bias, rough_slope=cfg.roughness_slope, rough_bias=cfg.roughness_bias,
+        albedo_multiplier=cfg.albedo_multiplier, shading_albedo=cfg.shading_albedo, env_h=cfg.env_h, env_w=cfg.env_w,
+        clip_near=cfg.clip_near, clip_far=cfg.clip_far)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _fptr(t: Optional[torch.Tensor]):
+    return C.cast(C.c_void_p(t.data_ptr() if t is not None else 0), _lib.fp)
+
+
+class Engine:
+    """Thin RAII wrapper over one `ra_handle` (one per device)."""
+
+    def __init__(self, config: Dict, device='cuda:0'):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('relightableavatar_b200 runs on CUDA (sm_100a) only; there is no CPU path')
+        self.config = dict(config)
+        cfg = ra_config(**config)
+        self.h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.ra_create(C.byref(self.h), C.byref(cfg))
+        if rc:
+            msg = self.lib.ra_last_error(self.h).decode() if self.h else 'ra_create failed'
+            raise RuntimeError(f'ra_create: {msg}')
+        self._keep = []          # tensors borrowed by the library until the next set_frame
+        self._wkeep = []
+        self.L = config['env_h'] * config['env_w']
+
+    def _check(self, rc, what):
+        if rc:
+            raise RuntimeError(f'{what}: {self.lib.ra_last_error(self.h).decode()}')
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, 'h', None):
+            torch.cuda.synchronize(self.device)
+            self.lib.ra_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def upload_weights(self, sd: Dict[str, torch.Tensor]):
+        """Extract the tensors named in SURVEY.md 8b from a state-dict; fold weight-norm (w = g v/||v||)."""
+        dev = self.device
+        f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        keep = []
+        w = ra_weights()
+
+        def put(arr, i, t):
+            t = f(t); keep.append(t); arr[i] = _fptr(t)
+
+        for l in range(9):
+            put(w.resd_w, l, sd[f'residual_deformation_network.mlp.linears.{l}.weight'])
+            put(w.resd_b, l, sd[f'residual_deformation_network.mlp.linears.{l}.bias'])
+            v, g = f(sd[f'signed_distance_network.mlp.lin{l}.weight_v']), f(sd[f'signed_distance_network.mlp.lin{l}.weight_g'])
+            put(w.sdf_w, l, g * v / v.norm(dim=1, keepdim=True))
+            put(w.sdf_b, l, sd[f'signed_distance_network.mlp.lin{l}.bias'])
+        w.sdf_beta = float(sd['signed_distance_network._beta'].clamp(1e-9, 1e6))
+        if 'render_network.l0.weight_v' in sd:
+            for l in range(5):
+                v, g = f(sd[f'render_network.l{l}.weight_v']), f(sd[f'render_network.l{l}.weight_g'])
+                put(w.render_w, l, g * v / v.norm(dim=1, keepdim=True))
+                put(w.render_b, l, sd[f'render_network.l{l}.bias'])
+        if self.config['relight']:
+            for l in range(3):
+                put(w.albedo_w, l, sd[f'albedo_network.linears.{l}.weight']); put(w.albedo_b, l, sd[f'albedo_network.linears.{l}.bias'])
+                put(w.rough_w, l, sd[f'roughness_network.linears.{l}.weight']); put(w.rough_b, l, sd[f'roughness_network.linears.{l}.bias'])
+            env = f(sd['global_env_map_'])
+            env = F.softplus(env.expand(*env.shape[:2], 3)).contiguous()        # relight_network.py:86-89
+            keep.append(env)
+            w.env_main, w.env_main_h, w.env_main_w = _fptr(env), env.shape[0], env.shape[1]
+            self.env_main = env
+            for name, key in (('light_xyz', 'light_xyz_'), ('light_area', 'light_area'), ('light_sharp', 'light_sharp')):
+                t = f(sd[key]); keep.append(t); setattr(w, name, _fptr(t))
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_upload_weights(self.h, C.byref(w), self._stream()), 'ra_upload_weights')
+        self._wkeep = keep
+
+    # ------------------------------------------------------------------ frame
+    def set_frame(self, batch: Dict, fix_material: int = 0):
+        dev = self.device
+
+        def g(key, shape=None):
+            t = batch[key]
+            t = torch.as_tensor(t)
+            if t.device != dev or t.dtype != torch.float32:
+                t = t.to(device=dev, dtype=torch.float32)
+            t = t[0] if (t.ndim > 1 and t.shape[0] == 1) else t
+            return t.contiguous()
+
+        fr = ra_frame()
+        keep = []
+        for name in ('R', 'Th', 'poses', 'A', 'big_A', 'weights', 'pverts', 'pnorm', 'tverts', 'wbounds'):
+            t = g(name); keep.append(t); setattr(fr, name, _fptr(t))
+        mc = None
+        if 'train_motion' in batch and batch['train_motion'] is not None:
+            mc = torch.as_tensor(batch['train_motion']['poses'])
+        elif 'train_poses' in batch:
+            mc = torch.as_tensor(batch['train_poses'])
+        if mc is not None:
+            mc = mc.to(device=dev, dtype=torch.float32)[0, max(fix_material, 0)].reshape(-1).contiguous()
+            keep.append(mc)
+        fr.mat_cond = _fptr(mc)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_set_frame(self.h, C.byref(fr), self._stream()), 'ra_set_frame')
+        self._keep = keep
+
+    # ------------------------------------------------------------------ render
+    def _rays(self, batch):
+        dev = self.device
+        c = lambda k: torch.as_tensor(batch[k]).to(device=dev, dtype=torch.float32)[0].contiguous()
+        return c('ray_o'), c('ray_d'), c('near'), c('far')
+
+    def _alloc_outputs(self, P, keys):
+        out = {}
+        for k in keys:
+            if k in ('acc_map', 'depth_map', 'roughness_map'):
+                out[k] = torch.empty(P, device=self.device, dtype=torch.float32)
+            elif k in ('lvis_map', 'ldot_map'):
+                out[k] = torch.empty(P, self.L, device=self.device, dtype=torch.float32)
+            else:
+                out[k] = torch.empty(P, 3, device=self.device, dtype=torch.float32)
+        o = ra_outputs()
+        for k in OUTPUT_MAPS:
+            setattr(o, k, _fptr(out.get(k)))
+        return out, o
+
+    def render(self, mode: str, ray_o, ray_d, near, far, keys):
+        P = ray_o.shape[0]
+        out, o = self._alloc_outputs(P, keys)
+        fn = {'relight': self.lib.ra_render_relight, 'anisdf_trace': self.lib.ra_render_anisdf_trace,
+              'anisdf_volume': self.lib.ra_render_anisdf_volume}[mode]
+        self._rays_keep = (ray_o, ray_d, near, far)
+        with torch.cuda.device(self.device):
+            self._check(fn(self.h, _ptr(ray_o), _ptr(ray_d), _ptr(near), _ptr(far), P, C.byref(o), self._stream()), mode)
+        return out
+
+    def relight_envmaps(self, probes: torch.Tensor, P: int, want_spec=True):
+        n = probes.shape[0]
+        rgb = torch.empty(n, P, 3, device=self.device); shade = torch.empty_like(rgb)
+        spec = torch.empty_like(rgb) if want_spec else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_relight_envmaps(self.h, _ptr(probes), n, _ptr(rgb), _ptr(shade), _ptr(spec), self._stream()),
+                        'ra_relight_envmaps')
+        return rgb, shade, spec
+
+    def query_sdf(self, x: torch.Tensor, dist_th: Optional[float] = None, smooth: bool = True) -> torch.Tensor:
+        x = x.to(device=self.device, dtype=torch.float32).reshape(-1, 3).contiguous()
+        out = torch.empty(x.shape[0], device=self.device)
+        th = float(dist_th if dist_th is not None else self.config['dist_th'])
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_query_sdf(self.h, _ptr(x), x.shape[0], th, int(smooth), _ptr(out), self._stream()), 'ra_query_sdf')
+        return out
+
+    def query_raw(self, x: torch.Tensor, v: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x = x.to(device=self.device, dtype=torch.float32).reshape(-1, 3).contiguous()
+        v = v.to(device=self.device, dtype=torch.float32).reshape(-1, 3).contiguous() if v is not None else None
+        Cn = 17 if self.config['relight'] else 16
+        out = torch.empty(x.shape[0], Cn, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_query_raw(self.h, _ptr(x), _ptr(v), x.shape[0], _ptr(out), self._stream()), 'ra_query_raw')
+        return out
+
+    def stats(self) -> Dict[str, int]:
+        s = ra_stats()
+        self._check(self.lib.ra_get_stats(self.h, C.byref(s)), 'ra_get_stats')
+        return {n: getattr(s, n) for n, _ in s._fields_}
+
+    def launch_count(self) -> int:
+        return int(self.lib.ra_launch_count(self.h))
+
+
+_MAIN_KEYS = {
+    'relight': ('rgb_map', 'acc_map', 'depth_map', 'surf_map', 'norm_map', 'cpts_map', 'bpts_map', 'albedo_map', 'roughness_map', 'shade_map'),
+    'anisdf_trace': ('rgb_map', 'acc_map', 'depth_map', 'surf_map', 'norm_map', 'cpts_map', 'bpts_map', 'resd_map'),
+    'anisdf_volume': ('rgb_map', 'acc_map', 'depth_map', 'norm_map', 'cpts_map', 'bpts_map', 'resd_map'),
+}
+
+
+class Renderer(torch.nn.Module):
+    """Drop-in for the reference's `Renderer(net)`; `render(batch)` returns the same dotdict layout.
+
+    `net` is the loaded reference network (any object with `state_dict()`); its tensors are read once.
+    `mode` selects which reference renderer is mirrored (see module docstring).  With a reference `cfg`
+    object pass `cfg=` to read the same keys the reference reads; otherwise the xuzhen_12v_geo values apply.
+    """
+
+    def __init__(self, net, mode: str = 'relight', cfg=None, device='cuda:0', precision: str = 'tc', max_rays: int = 1 << 17,
+                 test_light=('main',), return_lvis: bool = False, to_cpu: bool = False, **overrides):
+        super().__init__()
+        self.net = net
+        self.mode = mode
+        relight = mode == 'relight'
+        conf = config_from_reference_cfg(cfg, relight) if cfg is not None else default_config(relight)
+        conf.update(precision=PRECISION[precision], max_rays=int(max_rays))
+        conf.update(overrides)
+        self.engine = Engine(conf, device)
+        self.engine.upload_weights(net.state_dict())
+        self.fix_material = getattr(cfg, 'fix_material', 0) if cfg is not None else 0
+        self.test_light = tuple(test_light)
+        self.return_lvis = return_lvis
+        self.to_cpu = to_cpu
+
+    @torch.no_grad()
+    def render(self, batch) -> dotdict:
+        eng = self.engine
+        eng.set_frame(batch, self.fix_material)
+        ray_o, ray_d, near, far = eng._rays(batch)
+        P = ray_o.shape[0]
+        keys = list(_MAIN_KEYS[self.mode])
+        if self.mode == 'relight' and self.return_lvis:
+            keys += ['lvis_map', 'ldot_map']
+        if self.mode != 'relight':
+            out = eng.render(self.mode, ray_o, ray_d, near, far, keys)
+            return dotdict({k: v[None] for k, v in out.items()})
+        # novel_light_sphere_tracing.Renderer.render (:101-221): main pass, then one cheap re-shade per env-map
+        torch.cuda.synchronize(eng.device)
+        tick = time.perf_counter()
+        main = eng.render('relight', ray_o, ray_d, near, far, keys)
+        torch.cuda.synchronize(eng.device)
+        diff = time.perf_counter() - tick
+        relight = dotdict()
+        conv = (lambda t: t.cpu()) if self.to_cpu else (lambda t: t)
+        main_b = dotdict({k: conv(v[None]) for k, v in main.items()})
+        main_b.envmap = dotdict(probe=conv(eng.env_main[None]))
+        if 'main' in self.test_light:
+            relight.main = main_b
+        lights = batch.get('novel_lights') or {}
+        names = [n for n in lights if n in self.test_light or 'all' in self.test_light]
+        if names:
+            probes = torch.stack([torch.as_tensor(lights[n]['probe'] if isinstance(lights[n], dict) else lights[n])
+                                  .to(device=eng.device, dtype=torch.float32).reshape(eng.config['env_h'], eng.config['env_w'], 3)
+                                  for n in names]).contiguous()
+            rgb, shade, spec = eng.relight_envmaps(probes, P)
+            for i, n in enumerate(names):
+                human = dotdict(main_b)
+                human.update(rgb_map=conv(rgb[i][None]), shade_map=conv(shade[i][None]), spec_map=conv(spec[i][None]))
+                human.envmap = dotdict(probe=conv(probes[i][None]))
+                relight[n] = human
+        relight.diff = diff
+        return relight

@@ -1,0 +1,36 @@
+"""The C-ABI library builds for sm_100a, loads, and exports every symbol include/ra_b200.h declares (CPU only,
+no compute calls)."""
+import ctypes
+import os
+import re
+
+from relightableavatar_b200 import _lib, build
+
+
+def test_library_builds_and_exports_header_symbols():
+    path = build.build(verbose=False)
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'ra_b200.h')).read()
+    declared = set(re.findall(r'\b(ra_[a-z_]+)\s*\(', hdr))
+    assert declared, 'no declarations parsed'
+    for s in declared:
+        assert hasattr(lib, s), f'{s} declared in ra_b200.h but not exported'
+    assert set(_lib.EXPORTS) <= declared
+
+
+def test_ctypes_struct_sizes_match_header():
+    # 36 4-byte fields in ra_config; pointers are 8 bytes
+    assert ctypes.sizeof(_lib.ra_config) == 36 * 4
+    assert ctypes.sizeof(_lib.ra_frame) == 11 * 8
+    assert ctypes.sizeof(_lib.ra_outputs) == 13 * 8
+    assert ctypes.sizeof(_lib.ra_stats) == 6 * 8
+
+
+def test_product_never_imports_oracle():
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'relightableavatar_b200')
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith('.py'):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f'{f} imports the oracle'

@@ -1,0 +1,164 @@
+"""-m gpu: the CUDA path, called through the C-ABI, against the oracle on the same seeded inputs.
+Tolerances are fp32 tolerances of the path (stated per check); discontinuities of the algorithm (shell membership,
+nearest-vertex order, ReLU kinks under the normal) make a handful of samples flip, hence quantiles on some maps."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ra_oracle as O
+from relightableavatar_b200 import scene
+from relightableavatar_b200.renderer import Engine, Renderer, default_config
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _err(a, b):
+    return (a.double().cpu() - b.double().cpu()).abs()
+
+
+def _sample_points(b, n, seed=0, spread=0.06):
+    g = torch.Generator().manual_seed(seed)
+    wv = torch.as_tensor(b['wverts'][0])
+    idx = torch.randint(0, wv.shape[0], (n,), generator=g)
+    near = wv[idx] + torch.randn(n, 3, generator=g) * spread
+    far = wv[idx[: n // 8]] + torch.randn(n // 8, 3, generator=g) * 0.5
+    return torch.cat([near, far]).float()
+
+
+@pytest.fixture(scope='module')
+def relight_setup():
+    b = scene.make_batch(64, 64, seed=0, n_env=2)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    return b, sd
+
+
+@pytest.mark.parametrize('precision,tol_q99,tol_max', [('fp32', 2e-5, 2e-3), ('tc', 2e-3, 2e-2)])
+def test_query_sdf(relight_setup, precision, tol_q99, tol_max):
+    b, sd = relight_setup
+    cfg = O.Cfg()
+    eng = Engine(default_config(True, precision={'fp32': 0, 'tc': 1}[precision], max_rays=8192), DEV)
+    eng.upload_weights(sd); eng.set_frame(b)
+    x = _sample_points(b, 20000)
+    got = eng.query_sdf(x, 0.125, True)
+    W = O.Weights(sd, torch.float32, DEV); fr = O.Frame.from_batch(b, cfg, torch.float32, DEV)
+    with torch.no_grad():
+        ref = O.hdq_distance(x.to(DEV), fr, W, cfg, 0.125, True)[:, 0]
+    e = _err(got, ref)
+    assert torch.quantile(e, 0.99) <= tol_q99, f'q99 {torch.quantile(e, 0.99):.3e}'
+    # shell-membership flips at the 12.5 cm boundary are the only large outliers
+    assert (e > tol_max).float().mean() < 2e-3, f'outlier fraction {(e > tol_max).float().mean():.3e} max {e.max():.3e}'
+    eng.close()
+
+
+@pytest.mark.parametrize('relight', [True, False])
+def test_query_raw(relight_setup, relight):
+    b, _ = relight_setup
+    sd = scene.make_state_dict(0, relight=relight, fitted=True)
+    cfg = O.Cfg() if relight else O.anisdf_cfg()
+    eng = Engine(default_config(relight, precision=0, max_rays=8192), DEV)
+    eng.upload_weights(sd); eng.set_frame(b)
+    x = _sample_points(b, 6000, seed=1, spread=0.03)
+    v = torch.nn.functional.normalize(torch.randn(x.shape[0], 3, generator=torch.Generator().manual_seed(2)), dim=-1)
+    got = eng.query_raw(x, v)
+    W = O.Weights(sd, torch.float32, DEV); fr = O.Frame.from_batch(b, cfg, torch.float32, DEV)
+    ref = O.network_forward(x.to(DEV), v.to(DEV), fr, W, cfg)
+    nz_g, nz_r = (got.abs().sum(-1) > 0).cpu(), (ref.abs().sum(-1) > 0).cpu()
+    assert (nz_g != nz_r).float().mean() < 2e-3          # same in-shell set up to boundary flips
+    both = nz_g & nz_r
+    e = _err(got, ref)[both]
+    C = got.shape[1]
+    norm_cols = slice(13, 16) if relight else slice(9, 12)
+    other = [c for c in range(C) if not (norm_cols.start <= c < norm_cols.stop)]
+    assert torch.quantile(e[:, other].flatten(), 0.999) <= 5e-5, torch.quantile(e[:, other].flatten(), 0.999)
+    assert torch.quantile(e[:, norm_cols].flatten(), 0.99) <= 2e-3, torch.quantile(e[:, norm_cols].flatten(), 0.99)
+    eng.close()
+
+
+def _render_pair(b, sd, relight, precision, probes=None):
+    cfg = O.Cfg() if relight else O.anisdf_cfg()
+    net = scene.SyntheticNet(sd, relight)
+    mode = 'relight' if relight else 'anisdf_trace'
+    r = Renderer(net, mode=mode, device=DEV, precision=precision, max_rays=8192, test_light=('main', 'all'), return_lvis=True)
+    out = r.render(b)
+    if relight:
+        ref = O.render_novel_light(b, sd, cfg, probes, torch.float32, DEV)
+    else:
+        ref = O.render_sphere_tracing(b, sd, cfg, torch.float32, DEV)
+    return out, ref, r
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tc'])
+def test_render_relight_vs_oracle(relight_setup, precision):
+    b, sd = relight_setup
+    probes = {k: v[0] for k, v in b['novel_lights'].items()}
+    out, ref, r = _render_pair(b, sd, True, precision, probes)
+    main = out['main']
+    fg_g, fg_r = (main['acc_map'][0] > 0).cpu(), (ref['main']['acc_map'] > 0).cpu()
+    assert fg_r.sum() > 100
+    assert (fg_g != fg_r).sum() <= max(2, 0.01 * fg_r.sum())
+    tol = 1e-3 if precision == 'fp32' else 1e-2
+    for k in ('rgb_map', 'acc_map', 'surf_map', 'albedo_map', 'roughness_map', 'shade_map', 'norm_map'):
+        e = _err(main[k][0], ref['main'][k])
+        assert torch.quantile(e.flatten(), 0.98) <= tol, f'{k}: q98 {torch.quantile(e.flatten(), 0.98):.3e}'
+    for n in probes:
+        img_g = O.assemble_image(b, out[n]['rgb_map'][0].cpu())
+        img_r = O.assemble_image(b, ref[n]['rgb_map'].cpu())
+        p = O.psnr(img_g, img_r)
+        assert p >= (45 if precision == 'fp32' else 35), f'{n}: PSNR {p:.1f} dB'
+    st = r.engine.stats()
+    assert st['n_fg'] == int(fg_g.sum()) and st['n_shadow_rays'] > 0 and st['n_queries_in_shell'] > 0
+
+
+def test_render_anisdf_trace_vs_oracle(relight_setup):
+    b, _ = relight_setup
+    sd = scene.make_state_dict(0, relight=False, fitted=True)
+    out, ref, _ = _render_pair(b, sd, False, 'fp32')
+    for k in ('rgb_map', 'acc_map', 'surf_map', 'norm_map', 'cpts_map', 'bpts_map'):
+        e = _err(out[k][0], ref[k])
+        assert torch.quantile(e.flatten(), 0.98) <= 1e-3, f'{k}: q98 {torch.quantile(e.flatten(), 0.98):.3e}'
+
+
+def test_render_volume_vs_oracle():
+    b = scene.make_batch(32, 32, seed=0, n_env=0)
+    sd = scene.make_state_dict(0, relight=False, fitted=True)
+    r = Renderer(scene.SyntheticNet(sd, False), mode='anisdf_volume', device=DEV, precision='fp32', max_rays=8192)
+    out = r.render(b)
+    ref = O.render_volume(b, sd, O.anisdf_cfg(), torch.float32, DEV)
+    for k in ('rgb_map', 'acc_map', 'depth_map', 'cpts_map', 'norm_map'):
+        e = _err(out[k][0], ref[k])
+        assert torch.quantile(e.flatten(), 0.98) <= 2e-3, f'{k}: q98 {torch.quantile(e.flatten(), 0.98):.3e}'
+
+
+def test_golden_relight_through_cabi():
+    """The committed reference outputs (tests/golden/relight_48.npz) against the CUDA path directly."""
+    import os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'relight_48.npz')
+    if not os.path.exists(p):
+        pytest.skip('golden fixture missing')
+    g = dict(np.load(p))
+    H, n_env = int(g['_H']), int(g['_n_env'])
+    b = scene.make_batch(H, H, seed=0, n_env=n_env)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=8192, test_light=('main', 'all'))
+    out = r.render(b)
+    for k in ('rgb_map', 'acc_map', 'surf_map', 'albedo_map', 'shade_map'):
+        e = np.abs(out['main'][k][0].cpu().numpy() - g['main.' + k][0])
+        assert np.quantile(e, 0.98) <= 1e-3, f'{k}: q98 {np.quantile(e, 0.98):.3e}'
+    for n in b['novel_lights']:
+        e = np.abs(out[n]['rgb_map'][0].cpu().numpy() - g[f'{n}.rgb_map'][0])
+        assert np.quantile(e, 0.98) <= 1e-3, f'{n}: q98 {np.quantile(e, 0.98):.3e}'
+
+
+def test_empty_rays_are_tolerated(relight_setup):
+    b, sd = relight_setup
+    b2 = dict(b)
+    for k in ('ray_o', 'ray_d'):
+        b2[k] = b[k][:, :0]
+    for k in ('near', 'far'):
+        b2[k] = b[k][:, :0]
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=1024)
+    out = r.render(b2)
+    assert out['main']['rgb_map'].shape == (1, 0, 3)

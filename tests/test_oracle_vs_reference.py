@@ -1,0 +1,88 @@
+"""Pins the oracle (oracle/ra_oracle.py) against golden vectors produced by the UNMODIFIED reference
+renderer under the import-shim harness (tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ra_oracle as O
+from relightableavatar_b200 import scene
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _load(name):
+    p = os.path.join(GOLD, name + '.npz')
+    if not os.path.exists(p):
+        pytest.skip(f'{p} missing')
+    return dict(np.load(p))
+
+
+def _close(name, a, r, atol, q=1.0):
+    a = a.detach().cpu().numpy() if hasattr(a, 'detach') else np.asarray(a)
+    d = np.abs(a - r)
+    worst = np.quantile(d, q) if q < 1.0 else d.max()
+    assert worst <= atol, f'{name}: err {worst:.3e} (q={q}) > {atol:.1e}; max {d.max():.3e}'
+
+
+def test_relight_matches_reference():
+    g = _load('relight_48')
+    H, n_env = int(g['_H']), int(g['_n_env'])
+    b = scene.make_batch(H, H, seed=0, n_env=n_env)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    probes = {k: v[0] for k, v in b['novel_lights'].items()}
+    out = O.render_novel_light(b, sd, O.Cfg(), probes)
+    assert int((out['main']['acc_map'] > 0).sum()) == int((g['main.acc_map'][0] > 0).sum())
+    assert int((g['main.acc_map'][0] > 0).sum()) > 50
+    for k in ('rgb_map', 'acc_map', 'surf_map', 'bpts_map', 'cpts_map', 'shade_map', 'depth_map', 'albedo_map', 'roughness_map'):
+        _close('main.' + k, out['main'][k], g['main.' + k][0], 2e-4)
+    # autograd normals cross ReLU kinks of the residual MLP: isolated fp32 re-ordering flips (SURVEY.md App. A note)
+    _close('main.norm_map', out['main']['norm_map'], g['main.norm_map'][0], 2e-3, q=0.99)
+    for n in probes:
+        for k in ('rgb_map', 'shade_map', 'spec_map'):
+            _close(f'{n}.{k}', out[n][k], g[f'{n}.{k}'][0], 5e-4)
+    _close('lvis_map', out['_main_full']['lvis_map'], g['lvis_map'][0], 2e-3, q=0.999)
+    _close('ldot_map', out['_main_full']['ldot_map'], g['ldot_map'][0], 2e-3, q=0.999)
+    np.testing.assert_allclose(out['_main_full']['wbounds_after'].numpy(), g['wbounds_after'][0], atol=1e-6)
+
+
+def test_anisdf_trace_matches_reference():
+    g = _load('anisdf_trace_48')
+    H = int(g['_H'])
+    b = scene.make_batch(H, H, seed=0, n_env=0)
+    sd = scene.make_state_dict(0, relight=False, fitted=True)
+    out = O.render_sphere_tracing(b, sd, O.anisdf_cfg())
+    assert int((g['acc_map'][0] > 0).sum()) > 50
+    for k in ('rgb_map', 'acc_map', 'surf_map', 'bpts_map', 'cpts_map', 'depth_map', 'resd_map'):
+        if k in g:
+            _close(k, out[k], g[k][0], 2e-4)
+    _close('norm_map', out['norm_map'], g['norm_map'][0], 2e-3, q=0.99)
+
+
+def test_anisdf_volume_matches_reference():
+    g = _load('anisdf_volume_24')
+    H = int(g['_H'])
+    b = scene.make_batch(H, H, seed=0, n_env=0)
+    sd = scene.make_state_dict(0, relight=False, fitted=True)
+    out = O.render_volume(b, sd, O.anisdf_cfg())
+    for k in ('rgb_map', 'acc_map', 'depth_map', 'cpts_map', 'bpts_map', 'resd_map'):
+        _close(k, out[k], g[k][0], 3e-4)
+    _close('norm_map', out['norm_map'], g['norm_map'][0], 3e-3, q=0.99)
+
+
+def test_analytic_invariants():
+    """Invariants the reference asserts or implies (SURVEY.md 8c last row)."""
+    xyz, area = scene.gen_light_xyz()
+    assert abs(float(area.sum()) - 4 * np.pi) < 1e-4 and (area > 0).all()          # relight_utils.py:461-463
+    occ = O.sdf_to_occ(torch.linspace(-0.2, 0.2, 101), torch.tensor(0.1))
+    assert float(occ.min()) >= 0 and float(occ.max()) < 1
+    w = O.volume_weights(torch.rand(64, 16))
+    assert float(w.sum(-1).max()) <= 1 + 1e-5
+    R = torch.linalg.qr(torch.randn(8, 3, 3))[0]
+    assert torch.allclose(O.inverse_3x3(R) @ R, torch.eye(3).expand(8, 3, 3), atol=1e-5)
+    # sphere tracing of an analytic unit sphere converges to the known hit
+    o = torch.tensor([[0., 0., -3.]]); d = torch.tensor([[0., 0., 1.]])
+    surf, *_ = O.sphere_tracing(o, d, torch.tensor([[0.5]]), torch.tensor([[6.]]), lambda x: x.norm(dim=-1, keepdim=True) - 1,
+                                16, 1000., 0., 0.02, 1e-8, 1, soft=False)
+    assert abs(float(surf[0, 2]) + 1) < 2e-2
