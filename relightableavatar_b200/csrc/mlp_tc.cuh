@@ -1,11 +1,461 @@
-// placeholder, replaced below
+// Fused distance-query MLP on the 5th-gen tensor cores (tcgen05 / TMEM / TMA bulk copies), sm_100a.
+//
+// One launch evaluates, for every in-shell query point of the work list, the residual-deformation MLP
+// (base_network.py:34-42) and the SDF MLP (net_utils.py:1337-1352, output 0 only):
+//     bpts -> PE10 -> 9 linears (ReLU, skip@4) -> 0.05*tanh -> cpts -> PE8 -> 9 linears (Softplus100, skip@4) -> sdf
+// 18 dependent GEMMs per 128-point tile with the activations never leaving the SM:
+//   * operands fp16, accumulation fp32 in TMEM (tcgen05.mma kind::f16, M=128, N<=256, K=16 per instruction);
+//   * A (activations): shared memory, canonical K-major no-swizzle layout [K/8][128 rows][8 halves];
+//     written by the epilogue warps of the previous layer straight from TMEM (tcgen05.ld);
+//   * B (weights): streamed from L2 by the TMA engine (cp.async.bulk + mbarrier complete_tx) in 32-wide K chunks
+//     through a 2-stage ring, pre-packed on the host into the exact shared-memory image;
+//   * the 156-d pose condition is folded into the biases of layers 0 and 4 once per frame;
+//     the SDF skip input cat([h3, PE8])/sqrt(2) is realised by a column permutation of W4.
+// Two CTAs per SM (114 KB smem, 256 TMEM columns each): while one CTA's epilogue warps run bias/activation
+// out of TMEM, the other CTA's MMAs own the tensor pipe.  Warp roles per CTA: 0 = TMA producer, 1 = MMA
+// issuer (+ TMEM allocator), 2..9 = epilogue (warp%4 = TMEM lane quarter, two column halves).
 #pragma once
-#include "common.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
 #include <string>
-struct ra_weights;
-struct TcWeights { int dummy; };
-static int tc_init(TcWeights&, std::string&) { return 0; }
-static void tc_free(TcWeights&) {}
-static int tc_upload(TcWeights&, const ra_weights*, std::string&, cudaStream_t) { return 0; }
-static void tc_set_frame(TcWeights&, const FrameConst*, cudaStream_t, int64_t&) {}
-static void tc_distance(TcWeights&, const float*, float*, const int*, float, int, cudaStream_t, int64_t&) {}
+#include <vector>
+#include <cmath>
+#include "common.cuh"
+#include "../../include/ra_b200.h"
+
+#define TC_LAYERS 18
+#define TC_TILE_M 128
+#define TC_KCHUNK 32
+#define TC_STAGES 2
+#define TC_THREADS 320
+#define TC_ACT_BYTES (128 * 256 * 2)
+#define TC_PE_BYTES (128 * 64 * 2)
+#define TC_STAGE_BYTES (TC_KCHUNK * 256 * 2)
+#define TC_SMEM_BYTES (TC_ACT_BYTES + TC_PE_BYTES + TC_STAGES * TC_STAGE_BYTES + 256)
+
+enum { TC_EPI_RELU = 0, TC_EPI_RESD_FINAL = 1, TC_EPI_SOFTPLUS = 2, TC_EPI_S3 = 3, TC_EPI_SDF_FINAL = 4 };
+
+struct TcLayer {
+    int N;            // accumulator columns (multiple of 16)
+    int nchunks;      // K / 32
+    int pe_from;      // chunks >= pe_from read A from the PE buffer (chunk - pe_from), earlier ones from ACT
+    int epi;
+    unsigned goff;    // byte offset of the first chunk image in the weight blob
+};
+
+struct TcParams {
+    TcLayer layer[TC_LAYERS];
+    const float* bias[TC_LAYERS];
+    const unsigned char* blob;
+    const float* bpts;
+    float* out;
+    const int* count;
+    float resd_limit;
+};
+
+struct TcWeights {
+    unsigned char* blob = nullptr;
+    float* bias = nullptr;        // [18][256]
+    TcParams p{};
+    bool ready = false;
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, no swizzle: core matrix = 8 rows x 16 B; SBO = stride between 8-row groups, LBO = stride between the
+// two K core matrices of one K=16 step (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_f16(int N) {
+    // c_format F32 (bit 4), a/b F16 (0), K-major both, n_dim = N>>3 @17, m_dim = 128>>4 @24
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+}
+__device__ __forceinline__ float softplus100_fast(float z) {
+    float t = 100.f * z;
+    return (t > 20.f) ? z : 0.01f * __logf(1.f + __expf(t));
+}
+
+// write 8 consecutive K values (cols k0..k0+7, k0 % 8 == 0) of this thread's row into a K-major buffer
+__device__ __forceinline__ void put8(uint32_t buf, int row, int k0, const float* v) {
+    st_shared_v4(buf + (uint32_t)(k0 >> 3) * 2048u + (uint32_t)row * 16u, pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]),
+                 pack_h2(v[6], v[7]));
+}
+
+// positional encoding features [f0, f1) of x (feature order: x,y,z, then per level sin xyz, cos xyz) into the PE buffer
+__device__ __forceinline__ float pe_feature(float3 x, int idx) {
+    if (idx < 3) return idx == 0 ? x.x : (idx == 1 ? x.y : x.z);
+    int j = idx - 3, l = j / 6, r = j % 6, c = r % 3;
+    float v = (c == 0 ? x.x : (c == 1 ? x.y : x.z)) * (float)(1 << l);
+    return (r < 3) ? sinf(v) : cosf(v);
+}
+__device__ __forceinline__ void write_pe(uint32_t pe_buf, int row, float3 x, int nfeat, int chunk0, int chunk1) {
+    for (int ch = chunk0; ch < chunk1; ch++) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int idx = ch * 8 + j;
+            v[j] = (idx < nfeat) ? pe_feature(x, idx) : 0.f;
+        }
+        put8(pe_buf, row, ch * 8, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(const __grid_constant__ TcParams P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_act = s_base;
+    const uint32_t s_pe = s_base + TC_ACT_BYTES;
+    const uint32_t s_w = s_pe + TC_PE_BYTES;
+    const uint32_t s_bar = s_w + TC_STAGES * TC_STAGE_BYTES;   // barriers: full[2], empty[2], act_ready, acc_ready ; tmem ptr
+    const uint32_t bar_full = s_bar, bar_empty = s_bar + 16, bar_act = s_bar + 32, bar_acc = s_bar + 40;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + (s_bar - s_base) + 64);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int count = *P.count;
+    const int n_tiles = (count + TC_TILE_M - 1) / TC_TILE_M;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_act, 8);
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_bar + 64), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: stream every layer's weight chunks, once per tile =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int l = 0; l < TC_LAYERS; l++) {
+                    const uint32_t bytes = (uint32_t)P.layer[l].N * TC_KCHUNK * 2;
+                    const unsigned char* src = P.blob + P.layer[l].goff;
+                    for (int c = 0; c < P.layer[l].nchunks; c++, it++) {
+                        uint32_t s = it & 1, ph = (it >> 1) & 1;
+                        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                        mbar_expect_tx(bar_full + 8 * s, bytes);
+                        tma_bulk_g2s(s_w + s * TC_STAGE_BYTES, src + (size_t)c * bytes, bytes, bar_full + 8 * s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t it = 0, lc = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int l = 0; l < TC_LAYERS; l++, lc++) {
+                    const int N = P.layer[l].N;
+                    const uint32_t idesc = make_idesc_f16(N);
+                    const uint32_t lbo_b = (uint32_t)N * 16u;
+                    mbar_wait(bar_act, lc & 1);
+                    tc_fence_after();
+                    for (int c = 0; c < P.layer[l].nchunks; c++, it++) {
+                        uint32_t s = it & 1, ph = (it >> 1) & 1;
+                        mbar_wait(bar_full + 8 * s, ph);
+                        tc_fence_after();
+                        uint32_t a_base = (c >= P.layer[l].pe_from) ? (s_pe + (uint32_t)(c - P.layer[l].pe_from) * 4u * 2048u)
+                                                                     : (s_act + (uint32_t)c * 4u * 2048u);
+                        uint32_t b_base = s_w + s * TC_STAGE_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < TC_KCHUNK / 16; kk++) {
+                            uint64_t ad = make_sdesc(a_base + (uint32_t)kk * 2u * 2048u, 2048u, 128u);
+                            uint64_t bd = make_sdesc(b_base + (uint32_t)kk * 2u * lbo_b, lbo_b, 128u);
+                            umma_f16(tmem, ad, bd, idesc, (c | kk) ? 1u : 0u);
+                        }
+                        umma_commit(bar_empty + 8 * s);      // frees the weight stage when these MMAs retire
+                    }
+                    umma_commit(bar_acc);                     // accumulator of this layer complete
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int e = warp - 2;
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = e >> 2;                // column half: 0 -> cols [0,128), 1 -> [128,256)
+        const int row = q * 32 + lane;
+        const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t lc = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int gidx = tile * TC_TILE_M + row;
+            float3 bp = make3(0.f, 0.f, 0.f);
+            if (gidx < count) bp = make3(P.bpts[(size_t)gidx * 3], P.bpts[(size_t)gidx * 3 + 1], P.bpts[(size_t)gidx * 3 + 2]);
+            float3 cp = bp;
+            // prologue: PE10(bp) -> PE buffer (63 features, padded to 64); the two column-half warps split the chunks
+            write_pe(s_pe, row, bp, 63, half * 4, half * 4 + 4);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_act);
+            for (int l = 0; l < TC_LAYERS; l++, lc++) {
+                const int epi = P.layer[l].epi;
+                const float* __restrict__ bias = P.bias[l];
+                mbar_wait(bar_acc, lc & 1);
+                tc_fence_after();
+                if (epi == TC_EPI_RELU || epi == TC_EPI_SOFTPLUS) {
+#pragma unroll 1
+                    for (int cb = 0; cb < 4; cb++) {
+                        const int c0 = half * 128 + cb * 32;
+                        uint32_t r[32];
+                        tmem_ld32(t_lane + (uint32_t)c0, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                float z = __uint_as_float(r[g * 8 + j]) + __ldg(&bias[c0 + g * 8 + j]);
+                                v[j] = (epi == TC_EPI_RELU) ? fmaxf(z, 0.f) : softplus100_fast(z);
+                            }
+                            put8(s_act, row, c0 + g * 8, v);
+                        }
+                    }
+                } else if (epi == TC_EPI_S3) {
+                    // S3: 205 outputs -> ACT cols [48, 253); PE8(cp) features 0..47 -> cols [0,48), 48..50 -> cols 253..255
+                    // half 0: accumulator cols [0,104); half 1: [104,208) + PE copies
+                    const int a0 = half ? 104 : 0;
+#pragma unroll 1
+                    for (int cb = 0; cb < 13; cb++) {            // 13 groups of 8 accumulator columns
+                        const int c0 = a0 + cb * 8;
+                        uint32_t r[16];
+                        tmem_ld16(t_lane + (uint32_t)(c0 & ~15), r);   // 16-col aligned load, pick the 8 we need
+                        tmem_ld_wait();
+                        const int o = c0 & 15;
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            int n = c0 + j;
+                            float z = __uint_as_float(o ? r[8 + j] : r[j]) + ((n < 205) ? __ldg(&bias[n]) : 0.f);
+                            v[j] = softplus100_fast(z);
+                        }
+                        if (c0 == 200) {      // cols 248..255: outputs 200..204 then PE8 features 48,49,50
+                            v[5] = pe_feature(cp, 48); v[6] = pe_feature(cp, 49); v[7] = pe_feature(cp, 50);
+                        }
+                        put8(s_act, row, 48 + c0, v);
+                    }
+                    // PE8 features 0..47 (6 chunks) copied from the PE buffer: 3 chunks per half
+                    for (int ch = half * 3; ch < half * 3 + 3; ch++) {
+                        uint32_t a, b, c, d;
+                        ld_shared_v4(s_pe + (uint32_t)ch * 2048u + (uint32_t)row * 16u, a, b, c, d);
+                        st_shared_v4(s_act + (uint32_t)ch * 2048u + (uint32_t)row * 16u, a, b, c, d);
+                    }
+                } else if (epi == TC_EPI_RESD_FINAL) {
+                    uint32_t r[16];
+                    tmem_ld16(t_lane, r);
+                    tmem_ld_wait();
+                    float rx = tanhf(__uint_as_float(r[0]) + __ldg(&bias[0])) * P.resd_limit;
+                    float ry = tanhf(__uint_as_float(r[1]) + __ldg(&bias[1])) * P.resd_limit;
+                    float rz = tanhf(__uint_as_float(r[2]) + __ldg(&bias[2])) * P.resd_limit;
+                    cp = make3(bp.x + rx, bp.y + ry, bp.z + rz);
+                    // PE8(cp): 51 features padded to 64 -> PE buffer (input of S0, later copied into the S4 skip columns)
+                    write_pe(s_pe, row, cp, 51, half * 4, half * 4 + 4);
+                } else {   // TC_EPI_SDF_FINAL
+                    if (half == 0) {
+                        uint32_t r[16];
+                        tmem_ld16(t_lane, r);
+                        tmem_ld_wait();
+                        if (gidx < count) P.out[gidx] = __uint_as_float(r[0]) + __ldg(&bias[0]);
+                    }
+                }
+                if (l + 1 < TC_LAYERS) {
+                    tc_fence_before();
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_act);
+                }
+            }
+        }
+    }
+    // teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static int tc_init(TcWeights& t, std::string& err) {
+    cudaError_t e = cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(k_mlp_tc): ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+static void tc_free(TcWeights& t) {
+    if (t.blob) cudaFree(t.blob);
+    if (t.bias) cudaFree(t.bias);
+    t.blob = nullptr; t.bias = nullptr;
+}
+
+// Pack one layer: src (N_src, K_src) fp32 row-major; colmap[k] = source column for packed column k (-1 -> 0); rows >= N_src -> 0.
+static void tc_pack_layer(std::vector<__half>& blob, const std::vector<float>& w, int N_src, int K_src, const std::vector<int>& colmap,
+                          int N_pad, float scale, int row0 = 0) {
+    int K = (int)colmap.size();
+    int nch = K / TC_KCHUNK;
+    size_t base = blob.size();
+    blob.resize(base + (size_t)nch * TC_KCHUNK * N_pad, __float2half(0.f));
+    for (int c = 0; c < nch; c++)
+        for (int kq = 0; kq < TC_KCHUNK / 8; kq++)
+            for (int n = 0; n < N_pad; n++)
+                for (int j = 0; j < 8; j++) {
+                    int k = c * TC_KCHUNK + kq * 8 + j;
+                    float v = 0.f;
+                    int sn = row0 + n;
+                    if (n < N_src && colmap[k] >= 0) v = w[(size_t)sn * K_src + colmap[k]] * scale;
+                    blob[base + (size_t)c * TC_KCHUNK * N_pad + ((size_t)kq * N_pad + n) * 8 + j] = __float2half_rn(v);
+                }
+}
+
+static int tc_upload(TcWeights& t, const ra_weights* w, std::string& err, cudaStream_t st) {
+    auto fetch = [&](const float* src, size_t n, std::vector<float>& dst) -> bool {
+        dst.resize(n);
+        return cudaMemcpyAsync(dst.data(), src, n * sizeof(float), cudaMemcpyDefault, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
+    };
+    static const int rK[9] = {219, 256, 256, 256, 475, 256, 256, 256, 256};
+    static const int sN[9] = {256, 256, 256, 205, 256, 256, 256, 256, 257};
+    static const int sK[9] = {51, 256, 256, 256, 256, 256, 256, 256, 256};
+    std::vector<__half> blob;
+    std::vector<float> bias((size_t)TC_LAYERS * 256, 0.f);
+    TcParams& P = t.p;
+    auto ident = [](int K_used, int K_pad) { std::vector<int> m(K_pad, -1); for (int k = 0; k < K_used; k++) m[k] = k; return m; };
+    for (int l = 0; l < 9; l++) {           // residual MLP
+        std::vector<float> hw, hb;
+        int N = (l == 8) ? 3 : 256;
+        if (!fetch(w->resd_w[l], (size_t)N * rK[l], hw) || !fetch(w->resd_b[l], N, hb)) { err = "tc_upload: copy failed"; return 1; }
+        std::vector<int> cm = (l == 0) ? ident(63, 64) : (l == 4 ? ident(319, 320) : ident(256, 256));
+        int Np = (l == 8) ? 16 : 256;
+        P.layer[l].N = Np; P.layer[l].nchunks = (int)cm.size() / TC_KCHUNK; P.layer[l].goff = (unsigned)(blob.size() * 2);
+        P.layer[l].pe_from = (l == 0) ? 0 : (l == 4 ? 8 : 1 << 20);
+        P.layer[l].epi = (l == 8) ? TC_EPI_RESD_FINAL : TC_EPI_RELU;
+        tc_pack_layer(blob, hw, N, rK[l], cm, Np, 1.f);
+        for (int n = 0; n < N; n++) bias[(size_t)l * 256 + n] = hb[n];
+    }
+    const float rs2 = (float)(1.0 / std::sqrt(2.0));
+    for (int l = 0; l < 9; l++) {           // SDF MLP
+        std::vector<float> hw, hb;
+        if (!fetch(w->sdf_w[l], (size_t)sN[l] * sK[l], hw) || !fetch(w->sdf_b[l], sN[l], hb)) { err = "tc_upload: copy failed"; return 1; }
+        int L = 9 + l;
+        std::vector<int> cm;
+        int Nsrc = sN[l], Np = 256;
+        float scale = 1.f;
+        if (l == 0) cm = ident(51, 64);
+        else if (l == 4) {                  // packed col j: [PE 0..47 | h3 0..204 | PE 48..50]; source cols: h3 at 0..204, PE at 205..255
+            cm.assign(256, -1);
+            for (int j = 0; j < 48; j++) cm[j] = 205 + j;
+            for (int j = 0; j < 205; j++) cm[48 + j] = j;
+            for (int j = 0; j < 3; j++) cm[253 + j] = 205 + 48 + j;
+            scale = rs2;
+        } else cm = ident(256, 256);
+        if (l == 3) Np = 208;
+        if (l == 8) { Nsrc = 1; Np = 16; }  // only row 0 (the sdf) is needed for a distance query
+        P.layer[L].N = Np; P.layer[L].nchunks = (int)cm.size() / TC_KCHUNK; P.layer[L].goff = (unsigned)(blob.size() * 2);
+        P.layer[L].pe_from = (l == 0) ? 0 : 1 << 20;
+        P.layer[L].epi = (l == 8) ? TC_EPI_SDF_FINAL : (l == 3 ? TC_EPI_S3 : TC_EPI_SOFTPLUS);
+        tc_pack_layer(blob, hw, Nsrc, sK[l], cm, Np, scale);
+        for (int n = 0; n < std::min(Nsrc, 256); n++) bias[(size_t)L * 256 + n] = hb[n];
+    }
+    tc_free(t);
+    if (cudaMalloc((void**)&t.blob, blob.size() * 2) != cudaSuccess || cudaMalloc((void**)&t.bias, bias.size() * 4) != cudaSuccess) {
+        err = "tc_upload: cudaMalloc failed"; return 1;
+    }
+    cudaMemcpy(t.blob, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(t.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
+    for (int l = 0; l < TC_LAYERS; l++) P.bias[l] = t.bias + (size_t)l * 256;
+    P.blob = t.blob;
+    t.ready = true;
+    return 0;
+}
+
+// per frame: layers 0 and 4 of the residual MLP take their (pose-folded) biases from the frame constants
+static void tc_set_frame(TcWeights& t, const FrameConst* fc, cudaStream_t, int64_t&) {
+    t.p.bias[0] = &fc->resd_b0[0];
+    t.p.bias[4] = &fc->resd_b4[0];
+}
+
+static void tc_distance(TcWeights& t, const float* bpts, float* out, const int* count, float resd_limit, int sms, cudaStream_t st,
+                        int64_t& launches) {
+    TcParams p = t.p;
+    p.bpts = bpts; p.out = out; p.count = count; p.resd_limit = resd_limit;
+    k_mlp_tc<<<2 * sms, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
+    launches++;
+}
