@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py -- relit 512x512 frames/s of the RelightableAvatar inference hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the config the metric is quoted on): xuzhen_12v_geo_fix_mat relighting,
+learned ("main") env-map, 512x512, synthetic scene of relightableavatar_b200/scene.py (seeded body / pose
+sequence / fitted SDF weights; no dataset or checkpoint exists offline).  One step = one frame through
+`Renderer.render`: per-frame state upload (set_frame), 16-iteration surface trace, 3-sample surface attributes with
+analytic normals, 4-iteration soft-shadow trace over the 16x32 light grid, microfacet light sum.  With N > 1 the
+frames of the sequence are sharded over the ranks (rank r renders frame step*N + r; weak scaling) and every step
+ends with ONE all-gather of the finished pixels (rgb + acc).
+
+`value`  : whole-job frames/s with the frame inputs already resident in HBM.
+`e2e`    : the same through the public plugin call with HOST (pinned) inputs: H2D of the frame + rays and D2H of the
+           finished rgb/acc maps inside the timed region.
+`--impl reference`: the reference's CPU path (the oracle port of oracle/ra_oracle.py, all host threads) on a bounded
+           sample of the same workload (a 32x32 rendering of the same view), scaled to 512x512 frames by ray count.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_QUERY = 2_192_384          # resd MLP 571,648 MAC + SDF MLP 524,544 MAC per in-shell distance query
+H = W = 512
+SAMPLE_H = 32
+SEQ_FRAMES = 8                      # distinct frames of the pose sequence cycled through
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.idx}', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def cpu_reference_step(cfg, batch, sd, O, torch):
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        out = O.render_sphere_tracing(batch, sd, cfg, torch.float32, 'cpu', want_lvis=False)
+    return time.perf_counter() - t0, out
+
+
+def run_reference(args):
+    """The reference's CPU path (oracle port) on the host cores; rank 0 only."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    import torch
+    from oracle import ra_oracle as O
+    from relightableavatar_b200 import scene
+    torch.set_num_threads(os.cpu_count())
+    b = scene.make_batch(SAMPLE_H, SAMPLE_H, seed=0, n_env=0)
+    P_full = scene.make_batch(H, W, seed=0, n_env=0)['ray_o'].shape[1]
+    P_s = b['ray_o'].shape[1]
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    cfg = O.Cfg()
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_step(cfg, b, sd, O, torch)
+    ts = [cpu_reference_step(cfg, b, sd, O, torch)[0] for _ in range(max(args.steps, 1))]
+    t = sum(ts) / len(ts)
+    fps = (P_s / P_full) / t
+    sample = f'{SAMPLE_H}x{SAMPLE_H} relight rendering of the same view ({P_s} of {P_full} rays), scaled by ray count'
+    line = {'impl': 'reference', 'metric': 'relit 512x512 frames/sec', 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'xuzhen_12v_geo_fix_mat relighting, 1 envmap (main), 512x512', 'sample': sample},
+            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
+            'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default='tc', choices=['tc', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from relightableavatar_b200 import scene
+    from relightableavatar_b200.renderer import Renderer
+
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if world > 1:
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device(f'cuda:{local}'))
+    torch.cuda.set_device(local)
+    dev = torch.device(f'cuda:{local}')
+
+    # ---- workload: a short pose sequence, host (pinned) and device copies
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    frames_host, frames_dev = [], []
+    tensor_keys = ('ray_o', 'ray_d', 'near', 'far', 'R', 'Th', 'poses', 'A', 'big_A', 'weights', 'pverts', 'pnorm', 'tverts', 'wbounds', 'train_poses')
+    P_max = 0
+    for f in range(SEQ_FRAMES):
+        b = scene.make_batch(H, W, frame=f, n_frames=SEQ_FRAMES, seed=0, n_env=0)
+        hb = {k: torch.from_numpy(b[k]).pin_memory() for k in tensor_keys}
+        hb['mask_at_box'] = torch.from_numpy(b['mask_at_box'])
+        frames_host.append(hb)
+        frames_dev.append({k: v.to(dev) for k, v in hb.items() if k in tensor_keys})
+        P_max = max(P_max, b['ray_o'].shape[1])
+    h2d_bytes = int(statistics.mean(sum(v.numel() * v.element_size() for k, v in hb.items() if k in tensor_keys) for hb in frames_host))
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=dev, precision=args.precision, max_rays=P_max + 1024, test_light=('main',), sync_timing=False)
+    eng = r.engine
+    pad = P_max
+    out_host = torch.empty(pad, 4).pin_memory()
+
+    def frame_of(step):
+        return (step * world + rank) % SEQ_FRAMES
+
+    def step_device(step):
+        out = r.render(frames_dev[frame_of(step)])['main']
+        px = torch.cat([out['rgb_map'][0], out['acc_map'][0][:, None]], dim=1)
+        if world > 1:
+            buf = torch.zeros(pad, 4, device=dev)
+            buf[: px.shape[0]] = px
+            g = torch.empty(world * pad, 4, device=dev)
+            dist.all_gather_into_tensor(g, buf)          # the single collective of the step
+            return g
+        return px
+
+    def step_e2e(step):
+        hb = frames_host[frame_of(step)]
+        db = {k: v.to(dev, non_blocking=True) for k, v in hb.items() if k in tensor_keys}
+        out = r.render(db)['main']
+        px = torch.cat([out['rgb_map'][0], out['acc_map'][0][:, None]], dim=1)
+        if world > 1:
+            buf = torch.zeros(pad, 4, device=dev)
+            buf[: px.shape[0]] = px
+            g = torch.empty(world * pad, 4, device=dev)
+            dist.all_gather_into_tensor(g, buf)
+        out_host[: px.shape[0]].copy_(px, non_blocking=True)
+        torch.cuda.current_stream().synchronize()        # the caller reads the finished pixels
+        return px.shape[0] * 16
+
+    def timed(fn, steps, warmup):
+        for s in range(warmup):
+            fn(s)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ret = None
+        for s in range(steps):
+            ret = fn(warmup + s)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), ret
+
+    # ---- device-resident throughput (+ per-kernel timing of the fused MLP kernel + clocks)
+    sampler = ClockSampler(local)
+    eng.profile_enable(True)
+    l0 = eng.launch_count()
+    for s in range(args.warmup):
+        step_device(s)
+    eng.profile_read()
+    l0 = eng.launch_count()
+    sampler.start()
+    ms_dev, _ = timed(step_device, args.steps, 0)
+    clocks = sampler.stop()
+    prof = eng.profile_read()
+    launches = eng.launch_count() - l0
+    eng.profile_enable(False)
+    stats = eng.stats()
+    # in-shell queries summed over the timed steps are not kept per step; the last frame's count x steps is
+    # exact only for a 1-frame sequence, so accumulate from a dedicated pass:
+    inshell = 0
+    nq = 0
+    for s in range(args.steps):
+        step_device(args.warmup + s)
+        st = eng.stats()
+        inshell += st['n_queries_in_shell']; nq += st['n_queries']
+    # ---- end-to-end (host buffers in, host pixels out)
+    ms_e2e, d2h_bytes = timed(step_e2e, args.steps, args.warmup)
+
+    frames = args.steps * world
+    value = frames / (ms_dev / 1e3)
+    e2e = frames / (ms_e2e / 1e3)
+    peaks, which = load_peaks()
+    mlp_s = prof['mlp_ms'] / 1e3
+    achieved = inshell * FLOP_PER_QUERY / max(mlp_s, 1e-9) / 1e12
+    peak = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
+    line = {
+        'metric': 'relit 512x512 frames/sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f16 tensor-core operands, f32 accumulate (distance MLPs); f32 elsewhere' if args.precision == 'tc' else 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'xuzhen_12v_geo_fix_mat relighting, 1 envmap (main), 512x512, 1 frame per GPU per step',
+                   'P_rays': stats['n_rays'], 'S_fg': stats['n_fg'], 'shadow_rays': stats['n_shadow_rays'],
+                   'queries_per_frame': nq // max(args.steps, 1), 'in_shell_fraction': round(inshell / max(nq, 1), 4),
+                   'parallelism': f'frame-sharded x{world}, one all-gather of pixels per step' if world > 1 else 'single GPU',
+                   'l2': 'per-frame workspace (query lists + 2x141 MB visibility maps) exceeds the 126 MB L2; no explicit flush; the 1.95 MB fp16 weight image is L2-resident by design'},
+        'clocks': clocks,
+        'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': int(d2h_bytes)},
+        'gpu_launches': int(launches),
+        'roofline': {'kernel': 'k_mlp_tc (fused residual+SDF MLP, tcgen05)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak,
+                     'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': f'{which} bf16_tflops_sustained',
+                     'algorithmic_flop_per_query': FLOP_PER_QUERY, 'kernel_ms_per_step': prof['mlp_ms'] / args.steps,
+                     'kernel_launches_per_step': prof['mlp_launches'] / args.steps,
+                     'kernel_share_of_step': prof['mlp_ms'] / ms_dev, 'stage_ms_per_step': {k: v / args.steps for k, v in prof['stage_ms'].items()}},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ra_oracle as O
+        torch.set_num_threads(os.cpu_count())
+        b = scene.make_batch(SAMPLE_H, SAMPLE_H, seed=0, n_env=0)
+        t, _ = cpu_reference_step(O.Cfg(), b, sd, O, torch)      # warm
+        ts = [cpu_reference_step(O.Cfg(), b, sd, O, torch)[0] for _ in range(3)]
+        t = statistics.median(ts)
+        P_s = b['ray_o'].shape[1]
+        line['cpu_baseline'] = {'value': (P_s / stats['n_rays']) / t, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                'sample': f'{SAMPLE_H}x{SAMPLE_H} relight rendering of the same view ({P_s} of {stats["n_rays"]} rays, {t:.2f} s), scaled by ray count'}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -141,6 +141,12 @@ int ra_query_sdf(ra_handle* h, const float* x, int64_t n, float dist_th, int32_t
 int ra_query_raw(ra_handle* h, const float* x, const float* v, int64_t n, float* raw, void* stream);
 
 int ra_get_stats(ra_handle* h, ra_stats* out);   /* synchronises the device */
+/* Device-side timing for bench.py's roofline line: when enabled, every launch of the fused MLP kernel and every
+ * stage boundary of a render call is bracketed with CUDA events on the launching stream.  ra_profile_read
+ * synchronises, returns the sums accumulated since the previous read and resets them.
+ * stage_ms[4] = {surface tracing, surface attributes, light visibility, shading}. */
+int ra_profile_enable(ra_handle* h, int32_t on);
+int ra_profile_read(ra_handle* h, double* mlp_ms, int64_t* mlp_launches, double* stage_ms);
 /* number of kernels the library launched since creation (bench.py's gpu_launches) */
 int64_t ra_launch_count(ra_handle* h);
 

@@ -78,6 +78,12 @@ struct ra_handle {
     // ---- fp32 MLP chunk buffers
     float *Xr0, *ra_[8], *Xr4, *z8, *resd_o, *cpts_o, *Xs0, *sb_[8], *Xs4, *out257, *GA, *GB, *dpe0, *dpes, *gcp, *u4, *gbp, *nrm_o;
     float *hd1, *hd2, *head_a, *head_r, *Xrn, *rn1, *rn2;
+    // profiling (bench.py): event pairs around the MLP kernel + stage marks
+    bool prof = false;
+    std::vector<cudaEvent_t> ev_mlp;      // pairs
+    size_t ev_mlp_used = 0;
+    std::vector<cudaEvent_t> ev_stage;    // 5 marks per render
+    size_t ev_stage_used = 0;
     // last render
     int64_t last_P = 0; const float* last_ray_o = nullptr; int chunk_actual = 1;
 };
@@ -415,9 +421,19 @@ static int attr_pass(ra_handle* h, cudaStream_t st, int64_t max_rows, bool sync_
 }
 
 // distance MLPs over the query list (net sdf into q.net)
+static cudaEvent_t prof_event(std::vector<cudaEvent_t>& pool, size_t& used) {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[used++];
+}
+static void prof_stage(ra_handle* h, cudaStream_t st) {
+    if (h->prof) cudaEventRecord(prof_event(h->ev_stage, h->ev_stage_used), st);
+}
+
 static int distance_pass(ra_handle* h, cudaStream_t st) {
     if (h->cfg.precision == RA_PRECISION_TC) {
+        if (h->prof) cudaEventRecord(prof_event(h->ev_mlp, h->ev_mlp_used), st);
         tc_distance(h->tc, h->q.bpts, h->q.net, h->q.count, h->cfg.resd_limit, h->sms, st, h->launches);
+        if (h->prof) cudaEventRecord(prof_event(h->ev_mlp, h->ev_mlp_used), st);
         return 0;
     }
     int c = 0;
@@ -457,12 +473,14 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     TraceCfg tc{c.st_iter, c.st_tan_i, c.st_relax, c.st_offset, c.st_eps, c.st_skip, c.dist_th, c.blend_radius};
     int N = c.n_verts;
     int g = grid_for(h, P, 128, 16);
+    prof_stage(h, st);
     for (int it = 0; it <= c.st_iter; it++) {
         CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
         LAUNCH(h, k_trace_surface, g, 128, 0, st, it, tc, h->fc, h->sv, N, ray_o, ray_d, near_, far_, (int)P, h->ss, h->q, h->cnt,
                h->surf, h->acc, h->depth, h->fg_ray);
         if (it < c.st_iter && distance_pass(h, st)) return 1;
     }
+    prof_stage(h, st);
     // surface samples -> attributes
     int C = c.relight ? 17 : 16;
     CK(cudaMemsetAsync(h->raw, 0, (size_t)P * c.n_samples * C * sizeof(float), st));
@@ -475,6 +493,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     LAUNCH(h, k_surface_blend, grid_for(h, P), 256, 0, st, c.relight, h->cnt.n_fg, h->fg_ray, h->raw, c.n_samples, h->acc, h->surf, h->depth,
            c.albedo_slope, c.albedo_bias, c.rough_slope, c.rough_bias, c.albedo_multiplier, h->fm, om);
     if (!c.relight) { CK(cudaGetLastError()); return 0; }
+    prof_stage(h, st);
     // light visibility (DFSS)
     int L = c.env_h * c.env_w;
     LAUNCH(h, k_shadow_gen, grid_for(h, P * L / 4, 256, 16), 256, 0, st, h->fc, h->cnt.n_fg, h->fg_ray, h->surf, h->fm.norm, h->ldir, L,
@@ -487,11 +506,13 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
                h->q, h->cnt, h->lvis);
         if (it < c.lv_iter && distance_pass(h, st)) return 1;
     }
+    prof_stage(h, st);
     LAUNCH(h, k_shade, grid_for(h, P * 32, 256, 8), 256, 0, st, h->cnt.n_fg, h->fg_ray, ray_o, h->surf, h->acc, h->fm, h->lvis, h->ldot,
            h->lxyz, h->larea, L, h->env_main, h->emh, h->emw, c.fresnel_f0, c.shading_albedo, 0, 1, out->rgb_map, out->shade_map,
            (float*)nullptr);
     if (out->lvis_map || out->ldot_map)
         LAUNCH(h, k_scatter_lmaps, grid_for(h, P * L / 4), 256, 0, st, h->cnt.n_fg, h->fg_ray, h->acc, h->lvis, h->ldot, L, out->lvis_map, out->ldot_map);
+    prof_stage(h, st);
     CK(cudaGetLastError());
     return 0;
 }
@@ -598,5 +619,34 @@ extern "C" int ra_get_stats(ra_handle* h, ra_stats* out) {
     unsigned long long q[2];
     memcpy(q, &c[8], 16);
     out->n_queries = (int64_t)q[0]; out->n_queries_in_shell = (int64_t)q[1];
+    return 0;
+}
+
+extern "C" int ra_profile_enable(ra_handle* h, int32_t on) {
+    h->prof = on != 0;
+    h->ev_mlp_used = 0; h->ev_stage_used = 0;
+    return 0;
+}
+
+extern "C" int ra_profile_read(ra_handle* h, double* mlp_ms, int64_t* mlp_launches, double* stage_ms) {
+    CK(cudaDeviceSynchronize());
+    double ms = 0;
+    for (size_t i = 0; i + 1 < h->ev_mlp_used; i += 2) {
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, h->ev_mlp[i], h->ev_mlp[i + 1]));
+        ms += t;
+    }
+    if (mlp_ms) *mlp_ms = ms;
+    if (mlp_launches) *mlp_launches = (int64_t)(h->ev_mlp_used / 2);
+    if (stage_ms) {
+        for (int k = 0; k < 4; k++) stage_ms[k] = 0;
+        for (size_t i = 0; i + 4 < h->ev_stage_used; i += 5)
+            for (int k = 0; k < 4; k++) {
+                float t = 0;
+                CK(cudaEventElapsedTime(&t, h->ev_stage[i + k], h->ev_stage[i + k + 1]));
+                stage_ms[k] += t;
+            }
+    }
+    h->ev_mlp_used = 0; h->ev_stage_used = 0;
     return 0;
 }

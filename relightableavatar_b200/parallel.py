@@ -1,0 +1,86 @@
+"""Multi-GPU sharding of the rendering path: one process per GPU, torch.distributed (NCCL over NVLink) as plumbing.
+
+Every ray is independent given the per-frame read-only state, so there is no data-path collective
+inside the renderer.  Two partitions are offered, both ending in ONE all-gather of finished pixels:
+
+* frame sharding (BASELINE config 5; weak scaling): rank r renders frames r, r+W, r+2W, ... of a sequence;
+* tile sharding (BASELINE config 4; strong scaling): the P in-box rays of one frame are dealt to the ranks in
+  interleaved blocks of 32 rays (foreground/background and lit/unlit work balance), every rank renders its rays for
+  all env-maps, and the fixed-size padded pixel blocks are all-gathered and de-interleaved.
+
+The partition logic is pure index arithmetic and is covered on CPU with the gloo backend (tests/test_parallel.py).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+import torch.distributed as dist
+
+BLOCK = 32
+
+
+def frame_indices(n_frames: int, rank: int, world: int) -> List[int]:
+    return list(range(rank, n_frames, world))
+
+
+def tile_partition(P: int, rank: int, world: int, block: int = BLOCK) -> torch.Tensor:
+    """Indices (ascending) of the rays owned by `rank`: blocks of `block` consecutive rays dealt round-robin."""
+    idx = torch.arange(P)
+    return idx[(idx // block) % world == rank]
+
+
+def padded_count(P: int, world: int, block: int = BLOCK) -> int:
+    """Upper bound of any rank's ray count (the all-gather block size)."""
+    n_blocks = (P + block - 1) // block
+    return ((n_blocks + world - 1) // world) * block
+
+
+def shard_batch_rays(batch: Dict, rank: int, world: int) -> Tuple[Dict, torch.Tensor]:
+    """Returns a shallow copy of `batch` whose ray tensors hold only this rank's rays, and the owned indices."""
+    P = batch['ray_o'].shape[1]
+    own = tile_partition(P, rank, world)
+    b = dict(batch)
+    for k in ('ray_o', 'ray_d', 'near', 'far'):
+        t = torch.as_tensor(batch[k])
+        b[k] = t[:, own.to(t.device)]
+    return b, own
+
+
+def allgather_pixels(local: torch.Tensor, n_pad: int, group=None) -> torch.Tensor:
+    """local (n_local, C) -> (world, n_pad, C) on every rank with ONE collective (rows beyond n_local are zero)."""
+    world = dist.get_world_size(group)
+    buf = torch.zeros(n_pad, local.shape[1], dtype=local.dtype, device=local.device)
+    buf[: local.shape[0]] = local
+    out = torch.empty(world * n_pad, local.shape[1], dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    return out.view(world, n_pad, local.shape[1])
+
+
+def deinterleave(gathered: torch.Tensor, P: int, world: int, block: int = BLOCK) -> torch.Tensor:
+    """(world, n_pad, C) blocks -> (P, C) in original ray order."""
+    out = torch.empty(P, gathered.shape[-1], dtype=gathered.dtype, device=gathered.device)
+    for r in range(world):
+        own = tile_partition(P, r, world, block).to(gathered.device)
+        out[own] = gathered[r, : own.numel()]
+    return out
+
+
+def render_tile_sharded(render_fn, batch: Dict, keys=('rgb_map', 'acc_map'), group=None) -> Dict[str, torch.Tensor]:
+    """`render_fn(batch) -> {key: (1, P_local, C) or (1, P_local)}` on this rank's rays; returns full-frame (1, P, C) maps."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    P = batch['ray_o'].shape[1]
+    local_batch, own = shard_batch_rays(batch, rank, world)
+    out = render_fn(local_batch)
+    cols, widths = [], []
+    for k in keys:
+        t = out[k][0]
+        t = t[:, None] if t.ndim == 1 else t
+        cols.append(t); widths.append(t.shape[1])
+    packed = torch.cat(cols, dim=1).contiguous()
+    full = deinterleave(allgather_pixels(packed, padded_count(P, world), group), P, world)
+    res, c0 = {}, 0
+    for k, w in zip(keys, widths):
+        res[k] = full[:, c0:c0 + w][None] if w > 1 else full[:, c0][None]
+        c0 += w
+    return res

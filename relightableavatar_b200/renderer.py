@@ -242,6 +242,15 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.ra_launch_count(self.h))
 
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.ra_profile_enable(self.h, int(on)), 'ra_profile_enable')
+
+    def profile_read(self):
+        ms, n = C.c_double(0), C.c_int64(0)
+        st = (C.c_double * 4)()
+        self._check(self.lib.ra_profile_read(self.h, C.byref(ms), C.byref(n), st), 'ra_profile_read')
+        return dict(mlp_ms=ms.value, mlp_launches=n.value, stage_ms=dict(zip(('surface', 'attributes', 'visibility', 'shading'), list(st))))
+
 
 _MAIN_KEYS = {
     'relight': ('rgb_map', 'acc_map', 'depth_map', 'surf_map', 'norm_map', 'cpts_map', 'bpts_map', 'albedo_map', 'roughness_map', 'shade_map'),
@@ -259,7 +268,7 @@ class Renderer(torch.nn.Module):
     """
 
     def __init__(self, net, mode: str = 'relight', cfg=None, device='cuda:0', precision: str = 'tc', max_rays: int = 1 << 17,
-                 test_light=('main',), return_lvis: bool = False, to_cpu: bool = False, **overrides):
+                 test_light=('main',), return_lvis: bool = False, to_cpu: bool = False, sync_timing: bool = True, **overrides):
         super().__init__()
         self.net = net
         self.mode = mode
@@ -273,6 +282,7 @@ class Renderer(torch.nn.Module):
         self.test_light = tuple(test_light)
         self.return_lvis = return_lvis
         self.to_cpu = to_cpu
+        self.sync_timing = sync_timing     # reference behaviour: cuda.synchronize + perf_counter around the main pass
 
     @torch.no_grad()
     def render(self, batch) -> dotdict:
@@ -287,10 +297,12 @@ class Renderer(torch.nn.Module):
             out = eng.render(self.mode, ray_o, ray_d, near, far, keys)
             return dotdict({k: v[None] for k, v in out.items()})
         # novel_light_sphere_tracing.Renderer.render (:101-221): main pass, then one cheap re-shade per env-map
-        torch.cuda.synchronize(eng.device)
+        if self.sync_timing:
+            torch.cuda.synchronize(eng.device)
         tick = time.perf_counter()
         main = eng.render('relight', ray_o, ray_d, near, far, keys)
-        torch.cuda.synchronize(eng.device)
+        if self.sync_timing:
+            torch.cuda.synchronize(eng.device)
         diff = time.perf_counter() - tick
         relight = dotdict()
         conv = (lambda t: t.cpu()) if self.to_cpu else (lambda t: t)
