@@ -31,7 +31,7 @@
 #define TC_ACT_BYTES (128 * 256 * 2)
 #define TC_PE_BYTES (128 * 64 * 2)
 #define TC_STAGE_BYTES (TC_KCHUNK * 256 * 2)
-#define TC_SMEM_BYTES (TC_ACT_BYTES + TC_PE_BYTES + TC_STAGES * TC_STAGE_BYTES + 256)
+#define TC_SMEM_BYTES (TC_ACT_BYTES + TC_PE_BYTES + TC_STAGES * TC_STAGE_BYTES + 512)
 
 enum { TC_EPI_RELU = 0, TC_EPI_RESD_FINAL = 1, TC_EPI_SOFTPLUS = 2, TC_EPI_S3 = 3, TC_EPI_SDF_FINAL = 4 };
 
@@ -41,6 +41,7 @@ struct TcLayer {
     int pe_from;      // chunks >= pe_from read A from the PE buffer (chunk - pe_from), earlier ones from ACT
     int epi;
     unsigned goff;    // byte offset of the first chunk image in the weight blob
+    unsigned boff;    // byte offset of the bias chunk: [2][N][8] halves, k=0: fp16(b), k=1: fp16(b - fp16(b)), rest 0
 };
 
 struct TcParams {
@@ -77,7 +78,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n\t"
         ".reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x4000;\n\t"
         "@P1 bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t"
@@ -144,9 +145,22 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
 }
-__device__ __forceinline__ float softplus100_fast(float z) {
-    float t = 100.f * z;
-    return (t > 20.f) ? z : 0.01f * __logf(1.f + __expf(t));
+// ---- half2 epilogue math -------------------------------------------------------------------------------
+// softplus_100(z) = max(z, 0) + g(|z|),  g(a) = log1p(exp(-100 a)) / 100  in (0, 0.00693].
+// g is evaluated in half2: e = 2^(-144.27 a) (one MUFU.EX2.F16x2 per PAIR), log1p(e)/100 ~ e (c1 + c2 e + c3 e^2),
+// max abs error 5.4e-6 -- below the fp16 quantisation of the activations this value is rounded to anyway.
+__device__ __forceinline__ uint32_t h2_softplus100(float a, float b) {
+    const __half2 z = __floats2half2_rn(a, b);
+    const __half2 az = __habs2(z);
+    const __half2 e = h2exp2(__hmul2(az, __float2half2_rn(-144.269504f)));
+    __half2 p = __hfma2(e, __float2half2_rn(0.0011465454f), __float2half2_rn(-0.0040842847f));
+    p = __hfma2(p, e, __float2half2_rn(0.0098745818f));
+    const __half2 r = __hfma2(p, e, __hmax2(z, __float2half2_rn(0.f)));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t h2_relu(float a, float b) {
+    const __half2 r = __hmax2(__floats2half2_rn(a, b), __float2half2_rn(0.f));
+    return *reinterpret_cast<const uint32_t*>(&r);
 }
 
 // write 8 consecutive K values (cols k0..k0+7, k0 % 8 == 0) of this thread's row into a K-major buffer
@@ -155,22 +169,74 @@ __device__ __forceinline__ void put8(uint32_t buf, int row, int k0, const float*
                  pack_h2(v[6], v[7]));
 }
 
-// positional encoding features [f0, f1) of x (feature order: x,y,z, then per level sin xyz, cos xyz) into the PE buffer
+// Positional encoding [x, sin(2^l x), cos(2^l x)]_l (embedder.py:26-37) of this thread's point into chunks [ch0, ch1)
+// of a 64-wide K-major buffer.  An accurate sincosf anchors every 4th octave; the octaves in between come from the
+// double-angle recurrence (3 doublings: error <= 8 ulp-ish, far below fp16 quantisation).
+template <int L>
+__device__ __forceinline__ void write_pe(uint32_t buf, int row, float3 x, int ch0, int ch1) {
+    float v[8];
+    int n = 0, ch = 0;
+    auto push = [&](float f) {
+        v[n++] = f;
+        if (n == 8) {
+            if (ch >= ch0 && ch < ch1) put8(buf, row, ch * 8, v);
+            ch++; n = 0;
+        }
+    };
+    push(x.x); push(x.y); push(x.z);
+    float s[3], c[3];
+    const float xs[3] = {x.x, x.y, x.z};
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+        if ((l & 3) == 0) {
+#pragma unroll
+            for (int a = 0; a < 3; a++) sincosf(xs[a] * (float)(1 << l), &s[a], &c[a]);
+        } else {
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                float s2 = 2.f * s[a] * c[a];
+                float c2 = (c[a] - s[a]) * (c[a] + s[a]);
+                s[a] = s2; c[a] = c2;
+            }
+        }
+        push(s[0]); push(s[1]); push(s[2]); push(c[0]); push(c[1]); push(c[2]);
+    }
+#pragma unroll
+    for (int k = 3 + 6 * L; k < 64; k++) push(0.f);
+}
+// one PE8 feature by index (used for the three features that land in a mixed chunk of the S4 skip input)
 __device__ __forceinline__ float pe_feature(float3 x, int idx) {
     if (idx < 3) return idx == 0 ? x.x : (idx == 1 ? x.y : x.z);
     int j = idx - 3, l = j / 6, r = j % 6, c = r % 3;
     float v = (c == 0 ? x.x : (c == 1 ? x.y : x.z)) * (float)(1 << l);
     return (r < 3) ? sinf(v) : cosf(v);
 }
-__device__ __forceinline__ void write_pe(uint32_t pe_buf, int row, float3 x, int nfeat, int chunk0, int chunk1) {
-    for (int ch = chunk0; ch < chunk1; ch++) {
-        float v[8];
+
+// hidden-layer epilogue: 128 accumulator columns of this warp's rows -> activation -> fp16 A operand of the next layer.
+// Biases are already inside the accumulator (added by a K=16 rank-2 MMA step, see the MMA issuer).
+template <bool SOFTPLUS>
+__device__ __forceinline__ void epi_hidden(uint32_t t_lane, uint32_t s_act, int row, int half) {
+    uint32_t ra[32], rb[32];
+    const int cbase = half * 128;
+    tmem_ld32(t_lane + (uint32_t)cbase, ra);
+    tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            int idx = ch * 8 + j;
-            v[j] = (idx < nfeat) ? pe_feature(x, idx) : 0.f;
+    for (int cb = 0; cb < 4; cb++) {
+        uint32_t* cur = (cb & 1) ? rb : ra;
+        uint32_t* nxt = (cb & 1) ? ra : rb;
+        if (cb < 3) tmem_ld32(t_lane + (uint32_t)(cbase + (cb + 1) * 32), nxt);     // in flight while we work on `cur`
+        const int c0 = cbase + cb * 32;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            uint32_t h[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float a = __uint_as_float(cur[g * 8 + 2 * j]), b = __uint_as_float(cur[g * 8 + 2 * j + 1]);
+                h[j] = SOFTPLUS ? h2_softplus100(a, b) : h2_relu(a, b);
+            }
+            st_shared_v4(s_act + (uint32_t)((c0 >> 3) + g) * 2048u + (uint32_t)row * 16u, h[0], h[1], h[2], h[3]);
         }
-        put8(pe_buf, row, ch * 8, v);
+        if (cb < 3) tmem_ld_wait();
     }
 }
 
@@ -183,6 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(const __grid_constant_
     const uint32_t s_w = s_pe + TC_PE_BYTES;
     const uint32_t s_bar = s_w + TC_STAGES * TC_STAGE_BYTES;   // barriers: full[2], empty[2], act_ready, acc_ready ; tmem ptr
     const uint32_t bar_full = s_bar, bar_empty = s_bar + 16, bar_act = s_bar + 32, bar_acc = s_bar + 40;
+    const uint32_t s_ones = s_bar + 128;    // 256 B: core matrix of rows [1,1,0,0,0,0,0,0], then a zero core matrix
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + (s_bar - s_base) + 64);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,6 +262,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(const __grid_constant_
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x < 64) {     // "ones" A operand of the bias step: every row reads (1, 1, 0, ..., 0) over K = 16
+        uint32_t v = (threadIdx.x < 32 && (threadIdx.x & 3) == 0) ? 0x3C003C00u : 0u;     // half2(1, 1) in the first word of each 16 B row
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(s_ones + threadIdx.x * 4), "r"(v) : "memory");
+        fence_async_smem();
+    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_bar + 64), "r"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -205,18 +277,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(const __grid_constant_
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer: stream every layer's weight chunks, once per tile =====================
+        // ===================== TMA producer: stream every layer's weight chunks (+ its bias chunk), once per tile =====================
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int l = 0; l < TC_LAYERS; l++) {
                     const uint32_t bytes = (uint32_t)P.layer[l].N * TC_KCHUNK * 2;
                     const unsigned char* src = P.blob + P.layer[l].goff;
-                    for (int c = 0; c < P.layer[l].nchunks; c++, it++) {
+                    const int nch = P.layer[l].nchunks;
+                    for (int c = 0; c <= nch; c++, it++) {
                         uint32_t s = it & 1, ph = (it >> 1) & 1;
+                        const uint32_t nb = (c < nch) ? bytes : bytes / 2;
+                        const unsigned char* g = (c < nch) ? src + (size_t)c * bytes : P.blob + P.layer[l].boff;
                         mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                        mbar_expect_tx(bar_full + 8 * s, bytes);
-                        tma_bulk_g2s(s_w + s * TC_STAGE_BYTES, src + (size_t)c * bytes, bytes, bar_full + 8 * s);
+                        mbar_expect_tx(bar_full + 8 * s, nb);
+                        tma_bulk_g2s(s_w + s * TC_STAGE_BYTES, g, nb, bar_full + 8 * s);
                     }
                 }
             }
@@ -230,20 +305,28 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(const __grid_constant_
                     const int N = P.layer[l].N;
                     const uint32_t idesc = make_idesc_f16(N);
                     const uint32_t lbo_b = (uint32_t)N * 16u;
+                    const int nch = P.layer[l].nchunks;
                     mbar_wait(bar_act, lc & 1);
                     tc_fence_after();
-                    for (int c = 0; c < P.layer[l].nchunks; c++, it++) {
+                    for (int c = 0; c <= nch; c++, it++) {
                         uint32_t s = it & 1, ph = (it >> 1) & 1;
                         mbar_wait(bar_full + 8 * s, ph);
                         tc_fence_after();
-                        uint32_t a_base = (c >= P.layer[l].pe_from) ? (s_pe + (uint32_t)(c - P.layer[l].pe_from) * 4u * 2048u)
-                                                                     : (s_act + (uint32_t)c * 4u * 2048u);
                         uint32_t b_base = s_w + s * TC_STAGE_BYTES;
+                        if (c < nch) {
+                            uint32_t a_base = (c >= P.layer[l].pe_from) ? (s_pe + (uint32_t)(c - P.layer[l].pe_from) * 4u * 2048u)
+                                                                         : (s_act + (uint32_t)c * 4u * 2048u);
 #pragma unroll
-                        for (int kk = 0; kk < TC_KCHUNK / 16; kk++) {
-                            uint64_t ad = make_sdesc(a_base + (uint32_t)kk * 2u * 2048u, 2048u, 128u);
-                            uint64_t bd = make_sdesc(b_base + (uint32_t)kk * 2u * lbo_b, lbo_b, 128u);
-                            umma_f16(tmem, ad, bd, idesc, (c | kk) ? 1u : 0u);
+                            for (int kk = 0; kk < TC_KCHUNK / 16; kk++) {
+                                uint64_t ad = make_sdesc(a_base + (uint32_t)kk * 2u * 2048u, 2048u, 128u);
+                                uint64_t bd = make_sdesc(b_base + (uint32_t)kk * 2u * lbo_b, lbo_b, 128u);
+                                umma_f16(tmem, ad, bd, idesc, (c | kk) ? 1u : 0u);
+                            }
+                        } else {
+                            // bias step: D += ones(128 x 16) * [b_hi; b_lo; 0...]  -- A rows all alias one core matrix (SBO = 0)
+                            uint64_t ad = make_sdesc(s_ones, 128u, 0u);
+                            uint64_t bd = make_sdesc(b_base, lbo_b, 128u);
+                            umma_f16(tmem, ad, bd, idesc, 1u);
                         }
                         umma_commit(bar_empty + 8 * s);      // frees the weight stage when these MMAs retire
                     }
@@ -265,36 +348,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(const __grid_constant_
             if (gidx < count) bp = make3(P.bpts[(size_t)gidx * 3], P.bpts[(size_t)gidx * 3 + 1], P.bpts[(size_t)gidx * 3 + 2]);
             float3 cp = bp;
             // prologue: PE10(bp) -> PE buffer (63 features, padded to 64); the two column-half warps split the chunks
-            write_pe(s_pe, row, bp, 63, half * 4, half * 4 + 4);
+            write_pe<10>(s_pe, row, bp, half * 4, half * 4 + 4);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_act);
+#pragma unroll 1
             for (int l = 0; l < TC_LAYERS; l++, lc++) {
                 const int epi = P.layer[l].epi;
-                const float* __restrict__ bias = P.bias[l];
                 mbar_wait(bar_acc, lc & 1);
                 tc_fence_after();
-                if (epi == TC_EPI_RELU || epi == TC_EPI_SOFTPLUS) {
-#pragma unroll 1
-                    for (int cb = 0; cb < 4; cb++) {
-                        const int c0 = half * 128 + cb * 32;
-                        uint32_t r[32];
-                        tmem_ld32(t_lane + (uint32_t)c0, r);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int g = 0; g < 4; g++) {
-                            float v[8];
-#pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                float z = __uint_as_float(r[g * 8 + j]) + __ldg(&bias[c0 + g * 8 + j]);
-                                v[j] = (epi == TC_EPI_RELU) ? fmaxf(z, 0.f) : softplus100_fast(z);
-                            }
-                            put8(s_act, row, c0 + g * 8, v);
-                        }
-                    }
+                if (epi == TC_EPI_RELU) {
+                    epi_hidden<false>(t_lane, s_act, row, half);
+                } else if (epi == TC_EPI_SOFTPLUS) {
+                    epi_hidden<true>(t_lane, s_act, row, half);
                 } else if (epi == TC_EPI_S3) {
                     // S3: 205 outputs -> ACT cols [48, 253); PE8(cp) features 0..47 -> cols [0,48), 48..50 -> cols 253..255
-                    // half 0: accumulator cols [0,104); half 1: [104,208) + PE copies
+                    // half 0: accumulator cols [0,104); half 1: [104,208) + the tail
                     const int a0 = half ? 104 : 0;
 #pragma unroll 1
                     for (int cb = 0; cb < 13; cb++) {            // 13 groups of 8 accumulator columns
@@ -305,15 +374,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(const __grid_constant_
                         const int o = c0 & 15;
                         float v[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            int n = c0 + j;
-                            float z = __uint_as_float(o ? r[8 + j] : r[j]) + ((n < 205) ? __ldg(&bias[n]) : 0.f);
-                            v[j] = softplus100_fast(z);
-                        }
+                        for (int j = 0; j < 8; j++) v[j] = __uint_as_float(o ? r[8 + j] : r[j]);
+                        uint32_t h[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) h[j] = h2_softplus100(v[2 * j], v[2 * j + 1]);
                         if (c0 == 200) {      // cols 248..255: outputs 200..204 then PE8 features 48,49,50
-                            v[5] = pe_feature(cp, 48); v[6] = pe_feature(cp, 49); v[7] = pe_feature(cp, 50);
+                            float p48 = pe_feature(cp, 48), p49 = pe_feature(cp, 49), p50 = pe_feature(cp, 50);
+                            h[2] = (h[2] & 0x0000FFFFu) | (pack_h2(0.f, p48) & 0xFFFF0000u);
+                            h[3] = pack_h2(p49, p50);
                         }
-                        put8(s_act, row, 48 + c0, v);
+                        st_shared_v4(s_act + (uint32_t)((48 + c0) >> 3) * 2048u + (uint32_t)row * 16u, h[0], h[1], h[2], h[3]);
                     }
                     // PE8 features 0..47 (6 chunks) copied from the PE buffer: 3 chunks per half
                     for (int ch = half * 3; ch < half * 3 + 3; ch++) {
@@ -325,18 +395,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(const __grid_constant_
                     uint32_t r[16];
                     tmem_ld16(t_lane, r);
                     tmem_ld_wait();
-                    float rx = tanhf(__uint_as_float(r[0]) + __ldg(&bias[0])) * P.resd_limit;
-                    float ry = tanhf(__uint_as_float(r[1]) + __ldg(&bias[1])) * P.resd_limit;
-                    float rz = tanhf(__uint_as_float(r[2]) + __ldg(&bias[2])) * P.resd_limit;
+                    float rx = tanhf(__uint_as_float(r[0])) * P.resd_limit;
+                    float ry = tanhf(__uint_as_float(r[1])) * P.resd_limit;
+                    float rz = tanhf(__uint_as_float(r[2])) * P.resd_limit;
                     cp = make3(bp.x + rx, bp.y + ry, bp.z + rz);
                     // PE8(cp): 51 features padded to 64 -> PE buffer (input of S0, later copied into the S4 skip columns)
-                    write_pe(s_pe, row, cp, 51, half * 4, half * 4 + 4);
+                    write_pe<8>(s_pe, row, cp, half * 4, half * 4 + 4);
                 } else {   // TC_EPI_SDF_FINAL
                     if (half == 0) {
                         uint32_t r[16];
                         tmem_ld16(t_lane, r);
                         tmem_ld_wait();
-                        if (gidx < count) P.out[gidx] = __uint_as_float(r[0]) + __ldg(&bias[0]);
+                        if (gidx < count) P.out[gidx] = __uint_as_float(r[0]);
                     }
                 }
                 if (l + 1 < TC_LAYERS) {
@@ -352,6 +422,20 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+}
+
+// per frame: the pose-folded biases of residual layers 0 and 4 -> their fp16 hi/lo bias chunks in the weight blob
+__global__ void k_tc_pack_bias(const float* __restrict__ b0, const float* __restrict__ b4, __half* dst0, __half* dst4) {
+    int n = threadIdx.x;     // 256 threads
+    for (int w = 0; w < 2; w++) {
+        const float b = (w ? b4 : b0)[n];
+        __half* d = (w ? dst4 : dst0);
+        __half hi = __float2half_rn(b);
+        __half lo = __float2half_rn(b - __half2float(hi));
+        d[n * 8 + 0] = hi; d[n * 8 + 1] = lo;
+        for (int j = 2; j < 8; j++) d[n * 8 + j] = __float2half_rn(0.f);
+        for (int j = 0; j < 8; j++) d[(256 + n) * 8 + j] = __float2half_rn(0.f);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -386,6 +470,17 @@ static void tc_pack_layer(std::vector<__half>& blob, const std::vector<float>& w
                 }
 }
 
+// bias chunk image [2][N_pad][8] halves: k = 0 holds fp16(b), k = 1 holds fp16(b - fp16(b)); multiplied by the all-ones A step
+static void tc_pack_bias(std::vector<__half>& blob, const std::vector<float>& b, int N_src, int N_pad) {
+    size_t base = blob.size();
+    blob.resize(base + (size_t)2 * N_pad * 8, __float2half(0.f));
+    for (int n = 0; n < N_src; n++) {
+        __half hi = __float2half_rn(b[n]);
+        blob[base + (size_t)n * 8 + 0] = hi;
+        blob[base + (size_t)n * 8 + 1] = __float2half_rn(b[n] - __half2float(hi));
+    }
+}
+
 static int tc_upload(TcWeights& t, const ra_weights* w, std::string& err, cudaStream_t st) {
     auto fetch = [&](const float* src, size_t n, std::vector<float>& dst) -> bool {
         dst.resize(n);
@@ -409,6 +504,8 @@ static int tc_upload(TcWeights& t, const ra_weights* w, std::string& err, cudaSt
         P.layer[l].epi = (l == 8) ? TC_EPI_RESD_FINAL : TC_EPI_RELU;
         tc_pack_layer(blob, hw, N, rK[l], cm, Np, 1.f);
         for (int n = 0; n < N; n++) bias[(size_t)l * 256 + n] = hb[n];
+        P.layer[l].boff = (unsigned)(blob.size() * 2);
+        tc_pack_bias(blob, hb, N, Np);
     }
     const float rs2 = (float)(1.0 / std::sqrt(2.0));
     for (int l = 0; l < 9; l++) {           // SDF MLP
@@ -433,6 +530,8 @@ static int tc_upload(TcWeights& t, const ra_weights* w, std::string& err, cudaSt
         P.layer[L].epi = (l == 8) ? TC_EPI_SDF_FINAL : (l == 3 ? TC_EPI_S3 : TC_EPI_SOFTPLUS);
         tc_pack_layer(blob, hw, Nsrc, sK[l], cm, Np, scale);
         for (int n = 0; n < std::min(Nsrc, 256); n++) bias[(size_t)L * 256 + n] = hb[n];
+        P.layer[L].boff = (unsigned)(blob.size() * 2);
+        tc_pack_bias(blob, hb, std::min(Nsrc, 256), Np);
     }
     tc_free(t);
     if (cudaMalloc((void**)&t.blob, blob.size() * 2) != cudaSuccess || cudaMalloc((void**)&t.bias, bias.size() * 4) != cudaSuccess) {
@@ -447,9 +546,12 @@ static int tc_upload(TcWeights& t, const ra_weights* w, std::string& err, cudaSt
 }
 
 // per frame: layers 0 and 4 of the residual MLP take their (pose-folded) biases from the frame constants
-static void tc_set_frame(TcWeights& t, const FrameConst* fc, cudaStream_t, int64_t&) {
+static void tc_set_frame(TcWeights& t, const FrameConst* fc, cudaStream_t st, int64_t& launches) {
     t.p.bias[0] = &fc->resd_b0[0];
     t.p.bias[4] = &fc->resd_b4[0];
+    k_tc_pack_bias<<<1, 256, 0, st>>>(&fc->resd_b0[0], &fc->resd_b4[0], reinterpret_cast<__half*>(t.blob + t.p.layer[0].boff),
+                                      reinterpret_cast<__half*>(t.blob + t.p.layer[4].boff));
+    launches++;
 }
 
 static void tc_distance(TcWeights& t, const float* bpts, float* out, const int* count, float resd_limit, int sms, cudaStream_t st,
