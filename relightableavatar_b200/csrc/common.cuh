@@ -8,7 +8,9 @@
 #define RA_MAX_GRID_DIM 64
 #define RA_MAX_CELLS (RA_MAX_GRID_DIM * RA_MAX_GRID_DIM * RA_MAX_GRID_DIM)
 #define RA_NLIGHT_MAX 512
-#define RA_KNN_RMAX 3
+#define RA_KNN_RMAX 2
+#define RA_GRID2_RATIO 3.0f
+#define RA_MAX_OCC 8192
 
 // Per-frame constants living in device memory (written by k_frame_prep, read by every kernel).
 struct FrameConst {
@@ -18,6 +20,11 @@ struct FrameConst {
     float g_h, g_inv_h;
     int g_dim[3];
     int g_cells;
+    float g2_org[3];       // coarse second-level grid for query points far from the body
+    float g2_h, g2_inv_h;
+    int g2_dim[3];
+    int g2_cells;
+    int n_occ;             // occupied coarse cells (list in SortedVerts::occ_lo/occ_hi)
     float wb[6];           // wbounds (2,3) as given (unpadded)
     float resd_b0[256];    // layer-0 bias + W0[:,63:219] . poses      (cond folded, base_network.py:34-40)
     float resd_b4[256];    // layer-4 bias + W4[:,256+63:475] . poses
@@ -31,6 +38,10 @@ struct SortedVerts {
     float4* tv;     // big-pose vertex xyz
     float* T;       // [N][24]: A_v (3x4 row-major) then bigA_v (3x4): sum_j weights[v][j] * A_j
     int* cell_start;  // [cells+1]
+    float4* pos2;     // vertices in coarse-cell order: xyz, w = index into pos/nrm/tv/T (int bits)
+    int* cell_start2; // [cells2+1]
+    float4* occ_lo;   // occupied coarse cells: tight bbox min xyz, w = first vertex (int bits) in pos2
+    float4* occ_hi;   //                        tight bbox max xyz, w = end vertex (int bits)
 };
 
 struct KnnOut {

@@ -51,6 +51,19 @@ __global__ void k_frame_prep(FrameConst* fc, const float* __restrict__ R, const 
         fc->g_h = h;
         fc->g_inv_h = 1.0f / h;
         fc->g_cells = cells;
+        float h2 = h * RA_GRID2_RATIO;
+        int cells2 = 1;
+        for (int a = 0; a < 3; a++) {
+            fc->g2_org[a] = lo[a] - 0.5f * h2;
+            int d = (int)floorf((hi[a] - lo[a] + h2) / h2) + 1;
+            d = min(max(d, 1), RA_MAX_GRID_DIM);
+            fc->g2_dim[a] = d;
+            cells2 *= d;
+        }
+        fc->g2_h = h2;
+        fc->g2_inv_h = 1.0f / h2;
+        fc->g2_cells = cells2;
+        fc->n_occ = 0;
         for (int i = 0; i < 9; i++) fc->R[i] = R[i];
         for (int i = 0; i < 3; i++) fc->Th[i] = Th[i];
         for (int i = 0; i < 6; i++) fc->wb[i] = wbounds ? wbounds[i] : 0.f;
@@ -78,28 +91,73 @@ __global__ void k_frame_prep(FrameConst* fc, const float* __restrict__ R, const 
     }
 }
 
-__device__ __forceinline__ int cell_of(const FrameConst* fc, float3 p, int& cx, int& cy, int& cz) {
-    cx = min(max((int)floorf((p.x - fc->g_org[0]) * fc->g_inv_h), 0), fc->g_dim[0] - 1);
-    cy = min(max((int)floorf((p.y - fc->g_org[1]) * fc->g_inv_h), 0), fc->g_dim[1] - 1);
-    cz = min(max((int)floorf((p.z - fc->g_org[2]) * fc->g_inv_h), 0), fc->g_dim[2] - 1);
-    return (cz * fc->g_dim[1] + cy) * fc->g_dim[0] + cx;
+struct GridRef { float org[3]; float h, inv_h; int dim[3]; int cells; };
+__device__ __forceinline__ GridRef grid_ref(const FrameConst* fc, int level) {
+    GridRef g;
+    if (level == 0) {
+        g.org[0] = fc->g_org[0]; g.org[1] = fc->g_org[1]; g.org[2] = fc->g_org[2]; g.h = fc->g_h; g.inv_h = fc->g_inv_h;
+        g.dim[0] = fc->g_dim[0]; g.dim[1] = fc->g_dim[1]; g.dim[2] = fc->g_dim[2]; g.cells = fc->g_cells;
+    } else {
+        g.org[0] = fc->g2_org[0]; g.org[1] = fc->g2_org[1]; g.org[2] = fc->g2_org[2]; g.h = fc->g2_h; g.inv_h = fc->g2_inv_h;
+        g.dim[0] = fc->g2_dim[0]; g.dim[1] = fc->g2_dim[1]; g.dim[2] = fc->g2_dim[2]; g.cells = fc->g2_cells;
+    }
+    return g;
+}
+__device__ __forceinline__ int cell_of(const GridRef& g, float3 p, int& cx, int& cy, int& cz) {
+    cx = min(max((int)floorf((p.x - g.org[0]) * g.inv_h), 0), g.dim[0] - 1);
+    cy = min(max((int)floorf((p.y - g.org[1]) * g.inv_h), 0), g.dim[1] - 1);
+    cz = min(max((int)floorf((p.z - g.org[2]) * g.inv_h), 0), g.dim[2] - 1);
+    return (cz * g.dim[1] + cy) * g.dim[0] + cx;
 }
 
-__global__ void k_grid_count(const FrameConst* fc, const float* __restrict__ pverts, int nverts, int* cell_count,
-                             int* vert_cell) {
+// level 0: vertices in input order; level 1: vertices taken from the level-0 sorted array (so ids refer to it)
+__global__ void k_grid_count(const FrameConst* fc, int level, const float* __restrict__ pverts, const float4* __restrict__ spos,
+                             int nverts, int* cell_count, int* vert_cell) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nverts) return;
+    GridRef g = grid_ref(fc, level);
     int cx, cy, cz;
-    int c = cell_of(fc, make3(pverts[i * 3], pverts[i * 3 + 1], pverts[i * 3 + 2]), cx, cy, cz);
+    float3 p = level == 0 ? make3(pverts[i * 3], pverts[i * 3 + 1], pverts[i * 3 + 2]) : make3(spos[i].x, spos[i].y, spos[i].z);
+    int c = cell_of(g, p, cx, cy, cz);
     vert_cell[i] = c;
     atomicAdd(&cell_count[c], 1);
 }
 
+__global__ void k_grid_fill2(const float4* __restrict__ spos, int nverts, const int* __restrict__ vert_cell,
+                             const int* __restrict__ cell_start, int* cell_fill, float4* pos2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nverts) return;
+    int c = vert_cell[i];
+    int dst = cell_start[c] + atomicAdd(&cell_fill[c], 1);
+    float4 v = spos[i];
+    pos2[dst] = make_float4(v.x, v.y, v.z, __int_as_float(i));
+}
+
+// list of occupied coarse cells with the tight bounding box of their vertices (far-point 3-NN pruning)
+__global__ void k_grid_occ(FrameConst* fc, const int* __restrict__ cell_start2, const float4* __restrict__ pos2, float4* occ_lo, float4* occ_hi) {
+    int n = fc->g2_cells;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        int s = cell_start2[c], e = cell_start2[c + 1];
+        if (e <= s) continue;
+        float3 lo = make3(3e38f, 3e38f, 3e38f), hi = make3(-3e38f, -3e38f, -3e38f);
+        for (int v = s; v < e; v++) {
+            float4 q = pos2[v];
+            lo = make3(fminf(lo.x, q.x), fminf(lo.y, q.y), fminf(lo.z, q.z));
+            hi = make3(fmaxf(hi.x, q.x), fmaxf(hi.y, q.y), fmaxf(hi.z, q.z));
+        }
+        int idx = atomicAdd(&fc->n_occ, 1);
+        if (idx < RA_MAX_OCC) {
+            occ_lo[idx] = make_float4(lo.x, lo.y, lo.z, __int_as_float(s));
+            occ_hi[idx] = make_float4(hi.x, hi.y, hi.z, __int_as_float(e));
+        }
+    }
+}
+
 // single block exclusive scan over g_cells (+1) entries; also resets the fill cursors
-__global__ void k_grid_scan(const FrameConst* fc, const int* __restrict__ cell_count, int* cell_start, int* cell_fill) {
+__global__ void k_grid_scan(const FrameConst* fc, int level, int* cell_count, int* cell_start, int* cell_fill) {
     __shared__ int carry;
     __shared__ int wsum[32];
-    int n = fc->g_cells;
+    int n = level == 0 ? fc->g_cells : fc->g2_cells;
     int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) carry = 0;
     __syncthreads();
@@ -123,7 +181,7 @@ __global__ void k_grid_scan(const FrameConst* fc, const int* __restrict__ cell_c
         }
         __syncthreads();
         int excl = carry + (wid ? wsum[wid - 1] : 0) + x - v;
-        if (i < n) { cell_start[i] = excl; cell_fill[i] = 0; }
+        if (i < n) { cell_start[i] = excl; cell_fill[i] = 0; cell_count[i] = 0; }
         __syncthreads();
         if (tid == blockDim.x - 1) carry = excl + v;
         __syncthreads();
@@ -186,18 +244,22 @@ __device__ __forceinline__ void knn_range(KnnOut& o, float3 p, const float4* __r
     for (int v = s; v < e; v++) knn_insert(o, dist2_ref(p, __ldg(&pos[v])), v);
 }
 
-// Exact 3 nearest vertices (K=3 of pytorch3d.ops.knn_points at sample_utils.py:122): expanding cube
-// shells over the uniform grid until the 3rd best distance is within the explored block; brute force
-// over all vertices beyond RA_KNN_RMAX rings (points far from the body).
-__device__ void knn3_query(const FrameConst* __restrict__ fc, const SortedVerts& sv, int nverts, float3 p, KnnOut& o) {
-    o.d2[0] = o.d2[1] = o.d2[2] = 3.0e38f;
-    o.id[0] = o.id[1] = o.id[2] = 0;
+// One level of the exact ring search: expanding cube shells over a uniform grid until the 3rd best distance is
+// provably inside the explored block.  Returns true when the result is final.
+template <bool ID_FROM_W>
+__device__ __forceinline__ bool knn_rings(const GridRef& g, const int* __restrict__ cell_start, const float4* __restrict__ pos, int rmax,
+                                          float3 p, KnnOut& o) {
     int cx, cy, cz;
-    cell_of(fc, p, cx, cy, cz);
-    const int dx_ = fc->g_dim[0], dy_ = fc->g_dim[1], dz_ = fc->g_dim[2];
-    const float h = fc->g_h;
-    bool done = false;
-    for (int r = 0; r <= RA_KNN_RMAX && !done; r++) {
+    cell_of(g, p, cx, cy, cz);
+    const int dx_ = g.dim[0], dy_ = g.dim[1], dz_ = g.dim[2];
+    const float h = g.h;
+    auto scan = [&](int s, int e) {
+        for (int v = s; v < e; v++) {
+            float4 q = __ldg(&pos[v]);
+            knn_insert(o, dist2_ref(p, q), ID_FROM_W ? __float_as_int(q.w) : v);
+        }
+    };
+    for (int r = 0; r <= rmax; r++) {
         int z0 = max(cz - r, 0), z1 = min(cz + r, dz_ - 1);
         int y0 = max(cy - r, 0), y1 = min(cy + r, dy_ - 1);
         int x0 = max(cx - r, 0), x1 = min(cx + r, dx_ - 1);
@@ -207,28 +269,65 @@ __device__ void knn3_query(const FrameConst* __restrict__ fc, const SortedVerts&
                 bool yf = zf || (y == cy - r) || (y == cy + r);
                 int row = (z * dy_ + y) * dx_;
                 if (yf) {
-                    knn_range(o, p, sv.pos, __ldg(&sv.cell_start[row + x0]), __ldg(&sv.cell_start[row + x1 + 1]));
+                    scan(__ldg(&cell_start[row + x0]), __ldg(&cell_start[row + x1 + 1]));
                 } else {
-                    if (cx - r >= 0) knn_range(o, p, sv.pos, __ldg(&sv.cell_start[row + cx - r]), __ldg(&sv.cell_start[row + cx - r + 1]));
-                    if (cx + r < dx_ && r > 0) knn_range(o, p, sv.pos, __ldg(&sv.cell_start[row + cx + r]), __ldg(&sv.cell_start[row + cx + r + 1]));
+                    if (cx - r >= 0) scan(__ldg(&cell_start[row + cx - r]), __ldg(&cell_start[row + cx - r + 1]));
+                    if (cx + r < dx_) scan(__ldg(&cell_start[row + cx + r]), __ldg(&cell_start[row + cx + r + 1]));
                 }
             }
         }
         // distance from p to the nearest face of the explored block that still has unexplored cells behind it
         float bound = 3.0e38f;
-        if (cx - r > 0) bound = fminf(bound, p.x - (fc->g_org[0] + (cx - r) * h));
-        if (cx + r < dx_ - 1) bound = fminf(bound, (fc->g_org[0] + (cx + r + 1) * h) - p.x);
-        if (cy - r > 0) bound = fminf(bound, p.y - (fc->g_org[1] + (cy - r) * h));
-        if (cy + r < dy_ - 1) bound = fminf(bound, (fc->g_org[1] + (cy + r + 1) * h) - p.y);
-        if (cz - r > 0) bound = fminf(bound, p.z - (fc->g_org[2] + (cz - r) * h));
-        if (cz + r < dz_ - 1) bound = fminf(bound, (fc->g_org[2] + (cz + r + 1) * h) - p.z);
-        // safety margin of one part in 1e5 against fp32 rounding of the face coordinates
-        if (bound > 0.f && o.d2[2] <= bound * bound * 0.9999f) done = true;
-        if (bound == 3.0e38f) done = true;   // whole grid explored
+        if (cx - r > 0) bound = fminf(bound, p.x - (g.org[0] + (cx - r) * h));
+        if (cx + r < dx_ - 1) bound = fminf(bound, (g.org[0] + (cx + r + 1) * h) - p.x);
+        if (cy - r > 0) bound = fminf(bound, p.y - (g.org[1] + (cy - r) * h));
+        if (cy + r < dy_ - 1) bound = fminf(bound, (g.org[1] + (cy + r + 1) * h) - p.y);
+        if (cz - r > 0) bound = fminf(bound, p.z - (g.org[2] + (cz - r) * h));
+        if (cz + r < dz_ - 1) bound = fminf(bound, (g.org[2] + (cz + r + 1) * h) - p.z);
+        // 1e-4 relative safety margin against fp32 rounding of the face coordinates
+        if (bound > 0.f && o.d2[2] <= bound * bound * 0.9999f) return true;
+        if (bound == 3.0e38f) return true;   // whole grid explored
     }
-    if (!done) {
-        o.d2[0] = o.d2[1] = o.d2[2] = 3.0e38f;
-        knn_range(o, p, sv.pos, 0, nverts);
+    return false;
+}
+
+__device__ __forceinline__ float bbox_dist2(float3 p, float4 lo, float4 hi) {
+    float dx = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.f);
+    float dy = fmaxf(fmaxf(lo.y - p.y, p.y - hi.y), 0.f);
+    float dz = fmaxf(fmaxf(lo.z - p.z, p.z - hi.z), 0.f);
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// Exact 3 nearest vertices (K=3 of pytorch3d.ops.knn_points at sample_utils.py:122).
+// Near the body: expanding shells over the fine grid (cell ~4 cm).  Farther away: branch-and-bound over the list of
+// occupied coarse cells (tight vertex bounding boxes): nearest cell first, then every cell whose box is closer than
+// the current 3rd-best distance.  Both are exact; brute force only if the cell list overflowed.
+__device__ void knn3_query(const FrameConst* __restrict__ fc, const SortedVerts& sv, int nverts, float3 p, KnnOut& o) {
+    o.d2[0] = o.d2[1] = o.d2[2] = 3.0e38f;
+    o.id[0] = o.id[1] = o.id[2] = 0;
+    if (knn_rings<false>(grid_ref(fc, 0), sv.cell_start, sv.pos, RA_KNN_RMAX, p, o)) return;
+    o.d2[0] = o.d2[1] = o.d2[2] = 3.0e38f;
+    const int n = fc->n_occ;
+    if (n > RA_MAX_OCC) { knn_range(o, p, sv.pos, 0, nverts); return; }
+    auto scan = [&](int c) {
+        int s = __float_as_int(__ldg(&sv.occ_lo[c]).w), e = __float_as_int(__ldg(&sv.occ_hi[c]).w);
+        for (int v = s; v < e; v++) {
+            float4 q = __ldg(&sv.pos2[v]);
+            knn_insert(o, dist2_ref(p, q), __float_as_int(q.w));
+        }
+    };
+    float best = 3.0e38f;
+    int bc = 0;
+    for (int c = 0; c < n; c++) {
+        float lb = bbox_dist2(p, __ldg(&sv.occ_lo[c]), __ldg(&sv.occ_hi[c]));
+        if (lb < best) { best = lb; bc = c; }
+    }
+    scan(bc);
+    for (int c = 0; c < n; c++) {
+        if (c == bc) continue;
+        float lb = bbox_dist2(p, __ldg(&sv.occ_lo[c]), __ldg(&sv.occ_hi[c]));
+        // 1e-4 relative slack: the box distance is rounded independently of dist2_ref
+        if (lb * 0.9999f <= o.d2[2]) scan(c);
     }
 }
 

@@ -166,6 +166,8 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     CK(dalloc(&h->fc, 1));
     CK(dalloc(&h->sv.pos, N)); CK(dalloc(&h->sv.nrm, N)); CK(dalloc(&h->sv.tv, N)); CK(dalloc(&h->sv.T, (size_t)N * 24));
     CK(dalloc(&h->sv.cell_start, RA_MAX_CELLS + 1));
+    CK(dalloc(&h->sv.pos2, N)); CK(dalloc(&h->sv.cell_start2, RA_MAX_CELLS + 1));
+    CK(dalloc(&h->sv.occ_lo, RA_MAX_OCC)); CK(dalloc(&h->sv.occ_hi, RA_MAX_OCC));
     CK(dalloc(&h->cell_count, RA_MAX_CELLS + 1)); CK(dalloc(&h->cell_fill, RA_MAX_CELLS + 1)); CK(dalloc(&h->vert_cell, N));
     float** ssp[] = {&h->ss.t, &h->ss.occ, &h->ss.d0, &h->ss.cd, &h->ss.dt, &h->ss.st, &h->ss.off, &h->ss.rlx, &h->ss.q_smpl};
     for (auto p : ssp) CK(dalloc(p, P));
@@ -291,10 +293,15 @@ extern "C" int ra_set_frame(ra_handle* h, const ra_frame* f, void* stream) {
     int N = h->cfg.n_verts;
     LAUNCH(h, k_frame_prep, 1, 1024, 0, st, h->fc, f->R, f->Th, f->pverts, N, f->wbounds, f->poses, f->mat_cond,
            h->resd_w0_raw, h->resd_b0_raw, h->resd_w4_raw, h->resd_b4_raw, h->rend_w3_raw, h->rend_b3_raw, h->cell_count, 0.04f);
-    LAUNCH(h, k_grid_count, (N + 255) / 256, 256, 0, st, h->fc, f->pverts, N, h->cell_count, h->vert_cell);
-    LAUNCH(h, k_grid_scan, 1, 1024, 0, st, h->fc, h->cell_count, h->sv.cell_start, h->cell_fill);
+    LAUNCH(h, k_grid_count, (N + 255) / 256, 256, 0, st, h->fc, 0, f->pverts, (const float4*)nullptr, N, h->cell_count, h->vert_cell);
+    LAUNCH(h, k_grid_scan, 1, 1024, 0, st, h->fc, 0, h->cell_count, h->sv.cell_start, h->cell_fill);
     LAUNCH(h, k_grid_fill, (N + 127) / 128, 128, 0, st, h->fc, f->pverts, f->pnorm, f->tverts, f->weights, f->A, f->big_A, N,
            h->cfg.n_bones, h->vert_cell, h->sv.cell_start, h->cell_fill, h->sv);
+    // coarse second level over the cell-sorted vertices
+    LAUNCH(h, k_grid_count, (N + 255) / 256, 256, 0, st, h->fc, 1, f->pverts, (const float4*)h->sv.pos, N, h->cell_count, h->vert_cell);
+    LAUNCH(h, k_grid_scan, 1, 1024, 0, st, h->fc, 1, h->cell_count, h->sv.cell_start2, h->cell_fill);
+    LAUNCH(h, k_grid_fill2, (N + 255) / 256, 256, 0, st, (const float4*)h->sv.pos, N, h->vert_cell, h->sv.cell_start2, h->cell_fill, h->sv.pos2);
+    LAUNCH(h, k_grid_occ, 8, 256, 0, st, h->fc, h->sv.cell_start2, (const float4*)h->sv.pos2, h->sv.occ_lo, h->sv.occ_hi);
     if (h->cfg.precision == RA_PRECISION_TC) tc_set_frame(h->tc, h->fc, st, h->launches);
     CK(cudaGetLastError());
     h->have_frame = true;

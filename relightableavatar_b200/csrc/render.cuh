@@ -185,33 +185,38 @@ __global__ void k_trace_shadow(int it, TraceCfg cfg, const FrameConst* __restric
             if (it == 0) t = nr;
             else {
                 t = sr.t[i]; occ = sr.occ[i]; d0 = sr.d0[i];
-                int slot = sr.q_slot[i];
-                float smpl = sr.q_smpl[i];
-                float d1 = (slot >= 0) ? hdq_blend(q.net[slot], smpl, cfg.th, true) : smpl;
-                int pi = it - 1;
-                float tanv = 1.0f / lsharp[l];
-                float off = cfg.offset, rlx = cfg.relax;
-                if (pi >= cfg.skip) {
-                    float dx0 = d0 + rlx * d0 + off;
-                    float dx1 = d1 + rlx * d1 + off;
-                    float dy = (dx1 * dx1) / (2.f * dx0);
-                    float dx = (sqrtf(dx1 * dx1 - dy * dy) - off) / (1.f + rlx);
-                    float c = fmaxf(dx, 0.f) / fmaxf(fmaxf(t - dy, nr), cfg.eps) / (tanv * 2.f);
-                    bool m = (c < occ) && (dy < t) && (dx1 > 0.f) && (dx0 > 0.f) && (dx > 0.f) && (dy > 0.f) && (dy < dx0);
-                    if (m) occ = c;
-                    float c2 = fmaxf(d1, 0.f) / fmaxf(fmaxf(t, nr), cfg.eps) / (tanv * 2.f);
-                    if (c2 < occ) occ = c2;
+                // occ only ever decreases towards 0 (min of non-negative terms): a fully occluded ray is final.
+                // Skipping its remaining queries changes nothing in the result (exact early termination).
+                if (occ > 0.f) {
+                    int slot = sr.q_slot[i];
+                    float smpl = sr.q_smpl[i];
+                    float d1 = (slot >= 0) ? hdq_blend(q.net[slot], smpl, cfg.th, true) : smpl;
+                    int pi = it - 1;
+                    float tanv = 1.0f / lsharp[l];
+                    float off = cfg.offset, rlx = cfg.relax;
+                    if (pi >= cfg.skip) {
+                        float dx0 = d0 + rlx * d0 + off;
+                        float dx1 = d1 + rlx * d1 + off;
+                        float dy = (dx1 * dx1) / (2.f * dx0);
+                        float dx = (sqrtf(dx1 * dx1 - dy * dy) - off) / (1.f + rlx);
+                        float c = fmaxf(dx, 0.f) / fmaxf(fmaxf(t - dy, nr), cfg.eps) / (tanv * 2.f);
+                        bool m = (c < occ) && (dy < t) && (dx1 > 0.f) && (dx0 > 0.f) && (dx > 0.f) && (dy > 0.f) && (dy < dx0);
+                        if (m) occ = c;
+                        float c2 = fmaxf(d1, 0.f) / fmaxf(fmaxf(t, nr), cfg.eps) / (tanv * 2.f);
+                        if (c2 < occ) occ = c2;
+                    }
+                    float dt = d1 + rlx * d1 + off;
+                    t = fmaxf(fminf(t + dt, fr), nr);
+                    d0 = d1;
                 }
-                float dt = d1 + rlx * d1 + off;
-                t = fmaxf(fminf(t + dt, fr), nr);
-                d0 = d1;
             }
         }
+        const bool alive = valid && (occ > 0.f);
         if (it < cfg.iters) {
             HdqFront hf; hf.in_shell = false; hf.smpl = 0.f;
-            if (valid) hdq_front<false>(fc, sv, nverts, o + d * t, cfg.th, cfg.blend_radius, hf);
-            bool ins = valid && hf.in_shell;
-            count_queries(cnt, valid, ins);
+            if (alive) hdq_front<false>(fc, sv, nverts, o + d * t, cfg.th, cfg.blend_radius, hf);
+            bool ins = alive && hf.in_shell;
+            count_queries(cnt, alive, ins);
             int slot = warp_append(q.count, ins);
             if (ins) { q.bpts[(size_t)slot * 3] = hf.bpts.x; q.bpts[(size_t)slot * 3 + 1] = hf.bpts.y; q.bpts[(size_t)slot * 3 + 2] = hf.bpts.z; }
             if (valid) { sr.t[i] = t; sr.occ[i] = occ; sr.d0[i] = d0; sr.q_smpl[i] = hf.smpl; sr.q_slot[i] = slot; }
