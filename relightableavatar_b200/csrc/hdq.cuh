@@ -13,7 +13,7 @@ __global__ void k_frame_prep(FrameConst* fc, const float* __restrict__ R, const 
                              const float* __restrict__ resd_w0, const float* __restrict__ resd_b0,   // (256,219)
                              const float* __restrict__ resd_w4, const float* __restrict__ resd_b4,   // (256,475)
                              const float* __restrict__ rend_w3, const float* __restrict__ rend_b3,   // (256,412) or null
-                             int* cell_count, float cell_h) {
+                             int* cell_count, float cell_h, float grid2_ratio) {
     __shared__ float smin[3][32], smax[3][32];
     int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
@@ -51,7 +51,7 @@ __global__ void k_frame_prep(FrameConst* fc, const float* __restrict__ R, const 
         fc->g_h = h;
         fc->g_inv_h = 1.0f / h;
         fc->g_cells = cells;
-        float h2 = h * RA_GRID2_RATIO;
+        float h2 = h * grid2_ratio;
         int cells2 = 1;
         for (int a = 0; a < 3; a++) {
             fc->g2_org[a] = lo[a] - 0.5f * h2;
@@ -302,32 +302,123 @@ __device__ __forceinline__ float bbox_dist2(float3 p, float4 lo, float4 hi) {
 // Near the body: expanding shells over the fine grid (cell ~4 cm).  Farther away: branch-and-bound over the list of
 // occupied coarse cells (tight vertex bounding boxes): nearest cell first, then every cell whose box is closer than
 // the current 3rd-best distance.  Both are exact; brute force only if the cell list overflowed.
-__device__ void knn3_query(const FrameConst* __restrict__ fc, const SortedVerts& sv, int nverts, float3 p, KnnOut& o) {
+#ifdef RA_KNN_STATS
+__device__ unsigned long long g_knn_stats[8];   // [0] near-path queries, [1] far-path queries, [2] far cells scanned, [3] far verts scanned
+#define KNN_STAT(i, v) atomicAdd(&g_knn_stats[i], (unsigned long long)(v))
+#else
+#define KNN_STAT(i, v)
+#endif
+// near phase: fine-grid shells; returns true when the result is final (o may hold seed candidates otherwise)
+__device__ __forceinline__ bool knn3_near(const FrameConst* __restrict__ fc, const SortedVerts& sv, float3 p, KnnOut& o) {
     o.d2[0] = o.d2[1] = o.d2[2] = 3.0e38f;
     o.id[0] = o.id[1] = o.id[2] = 0;
-    if (knn_rings<false>(grid_ref(fc, 0), sv.cell_start, sv.pos, RA_KNN_RMAX, p, o)) return;
-    o.d2[0] = o.d2[1] = o.d2[2] = 3.0e38f;
+    return knn_rings<false>(grid_ref(fc, 0), sv.cell_start, sv.pos, RA_KNN_RMAX, p, o);
+}
+
+// far phase: branch-and-bound over the occupied coarse cells, seeded with whatever the near phase found
+__device__ void knn3_far(const FrameConst* __restrict__ fc, const SortedVerts& sv, int nverts, float3 p, KnnOut& o) {
+    // The candidates found so far are real vertices: o.d2[2] (if finite) is an upper bound of the true 3rd distance.
     const int n = fc->n_occ;
-    if (n > RA_MAX_OCC) { knn_range(o, p, sv.pos, 0, nverts); return; }
+    if (n > RA_MAX_OCC) { o.d2[0] = o.d2[1] = o.d2[2] = 3.0e38f; knn_range(o, p, sv.pos, 0, nverts); return; }
     auto scan = [&](int c) {
         int s = __float_as_int(__ldg(&sv.occ_lo[c]).w), e = __float_as_int(__ldg(&sv.occ_hi[c]).w);
+        KNN_STAT(2, 1); KNN_STAT(3, e - s);
         for (int v = s; v < e; v++) {
             float4 q = __ldg(&sv.pos2[v]);
-            knn_insert(o, dist2_ref(p, q), __float_as_int(q.w));
+            float d2 = dist2_ref(p, q);
+            int id = __float_as_int(q.w);
+            if (d2 < o.d2[2] && id != o.id[0] && id != o.id[1] && id != o.id[2]) knn_insert(o, d2, id);
         }
     };
-    float best = 3.0e38f;
-    int bc = 0;
-    for (int c = 0; c < n; c++) {
-        float lb = bbox_dist2(p, __ldg(&sv.occ_lo[c]), __ldg(&sv.occ_hi[c]));
-        if (lb < best) { best = lb; bc = c; }
+    int bc = -1;
+    if (o.d2[2] >= 3.0e38f) {          // fewer than 3 candidates yet: visit the nearest occupied cell first
+        float best = 3.0e38f;
+        for (int c = 0; c < n; c++) {
+            float lb = bbox_dist2(p, __ldg(&sv.occ_lo[c]), __ldg(&sv.occ_hi[c]));
+            if (lb < best) { best = lb; bc = c; }
+        }
+        scan(bc);
     }
-    scan(bc);
     for (int c = 0; c < n; c++) {
         if (c == bc) continue;
         float lb = bbox_dist2(p, __ldg(&sv.occ_lo[c]), __ldg(&sv.occ_hi[c]));
         // 1e-4 relative slack: the box distance is rounded independently of dist2_ref
         if (lb * 0.9999f <= o.d2[2]) scan(c);
+    }
+}
+
+__device__ __forceinline__ void knn_merge_xor(KnnOut& o, int mask) {
+    // merge this lane's sorted triple with its partner's (disjoint vertex sets)
+    float d0 = __shfl_xor_sync(0xffffffffu, o.d2[0], mask), d1 = __shfl_xor_sync(0xffffffffu, o.d2[1], mask), d2 = __shfl_xor_sync(0xffffffffu, o.d2[2], mask);
+    int i0 = __shfl_xor_sync(0xffffffffu, o.id[0], mask), i1 = __shfl_xor_sync(0xffffffffu, o.id[1], mask), i2 = __shfl_xor_sync(0xffffffffu, o.id[2], mask);
+    knn_insert(o, d0, i0); knn_insert(o, d1, i1); knn_insert(o, d2, i2);
+}
+
+// Warp-cooperative exact 3-NN.  MUST be called by all 32 lanes (warp-uniform call site).  Every lane first runs the
+// fine-grid search for its own point; the points it cannot finish (far from the body) are then processed one at a
+// time by the WHOLE warp: lanes split the occupied coarse cells for the box test and stride over the vertices of the
+// qualifying cells, followed by a shuffle merge of the per-lane triples.  This keeps the long far phase convergent
+// instead of a few lanes dragging their idle neighbours through it.
+__device__ void knn3_warp(const FrameConst* __restrict__ fc, const SortedVerts& sv, int nverts, float3 p, bool active, KnnOut& o) {
+    const int lane = threadIdx.x & 31;
+    bool done = true;
+    if (active) done = knn3_near(fc, sv, p, o);
+    if (active) { if (done) KNN_STAT(0, 1); else KNN_STAT(1, 1); }
+    unsigned need = __ballot_sync(0xffffffffu, active && !done);
+    const int n = fc->n_occ;
+    if (__popc(need) > 12) {
+        // most of the warp is far from the body (e.g. rays entering the box): the lanes are already coherent,
+        // every lane finishes its own point
+        if (active && !done) knn3_far(fc, sv, nverts, p, o);
+        return;
+    }
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const float3 q = make3(__shfl_sync(0xffffffffu, p.x, src), __shfl_sync(0xffffffffu, p.y, src), __shfl_sync(0xffffffffu, p.z, src));
+        float B = __shfl_sync(0xffffffffu, o.d2[2], src);      // upper bound of the true 3rd distance (inf if < 3 seeds)
+        KnnOut w;
+        w.d2[0] = w.d2[1] = w.d2[2] = 3.0e38f; w.id[0] = w.id[1] = w.id[2] = 0;
+        if (n > RA_MAX_OCC) {                                   // cell list overflow: cooperative brute force
+            for (int v = lane; v < nverts; v += 32) knn_insert(w, dist2_ref(q, __ldg(&sv.pos[v])), v);
+        } else {
+            int skip = -1;
+            if (B >= 3.0e38f) {
+                // bootstrap: nearest occupied cell (warp arg-min of the box distance), scanned cooperatively
+                float best = 3.0e38f; int bc = 0;
+                for (int c = lane; c < n; c += 32) {
+                    float lb = bbox_dist2(q, __ldg(&sv.occ_lo[c]), __ldg(&sv.occ_hi[c]));
+                    if (lb < best) { best = lb; bc = c; }
+                }
+                for (int m = 16; m; m >>= 1) {
+                    float ob = __shfl_xor_sync(0xffffffffu, best, m); int oc = __shfl_xor_sync(0xffffffffu, bc, m);
+                    if (ob < best || (ob == best && oc < bc)) { best = ob; bc = oc; }
+                }
+                skip = bc;
+                int s = __float_as_int(__ldg(&sv.occ_lo[bc]).w), e = __float_as_int(__ldg(&sv.occ_hi[bc]).w);
+                for (int v = s + lane; v < e; v += 32) { float4 t = __ldg(&sv.pos2[v]); knn_insert(w, dist2_ref(q, t), __float_as_int(t.w)); }
+                KnnOut m3 = w;
+                for (int m = 16; m; m >>= 1) knn_merge_xor(m3, m);
+                B = m3.d2[2];                                   // still inf if that cell held < 3 vertices: every cell qualifies
+            }
+            for (int c0 = 0; c0 < n; c0 += 32) {
+                const int c = c0 + lane;
+                bool qual = false;
+                if (c < n && c != skip) qual = bbox_dist2(q, __ldg(&sv.occ_lo[c]), __ldg(&sv.occ_hi[c])) * 0.9999f <= B;
+                unsigned qm = __ballot_sync(0xffffffffu, qual);
+                while (qm) {
+                    const int cc = c0 + __ffs(qm) - 1;
+                    qm &= qm - 1;
+                    int s = __float_as_int(__ldg(&sv.occ_lo[cc]).w), e = __float_as_int(__ldg(&sv.occ_hi[cc]).w);
+                    for (int v = s + lane; v < e; v += 32) {
+                        float4 t = __ldg(&sv.pos2[v]);
+                        knn_insert(w, dist2_ref(q, t), __float_as_int(t.w));
+                    }
+                }
+            }
+        }
+        for (int m = 16; m; m >>= 1) knn_merge_xor(w, m);
+        if (lane == src) o = w;
     }
 }
 
@@ -355,8 +446,9 @@ __device__ __forceinline__ void inverse3x3_ref(const float* R, float* M) {
     M[6] = m20 / inv; M[7] = m21 / inv; M[8] = m22 / inv;
 }
 
+// MUST be called by all 32 lanes of a warp (warp-cooperative 3-NN inside); `active` = this lane has a point.
 template <bool WANT_MATS>
-__device__ void hdq_front(const FrameConst* __restrict__ fc, const SortedVerts& sv, int nverts, float3 x, float th,
+__device__ void hdq_front(const FrameConst* __restrict__ fc, const SortedVerts& sv, int nverts, float3 x, bool active, float th,
                           float blend_radius, HdqFront& out) {
     // world -> pose: (x - Th) @ R      blend_utils.py:252-261
     float3 q = make3(x.x - fc->Th[0], x.y - fc->Th[1], x.z - fc->Th[2]);
@@ -364,7 +456,10 @@ __device__ void hdq_front(const FrameConst* __restrict__ fc, const SortedVerts& 
                      q.x * fc->R[1] + q.y * fc->R[4] + q.z * fc->R[7],
                      q.x * fc->R[2] + q.y * fc->R[5] + q.z * fc->R[8]);
     KnnOut nn;
-    knn3_query(fc, sv, nverts, p, nn);
+    knn3_warp(fc, sv, nverts, p, active, nn);
+    out.in_shell = false;
+    out.smpl = 0.f;
+    if (!active) return;
     float th2 = th * th;
     float sdfk[3];
     float4 tv0 = __ldg(&sv.tv[nn.id[0]]);

@@ -45,6 +45,7 @@ struct ra_handle {
     std::string err;
     int64_t launches = 0;
     int dev = 0, sms = 148;
+    float cell_h = 0.04f, grid2_ratio = 4.0f;   // tunables (env RA_CELL_H / RA_GRID2_RATIO)
     bool have_weights = false, have_frame = false;
     // ---- weights
     Lin resd[9], sdf[9], rend[5], alb[3], rgh[3];
@@ -156,6 +157,8 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->dev));
     h->sms = prop.multiProcessorCount;
+    if (const char* e = getenv("RA_CELL_H")) h->cell_h = (float)atof(e);
+    if (const char* e = getenv("RA_GRID2_RATIO")) h->grid2_ratio = (float)atof(e);
     if (prop.major != 10) { h->err = "ra_b200 requires an sm_100 (B200) device"; return 1; }
     int64_t P = cfg->max_rays;
     int L = cfg->env_h * cfg->env_w;
@@ -292,7 +295,7 @@ extern "C" int ra_set_frame(ra_handle* h, const ra_frame* f, void* stream) {
     h->frame = *f;
     int N = h->cfg.n_verts;
     LAUNCH(h, k_frame_prep, 1, 1024, 0, st, h->fc, f->R, f->Th, f->pverts, N, f->wbounds, f->poses, f->mat_cond,
-           h->resd_w0_raw, h->resd_b0_raw, h->resd_w4_raw, h->resd_b4_raw, h->rend_w3_raw, h->rend_b3_raw, h->cell_count, 0.04f);
+           h->resd_w0_raw, h->resd_b0_raw, h->resd_w4_raw, h->resd_b4_raw, h->rend_w3_raw, h->rend_b3_raw, h->cell_count, h->cell_h, h->grid2_ratio);
     LAUNCH(h, k_grid_count, (N + 255) / 256, 256, 0, st, h->fc, 0, f->pverts, (const float4*)nullptr, N, h->cell_count, h->vert_cell);
     LAUNCH(h, k_grid_scan, 1, 1024, 0, st, h->fc, 0, h->cell_count, h->sv.cell_start, h->cell_fill);
     LAUNCH(h, k_grid_fill, (N + 127) / 128, 128, 0, st, h->fc, f->pverts, f->pnorm, f->tverts, f->weights, f->A, f->big_A, N,
@@ -479,11 +482,11 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     if (P == 0) return 0;
     TraceCfg tc{c.st_iter, c.st_tan_i, c.st_relax, c.st_offset, c.st_eps, c.st_skip, c.dist_th, c.blend_radius};
     int N = c.n_verts;
-    int g = grid_for(h, P, 128, 16);
+    int g = grid_for(h, P, 256, 8);
     prof_stage(h, st);
     for (int it = 0; it <= c.st_iter; it++) {
         CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
-        LAUNCH(h, k_trace_surface, g, 128, 0, st, it, tc, h->fc, h->sv, N, ray_o, ray_d, near_, far_, (int)P, h->ss, h->q, h->cnt,
+        LAUNCH(h, k_trace_surface, g, 256, 0, st, it, tc, h->fc, h->sv, N, ray_o, ray_d, near_, far_, (int)P, h->ss, h->q, h->cnt,
                h->surf, h->acc, h->depth, h->fg_ray);
         if (it < c.st_iter && distance_pass(h, st)) return 1;
     }
@@ -491,7 +494,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     // surface samples -> attributes
     int C = c.relight ? 17 : 16;
     CK(cudaMemsetAsync(h->raw, 0, (size_t)P * c.n_samples * C * sizeof(float), st));
-    LAUNCH(h, k_attr_front, grid_for(h, P * c.n_samples, 128, 16), 128, 0, st, 1, h->fc, h->sv, N, c.dist_th, c.blend_radius,
+    LAUNCH(h, k_attr_front, grid_for(h, P * c.n_samples, 256, 8), 256, 0, st, 1, h->fc, h->sv, N, c.dist_th, c.blend_radius,
            (const float*)nullptr, (const float*)nullptr, 0LL, h->cnt.n_fg, h->fg_ray, h->surf, ray_o, ray_d, near_, far_, c.n_samples,
            c.surf_sample_range, c.clip_near, c.clip_far, 0LL, 0LL, h->al, h->cnt);
     if (attr_pass(h, st, P * c.n_samples, h->cfg.precision == RA_PRECISION_FP32)) return 1;
@@ -506,10 +509,10 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     LAUNCH(h, k_shadow_gen, grid_for(h, P * L / 4, 256, 16), 256, 0, st, h->fc, h->cnt.n_fg, h->fg_ray, h->surf, h->fm.norm, h->ldir, L,
            c.lv_near, c.bbox_margin, h->chunk_actual, h->lvis, h->ldot, h->sr, h->cnt.n_shadow);
     TraceCfg sc{c.lv_iter, 1.f, c.lv_relax, c.lv_offset, c.st_eps, c.st_skip, c.lv_dist_th, c.blend_radius};
-    int gs = grid_for(h, P * 64, 128, 16);
+    int gs = grid_for(h, P * 64, 256, 8);
     for (int it = 0; it <= c.lv_iter; it++) {
         CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
-        LAUNCH(h, k_trace_shadow, gs, 128, 0, st, it, sc, h->fc, h->sv, N, h->cnt.n_shadow, h->fg_ray, h->surf, h->ldir, h->lsharp, L, h->sr,
+        LAUNCH(h, k_trace_shadow, gs, 256, 0, st, it, sc, h->fc, h->sv, N, h->cnt.n_shadow, h->fg_ray, h->surf, h->ldir, h->lsharp, L, h->sr,
                h->q, h->cnt, h->lvis);
         if (it < c.lv_iter && distance_pass(h, st)) return 1;
     }
@@ -576,7 +579,7 @@ extern "C" int ra_render_anisdf_volume(ra_handle* h, const float* ray_o, const f
         int64_t nr = std::min<int64_t>(h->vol_rays, P - r0);
         CK(cudaMemsetAsync(h->al.count, 0, sizeof(int), st));
         CK(cudaMemsetAsync(h->raw, 0, (size_t)nr * S * 16 * sizeof(float), st));
-        LAUNCH(h, k_attr_front, grid_for(h, nr * S, 128, 16), 128, 0, st, 2, h->fc, h->sv, c.n_verts, c.dist_th, c.blend_radius,
+        LAUNCH(h, k_attr_front, grid_for(h, nr * S, 256, 8), 256, 0, st, 2, h->fc, h->sv, c.n_verts, c.dist_th, c.blend_radius,
                (const float*)nullptr, (const float*)nullptr, 0LL, h->cnt.n_fg, h->fg_ray, h->surf, ray_o, ray_d, near_, far_, S,
                c.surf_sample_range, c.clip_near, c.clip_far, (long long)r0, (long long)nr, h->al, h->cnt);
         if (attr_pass(h, st, nr * S, true)) return 1;
@@ -593,7 +596,7 @@ extern "C" int ra_query_sdf(ra_handle* h, const float* x, int64_t n, float dist_
     if (n > h->q_cap) { h->err = "too many query points"; return 1; }
     if (n == 0) return 0;
     CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
-    LAUNCH(h, k_points_front, grid_for(h, n, 128, 16), 128, 0, st, h->fc, h->sv, h->cfg.n_verts, x, (int)n, dist_th, h->cfg.blend_radius,
+    LAUNCH(h, k_points_front, grid_for(h, n, 256, 8), 256, 0, st, h->fc, h->sv, h->cfg.n_verts, x, (int)n, dist_th, h->cfg.blend_radius,
            h->pt_smpl, h->pt_slot, h->q, h->cnt);
     if (distance_pass(h, st)) return 1;
     LAUNCH(h, k_points_finish, grid_for(h, n), 256, 0, st, h->pt_smpl, h->pt_slot, h->q.net, (int)n, dist_th, smooth, sdf);
@@ -609,7 +612,7 @@ extern "C" int ra_query_raw(ra_handle* h, const float* x, const float* v, int64_
     if (n == 0) return 0;
     CK(cudaMemsetAsync(h->al.count, 0, sizeof(int), st));
     CK(cudaMemsetAsync(h->raw, 0, (size_t)n * C * sizeof(float), st));
-    LAUNCH(h, k_attr_front, grid_for(h, n, 128, 16), 128, 0, st, 0, h->fc, h->sv, h->cfg.n_verts, h->cfg.dist_th, h->cfg.blend_radius, x, v,
+    LAUNCH(h, k_attr_front, grid_for(h, n, 256, 8), 256, 0, st, 0, h->fc, h->sv, h->cfg.n_verts, h->cfg.dist_th, h->cfg.blend_radius, x, v,
            (long long)n, h->cnt.n_fg, h->fg_ray, h->surf, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr,
            (const float*)nullptr, 1, 0.f, 0.f, 0.f, 0LL, 0LL, h->al, h->cnt);
     if (attr_pass(h, st, n, true)) return 1;
@@ -657,3 +660,12 @@ extern "C" int ra_profile_read(ra_handle* h, double* mlp_ms, int64_t* mlp_launch
     h->ev_mlp_used = 0; h->ev_stage_used = 0;
     return 0;
 }
+
+#ifdef RA_KNN_STATS
+extern "C" int ra_debug_knn_stats(unsigned long long* out8, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, g_knn_stats, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_knn_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif

@@ -45,9 +45,8 @@ __global__ void k_trace_surface(int it, TraceCfg cfg, const FrameConst* __restri
                                 SurfState s, QueryList q, Counters cnt,
                                 // finalisation outputs (it == iters)
                                 float* surf, float* acc, float* depth, int* fg_ray) {
-    int lane = threadIdx.x & 31;
-    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < P; base += gridDim.x * blockDim.x) {
-        int i = base + lane;
+    for (int base = blockIdx.x * blockDim.x; base < P; base += gridDim.x * blockDim.x) {      // block-uniform trip count
+        int i = base + threadIdx.x;
         bool valid = i < P;
         float3 o = make3(0, 0, 0), d = make3(0, 0, 1);
         float nr = 0.f, fr = 0.f, t = 0.f, occ = 1.f, d0 = 1e9f, cd = 1e9f, dt = 1e9f, st = 0.f, off = cfg.offset, rlx = cfg.relax;
@@ -80,7 +79,7 @@ __global__ void k_trace_surface(int it, TraceCfg cfg, const FrameConst* __restri
         }
         if (it < cfg.iters) {
             HdqFront f; f.in_shell = false; f.smpl = 0.f;
-            if (valid) hdq_front<false>(fc, sv, nverts, o + d * t, cfg.th, cfg.blend_radius, f);
+            hdq_front<false>(fc, sv, nverts, o + d * t, valid, cfg.th, cfg.blend_radius, f);
             bool ins = valid && f.in_shell;
             count_queries(cnt, valid, ins);
             int slot = warp_append(q.count, ins);
@@ -168,10 +167,9 @@ __global__ void k_trace_shadow(int it, TraceCfg cfg, const FrameConst* __restric
                                const int* __restrict__ n_shadow, const int* __restrict__ fg_ray, const float* __restrict__ surf,
                                const float* __restrict__ ldir, const float* __restrict__ lsharp, int L,
                                ShadowRays sr, QueryList q, Counters cnt, float* lvis) {
-    int lane = threadIdx.x & 31;
     int N = *n_shadow;
-    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < N; base += gridDim.x * blockDim.x) {
-        int i = base + lane;
+    for (int base = blockIdx.x * blockDim.x; base < N; base += gridDim.x * blockDim.x) {      // block-uniform trip count
+        int i = base + threadIdx.x;
         bool valid = i < N;
         float3 o = make3(0, 0, 0), d = make3(0, 0, 1);
         float nr = 0.f, fr = 0.f, t = 0.f, occ = 1.f, d0 = 1e9f;
@@ -214,7 +212,7 @@ __global__ void k_trace_shadow(int it, TraceCfg cfg, const FrameConst* __restric
         const bool alive = valid && (occ > 0.f);
         if (it < cfg.iters) {
             HdqFront hf; hf.in_shell = false; hf.smpl = 0.f;
-            if (alive) hdq_front<false>(fc, sv, nverts, o + d * t, cfg.th, cfg.blend_radius, hf);
+            hdq_front<false>(fc, sv, nverts, o + d * t, alive, cfg.th, cfg.blend_radius, hf);
             bool ins = alive && hf.in_shell;
             count_queries(cnt, alive, ins);
             int slot = warp_append(q.count, ins);
@@ -230,12 +228,11 @@ __global__ void k_trace_shadow(int it, TraceCfg cfg, const FrameConst* __restric
 // x (n,3) -> front-end; in-shell points appended to the query list.  Used by ra_query_sdf.
 __global__ void k_points_front(const FrameConst* __restrict__ fc, SortedVerts sv, int nverts, const float* __restrict__ x, int n,
                                float th, float blend_radius, float* smpl, int* slot_out, QueryList q, Counters cnt) {
-    int lane = threadIdx.x & 31;
-    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
-        int i = base + lane;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {      // block-uniform trip count
+        int i = base + threadIdx.x;
         bool valid = i < n;
         HdqFront f; f.in_shell = false; f.smpl = 0.f;
-        if (valid) hdq_front<false>(fc, sv, nverts, make3(x[i * 3], x[i * 3 + 1], x[i * 3 + 2]), th, blend_radius, f);
+        hdq_front<false>(fc, sv, nverts, valid ? make3(x[i * 3], x[i * 3 + 1], x[i * 3 + 2]) : make3(0, 0, 0), valid, th, blend_radius, f);
         bool ins = valid && f.in_shell;
         count_queries(cnt, valid, ins);
         int slot = warp_append(q.count, ins);
@@ -271,10 +268,9 @@ __global__ void k_attr_front(int mode, const FrameConst* __restrict__ fc, Sorted
                              const float* __restrict__ far_, int n_samples, float sample_range, float clip_near, float clip_far,
                              long long ray0, long long n_rays,
                              AttrList al, Counters cnt) {
-    int lane = threadIdx.x & 31;
     long long total = (mode == 0) ? n_explicit : (mode == 1 ? (long long)(*n_fg) * n_samples : n_rays * n_samples);
-    for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += (long long)gridDim.x * blockDim.x) {
-        long long i = base + lane;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {   // block-uniform
+        long long i = base + threadIdx.x;
         bool valid = i < total;
         float3 px = make3(0, 0, 0), pv = make3(0, 0, 1);
         if (valid) {
@@ -299,7 +295,7 @@ __global__ void k_attr_front(int mode, const FrameConst* __restrict__ fc, Sorted
             }
         }
         HdqFront f; f.in_shell = false;
-        if (valid) hdq_front<true>(fc, sv, nverts, px, th, blend_radius, f);
+        hdq_front<true>(fc, sv, nverts, px, valid, th, blend_radius, f);
         bool ins = valid && f.in_shell;
         count_queries(cnt, false, false);
         int slot = warp_append(al.count, ins);
