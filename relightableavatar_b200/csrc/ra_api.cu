@@ -17,6 +17,7 @@
 #include "mlp_simt.cuh"
 #include "render.cuh"
 #include "mlp_tc.cuh"
+#include "mlp_tc2.cuh"
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -56,6 +57,8 @@ struct ra_handle {
     float *env_main = nullptr; int emh = 0, emw = 0;
     float *lxyz = nullptr, *larea = nullptr, *lsharp = nullptr, *ldir = nullptr;
     TcWeights tc;                    // fp16 UMMA images for the tcgen05 path
+    Tc2Weights tc2;                  // ... and for its 2-CTA (cta_group::2) variant
+    int tc_variant = 1;              // env RA_TC_VARIANT: 1 = single-CTA kernel, 2 = CTA-pair kernel
     // ---- frame
     FrameConst* fc = nullptr;
     SortedVerts sv{};
@@ -203,6 +206,8 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     CK(dalloc(&h->hd1, R * 128)); CK(dalloc(&h->hd2, R * 128)); CK(dalloc(&h->head_a, R * 4)); CK(dalloc(&h->head_r, R * 4));
     CK(dalloc(&h->Xrn, R * 288)); CK(dalloc(&h->rn1, R * 256)); CK(dalloc(&h->rn2, R * 256));
     if (tc_init(h->tc, h->err)) return 1;
+    if (tc2_init(h->tc2, h->err)) return 1;
+    if (const char* e = getenv("RA_TC_VARIANT")) h->tc_variant = atoi(e);
     return 0;
 }
 
@@ -213,6 +218,7 @@ extern "C" void ra_destroy(ra_handle* h) {
     for (float* b : bufs) if (b) cudaFree(b);
     for (int i = 0; i < 8; i++) { if (h->ra_[i]) cudaFree(h->ra_[i]); if (h->sb_[i]) cudaFree(h->sb_[i]); }
     tc_free(h->tc);
+    tc2_free(h->tc2);
     delete h;
 }
 
@@ -284,6 +290,7 @@ extern "C" int ra_upload_weights(ra_handle* h, const ra_weights* w, void* stream
         if (upload_raw(h, &h->ldir, dir.data(), dir.size(), st)) return 1;
     }
     if (tc_upload(h->tc, w, h->err, st)) return 1;
+    if (tc2_upload(h->tc2, w, h->err, st)) return 1;
     h->have_weights = true;
     return 0;
 }
@@ -305,7 +312,10 @@ extern "C" int ra_set_frame(ra_handle* h, const ra_frame* f, void* stream) {
     LAUNCH(h, k_grid_scan, 1, 1024, 0, st, h->fc, 1, h->cell_count, h->sv.cell_start2, h->cell_fill);
     LAUNCH(h, k_grid_fill2, (N + 255) / 256, 256, 0, st, (const float4*)h->sv.pos, N, h->vert_cell, h->sv.cell_start2, h->cell_fill, h->sv.pos2);
     LAUNCH(h, k_grid_occ, 8, 256, 0, st, h->fc, h->sv.cell_start2, (const float4*)h->sv.pos2, h->sv.occ_lo, h->sv.occ_hi);
-    if (h->cfg.precision == RA_PRECISION_TC) tc_set_frame(h->tc, h->fc, st, h->launches);
+    if (h->cfg.precision == RA_PRECISION_TC) {
+        if (h->tc_variant == 2) tc2_set_frame(h->tc2, h->fc, st, h->launches);
+        else tc_set_frame(h->tc, h->fc, st, h->launches);
+    }
     CK(cudaGetLastError());
     h->have_frame = true;
     return 0;
@@ -442,7 +452,8 @@ static void prof_stage(ra_handle* h, cudaStream_t st) {
 static int distance_pass(ra_handle* h, cudaStream_t st) {
     if (h->cfg.precision == RA_PRECISION_TC) {
         if (h->prof) cudaEventRecord(prof_event(h->ev_mlp, h->ev_mlp_used), st);
-        tc_distance(h->tc, h->q.bpts, h->q.net, h->q.count, h->cfg.resd_limit, h->sms, st, h->launches);
+        if (h->tc_variant == 2) tc2_distance(h->tc2, h->q.bpts, h->q.net, h->q.count, h->cfg.resd_limit, h->sms, st, h->launches);
+        else tc_distance(h->tc, h->q.bpts, h->q.net, h->q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         if (h->prof) cudaEventRecord(prof_event(h->ev_mlp, h->ev_mlp_used), st);
         return 0;
     }

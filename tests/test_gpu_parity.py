@@ -162,3 +162,52 @@ def test_empty_rays_are_tolerated(relight_setup):
     r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=1024)
     out = r.render(b2)
     assert out['main']['rgb_map'].shape == (1, 0, 3)
+
+
+def test_two_cta_kernel_variant_matches_single_cta(relight_setup, monkeypatch):
+    """k_mlp_tc2 (cta_group::2 pair kernel) evaluates the same arithmetic as k_mlp_tc: bit-identical distances."""
+    b, sd = relight_setup
+    x = _sample_points(b, 20000, seed=3)
+    outs = []
+    for variant in ('1', '2'):
+        monkeypatch.setenv('RA_TC_VARIANT', variant)
+        eng = Engine(default_config(True, precision=1, max_rays=8192), DEV)
+        eng.upload_weights(sd); eng.set_frame(b)
+        outs.append(eng.query_sdf(x, 0.125, True).clone())
+        eng.close()
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_relight_1024_config5_properties():
+    """BASELINE config 5 size (1024x1024 frame): size-independent properties instead of an oracle run:
+    acc in [0,1], maps premultiplied (zero where acc == 0), foreground share plausible, rgb finite and in [0,1],
+    and the 1024^2 image downsampled 2x agrees with the 512^2 rendering of the same view (PSNR)."""
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    net = scene.SyntheticNet(sd, True)
+    b_hi = scene.make_batch(1024, 1024, seed=0, n_env=0)
+    b_lo = scene.make_batch(512, 512, seed=0, n_env=0)
+    r = Renderer(net, mode='relight', device=DEV, precision='tc', max_rays=b_hi['ray_o'].shape[1] + 8, test_light=('main',), sync_timing=False)
+    hi = r.render(b_hi)['main']
+    lo = r.render(b_lo)['main']
+    acc = hi['acc_map'][0]
+    assert torch.isfinite(hi['rgb_map']).all() and float(acc.min()) >= 0 and float(acc.max()) <= 1
+    assert float(hi['rgb_map'].min()) >= 0 and float(hi['rgb_map'].max()) <= 1.0 + 1e-5
+    bg = acc == 0
+    assert float(hi['rgb_map'][0][bg].abs().max()) == 0 and float(hi['norm_map'][0][bg].abs().max()) == 0
+    frac = float((acc > 0).float().mean())
+    assert 0.05 < frac < 0.5
+    img_hi = O.assemble_image(b_hi, hi['rgb_map'][0].cpu()).permute(2, 0, 1)[None]
+    img_lo = O.assemble_image(b_lo, lo['rgb_map'][0].cpu())
+    down = torch.nn.functional.avg_pool2d(img_hi, 2)[0].permute(1, 2, 0)
+    assert O.psnr(down, img_lo) > 25.0
+
+
+def test_tile_sharded_equals_single_gpu_when_two_gpus():
+    """N>1 on real GPUs: rays dealt to 2 ranks, one all-gather, result identical to the 1-GPU frame."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29533', os.path.join(root, 'tools', 'tile_shard_check.py')], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'TILE_SHARD_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
