@@ -101,6 +101,7 @@ __global__ void k_skinny(const float* __restrict__ X, int ldx, const float* __re
                          int N, int K) {
     int total = *count;
     int M = min(total - row0, rows_cap);
+    if (M <= 0) return;
     int warps_per_block = blockDim.x >> 5;
     int lane = threadIdx.x & 31;
     for (int m = blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < M; m += gridDim.x * warps_per_block) {
@@ -128,6 +129,7 @@ __global__ void k_outer_small(const float* __restrict__ U, int ldu, const float*
                               int rows_cap) {
     int total = *count;
     int M = min(total - row0, rows_cap);
+    if (M <= 0) return;
     size_t n_el = (size_t)M * K;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (size_t)gridDim.x * blockDim.x) {
         int m = (int)(i / K), k = (int)(i % K);
@@ -161,6 +163,7 @@ __global__ void k_encode(const float* __restrict__ pts, int L, float* X0, int ld
                          int w1, const int* count, int row0, int rows_cap) {
     int total = *count;
     int M = min(total - row0, rows_cap);
+    if (M <= 0) return;
     for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
         size_t g = (size_t)m;
         float3 x = make3(pts[g * 3], pts[g * 3 + 1], pts[g * 3 + 2]);
@@ -177,6 +180,7 @@ __global__ void k_resd_finish(const float* __restrict__ z8, int ldz, const float
                               float* resd, float* cpts, const int* count, int row0, int rows_cap) {
     int total = *count;
     int M = min(total - row0, rows_cap);
+    if (M <= 0) return;
     for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
         size_t g = (size_t)m;
         for (int c = 0; c < 3; c++) {
@@ -213,6 +217,7 @@ __global__ void k_sdf_grad_to_cp(const float* __restrict__ cpts, const float* __
                                  float limit, float* gcp, float* u, int ldu, const int* count, int row0, int rows_cap) {
     int total = *count;
     int M = min(total - row0, rows_cap);
+    if (M <= 0) return;
     for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
         size_t g = (size_t)m;
         float3 x = make3(cpts[g * 3], cpts[g * 3 + 1], cpts[g * 3 + 2]);
@@ -232,6 +237,7 @@ __global__ void k_resd_grad_to_bp(const float* __restrict__ bpts, const float* _
                                   float* gbp, const int* count, int row0, int rows_cap) {
     int total = *count;
     int M = min(total - row0, rows_cap);
+    if (M <= 0) return;
     for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
         size_t g = (size_t)m;
         float3 x = make3(bpts[g * 3], bpts[g * 3 + 1], bpts[g * 3 + 2]);

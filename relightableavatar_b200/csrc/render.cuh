@@ -343,6 +343,7 @@ __device__ __forceinline__ float3 normal_to_world(float3 g, const float* mats, c
 __global__ void k_attr_normals(const FrameConst* __restrict__ fc, const float* __restrict__ gbp, const float* __restrict__ mats,
                                float* nrm, const int* count, int row0, int rows_cap) {
     int M = min(*count - row0, rows_cap);
+    if (M <= 0) return;
     for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
         float3 n = normal_to_world(make3(gbp[m * 3], gbp[m * 3 + 1], gbp[m * 3 + 2]), mats + (size_t)m * 18, fc);
         nrm[m * 3] = n.x; nrm[m * 3 + 1] = n.y; nrm[m * 3 + 2] = n.z;
@@ -353,6 +354,7 @@ __global__ void k_attr_normals(const FrameConst* __restrict__ fc, const float* _
 __global__ void k_render_input(const float* __restrict__ bvds, const float* __restrict__ nrm, const float* __restrict__ feat,
                                int ldo, float* X, int ldx, const int* count, int row0, int rows_cap) {
     int M = min(*count - row0, rows_cap);
+    if (M <= 0) return;
     for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
         float buf[64];
         pe_write(make3(bvds[m * 3], bvds[m * 3 + 1], bvds[m * 3 + 2]), 4, buf, 27);
@@ -373,6 +375,7 @@ __global__ void k_attr_finish(int relight, const float* __restrict__ bpts, const
                               float beta, float albedo_slope, float albedo_bias, float rough_slope, float rough_bias,
                               const int* __restrict__ src, float* raw, const int* count, int row0, int rows_cap) {
     int M = min(*count - row0, rows_cap);
+    if (M <= 0) return;
     int C = relight ? 17 : 16;
     for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
         float* r = raw + (size_t)src[m] * C;
