@@ -23,6 +23,13 @@
 #include "common.cuh"
 #include "../../include/ra_b200.h"
 
+// per-layer clock64 timeline of CTA 0 (tools/tc_timeline.py): compile with -DRA_TC_TIMELINE
+#ifdef RA_TC_TIMELINE
+#define TC_TL(x) x
+#else
+#define TC_TL(x)
+#endif
+
 #define TC_LAYERS 18
 #define TC_TILE_M 128
 #define TC_KCHUNK 32
@@ -52,6 +59,7 @@ struct TcParams {
     float* out;
     const int* count;
     float resd_limit;
+    unsigned long long* dbg;   // optional timeline of CTA 0, tile iteration 1 (debug builds of tools/tc_timeline.py)
 };
 
 struct TcWeights {
@@ -59,6 +67,7 @@ struct TcWeights {
     float* bias = nullptr;        // [18][256]
     TcParams p{};
     bool ready = false;
+    unsigned long long* dbg = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -306,8 +315,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(const __grid_constant_
                     const uint32_t idesc = make_idesc_f16(N);
                     const uint32_t lbo_b = (uint32_t)N * 16u;
                     const int nch = P.layer[l].nchunks;
+                    TC_TL(const bool rec = P.dbg && blockIdx.x == 0 && tile == (int)gridDim.x;)
+                    TC_TL(if (rec) P.dbg[l * 8 + 0] = clock64();)
                     mbar_wait(bar_act, lc & 1);
                     tc_fence_after();
+                    TC_TL(if (rec) P.dbg[l * 8 + 1] = clock64();)
                     for (int c = 0; c <= nch; c++, it++) {
                         uint32_t s = it & 1, ph = (it >> 1) & 1;
                         mbar_wait(bar_full + 8 * s, ph);
@@ -331,6 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(const __grid_constant_
                         umma_commit(bar_empty + 8 * s);      // frees the weight stage when these MMAs retire
                     }
                     umma_commit(bar_acc);                     // accumulator of this layer complete
+                    TC_TL(if (rec) P.dbg[l * 8 + 2] = clock64();)
                 }
             }
         }
@@ -355,8 +368,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(const __grid_constant_
 #pragma unroll 1
             for (int l = 0; l < TC_LAYERS; l++, lc++) {
                 const int epi = P.layer[l].epi;
+                TC_TL(const bool rec = P.dbg && blockIdx.x == 0 && tile == (int)gridDim.x && warp == 2 && lane == 0;)
+                TC_TL(if (rec) P.dbg[l * 8 + 3] = clock64();)
                 mbar_wait(bar_acc, lc & 1);
                 tc_fence_after();
+                TC_TL(if (rec) P.dbg[l * 8 + 4] = clock64();)
                 if (epi == TC_EPI_RELU) {
                     epi_hidden<false>(t_lane, s_act, row, half);
                 } else if (epi == TC_EPI_SOFTPLUS) {
@@ -409,12 +425,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(const __grid_constant_
                         if (gidx < count) P.out[gidx] = __uint_as_float(r[0]);
                     }
                 }
+                TC_TL(if (rec) P.dbg[l * 8 + 5] = clock64();)
                 if (l + 1 < TC_LAYERS) {
                     tc_fence_before();
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_act);
                 }
+                TC_TL(if (rec) P.dbg[l * 8 + 6] = clock64();)
             }
         }
     }
@@ -557,7 +575,7 @@ static void tc_set_frame(TcWeights& t, const FrameConst* fc, cudaStream_t st, in
 static void tc_distance(TcWeights& t, const float* bpts, float* out, const int* count, float resd_limit, int sms, cudaStream_t st,
                         int64_t& launches) {
     TcParams p = t.p;
-    p.bpts = bpts; p.out = out; p.count = count; p.resd_limit = resd_limit;
+    p.bpts = bpts; p.out = out; p.count = count; p.resd_limit = resd_limit; p.dbg = t.dbg;
     k_mlp_tc<<<2 * sms, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
     launches++;
 }

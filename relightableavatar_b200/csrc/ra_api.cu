@@ -18,6 +18,9 @@
 #include "render.cuh"
 #include "mlp_tc.cuh"
 #include "mlp_tc2.cuh"
+#include "mlp_tc3.cuh"
+#include "mlp_tc4.cuh"
+#include "mlp_tc5.cuh"
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -207,6 +210,9 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     CK(dalloc(&h->Xrn, R * 288)); CK(dalloc(&h->rn1, R * 256)); CK(dalloc(&h->rn2, R * 256));
     if (tc_init(h->tc, h->err)) return 1;
     if (tc2_init(h->tc2, h->err)) return 1;
+    if (tc3_init(h->err)) return 1;
+    if (tc4_init(h->err)) return 1;
+    if (tc5_init(h->err)) return 1;
     if (const char* e = getenv("RA_TC_VARIANT")) h->tc_variant = atoi(e);
     return 0;
 }
@@ -453,6 +459,9 @@ static int distance_pass(ra_handle* h, cudaStream_t st) {
     if (h->cfg.precision == RA_PRECISION_TC) {
         if (h->prof) cudaEventRecord(prof_event(h->ev_mlp, h->ev_mlp_used), st);
         if (h->tc_variant == 2) tc2_distance(h->tc2, h->q.bpts, h->q.net, h->q.count, h->cfg.resd_limit, h->sms, st, h->launches);
+        else if (h->tc_variant == 5) tc5_distance(h->tc, h->q.bpts, h->q.net, h->q.count, h->cfg.resd_limit, h->sms, st, h->launches);
+        else if (h->tc_variant == 4) tc4_distance(h->tc, h->q.bpts, h->q.net, h->q.count, h->cfg.resd_limit, h->sms, st, h->launches);
+        else if (h->tc_variant == 3) tc3_distance(h->tc, h->q.bpts, h->q.net, h->q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         else tc_distance(h->tc, h->q.bpts, h->q.net, h->q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         if (h->prof) cudaEventRecord(prof_event(h->ev_mlp, h->ev_mlp_used), st);
         return 0;
@@ -680,3 +689,15 @@ extern "C" int ra_debug_knn_stats(unsigned long long* out8, int reset) {
     return 0;
 }
 #endif
+
+// debug: per-layer clock64 timeline of CTA 0 of the fused MLP kernel (tools/tc_timeline.py)
+extern "C" int ra_debug_tc_timeline(ra_handle* h, unsigned long long* out, int enable) {
+    if (enable) {
+        if (!h->tc.dbg) { CK(cudaMalloc((void**)&h->tc.dbg, 18 * 8 * sizeof(unsigned long long))); }
+        CK(cudaMemset(h->tc.dbg, 0, 18 * 8 * sizeof(unsigned long long)));
+        return 0;
+    }
+    CK(cudaDeviceSynchronize());
+    if (h->tc.dbg && out) CK(cudaMemcpy(out, h->tc.dbg, 18 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
