@@ -9,17 +9,22 @@
 #include "mlp_tc.cuh"
 #include "mlp_tc2.cuh"   // cluster helpers (cluster_ctarank, cluster_sync_all, mbar_wait_cluster)
 
+#ifndef TC3_CS
+#define TC3_CS 2          // cluster size (4 and 8 measured 2x slower: 42 ms/frame): CTA r loads slice r of TC3_CS of every chunk and multicasts it to all
+#endif
+#define TC3_MASK ((uint16_t)((1u << TC3_CS) - 1u))
+
 __device__ __forceinline__ void tma_bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar), "h"((uint16_t)3) : "memory");
+                 "l"(src), "r"(bytes), "r"(bar), "h"(TC3_MASK) : "memory");
 }
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(TC3_MASK)
                  : "memory");
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 2) k_mlp_tc3(const __grid_constant__ TcParams P) {
+__global__ void __cluster_dims__(TC3_CS, 1, 1) __launch_bounds__(TC_THREADS, 2) k_mlp_tc3(const __grid_constant__ TcParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_act = s_base;
@@ -34,11 +39,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 2) k_mlp
     const int count = *P.count;
     const int n_tiles = (count + TC_TILE_M - 1) / TC_TILE_M;
     const uint32_t rank = cluster_ctarank();
-    const int n_pairs = (n_tiles + 1) / 2;
-    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_pairs = (n_tiles + TC3_CS - 1) / TC3_CS;      // groups of TC3_CS tiles, one per CTA of the cluster
+    const int cluster_id = blockIdx.x / TC3_CS, n_clusters = gridDim.x / TC3_CS;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 2); }   // empty: both CTAs' consumers must retire a stage
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, TC3_CS); }   // empty: both CTAs' consumers must retire a stage
         mbar_init(bar_act, 8);
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -72,7 +77,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 2) k_mlp
                         const unsigned char* g = (c < nch) ? src + (size_t)c * bytes : P.blob + P.layer[l].boff;
                         mbar_wait_cluster(bar_empty + 8 * s, ph ^ 1);
                         mbar_expect_tx(bar_full + 8 * s, nb);          // the whole chunk: my half + the peer's half
-                        tma_bulk_g2s_mc(s_w + s * TC_STAGE_BYTES + rank * (nb / 2), g + rank * (nb / 2), nb / 2, bar_full + 8 * s);
+                        tma_bulk_g2s_mc(s_w + s * TC_STAGE_BYTES + rank * (nb / TC3_CS), g + rank * (nb / TC3_CS), nb / TC3_CS, bar_full + 8 * s);
                     }
                 }
             }
@@ -124,7 +129,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 2) k_mlp
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t lc = 0;
         for (int pair = cluster_id; pair < n_pairs; pair += n_clusters) {
-            const int tile = pair * 2 + (int)rank;
+            const int tile = pair * TC3_CS + (int)rank;
             const int gidx = tile * TC_TILE_M + row;
             float3 bp = make3(0.f, 0.f, 0.f);
             if (gidx < count) bp = make3(P.bpts[(size_t)gidx * 3], P.bpts[(size_t)gidx * 3 + 1], P.bpts[(size_t)gidx * 3 + 2]);
