@@ -95,6 +95,102 @@ __global__ void __launch_bounds__(256) k_gemm(GemmArgs a) {
 }
 // All pointers are CHUNK-LOCAL: the host offsets per-point arrays by row0; row0 only bounds M.
 
+// ---- same GEMM on the (legacy mma.sync) tensor-core path with error-compensated 3xTF32 ---------------------------------
+// a = a_hi + a_lo with a_hi = tf32(a), a_lo = tf32(a - a_hi) (same for b);  a*b ~ a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32
+// accumulate: fp32-grade results (rel. error ~1e-6) at ~3x the CUDA-core SGEMM rate.  Used for the surface-attribute pass,
+// whose outputs (normals, albedo, roughness) are the pixel and therefore stay at fp32 accuracy.
+__device__ __forceinline__ uint32_t f2tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, const uint32_t* b) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+#define GTP 136      // padded tile width: 136 % 32 == 8 -> conflict-free fragment loads
+
+template <int EPI>
+__global__ void __launch_bounds__(256) k_gemm_tf32x3(GemmArgs a) {
+    int total = *a.count;
+    int M = min(total - a.row0, a.rows_cap);
+    int m0 = blockIdx.x * GBM;
+    if (m0 >= M) return;
+    int n0 = blockIdx.y * GBN;
+    __shared__ uint32_t Ah[2][GBK][GTP], Al[2][GBK][GTP], Bh[2][GBK][GTP], Bl[2][GBK][GTP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+    const int lrow = tid >> 1, lk = (tid & 1) * 4;
+    const float* Xp = a.X + (size_t)(m0 + lrow) * a.ldx + lk;
+    const float* Wp = a.W + (size_t)(n0 + lrow) * a.ldw + lk;
+    const bool xok = (m0 + lrow) < M, wok = (n0 + lrow) < a.N;
+    float acc[4][4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) acc[i][j][r] = 0.f;
+    auto stage = [&](int buf, float4 xa, float4 wa) {
+        const float xv[4] = {xa.x, xa.y, xa.z, xa.w}, wv[4] = {wa.x, wa.y, wa.z, wa.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t h = f2tf32(xv[q]);
+            Ah[buf][lk + q][lrow] = h; Al[buf][lk + q][lrow] = f2tf32(xv[q] - __uint_as_float(h));
+            uint32_t hb = f2tf32(wv[q]);
+            Bh[buf][lk + q][lrow] = hb; Bl[buf][lk + q][lrow] = f2tf32(wv[q] - __uint_as_float(hb));
+        }
+    };
+    float4 xa = xok ? *reinterpret_cast<const float4*>(Xp) : make_float4(0, 0, 0, 0);
+    float4 wa = wok ? __ldg(reinterpret_cast<const float4*>(Wp)) : make_float4(0, 0, 0, 0);
+    stage(0, xa, wa);
+    __syncthreads();
+    const int nk = a.K / GBK;
+    for (int kt = 0; kt < nk; kt++) {
+        const int cur = kt & 1;
+        if (kt + 1 < nk) {
+            xa = xok ? *reinterpret_cast<const float4*>(Xp + (kt + 1) * GBK) : make_float4(0, 0, 0, 0);
+            wa = wok ? __ldg(reinterpret_cast<const float4*>(Wp + (kt + 1) * GBK)) : make_float4(0, 0, 0, 0);
+        }
+        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int n = wn + j * 8 + g;
+            bh[j][0] = Bh[cur][t][n]; bh[j][1] = Bh[cur][t + 4][n];
+            bl[j][0] = Bl[cur][t][n]; bl[j][1] = Bl[cur][t + 4][n];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int m = wm + i * 16 + g;
+            uint32_t ah[4] = {Ah[cur][t][m], Ah[cur][t][m + 8], Ah[cur][t + 4][m], Ah[cur][t + 4][m + 8]};
+            uint32_t al[4] = {Al[cur][t][m], Al[cur][t][m + 8], Al[cur][t + 4][m], Al[cur][t + 4][m + 8]};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                mma_tf32(acc[i][j], al, bh[j]);
+                mma_tf32(acc[i][j], ah, bl[j]);
+                mma_tf32(acc[i][j], ah, bh[j]);
+            }
+        }
+        if (kt + 1 < nk) stage(cur ^ 1, xa, wa);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int m = m0 + wm + i * 16 + g + ((r & 2) ? 8 : 0);
+                const int n = n0 + wn + j * 8 + 2 * t + (r & 1);
+                if (m >= M || n >= a.N) continue;
+                float v = acc[i][j][r];
+                if (a.bias) v += __ldg(&a.bias[n]);
+                if (EPI == EPI_RELU) v = fmaxf(v, 0.f);
+                if (EPI == EPI_SOFTPLUS) v = softplus100(v);
+                if (EPI == EPI_MUL_DRELU) v = (a.aux[(size_t)m * a.ldaux + n] > 0.f) ? v : 0.f;
+                if (EPI == EPI_MUL_DSOFTPLUS) v *= dsoftplus100_from_act(a.aux[(size_t)m * a.ldaux + n]);
+                a.Y[(size_t)m * a.ldy + n] = v;
+            }
+}
+
+
 // Y[m, n] for n < N <= 4: one warp per row.
 __global__ void k_skinny(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
                          const float* __restrict__ bias, float* Y, int ldy, const int* count, int row0, int rows_cap,

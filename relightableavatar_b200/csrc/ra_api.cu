@@ -61,6 +61,7 @@ struct ra_handle {
     float *lxyz = nullptr, *larea = nullptr, *lsharp = nullptr, *ldir = nullptr;
     TcWeights tc;                    // fp16 UMMA images for the tcgen05 path
     Tc2Weights tc2;                  // ... and for its 2-CTA (cta_group::2) variant
+    int attr_tc = 1;                 // env RA_ATTR_TC: 1 = 3xTF32 tensor-core GEMMs in the fp32 MLP path, 0 = CUDA-core SGEMM
     int tc_variant = 1;              // env RA_TC_VARIANT: 1 = single-CTA kernel, 2 = CTA-pair kernel
     // ---- frame
     FrameConst* fc = nullptr;
@@ -148,7 +149,8 @@ static void gemm(ra_handle* h, cudaStream_t st, const float* X, int ldx, const f
                  int ldy, const float* aux, int ldaux, const int* count, int row0, int rows_cap, int N, int K) {
     GemmArgs a{X, ldx, W, ldw, bias, Y, ldy, aux, ldaux, count, row0, rows_cap, N, K};
     dim3 grid((rows_cap + GBM - 1) / GBM, (N + GBN - 1) / GBN);
-    LAUNCH(h, k_gemm<EPI>, grid, 256, 0, st, a);
+    if (h->attr_tc) LAUNCH(h, k_gemm_tf32x3<EPI>, grid, 256, 0, st, a);
+    else LAUNCH(h, k_gemm<EPI>, grid, 256, 0, st, a);
 }
 
 // ---------------------------------------------------------------------------------------------- create / destroy
@@ -214,6 +216,7 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     if (tc4_init(h->err)) return 1;
     if (tc5_init(h->err)) return 1;
     if (const char* e = getenv("RA_TC_VARIANT")) h->tc_variant = atoi(e);
+    if (const char* e = getenv("RA_ATTR_TC")) h->attr_tc = atoi(e);
     return 0;
 }
 
