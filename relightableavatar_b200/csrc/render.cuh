@@ -166,9 +166,12 @@ __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __res
 __global__ void k_trace_shadow(int it, TraceCfg cfg, const FrameConst* __restrict__ fc, SortedVerts sv, int nverts,
                                const int* __restrict__ n_shadow, const int* __restrict__ fg_ray, const float* __restrict__ surf,
                                const float* __restrict__ ldir, const float* __restrict__ lsharp, int L,
-                               ShadowRays sr, QueryList q, Counters cnt, float* lvis) {
-    int N = *n_shadow;
-    for (int base = blockIdx.x * blockDim.x; base < N; base += gridDim.x * blockDim.x) {      // block-uniform trip count
+                               ShadowRays sr, QueryList q, Counters cnt, float* lvis, int part, int nparts) {
+    // rays [lo, hi) of the list: the host runs the parts on different streams so that one part's CUDA-core work overlaps
+    // the other part's tensor-core MLP kernel
+    const long long Nall = *n_shadow;
+    const int lo = (int)(Nall * part / nparts), N = (int)(Nall * (part + 1) / nparts);
+    for (int base = lo + blockIdx.x * blockDim.x; base < N; base += gridDim.x * blockDim.x) {      // block-uniform trip count
         int i = base + threadIdx.x;
         bool valid = i < N;
         float3 o = make3(0, 0, 0), d = make3(0, 0, 1);
