@@ -127,6 +127,10 @@ int ra_render_relight(ra_handle* h, const float* ray_o, const float* ray_d, cons
  * Uses the maps of the preceding ra_render_relight call (kept in the workspace). */
 int ra_relight_envmaps(ra_handle* h, const float* probes, int32_t n_env, float* rgb, float* shade, float* spec,
                        void* stream);
+/* Env-map rotation sweep (vis_rotate_light; relight_utils.py:55-103 rotate_envmap / shift_image, novel_light_sphere_tracing.py:163-171):
+ * out (n_rot, env_h, env_w, 3) = probe (env_h, env_w, 3) shifted by j0 .. j0+n_rot-1 steps of 1/repeat texel along the longitude;
+ * feed the result to ra_relight_envmaps. */
+int ra_rotate_probes(ra_handle* h, const float* probe, int32_t repeat, int32_t j0, int32_t n_rot, float* out, void* stream);
 /* sphere_tracing_renderer.Renderer.render for the AniSDF network (config 1; raw 16-ch branch :634-635). */
 int ra_render_anisdf_trace(ra_handle* h, const float* ray_o, const float* ray_d, const float* near, const float* far,
                            int64_t P, const ra_outputs* out, void* stream);

@@ -613,6 +613,21 @@ def render_volume(batch: dict, sd: dict, cfg: Cfg, dtype=torch.float32, device='
     return {k: torch.cat([o[k] for o in outs]) for k in outs[0]}
 
 
+def rotate_probe(probe: torch.Tensor, j: int, repeat: int) -> torch.Tensor:
+    """rotate_envmap's shift_image applied to the probe (relight_utils.py:55-103): (eH,eW,3) -> (eH,eW,3)."""
+    image = probe[None]
+    B, H, W = image.shape[:3]
+    shift = W / (W * repeat) * j
+    i, jj = torch.meshgrid(torch.arange(0, H, device=image.device), torch.arange(0, W, device=image.device), indexing='ij')
+    grid = torch.stack([jj, i], dim=-1)[None].expand(B, H, W, 2).float() + 0.5
+    grid = grid.clone()
+    grid[..., 0] = grid[..., 0] + shift
+    grid[..., 0] = grid[..., 0] % W
+    grid[..., 0] = grid[..., 0] / W * 2 - 1
+    grid[..., 1] = grid[..., 1] / H * 2 - 1
+    return F.grid_sample(image.permute(0, 3, 1, 2), grid, align_corners=False, mode='bilinear', padding_mode='border').permute(0, 2, 3, 1)[0]
+
+
 def assemble_image(batch: dict, rgb_map: torch.Tensor) -> torch.Tensor:
     """Ray -> image scatter (base_visualizer.py:182-202), background 0."""
     mask = torch.as_tensor(batch['mask_at_box'][0])

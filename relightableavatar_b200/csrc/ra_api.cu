@@ -598,7 +598,7 @@ extern "C" int ra_relight_envmaps(ra_handle* h, const float* probes, int32_t n_e
     if (!c.relight || h->last_ray_o == nullptr) { h->err = "ra_relight_envmaps needs a preceding ra_render_relight"; return 1; }
     int64_t P = h->last_P;
     int L = c.env_h * c.env_w;
-    for (int e = 0; e < n_env; e++) {
+    for (int e = 0; e < n_env; e++) {      // background pixels: rgb = shade = 0, spec = probe-dependent constant (all-zero inputs)
         const float* probe = probes + (size_t)e * L * 3;
         float* r = rgb ? rgb + (size_t)e * P * 3 : nullptr;
         float* s = shade ? shade + (size_t)e * P * 3 : nullptr;
@@ -609,9 +609,13 @@ extern "C" int ra_relight_envmaps(ra_handle* h, const float* probes, int32_t n_e
             LAUNCH(h, k_bg_spec, 1, 32, 0, st, h->lxyz, h->larea, L, probe, c.env_h, c.env_w, c.fresnel_f0, h->bg_spec);
             LAUNCH(h, k_fill3, grid_for(h, P * 3), 256, 0, st, p, h->bg_spec, (long long)P);
         }
-        if (P)
-            LAUNCH(h, k_shade, grid_for(h, P * 32, 256, 8), 256, 0, st, h->cnt.n_fg, h->fg_ray, h->last_ray_o, h->surf, h->acc, h->fm, h->lvis,
-                   h->ldot, h->lxyz, h->larea, L, probe, c.env_h, c.env_w, c.fresnel_f0, c.shading_albedo, 1, 0, r, s, p);
+    }
+    for (int e0 = 0; e0 < n_env && P; e0 += RA_SHADE_MULTI) {      // foreground: up to 4 probes per pass over the visibility maps
+        int ne = std::min(RA_SHADE_MULTI, n_env - e0);
+        LAUNCH(h, k_shade_multi, grid_for(h, P * 32, 256, 8), 256, 0, st, h->cnt.n_fg, h->fg_ray, h->last_ray_o, h->surf, h->acc, h->fm, h->lvis,
+               h->ldot, h->lxyz, h->larea, L, probes + (size_t)e0 * L * 3, ne, c.env_h, c.env_w, c.fresnel_f0, c.shading_albedo,
+               rgb ? rgb + (size_t)e0 * P * 3 : nullptr, shade ? shade + (size_t)e0 * P * 3 : nullptr,
+               spec ? spec + (size_t)e0 * P * 3 : nullptr, (long long)P);
     }
     CK(cudaGetLastError());
     return 0;
@@ -732,5 +736,14 @@ extern "C" int ra_debug_tc_timeline(ra_handle* h, unsigned long long* out, int e
     }
     CK(cudaDeviceSynchronize());
     if (h->tc.dbg && out) CK(cudaMemcpy(out, h->tc.dbg, 18 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+/* rotate_envmap (relight_utils.py:55-103) for a sweep: out (n_rot,16,32,3) = probe shifted by j0..j0+n_rot-1 of env_w*repeat steps */
+extern "C" int ra_rotate_probes(ra_handle* h, const float* probe, int32_t repeat, int32_t j0, int32_t n_rot, float* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (repeat <= 0 || n_rot <= 0) { h->err = "ra_rotate_probes: repeat and n_rot must be positive"; return 1; }
+    LAUNCH(h, k_shift_probe, grid_for(h, (long long)n_rot * h->cfg.env_h * h->cfg.env_w), 256, 0, st, probe, h->cfg.env_h, h->cfg.env_w, repeat, j0, n_rot, out);
+    CK(cudaGetLastError());
     return 0;
 }

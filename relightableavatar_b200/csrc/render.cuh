@@ -471,7 +471,9 @@ __device__ __forceinline__ float sd_div(float a, float b) {
 }
 
 // bilinear env-map fetch, grid_sample(align_corners=False, padding_mode='border')   relight_utils.py:106-127
-__device__ __forceinline__ float3 envmap_fetch(const float* __restrict__ img, int H, int W, float3 d) {
+// split into the probe-independent tap computation and the per-probe gather
+struct EnvTap { int o00, o01, o10, o11; float w00, w01, w10, w11; };
+__device__ __forceinline__ EnvTap envmap_tap(int H, int W, float3 d) {
     const float PI = 3.14159265358979323846f;
     float theta = acosf(d.z) - 1e-6f;
     float phi = atan2f(d.y, d.x);
@@ -482,14 +484,22 @@ __device__ __forceinline__ float3 envmap_fetch(const float* __restrict__ img, in
     int x0 = (int)floorf(ix), y0 = (int)floorf(iy);
     float fx = ix - x0, fy = iy - y0;
     int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-    float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
-    if (x0 + 1 > W - 1) { w01 = 0.f; w11 = 0.f; }
-    if (y0 + 1 > H - 1) { w10 = 0.f; w11 = 0.f; }
-    const float* p00 = img + (y0 * W + x0) * 3; const float* p01 = img + (y0 * W + x1) * 3;
-    const float* p10 = img + (y1 * W + x0) * 3; const float* p11 = img + (y1 * W + x1) * 3;
-    return make3(p00[0] * w00 + p01[0] * w01 + p10[0] * w10 + p11[0] * w11,
-                 p00[1] * w00 + p01[1] * w01 + p10[1] * w10 + p11[1] * w11,
-                 p00[2] * w00 + p01[2] * w01 + p10[2] * w10 + p11[2] * w11);
+    EnvTap t;
+    t.w00 = (1.f - fx) * (1.f - fy); t.w01 = fx * (1.f - fy); t.w10 = (1.f - fx) * fy; t.w11 = fx * fy;
+    if (x0 + 1 > W - 1) { t.w01 = 0.f; t.w11 = 0.f; }
+    if (y0 + 1 > H - 1) { t.w10 = 0.f; t.w11 = 0.f; }
+    t.o00 = (y0 * W + x0) * 3; t.o01 = (y0 * W + x1) * 3; t.o10 = (y1 * W + x0) * 3; t.o11 = (y1 * W + x1) * 3;
+    return t;
+}
+__device__ __forceinline__ float3 envmap_gather(const float* __restrict__ img, const EnvTap& t) {
+    const float* p00 = img + t.o00; const float* p01 = img + t.o01; const float* p10 = img + t.o10; const float* p11 = img + t.o11;
+    return make3(p00[0] * t.w00 + p01[0] * t.w01 + p10[0] * t.w10 + p11[0] * t.w11,
+                 p00[1] * t.w00 + p01[1] * t.w01 + p10[1] * t.w10 + p11[1] * t.w11,
+                 p00[2] * t.w00 + p01[2] * t.w01 + p10[2] * t.w10 + p11[2] * t.w11);
+}
+__device__ __forceinline__ float3 envmap_fetch(const float* __restrict__ img, int H, int W, float3 d) {
+    EnvTap t = envmap_tap(H, W, d);
+    return envmap_gather(img, t);
 }
 
 // Microfacet (cancel_cosine=True): returns the scalar specular term and the lambert cosine factor l.n / pi
@@ -585,6 +595,93 @@ __global__ void k_shade(const int* __restrict__ n_fg, const int* __restrict__ fg
                 if (shade) shade[ray * 3 + c] = cs[c] * shading_albedo / PI * om;
                 if (spec) spec[ray * 3 + c] = cp[c];
             }
+        }
+    }
+}
+
+// ---- env-map rotation sweep -------------------------------------------------------------------------------
+// rotate_envmap's shift_image on the probe (relight_utils.py:55-103): bilinear shift along the longitude axis by
+// `shift` = eW / (eW*repeat) * j texels, wrap-around of the sample position, border clamp of the interpolation.
+// out[r][y][x][c] for r in [0, n_rot): j = j0 + r.
+__global__ void k_shift_probe(const float* __restrict__ probe, int H, int W, int repeat, int j0, int n_rot, float* out) {
+    int total = n_rot * H * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int x = i % W, y = (i / W) % H, r = i / (W * H);
+        float shift = (float)W / (float)(W * repeat) * (float)(j0 + r);
+        float gx = fmodf((float)x + 0.5f + shift, (float)W);
+        float nx = gx / (float)W * 2.f - 1.f;                       // the reference normalises, grid_sample un-normalises
+        float ix = ((nx + 1.f) * W - 1.f) / 2.f;
+        ix = clampf(ix, 0.f, (float)(W - 1));
+        int x0 = (int)floorf(ix);
+        float fx = ix - x0;
+        int x1 = min(x0 + 1, W - 1);
+        float w1 = (x0 + 1 > W - 1) ? 0.f : fx;
+        const float* p0 = probe + (y * W + x0) * 3; const float* p1 = probe + (y * W + x1) * 3;
+        for (int c = 0; c < 3; c++) out[(size_t)i * 3 + c] = p0[c] * (1.f - fx) + p1[c] * w1;
+    }
+}
+
+// Light sum for up to 4 probes of equal size at once: geometry, BRDF and visibility terms do not depend on the probe,
+// so a sweep over many env-maps (rotations) pays for them once per 4 probes and reads the (S_fg, L) visibility once.
+#define RA_SHADE_MULTI 4
+__global__ void k_shade_multi(const int* __restrict__ n_fg, const int* __restrict__ fg_ray, const float* __restrict__ ray_o,
+                              const float* __restrict__ surf_ray, const float* __restrict__ acc_ray, FgMaps fm,
+                              const float* __restrict__ lvis, const float* __restrict__ ldot, const float* __restrict__ lxyz,
+                              const float* __restrict__ larea, int L, const float* __restrict__ probes, int n_probe, int eh, int ew,
+                              float f0, float shading_albedo, float* rgb, float* shade, float* spec, long long P) {
+    const float PI = 3.14159265358979323846f;
+    int lane = threadIdx.x & 31;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    int n = *n_fg;
+    const int psz = eh * ew * 3;
+    for (int f = warp; f < n; f += nwarps) {
+        int ray = fg_ray[f];
+        float a = acc_ray[ray];
+        float3 sp = make3(surf_ray[ray * 3] * a, surf_ray[ray * 3 + 1] * a, surf_ray[ray * 3 + 2] * a);   // premultiplied inputs (a19)
+        float3 ro = make3(ray_o[ray * 3], ray_o[ray * 3 + 1], ray_o[ray * 3 + 2]);
+        float3 nr = make3(fm.norm[f * 3] * a, fm.norm[f * 3 + 1] * a, fm.norm[f * 3 + 2] * a);
+        float al[3] = {fm.albedo[f * 3] * a, fm.albedo[f * 3 + 1] * a, fm.albedo[f * 3 + 2] * a};
+        float rough = fm.rough[f] * a;
+        float3 s2c = normalize_ref(ro - sp);
+        float cr[RA_SHADE_MULTI][3], cs[RA_SHADE_MULTI][3], cp[RA_SHADE_MULTI][3];
+#pragma unroll
+        for (int e = 0; e < RA_SHADE_MULTI; e++)
+            for (int c = 0; c < 3; c++) { cr[e][c] = 0.f; cs[e][c] = 0.f; cp[e][c] = 0.f; }
+        for (int l = lane; l < L; l += 32) {
+            float3 s2l = normalize_ref(make3(lxyz[l * 3] - sp.x, lxyz[l * 3 + 1] - sp.y, lxyz[l * 3 + 2] - sp.z));
+            float sp_term, lk;
+            microfacet_eval(s2l, s2c, nr, rough, f0, sp_term, lk);
+            float lv = lvis[(size_t)f * L + l] * a, ld = ldot[(size_t)f * L + l] * a;
+            float ar = larea[l];
+            const EnvTap tap = envmap_tap(eh, ew, s2l);
+#pragma unroll
+            for (int e = 0; e < RA_SHADE_MULTI; e++) {
+                if (e < n_probe) {
+                    float3 li = envmap_gather(probes + (size_t)e * psz, tap);
+                    float lic[3] = {li.x, li.y, li.z};
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        float brdf = sp_term + al[c] * lk;
+                        float sh = lv * 1.f * ar * lic[c];
+                        cr[e][c] += brdf * sh;
+                        cs[e][c] += lv * ld * ar * lic[c];
+                        cp[e][c] += sp_term * (1.f * ar * lic[c]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < RA_SHADE_MULTI; e++) {
+            if (e >= n_probe) break;
+            for (int c = 0; c < 3; c++) { cr[e][c] = warp_sum(cr[e][c]); cs[e][c] = warp_sum(cs[e][c]); cp[e][c] = warp_sum(cp[e][c]); }
+            if (lane == 0)
+                for (int c = 0; c < 3; c++) {
+                    size_t o = ((size_t)e * P + ray) * 3 + c;
+                    if (rgb) rgb[o] = linear2srgb(cr[e][c]);
+                    if (shade) shade[o] = cs[e][c] * shading_albedo / PI;
+                    if (spec) spec[o] = cp[e][c];
+                }
         }
     }
 }

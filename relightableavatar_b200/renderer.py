@@ -217,6 +217,14 @@ class Engine:
                         'ra_relight_envmaps')
         return rgb, shade, spec
 
+    def rotate_probes(self, probe: torch.Tensor, repeat: int, j0: int, n_rot: int) -> torch.Tensor:
+        """rotate_envmap / shift_image (relight_utils.py:55-103): (eh, ew, 3) -> (n_rot, eh, ew, 3)."""
+        probe = probe.to(device=self.device, dtype=torch.float32).reshape(self.config['env_h'], self.config['env_w'], 3).contiguous()
+        out = torch.empty(n_rot, self.config['env_h'], self.config['env_w'], 3, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_rotate_probes(self.h, _ptr(probe), int(repeat), int(j0), int(n_rot), _ptr(out), self._stream()), 'ra_rotate_probes')
+        return out
+
     def query_sdf(self, x: torch.Tensor, dist_th: Optional[float] = None, smooth: bool = True) -> torch.Tensor:
         x = x.to(device=self.device, dtype=torch.float32).reshape(-1, 3).contiguous()
         out = torch.empty(x.shape[0], device=self.device)

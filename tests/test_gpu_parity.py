@@ -211,3 +211,24 @@ def test_tile_sharded_equals_single_gpu_when_two_gpus():
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
                         '--master-port', '29533', os.path.join(root, 'tools', 'tile_shard_check.py')], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and 'TILE_SHARD_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_envmap_rotation_sweep_f4(relight_setup):
+    """rotate_envmap sweep -- shifted probes + batched re-shade vs the oracle's restatement."""
+    b, sd = relight_setup
+    cfg = O.Cfg()
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=8192, test_light=('main',), sync_timing=False)
+    r.render(b)
+    name, probe = next(iter(b['novel_lights'].items()))
+    probe = torch.as_tensor(probe[0])
+    repeat, n_rot = 4, 6
+    rot = r.engine.rotate_probes(probe, repeat, 3, n_rot)                       # j = 3..8
+    ref_rot = torch.stack([O.rotate_probe(probe, 3 + k, repeat) for k in range(n_rot)])
+    assert float((rot.cpu() - ref_rot).abs().max()) < 1e-5
+    P = b['ray_o'].shape[1]
+    rgb, shade, spec = r.engine.relight_envmaps(rot, P)
+    ref = O.render_novel_light(b, sd, cfg, {f'r{k}': ref_rot[k] for k in range(n_rot)}, torch.float32, DEV, include_main=False)
+    for k in range(n_rot):
+        for got, key in ((rgb, 'rgb_map'), (shade, 'shade_map'), (spec, 'spec_map')):
+            e = _err(got[k], ref[f'r{k}'][key])
+            assert torch.quantile(e.flatten(), 0.98) <= 1e-3, f'rot {k} {key}: {torch.quantile(e.flatten(), 0.98):.3e}'
