@@ -131,6 +131,10 @@ int ra_relight_envmaps(ra_handle* h, const float* probes, int32_t n_env, float* 
  * out (n_rot, env_h, env_w, 3) = probe (env_h, env_w, 3) shifted by j0 .. j0+n_rot-1 steps of 1/repeat texel along the longitude;
  * feed the result to ra_relight_envmaps. */
 int ra_rotate_probes(ra_handle* h, const float* probe, int32_t repeat, int32_t j0, int32_t n_rot, float* out, void* stream);
+/* Image assembly (lib/visualizers/base_visualizer.py:182-202): img = bg; img[mask_at_box] = rgb_map; alpha[mask_at_box] = acc_map.
+ * mask_at_box: H*W bytes; out_f (H,W,4) fp32 and/or out_u8 (H,W,4) = clip(.,0,1)*255; either may be NULL. */
+int ra_assemble_image(ra_handle* h, const float* rgb_map, const float* acc_map, const unsigned char* mask_at_box, int32_t H, int32_t W,
+                      float bg_brightness, float* out_f, unsigned char* out_u8, void* stream);
 /* sphere_tracing_renderer.Renderer.render for the AniSDF network (config 1; raw 16-ch branch :634-635). */
 int ra_render_anisdf_trace(ra_handle* h, const float* ray_o, const float* ray_d, const float* near, const float* far,
                            int64_t P, const ra_outputs* out, void* stream);

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, 'libra_b200.so')
 
 EXPORTS = ['ra_create', 'ra_destroy', 'ra_last_error', 'ra_upload_weights', 'ra_set_frame', 'ra_render_relight',
            'ra_relight_envmaps', 'ra_render_anisdf_trace', 'ra_render_anisdf_volume', 'ra_query_sdf', 'ra_query_raw',
-           'ra_get_stats', 'ra_launch_count', 'ra_profile_enable', 'ra_profile_read', 'ra_rotate_probes']
+           'ra_get_stats', 'ra_launch_count', 'ra_profile_enable', 'ra_profile_read', 'ra_rotate_probes', 'ra_assemble_image']
 
 fp = C.POINTER(C.c_float)
 
@@ -78,6 +78,7 @@ def load():
     lib.ra_query_raw.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.ra_get_stats.argtypes = [vp, C.POINTER(ra_stats)]
     lib.ra_launch_count.argtypes = [vp]; lib.ra_launch_count.restype = i64
+    lib.ra_assemble_image.argtypes = [vp, vp, vp, vp, i32, i32, f32, vp, vp, vp]
     lib.ra_rotate_probes.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     lib.ra_profile_enable.argtypes = [vp, i32]
     lib.ra_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]

@@ -86,6 +86,7 @@ struct ra_handle {
     int* counters_blk = nullptr;     // n_fg, n_shadow, n_attr, q.count, (pad), n_queries(ull), n_inshell(ull)
     float *pt_smpl = nullptr; int* pt_slot = nullptr;     // ra_query_sdf scratch
     float* bg_spec = nullptr;
+    int* blk_cnt = nullptr; int64_t blk_cap = 0;      // image assembly scratch
     // ---- fp32 MLP chunk buffers
     float *Xr0, *ra_[8], *Xr4, *z8, *resd_o, *cpts_o, *Xs0, *sb_[8], *Xs4, *out257, *GA, *GB, *dpe0, *dpes, *gcp, *u4, *gbp, *nrm_o;
     float *hd1, *hd2, *head_a, *head_r, *Xrn, *rn1, *rn2;
@@ -744,6 +745,20 @@ extern "C" int ra_rotate_probes(ra_handle* h, const float* probe, int32_t repeat
     cudaStream_t st = (cudaStream_t)stream;
     if (repeat <= 0 || n_rot <= 0) { h->err = "ra_rotate_probes: repeat and n_rot must be positive"; return 1; }
     LAUNCH(h, k_shift_probe, grid_for(h, (long long)n_rot * h->cfg.env_h * h->cfg.env_w), 256, 0, st, probe, h->cfg.env_h, h->cfg.env_w, repeat, j0, n_rot, out);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+/* Visualizer.generate_image's ray -> image scatter (base_visualizer.py:182-202) + alpha channel + optional 8-bit quantisation.
+ * mask_at_box: H*W bytes (0/1); rgb_map (P,3), acc_map (P) in ray order; out_f (H,W,4) float and/or out_u8 (H,W,4) may be NULL. */
+extern "C" int ra_assemble_image(ra_handle* h, const float* rgb_map, const float* acc_map, const unsigned char* mask_at_box, int32_t H,
+                                 int32_t W, float bg_brightness, float* out_f, unsigned char* out_u8, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int n = H * W, nb = (n + 255) / 256;
+    if (nb > h->blk_cap) { if (h->blk_cnt) cudaFree(h->blk_cnt); CK(dalloc(&h->blk_cnt, (size_t)nb)); h->blk_cap = nb; }
+    LAUNCH(h, k_mask_count, nb, 256, 0, st, mask_at_box, n, h->blk_cnt);
+    LAUNCH(h, k_scan_blocks, 1, 1024, 0, st, h->blk_cnt, nb);
+    LAUNCH(h, k_assemble, nb, 256, 0, st, mask_at_box, n, h->blk_cnt, rgb_map, acc_map, bg_brightness, out_f, out_u8);
     CK(cudaGetLastError());
     return 0;
 }

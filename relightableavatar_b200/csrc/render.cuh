@@ -751,3 +751,58 @@ __global__ void k_volume_blend(const float* __restrict__ raw, int C, int n_sampl
         if (om.depth) om.depth[ray] = dep;
     }
 }
+
+// ---- image assembly: ray -> image scatter with alpha channel and 8-bit quantisation ----------------------
+// Visualizer.generate_image (lib/visualizers/base_visualizer.py:182-202): img = bg_brightness; img[mask_at_box] = rgb_map;
+// alpha[mask_at_box] = acc_map; RGBA.  Rays are the masked pixels in row-major order, so the ray of a pixel is its rank
+// among the masked pixels: per-block counts -> single-block scan -> in-block ballot rank.
+__global__ void k_mask_count(const unsigned char* __restrict__ mask, int n, int* blk_cnt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = __syncthreads_count(i < n && mask[i] != 0);
+    if (threadIdx.x == 0) blk_cnt[blockIdx.x] = c;
+}
+__global__ void k_scan_blocks(int* blk_cnt, int nb) {          // one block: exclusive scan in place
+    __shared__ int carry;
+    __shared__ int wsum[32];
+    int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += blockDim.x) {
+        int i = base + tid;
+        int v = (i < nb) ? blk_cnt[i] : 0, x = v;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int s = (lane < (blockDim.x >> 5)) ? wsum[lane] : 0;
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        int excl = carry + (wid ? wsum[wid - 1] : 0) + x - v;
+        if (i < nb) blk_cnt[i] = excl;
+        __syncthreads();
+        if (tid == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+}
+__global__ void k_assemble(const unsigned char* __restrict__ mask, int n, const int* __restrict__ blk_off, const float* __restrict__ rgb,
+                           const float* __restrict__ acc, float bg, float* out_f, unsigned char* out_u8) {
+    __shared__ int wcnt[32];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    bool m = i < n && mask[i] != 0;
+    unsigned bal = __ballot_sync(0xffffffffu, m);
+    if (lane == 0) wcnt[wid] = __popc(bal);
+    __syncthreads();
+    int base = blk_off[blockIdx.x];
+    for (int w = 0; w < wid; w++) base += wcnt[w];
+    int ray = base + __popc(bal & ((1u << lane) - 1u));
+    if (i >= n) return;
+    float v[4] = {bg, bg, bg, 0.f};
+    if (m) { v[0] = rgb[ray * 3]; v[1] = rgb[ray * 3 + 1]; v[2] = rgb[ray * 3 + 2]; v[3] = acc[ray]; }
+    for (int c = 0; c < 4; c++) {
+        if (out_f) out_f[(size_t)i * 4 + c] = v[c];
+        if (out_u8) out_u8[(size_t)i * 4 + c] = (unsigned char)(clampf(v[c], 0.f, 1.f) * 255.f);     // (img.clip(0,1) * 255).astype(uint8)
+    }
+}

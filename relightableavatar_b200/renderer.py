@@ -225,6 +225,19 @@ class Engine:
             self._check(self.lib.ra_rotate_probes(self.h, _ptr(probe), int(repeat), int(j0), int(n_rot), _ptr(out), self._stream()), 'ra_rotate_probes')
         return out
 
+    def assemble_image(self, rgb_map: torch.Tensor, acc_map: torch.Tensor, mask_at_box: torch.Tensor, bg_brightness: float = 0.0):
+        """Visualizer.generate_image's scatter (base_visualizer.py:182-202): -> (H,W,4) float RGBA and (H,W,4) uint8."""
+        mask = torch.as_tensor(mask_at_box).to(self.device).reshape(mask_at_box.shape[-2], mask_at_box.shape[-1]).to(torch.uint8).contiguous()
+        H, W = mask.shape
+        rgb = rgb_map.to(device=self.device, dtype=torch.float32).reshape(-1, 3).contiguous()
+        acc = acc_map.to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
+        out_f = torch.empty(H, W, 4, device=self.device)
+        out_u8 = torch.empty(H, W, 4, device=self.device, dtype=torch.uint8)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_assemble_image(self.h, _ptr(rgb), _ptr(acc), _ptr(mask), H, W, float(bg_brightness), _ptr(out_f), _ptr(out_u8),
+                                                   self._stream()), 'ra_assemble_image')
+        return out_f, out_u8
+
     def query_sdf(self, x: torch.Tensor, dist_th: Optional[float] = None, smooth: bool = True) -> torch.Tensor:
         x = x.to(device=self.device, dtype=torch.float32).reshape(-1, 3).contiguous()
         out = torch.empty(x.shape[0], device=self.device)

@@ -232,3 +232,16 @@ def test_envmap_rotation_sweep_f4(relight_setup):
         for got, key in ((rgb, 'rgb_map'), (shade, 'shade_map'), (spec, 'spec_map')):
             e = _err(got[k], ref[f'r{k}'][key])
             assert torch.quantile(e.flatten(), 0.98) <= 1e-3, f'rot {k} {key}: {torch.quantile(e.flatten(), 0.98):.3e}'
+
+
+def test_image_assembly_f3(relight_setup):
+    """ray -> image scatter + alpha + 8-bit, against the restated base_visualizer logic (exact)."""
+    b, sd = relight_setup
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=8192, test_light=('main',), sync_timing=False)
+    main = r.render(b)['main']
+    img_f, img_u8 = r.engine.assemble_image(main['rgb_map'][0], main['acc_map'][0], torch.as_tensor(b['mask_at_box'][0]))
+    ref_rgb = O.assemble_image(b, main['rgb_map'][0].cpu())
+    ref_a = O.assemble_image(b, main['acc_map'][0].cpu()[:, None])
+    ref = torch.cat([ref_rgb, ref_a], -1)
+    assert torch.equal(img_f.cpu(), ref)
+    assert torch.equal(img_u8.cpu(), (ref.clip(0, 1) * 255).to(torch.uint8))
