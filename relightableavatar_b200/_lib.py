@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libra_b200.so')
+LIB_PATH = os.environ.get('RA_LIB_PATH') or os.path.join(HERE, 'libra_b200.so')      # RA_LIB_PATH: instrumented debug builds (tools/)
 
 EXPORTS = ['ra_create', 'ra_destroy', 'ra_last_error', 'ra_upload_weights', 'ra_set_frame', 'ra_render_relight',
            'ra_relight_envmaps', 'ra_render_anisdf_trace', 'ra_render_anisdf_volume', 'ra_query_sdf', 'ra_query_raw',

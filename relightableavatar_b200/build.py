@@ -28,18 +28,22 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in DEPS if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = True) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = True, extra=(), out: str = OUT) -> str:
+    """`extra` / `out`: instrumented debug builds (e.g. extra=['-DRA_TC_TIMELINE'], out='.../libra_b200_tl.so')."""
+    if not force and out == OUT and not needs_build():
         return OUT
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-lcuda', '-o', OUT, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ['-lcuda', '-o', out, SRC]
     if verbose:
         print(' '.join(cmd), flush=True)
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + r.stdout)
-    return OUT
+    return out
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv))
+    if '--timeline' in sys.argv:
+        print(build(force=True, extra=['-DRA_TC_TIMELINE'], out=os.path.join(HERE, 'libra_b200_tl.so')))
+    else:
+        print(build(force='--force' in sys.argv))

@@ -155,16 +155,38 @@ __device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_
     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
 }
 // ---- half2 epilogue math -------------------------------------------------------------------------------
-// softplus_100(z) = max(z, 0) + g(|z|),  g(a) = log1p(exp(-100 a)) / 100  in (0, 0.00693].
-// g is evaluated in half2: e = 2^(-144.27 a) (one MUFU.EX2.F16x2 per PAIR), log1p(e)/100 ~ e (c1 + c2 e + c3 e^2),
-// max abs error 5.4e-6 -- below the fp16 quantisation of the activations this value is rounded to anyway.
-__device__ __forceinline__ uint32_t h2_softplus100(float a, float b) {
-    const __half2 z = __floats2half2_rn(a, b);
-    const __half2 az = __habs2(z);
-    const __half2 e = h2exp2(__hmul2(az, __float2half2_rn(-144.269504f)));
+// softplus_100(z) = max(z, 0) + g(|z|),  g(a) = log1p(exp(-100 a)) / 100  in (0, 0.00693], evaluated in half2.
+// Two evaluations of g (RA_SP_MODE selects; pairs = adjacent accumulator columns):
+//   exp  : e = 2^(-144.27 a) by the native ex2.approx.f16x2 (two MUFU.EX2.F16 + a PRMT), g ~ e (c1 + c2 e + c3 e^2).
+//          MUFU-bound: 2 MUFU per pair at 16 / clk / SM = 2048 clk per 128 x 256 tile, more than the tile's MMAs (2176).
+//   poly : w = max(1 - a / 0.075, 0), g ~ w (c1 + w (c2 + w (c3 + w (c4 + w c5)))): 6 HFMA2, no MUFU.
+//   mixed: even pairs exp, odd pairs poly -- balances the xu and fma pipes.
+// Emulated end to end on the fitted SDF net (fp16 operands / activations, fp32 accumulate, 40 k points near the surface):
+// mean |sdf error| 3.7e-5 with an exact softplus, 8.8e-5 exp, 5.3e-5 poly, 6.8e-5 mixed -- all at the fp16 operand floor.
+#ifndef RA_SP_MODE
+#define RA_SP_MODE 1      // measured (k_mlp_tc6 softplus-layer epilogue, clk per tile): exp 2600, mixed 2250, poly 2030
+#endif
+__device__ __forceinline__ __half2 h2_sp_exp(const __half2 z) {
+    const __half2 t = __hmul2(__habs2(z), __float2half2_rn(-144.269504f));
+    uint32_t eu;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(eu) : "r"(*reinterpret_cast<const uint32_t*>(&t)));
+    const __half2 e = *reinterpret_cast<const __half2*>(&eu);
     __half2 p = __hfma2(e, __float2half2_rn(0.0011465454f), __float2half2_rn(-0.0040842847f));
     p = __hfma2(p, e, __float2half2_rn(0.0098745818f));
-    const __half2 r = __hfma2(p, e, __hmax2(z, __float2half2_rn(0.f)));
+    return __hfma2(p, e, __hmax2(z, __float2half2_rn(0.f)));
+}
+__device__ __forceinline__ __half2 h2_sp_poly(const __half2 z) {
+    const __half2 w = __hmax2(__hfma2(__habs2(z), __float2half2_rn(-1.f / 0.075f), __float2half2_rn(1.f)), __float2half2_rn(0.f));
+    __half2 p = __hfma2(w, __float2half2_rn(0.01282501220703125f), __float2half2_rn(-0.006336212158203125f));
+    p = __hfma2(p, w, __float2half2_rn(-0.0011892318725585938f));
+    p = __hfma2(p, w, __float2half2_rn(0.001796722412109375f));
+    p = __hfma2(p, w, __float2half2_rn(-0.00015354156494140625f));
+    return __hfma2(p, w, __hmax2(z, __float2half2_rn(0.f)));
+}
+// `odd`: parity of the pair index (column / 2) -- compile-time at every call site
+__device__ __forceinline__ uint32_t h2_softplus100(float a, float b, bool odd) {
+    const __half2 z = __floats2half2_rn(a, b);
+    const __half2 r = (RA_SP_MODE == 1 || (RA_SP_MODE == 2 && odd)) ? h2_sp_poly(z) : h2_sp_exp(z);
     return *reinterpret_cast<const uint32_t*>(&r);
 }
 __device__ __forceinline__ uint32_t h2_relu(float a, float b) {
@@ -241,7 +263,7 @@ __device__ __forceinline__ void epi_hidden(uint32_t t_lane, uint32_t s_act, int 
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 float a = __uint_as_float(cur[g * 8 + 2 * j]), b = __uint_as_float(cur[g * 8 + 2 * j + 1]);
-                h[j] = SOFTPLUS ? h2_softplus100(a, b) : h2_relu(a, b);
+                h[j] = SOFTPLUS ? h2_softplus100(a, b, j & 1) : h2_relu(a, b);
             }
             st_shared_v4(s_act + (uint32_t)((c0 >> 3) + g) * 2048u + (uint32_t)row * 16u, h[0], h[1], h[2], h[3]);
         }
@@ -393,7 +415,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(const __grid_constant_
                         for (int j = 0; j < 8; j++) v[j] = __uint_as_float(o ? r[8 + j] : r[j]);
                         uint32_t h[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) h[j] = h2_softplus100(v[2 * j], v[2 * j + 1]);
+                        for (int j = 0; j < 4; j++) h[j] = h2_softplus100(v[2 * j], v[2 * j + 1], j & 1);
                         if (c0 == 200) {      // cols 248..255: outputs 200..204 then PE8 features 48,49,50
                             float p48 = pe_feature(cp, 48), p49 = pe_feature(cp, 49), p50 = pe_feature(cp, 50);
                             h[2] = (h[2] & 0x0000FFFFu) | (pack_h2(0.f, p48) & 0xFFFF0000u);

@@ -29,11 +29,13 @@ struct Tc2Params {
     float* out;
     const int* count;
     float resd_limit;
+    unsigned long long* dbg;   // optional timeline (debug builds, tools/tc6_timeline.py)
 };
 struct Tc2Weights {
     unsigned char* blob = nullptr;
     Tc2Params p{};
     bool ready = false;
+    unsigned long long* dbg = nullptr;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -46,7 +48,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
         "{\n\t"
         ".reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"      // default .release.cta (a cluster-scope release costs ~1000+ clk per arrive)
         "}" ::"r"(local_bar), "r"(cta) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -54,7 +56,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         "{\n\t"
         ".reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1, 0x4000;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x4000;\n\t"
         "@P1 bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t"
@@ -222,7 +224,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 2) k_mlp
                         for (int j = 0; j < 8; j++) v[j] = __uint_as_float(o ? r[8 + j] : r[j]);
                         uint32_t h[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) h[j] = h2_softplus100(v[2 * j], v[2 * j + 1]);
+                        for (int j = 0; j < 4; j++) h[j] = h2_softplus100(v[2 * j], v[2 * j + 1], j & 1);
                         if (c0 == 200) {
                             float p48 = pe_feature(cp, 48), p49 = pe_feature(cp, 49), p50 = pe_feature(cp, 50);
                             h[2] = (h[2] & 0x0000FFFFu) | (pack_h2(0.f, p48) & 0xFFFF0000u);
@@ -381,7 +383,7 @@ static void tc2_set_frame(Tc2Weights& t, const FrameConst* fc, cudaStream_t st, 
 static void tc2_distance(Tc2Weights& t, const float* bpts, float* out, const int* count, float resd_limit, int sms, cudaStream_t st,
                          int64_t& launches) {
     Tc2Params p = t.p;
-    p.bpts = bpts; p.out = out; p.count = count; p.resd_limit = resd_limit;
+    p.bpts = bpts; p.out = out; p.count = count; p.resd_limit = resd_limit; p.dbg = nullptr;
     k_mlp_tc2<<<2 * sms, TC_THREADS, TC2_SMEM_BYTES, st>>>(p);      // 148 clusters of 2 CTAs (compile-time __cluster_dims__)
     launches++;
 }

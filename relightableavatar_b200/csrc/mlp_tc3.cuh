@@ -164,7 +164,7 @@ __global__ void __cluster_dims__(TC3_CS, 1, 1) __launch_bounds__(TC_THREADS, 2) 
                         for (int j = 0; j < 8; j++) v[j] = __uint_as_float(o ? r[8 + j] : r[j]);
                         uint32_t h[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) h[j] = h2_softplus100(v[2 * j], v[2 * j + 1]);
+                        for (int j = 0; j < 4; j++) h[j] = h2_softplus100(v[2 * j], v[2 * j + 1], j & 1);
                         if (c0 == 200) {      // cols 248..255: outputs 200..204 then PE8 features 48,49,50
                             float p48 = pe_feature(cp, 48), p49 = pe_feature(cp, 49), p50 = pe_feature(cp, 50);
                             h[2] = (h[2] & 0x0000FFFFu) | (pack_h2(0.f, p48) & 0xFFFF0000u);

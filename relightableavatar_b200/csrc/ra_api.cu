@@ -21,6 +21,7 @@
 #include "mlp_tc3.cuh"
 #include "mlp_tc4.cuh"
 #include "mlp_tc5.cuh"
+#include "mlp_tc6.cuh"
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -62,7 +63,7 @@ struct ra_handle {
     TcWeights tc;                    // fp16 UMMA images for the tcgen05 path
     Tc2Weights tc2;                  // ... and for its 2-CTA (cta_group::2) variant
     int attr_tc = 1;                 // env RA_ATTR_TC: 1 = 3xTF32 tensor-core GEMMs in the fp32 MLP path, 0 = CUDA-core SGEMM
-    int tc_variant = 1;              // env RA_TC_VARIANT: 1 = single-CTA kernel, 2 = CTA-pair kernel
+    int tc_variant = 6;              // env RA_TC_VARIANT: 6 = CTA-pair two-slot kernel k_mlp_tc6 (default); 1 = single-CTA kernel; 2-5 = experiments
     // ---- frame
     FrameConst* fc = nullptr;
     SortedVerts sv{};
@@ -224,6 +225,7 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     if (tc3_init(h->err)) return 1;
     if (tc4_init(h->err)) return 1;
     if (tc5_init(h->err)) return 1;
+    if (tc6_init(h->err)) return 1;
     if (const char* e = getenv("RA_TC_VARIANT")) h->tc_variant = atoi(e);
     if (const char* e = getenv("RA_ATTR_TC")) h->attr_tc = atoi(e);
     return 0;
@@ -331,7 +333,7 @@ extern "C" int ra_set_frame(ra_handle* h, const ra_frame* f, void* stream) {
     LAUNCH(h, k_grid_fill2, (N + 255) / 256, 256, 0, st, (const float4*)h->sv.pos, N, h->vert_cell, h->sv.cell_start2, h->cell_fill, h->sv.pos2);
     LAUNCH(h, k_grid_occ, 8, 256, 0, st, h->fc, h->sv.cell_start2, (const float4*)h->sv.pos2, h->sv.occ_lo, h->sv.occ_hi);
     if (h->cfg.precision == RA_PRECISION_TC) {
-        if (h->tc_variant == 2) tc2_set_frame(h->tc2, h->fc, st, h->launches);
+        if (h->tc_variant == 2 || h->tc_variant == 6) tc2_set_frame(h->tc2, h->fc, st, h->launches);
         else tc_set_frame(h->tc, h->fc, st, h->launches);
     }
     CK(cudaGetLastError());
@@ -471,7 +473,8 @@ static int distance_pass(ra_handle* h, cudaStream_t st, const QueryList* ql = nu
     const QueryList& q = ql ? *ql : h->q;
     if (h->cfg.precision == RA_PRECISION_TC) {
         if (h->prof) cudaEventRecord(prof_event(h->ev_mlp, h->ev_mlp_used), st);
-        if (h->tc_variant == 2) tc2_distance(h->tc2, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
+        if (h->tc_variant == 6) tc6_distance(h->tc2, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
+        else if (h->tc_variant == 2) tc2_distance(h->tc2, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         else if (h->tc_variant == 5) tc5_distance(h->tc, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         else if (h->tc_variant == 4) tc4_distance(h->tc, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         else if (h->tc_variant == 3) tc3_distance(h->tc, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
@@ -731,12 +734,13 @@ extern "C" int ra_debug_knn_stats(unsigned long long* out8, int reset) {
 // debug: per-layer clock64 timeline of CTA 0 of the fused MLP kernel (tools/tc_timeline.py)
 extern "C" int ra_debug_tc_timeline(ra_handle* h, unsigned long long* out, int enable) {
     if (enable) {
-        if (!h->tc.dbg) { CK(cudaMalloc((void**)&h->tc.dbg, 18 * 8 * sizeof(unsigned long long))); }
-        CK(cudaMemset(h->tc.dbg, 0, 18 * 8 * sizeof(unsigned long long)));
+        if (!h->tc.dbg) { CK(cudaMalloc((void**)&h->tc.dbg, 512 * sizeof(unsigned long long))); h->tc2.dbg = h->tc.dbg; }
+        CK(cudaMemset(h->tc.dbg, 0, 512 * sizeof(unsigned long long)));
         return 0;
     }
     CK(cudaDeviceSynchronize());
-    if (h->tc.dbg && out) CK(cudaMemcpy(out, h->tc.dbg, 18 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    // 18 x 8 entries for the single-CTA kernel; 36 x 8 ((layer, slot) x 8) for the pair kernel k_mlp_tc6
+    if (h->tc.dbg && out) CK(cudaMemcpy(out, h->tc.dbg, (h->tc_variant == 6 ? 512 : 18 * 8) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return 0;
 }
 
