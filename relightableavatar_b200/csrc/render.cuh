@@ -50,6 +50,10 @@ __global__ void k_trace_surface(int it, TraceCfg cfg, const FrameConst* __restri
         bool valid = i < P;
         float3 o = make3(0, 0, 0), d = make3(0, 0, 1);
         float nr = 0.f, fr = 0.f, t = 0.f, occ = 1.f, d0 = 1e9f, cd = 1e9f, dt = 1e9f, st = 0.f, off = cfg.offset, rlx = cfg.relax;
+        // A ray whose front did not move (t clamped at near / far: every ray that misses the body ends up parked at
+        // `far`) would query the very same point again and get the very same distance: reuse it (exact), skip the query.
+        bool parked = false;
+        float d_keep = 0.f;
         if (valid) {
             o = make3(ray_o[i * 3], ray_o[i * 3 + 1], ray_o[i * 3 + 2]);
             d = make3(ray_d[i * 3], ray_d[i * 3 + 1], ray_d[i * 3 + 2]);
@@ -73,20 +77,24 @@ __global__ void k_trace_surface(int it, TraceCfg cfg, const FrameConst* __restri
                 }
                 if (d1u < cd) { cd = d1u; st = t; }
                 dt = d1 + rlx * d1 + off;
+                const float t_old = t;
                 t = fmaxf(fminf(t + dt, fr), nr);
                 d0 = d1;
+                parked = (t == t_old);
+                d_keep = d1;
             }
         }
         if (it < cfg.iters) {
             HdqFront f; f.in_shell = false; f.smpl = 0.f;
-            hdq_front<false>(fc, sv, nverts, o + d * t, valid, cfg.th, cfg.blend_radius, f);
-            bool ins = valid && f.in_shell;
-            count_queries(cnt, valid, ins);
+            const bool ask = valid && !parked;
+            hdq_front<false>(fc, sv, nverts, o + d * t, ask, cfg.th, cfg.blend_radius, f);
+            bool ins = ask && f.in_shell;
+            count_queries(cnt, ask, ins);
             int slot = warp_append(q.count, ins);
             if (ins) { q.bpts[slot * 3] = f.bpts.x; q.bpts[slot * 3 + 1] = f.bpts.y; q.bpts[slot * 3 + 2] = f.bpts.z; }
             if (valid) {
                 s.t[i] = t; s.occ[i] = occ; s.d0[i] = d0; s.cd[i] = cd; s.dt[i] = dt; s.st[i] = st; s.off[i] = off; s.rlx[i] = rlx;
-                s.q_smpl[i] = f.smpl; s.q_slot[i] = slot;
+                s.q_smpl[i] = parked ? d_keep : f.smpl; s.q_slot[i] = parked ? -1 : slot;     // slot -1: q_smpl is the final distance
             }
         } else {
             float a = 1.f - occ;
@@ -177,6 +185,8 @@ __global__ void k_trace_shadow(int it, TraceCfg cfg, const FrameConst* __restric
         float3 o = make3(0, 0, 0), d = make3(0, 0, 1);
         float nr = 0.f, fr = 0.f, t = 0.f, occ = 1.f, d0 = 1e9f;
         int f = 0, l = 0;
+        bool parked = false;        // front did not move (t clamped): same point, same distance -- reuse, no query (exact)
+        float d_keep = 0.f;
         if (valid) {
             f = sr.fg[i]; l = sr.light[i];
             int ray = fg_ray[f];
@@ -207,20 +217,27 @@ __global__ void k_trace_shadow(int it, TraceCfg cfg, const FrameConst* __restric
                         if (c2 < occ) occ = c2;
                     }
                     float dt = d1 + rlx * d1 + off;
+                    const float t_old = t;
                     t = fmaxf(fminf(t + dt, fr), nr);
                     d0 = d1;
+                    parked = (t == t_old);
+                    d_keep = d1;
                 }
             }
         }
         const bool alive = valid && (occ > 0.f);
         if (it < cfg.iters) {
             HdqFront hf; hf.in_shell = false; hf.smpl = 0.f;
-            hdq_front<false>(fc, sv, nverts, o + d * t, alive, cfg.th, cfg.blend_radius, hf);
-            bool ins = alive && hf.in_shell;
-            count_queries(cnt, alive, ins);
+            const bool ask = alive && !parked;
+            hdq_front<false>(fc, sv, nverts, o + d * t, ask, cfg.th, cfg.blend_radius, hf);
+            bool ins = ask && hf.in_shell;
+            count_queries(cnt, ask, ins);
             int slot = warp_append(q.count, ins);
             if (ins) { q.bpts[(size_t)slot * 3] = hf.bpts.x; q.bpts[(size_t)slot * 3 + 1] = hf.bpts.y; q.bpts[(size_t)slot * 3 + 2] = hf.bpts.z; }
-            if (valid) { sr.t[i] = t; sr.occ[i] = occ; sr.d0[i] = d0; sr.q_smpl[i] = hf.smpl; sr.q_slot[i] = slot; }
+            if (valid) {
+                sr.t[i] = t; sr.occ[i] = occ; sr.d0[i] = d0;
+                sr.q_smpl[i] = (alive && parked) ? d_keep : hf.smpl; sr.q_slot[i] = (alive && parked) ? -1 : slot;
+            }
         } else if (valid) {
             lvis[(size_t)f * L + l] = occ;
         }
