@@ -72,6 +72,17 @@ class Cfg:
     shading_albedo: float = 0.8
     fix_material: int = 0
     knn_chunk: int = 16384
+    # ground-plane shading (row f2): cfg.env_lvis (config.py:135-141), cfg.ground_* (:45, :104-107, :353)
+    gl_iter: int = 16
+    gl_offset: float = 0.01
+    gl_relax: float = 0.0
+    gl_near: float = 0.02
+    gl_dist_th: float = 0.005
+    ground_normal: tuple = (0.0, 0.0, 1.0)
+    ground_origin: tuple = (0.0, 0.0, 0.0)
+    ground_albedo: tuple = (0.05, 0.05, 0.05)
+    ground_attach_envmap: bool = True
+    ground_shading_multiplier: float = 1.0
 
 
 def anisdf_cfg() -> Cfg:
@@ -327,8 +338,10 @@ def near_far_aabb(bounds: torch.Tensor, ray_o: torch.Tensor, ray_d: torch.Tensor
     return t1.max(-1)[0], t2.min(-1)[0]
 
 
-def light_visibility(surf, norm, acc, W: Weights, fr: Frame, cfg: Cfg, bbox: torch.Tensor):
-    """sphere_tracing_renderer.py:265-344 -> lvis, ldot of shape (512, S)."""
+def light_visibility(surf, norm, acc, W: Weights, fr: Frame, cfg: Cfg, bbox: torch.Tensor, lv: Optional[dict] = None):
+    """sphere_tracing_renderer.py:265-344 -> lvis, ldot of shape (512, S).  `lv` overrides the obj_lvis tracing
+    parameters (iter, offset, relax, near, dist_th) -- render_ground passes cfg.env_lvis."""
+    lv = lv or dict(iter=cfg.lv_iter, offset=cfg.lv_offset, relax=cfg.lv_relax, near=cfg.lv_near, dist_th=cfg.lv_dist_th)
     S = surf.shape[0]
     L = W.light_xyz.reshape(-1, 3)
     ldir = normalize(L)                                                     # (512,3)
@@ -337,13 +350,18 @@ def light_visibility(surf, norm, acc, W: Weights, fr: Frame, cfg: Cfg, bbox: tor
     li, pi = lfrt.nonzero(as_tuple=True)
     ro, rd = surf[pi], ldir[li]
     near, far = near_far_aabb(bbox, ro, rd)
-    near, far = near[:, None].clip(cfg.lv_near), far[:, None].clip(cfg.lv_near)
+    near, far = near[:, None].clip(lv['near']), far[:, None].clip(lv['near'])
     lbox_sub = (near < far)[:, 0]
     ro, rd, near, far = ro[lbox_sub], rd[lbox_sub], near[lbox_sub], far[lbox_sub]
     tan_i = W.light_sharp.reshape(-1)[li][lbox_sub][:, None]
-    sdf_fn = lambda x: hdq_distance(x, fr, W, cfg, cfg.lv_dist_th, True)
-    _, _, occ, _, _ = sphere_tracing(ro, rd, near, far, sdf_fn, cfg.lv_iter, tan_i, cfg.lv_relax, cfg.lv_offset,
-                                     cfg.st_eps, cfg.st_skip, soft=True)
+    sdf_fn = lambda x: hdq_distance(x, fr, W, cfg, lv['dist_th'], True)
+    occ_parts = []
+    for s0 in range(0, ro.shape[0], 1 << 20):                               # bounded memory; rays are independent
+        sl = slice(s0, s0 + (1 << 20))
+        _, _, occ, _, _ = sphere_tracing(ro[sl], rd[sl], near[sl], far[sl], sdf_fn, lv['iter'], tan_i[sl], lv['relax'], lv['offset'],
+                                         cfg.st_eps, cfg.st_skip, soft=True)
+        occ_parts.append(occ)
+    occ = torch.cat(occ_parts) if occ_parts else ro.new_zeros(0, 1)
     lvis = torch.zeros_like(ldot)
     lbox = torch.zeros_like(lfrt)
     lbox[li[lbox_sub], pi[lbox_sub]] = True
@@ -542,9 +560,125 @@ _BLEND_KEYS = ['rgb_map', 'surf_map', 'albedo_map', 'roughness_map', 'norm_map',
                'depth_map', 'lvis_map', 'ldot_map', 'shade_map']
 
 
-def render_sphere_tracing(batch: dict, sd: dict, cfg: Cfg, dtype=torch.float32, device='cpu', want_lvis=True) -> dict:
-    """sphere_tracing_renderer.Renderer.render (:1066-1115), ground shading off: chunked
-    get_pixel_value with the in-place wbounds growth, then alpha_output_."""
+# ---------------------------------------------------------------------------------------------- ground plane (row f2)
+def get_rays_full(H: int, W: int, K: torch.Tensor, R: torch.Tensor, T: torch.Tensor):
+    """net_utils.get_rays (:403-420): every pixel of the H x W image -> ray_o, ray_d (H*W, 3)."""
+    ray_o = -(R.mT @ T).ravel()
+    i, j = torch.meshgrid(torch.arange(H, dtype=R.dtype, device=R.device), torch.arange(W, dtype=R.dtype, device=R.device), indexing='ij')
+    xy1 = torch.stack([j, i, torch.ones_like(i)], dim=2)
+    pixel_camera = xy1 @ torch.inverse(K).mT
+    pixel_world = (pixel_camera - T.ravel()) @ R
+    ray_o = ray_o[None, None].expand(pixel_world.shape)
+    ray_d = normalize(pixel_world - ray_o)
+    return ray_o.reshape(-1, 3), ray_d.reshape(-1, 3)
+
+
+def ground_plane_t(ray_o, ray_d, orig, norm, tangent_scale: float = 1.0, eps: float = 1e-8):
+    """t of moller_trumbore (mesh_utils.py:710-738) against compute_ground_tris(orig, norm) (net_utils.py:392-396).
+    The triangle is (o, o + a, o + b) with a = d x n, b = d x a for a RANDOM unit vector n, so E1 x E2 = |a|^2 d and
+    t = -((ray_o - o) . N) / (ray_d . N + eps) with N = |a|^2 d: the draw only scales how much the 1e-8 matters
+    (`tangent_scale` = |a|^2 in (0, 1]; relative effect on t <= 1e-8 / (|a|^2 |ray_d . d|))."""
+    N = norm * tangent_scale
+    invdet = 1.0 / -((ray_d * N).sum(-1) + eps)
+    return ((ray_o - orig) * N).sum(-1) * invdet
+
+
+def render_ground(ray_o, ray_d, acc, fr: Frame, W: Weights, cfg: Cfg, bbox, probe, image=None, tangent_scale: float = 1.0) -> dict:
+    """sphere_tracing_renderer.render_ground (:463-548) for one pixel chunk; every map is (P, .)."""
+    P = ray_o.shape[0]
+    norm = normalize(ray_o.new_tensor(cfg.ground_normal))
+    orig = ray_o.new_tensor(cfg.ground_origin)
+    t = ground_plane_t(ray_o, ray_d, orig, norm, tangent_scale)[:, None]
+    surf = ray_o + t * ray_d
+    normP = norm[None].expand(P, 3)
+    lv = dict(iter=cfg.gl_iter, offset=cfg.gl_offset, relax=cfg.gl_relax, near=cfg.gl_near, dist_th=cfg.gl_dist_th)
+    lvis, ldot = light_visibility(surf, normP, acc, W, fr, cfg, bbox, lv)                     # (512, P)
+    if cfg.ground_attach_envmap:
+        albedo = sample_envmap(image if image is not None else probe, ray_d)
+    else:
+        albedo = torch.ones_like(surf) * ray_o.new_tensor(cfg.ground_albedo)
+    dist = torch.where(t[:, 0] <= 0, torch.full_like(t[:, 0], 1e9), (surf - orig).norm(dim=-1))
+    weight = ((dist - cfg.env_r) / cfg.env_r).clip(0, 1)[None]                                # (1, P)
+    L = W.light_xyz.reshape(-1, 3)
+    ldot = (normalize(L)[:, None] * normP[None]).sum(-1)
+    lvis = lvis * (1 - weight) + torch.ones_like(lvis) * weight
+    light = sample_envmap(probe, normalize(L))                                                # (512, 3): the same for every pixel
+    area = W.light_area.reshape(-1)
+    shade = lvis[..., None] * ldot[..., None] * area[:, None, None] * light[:, None]          # evaluate_shade :369-376
+    rgb = ((albedo[None] / math.pi) * shade).sum(0)
+    rgb = linear2srgb(rgb)
+    shade = shade.sum(0) * cfg.shading_albedo / math.pi
+    return dict(rgb_map=rgb, surf_map=surf, albedo_map=albedo, roughness_map=torch.ones_like(albedo[:, 0]), spec_map=shade / 20,
+                norm_map=normP.clone(), shade_map=shade * cfg.ground_shading_multiplier, cpts_map=torch.zeros_like(surf),
+                bpts_map=torch.zeros_like(surf), depth_map=t[:, 0].clip(-cfg.env_r, cfg.env_r),
+                lvis_map=lvis.T.contiguous(), ldot_map=ldot.T.contiguous())
+
+
+def render_ground_novel(ray_d, albedo_map, lvis_map, ldot_map, W: Weights, cfg: Cfg, probe, image=None):
+    """novel_light_sphere_tracing.render_ground (:69-98): re-shade the floor from its stored (F,512) visibility maps."""
+    L = W.light_xyz.reshape(-1, 3)
+    light = sample_envmap(probe, normalize(L))
+    albedo = sample_envmap(image if image is not None else probe, ray_d) if cfg.ground_attach_envmap else albedo_map
+    area = W.light_area.reshape(-1)
+    shade = lvis_map.T[..., None] * ldot_map.T[..., None] * area[:, None, None] * light[:, None]
+    rgb = linear2srgb(((albedo[None] / math.pi) * shade).sum(0))
+    shade = shade.sum(0) / math.pi
+    return rgb, albedo, shade, shade / 20
+
+
+def blend_output(acc, inds, grd: dict, ret: dict) -> dict:
+    """blend_output_ (:433-451): image-sized maps = ground * acc_g + scatter(human) * (1 - acc_g); acc (F,), inds (P,)."""
+    out = dict(ret)
+    for k in _BLEND_KEYS:
+        if k in grd:
+            a = acc if grd[k].ndim == 1 else acc[:, None]
+            if k in ret:
+                sc = torch.zeros_like(grd[k])
+                sc[inds] = ret[k]
+                out[k] = grd[k] * a + sc * (1 - a)
+            else:
+                out[k] = grd[k] * a
+    sc = torch.zeros_like(acc)
+    sc[inds] = ret['acc_map']
+    out['acc_map'] = torch.zeros_like(acc) * acc + sc * (1 - acc)
+    return out
+
+
+def render_ground_pass(batch: dict, ret: dict, fr: Frame, W: Weights, cfg: Cfg, probe, dtype, device, tangent_scale=1.0,
+                       inds_fn=None) -> dict:
+    """The vis_ground_shading branch of Renderer.render (:1079-1101): all H*W pixels, chunked like the human pass
+    (the in-place wbounds growth simply continues).
+    `inds` (ray k -> image pixel): the reference takes it from batch_aware_indexing = topk(S, sorted=False) of the 0/1 mask
+    (net_utils.py:381-389), i.e. it RELIES on torch returning tied values in index order.  CPU torch does not (the
+    golden vectors made under the CPU harness are scrambled accordingly); the intended order -- and the product's -- is
+    mask.nonzero().  `inds_fn(mask) -> inds` lets the pinning test replay the CPU order."""
+    t = lambda a: torch.as_tensor(a).to(device=device, dtype=dtype)
+    H, Wd = int(batch['H']), int(batch['W'])
+    F_ = H * Wd
+    mask = torch.as_tensor(batch['mask_at_box'][0]).reshape(-1).to(device)
+    inds = mask.nonzero()[:, 0] if inds_fn is None else inds_fn(mask)
+    ray_o, ray_d = get_rays_full(H, Wd, t(batch['cam_K']), t(batch['cam_R']), t(batch['cam_T']))
+    acc = torch.ones(F_, dtype=dtype, device=device)
+    acc[inds] = 1 - ret['acc_map']
+    n_chunks = max(math.ceil(F_ / cfg.render_chunk), 1)
+    actual = math.ceil(F_ / n_chunks)
+    parts = []
+    for c in range(n_chunks):
+        sl = slice(c * actual, (c + 1) * actual)
+        fr.wbounds[0] -= cfg.bbox_margin
+        fr.wbounds[1] += cfg.bbox_margin
+        with torch.no_grad():
+            parts.append(render_ground(ray_o[sl], ray_d[sl], acc[sl], fr, W, cfg, fr.wbounds, probe, None, tangent_scale))
+    ground = {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
+    ground.update(ray_o=ray_o, ray_d=ray_d, acc_map=acc, inds=inds)
+    return ground
+
+
+def render_sphere_tracing(batch: dict, sd: dict, cfg: Cfg, dtype=torch.float32, device='cpu', want_lvis=True, ground=False,
+                          tangent_scale: float = 1.0, inds_fn=None) -> dict:
+    """sphere_tracing_renderer.Renderer.render (:1066-1115): chunked get_pixel_value with the in-place wbounds growth, then
+    alpha_output_ -- or, with ground=True (cfg.vis_ground_shading, vis_novel_light on), the UN-premultiplied human maps plus
+    ret['ground'] (the floor pass over all H*W pixels)."""
     W = Weights(sd, dtype, device)
     fr = Frame.from_batch(batch, cfg, dtype, device)
     t = lambda a: torch.as_tensor(a).to(device=device, dtype=dtype)
@@ -561,23 +695,35 @@ def render_sphere_tracing(batch: dict, sd: dict, cfg: Cfg, dtype=torch.float32, 
         with torch.no_grad():
             rets.append(render_human(ray_o[sl], ray_d[sl], near[sl], far[sl], fr, W, cfg, fr.wbounds, probe, want_lvis))
     ret = {k: torch.cat([r[k] for r in rets]) for k in rets[0]}
-    acc = ret['acc_map']
-    for k in _BLEND_KEYS:                                                     # alpha_output_ :454-460
-        if k in ret:
-            ret[k] = ret[k] * (acc if ret[k].ndim == 1 else acc[:, None])
+    if ground:
+        ret['ground'] = render_ground_pass(batch, ret, fr, W, cfg, probe, dtype, device, tangent_scale, inds_fn)
+    else:
+        acc = ret['acc_map']
+        for k in _BLEND_KEYS:                                                 # alpha_output_ :454-460
+            if k in ret:
+                ret[k] = ret[k] * (acc if ret[k].ndim == 1 else acc[:, None])
     ret['wbounds_after'] = fr.wbounds.clone()
     return ret
 
 
+_VISUAL = ['rgb_map', 'acc_map', 'norm_map', 'surf_map', 'bpts_map', 'cpts_map', 'spec_map', 'shade_map', 'depth_map', 'albedo_map',
+           'roughness_map']
+
+
 def render_novel_light(batch: dict, sd: dict, cfg: Cfg, probes: Dict[str, torch.Tensor], dtype=torch.float32,
-                       device='cpu', include_main=True) -> Dict[str, dict]:
-    """novel_light_sphere_tracing.Renderer.render (:101-221), no ground, no rotation: main pass, then one
-    cheap re-shade per env-map from the acc-premultiplied maps."""
-    main = render_sphere_tracing(batch, sd, cfg, dtype, device, want_lvis=True)
+                       device='cpu', include_main=True, ground=False, tangent_scale: float = 1.0, inds_fn=None) -> Dict[str, dict]:
+    """novel_light_sphere_tracing.Renderer.render (:101-221), no rotation: main pass, then one cheap re-shade per env-map
+    from the stored maps (acc-premultiplied without ground shading, raw with it) and, with ground=True, the floor
+    re-shade + blend_output_ into image-sized (H*W) maps."""
+    main = render_sphere_tracing(batch, sd, cfg, dtype, device, want_lvis=True, ground=ground, tangent_scale=tangent_scale, inds_fn=inds_fn)
     W = Weights(sd, dtype, device)
     out = {}
+    grd = main.get('ground')
     if include_main:
-        out['main'] = {k: main[k] for k in main if k not in ('lvis_map', 'ldot_map', 'ray_o', 'wbounds_after', 'resd_map')}
+        if ground:
+            out['main'] = blend_output(grd['acc_map'], grd['inds'], grd, {k: main[k] for k in _VISUAL if k in main})
+        else:
+            out['main'] = {k: main[k] for k in main if k not in ('lvis_map', 'ldot_map', 'ray_o', 'wbounds_after', 'resd_map')}
     for name, probe in probes.items():
         probe = torch.as_tensor(probe).to(device=device, dtype=dtype).reshape(16, 32, 3)
         with torch.no_grad():
@@ -585,6 +731,14 @@ def render_novel_light(batch: dict, sd: dict, cfg: Cfg, probes: Dict[str, torch.
                                             main['roughness_map'][:, None], main['lvis_map'].T, main['ldot_map'].T,
                                             probe, W, cfg)
         out[name] = dict(rgb_map=rgb, shade_map=shade, spec_map=spec)
+        if ground:
+            human = {k: main[k] for k in _VISUAL if k in main}
+            human.update(out[name])
+            with torch.no_grad():
+                g_rgb, g_alb, g_shade, g_spec = render_ground_novel(grd['ray_d'], grd['albedo_map'], grd['lvis_map'], grd['ldot_map'], W, cfg, probe)
+            g = {k: grd[k] for k in _VISUAL if k in grd}
+            g.update(rgb_map=g_rgb, albedo_map=g_alb, shade_map=g_shade, spec_map=g_spec)
+            out[name] = blend_output(grd['acc_map'], grd['inds'], g, human)
     out['_main_full'] = main
     return out
 

@@ -118,8 +118,11 @@ def setup_reference(mode: str):
     os.chdir(root)
     from lib.config import cfg, yacs
     cfg.merge_strain(yacs.load_cfg(open('configs/mobile_stage/xuzhen_12v_geo.yaml', 'r')))
-    if mode == 'relight':
+    if mode in ('relight', 'relight_ground'):
         cfg.relighting = True; cfg.vis_novel_light = True; cfg.vis_pose_sequence = True
+        if mode == 'relight_ground':            # the README showcase option (readme.md:64): ground-plane shading, row f2
+            cfg.vis_ground_shading = True
+            cfg.store_alpha_channel = False     # what parse_cfg would set (config.py:451-452)
         cfg.merge_from_other_cfg(cfg.relighting_cfg)
         cfg.merge_from_other_cfg(cfg.pose_seq_cfg)
         cfg.merge_from_other_cfg(cfg.novel_light_cfg)
@@ -163,20 +166,21 @@ def run(mode: str, H: int, seed: int, n_env: int, fitted: bool, threads: int = 0
     from relightableavatar_b200 import scene
     if threads:
         torch.set_num_threads(threads)
-    if mode == 'relight':
+    if mode.startswith('relight'):
         cfg.test_light = ['main'] + list(scene.make_envmaps(n_env, 10 + seed).keys()) if n_env else ['main']
     from lib.networks.make_network import make_network
     from lib.networks.renderer.make_renderer import make_renderer
     net = make_network(cfg)
-    sd = scene.make_state_dict(seed, relight=(mode == 'relight'), fitted=fitted)
+    sd = scene.make_state_dict(seed, relight=mode.startswith('relight'), fitted=fitted)
     missing, unexpected = net.load_state_dict(sd, strict=False)
     missing = [m for m in missing if 'freq_bands' not in m and 'embedder' not in m]
     assert not unexpected, unexpected
     assert not missing, missing
     net.eval()
     renderer = make_renderer(cfg, net)
-    b = scene.make_batch(H, H, seed=seed, n_env=n_env if mode == 'relight' else 0)
+    b = scene.make_batch(H, H, seed=seed, n_env=n_env if mode.startswith('relight') else 0)
     batch = to_ref_batch(b)
+    torch.manual_seed(0)        # compute_ground_tris draws a random tangent (net_utils.py:392-396)
     with torch.no_grad():
         out = renderer.render(batch)
     flat = {}

@@ -3,7 +3,7 @@
 
 Run in the dev container where /root/reference exists (the GPU box has no reference tree):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case names]
 
 Each fixture stores only the reference OUTPUTS plus the scene arguments; inputs are regenerated
 from the seed by relightableavatar_b200/scene.py (deterministic numpy / torch CPU generators).
@@ -23,6 +23,8 @@ CASES = [
     ('relight_48', 'relight', 48, 2, None),
     ('anisdf_trace_48', 'anisdf_trace', 48, 0, None),
     ('anisdf_volume_24', 'anisdf_volume', 24, 0, None),
+    # row f2: vis_ground_shading on (image-sized maps; the CPU harness scrambles `inds`, see oracle.render_ground_pass)
+    ('relight_ground_24', 'relight_ground', 24, 1, None),
 ]
 
 DROP_DUP = ('surf_map', 'depth_map', 'acc_map', 'albedo_map', 'roughness_map', 'norm_map', 'ray_o', 'cpts_map',
@@ -30,7 +32,10 @@ DROP_DUP = ('surf_map', 'depth_map', 'acc_map', 'albedo_map', 'roughness_map', '
 
 
 def main():
+    only = set(sys.argv[1:])
     for name, mode, H, n_env, _ in CASES:
+        if only and name not in only:
+            continue
         tmp = os.path.join('/tmp', f'golden_{name}.npz')
         subprocess.check_call([sys.executable, os.path.join(ROOT, 'oracle', 'ref_harness.py'), '--mode', mode,
                                '--H', str(H), '--n_env', str(n_env), '--out', tmp])
@@ -39,6 +44,8 @@ def main():
         seen_lvis = False
         for k, v in d.items():
             light, _, key = k.partition('.')
+            if mode == 'relight_ground' and light not in ('main', 'wbounds_after') and key not in ('rgb_map', 'shade_map', 'spec_map', 'albedo_map'):
+                continue                 # per-light copies of the blended main maps
             if mode == 'relight' and light not in ('main', 'wbounds_after'):
                 if key in ('lvis_map', 'ldot_map'):
                     if seen_lvis and light != first_light:

@@ -47,6 +47,28 @@ def test_relight_matches_reference():
     np.testing.assert_allclose(out['_main_full']['wbounds_after'].numpy(), g['wbounds_after'][0], atol=1e-6)
 
 
+def test_relight_ground_matches_reference():
+    """Row f2 (vis_ground_shading): floor pass over all H*W pixels + blend_output_, main light and one novel probe.
+    The reference orders `inds` by topk(sorted=False) of the mask; the fixture was made on CPU torch, so the same call
+    here replays that order (oracle.render_ground_pass explains; the product uses mask.nonzero())."""
+    g = _load('relight_ground_24')
+    H, n_env = int(g['_H']), int(g['_n_env'])
+    b = scene.make_batch(H, H, seed=0, n_env=n_env)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    probes = {k: v[0] for k, v in b['novel_lights'].items()}
+    cpu_order = lambda m: m.int().topk(int(m.sum()), dim=-1, sorted=False)[1]
+    out = O.render_novel_light(b, sd, O.Cfg(), probes, ground=True, inds_fn=cpu_order)
+    assert out['main']['rgb_map'].shape[0] == H * H
+    for k in ('rgb_map', 'acc_map', 'surf_map', 'shade_map', 'spec_map', 'depth_map', 'albedo_map', 'roughness_map', 'bpts_map', 'cpts_map', 'ldot_map'):
+        _close('main.' + k, out['main'][k], g['main.' + k][0], 2e-4)
+    _close('main.norm_map', out['main']['norm_map'], g['main.norm_map'][0], 2e-3, q=0.99)
+    _close('main.lvis_map', out['main']['lvis_map'], g['main.lvis_map'][0], 2e-3, q=0.999)
+    for n in probes:
+        for k in ('rgb_map', 'shade_map', 'spec_map', 'albedo_map'):
+            _close(f'{n}.{k}', out[n][k], g[f'{n}.{k}'][0], 5e-4)
+    np.testing.assert_allclose(out['_main_full']['wbounds_after'].numpy(), g['wbounds_after'][0], atol=1e-6)
+
+
 def test_anisdf_trace_matches_reference():
     g = _load('anisdf_trace_48')
     H = int(g['_H'])
