@@ -135,6 +135,57 @@ int ra_rotate_probes(ra_handle* h, const float* probe, int32_t repeat, int32_t j
  * mask_at_box: H*W bytes; out_f (H,W,4) fp32 and/or out_u8 (H,W,4) = clip(.,0,1)*255; either may be NULL. */
 int ra_assemble_image(ra_handle* h, const float* rgb_map, const float* acc_map, const unsigned char* mask_at_box, int32_t H, int32_t W,
                       float bg_brightness, float* out_f, unsigned char* out_u8, void* stream);
+/* ---- ground-plane shading (cfg.vis_ground_shading) -------------------------------------------------
+ * Reference: sphere_tracing_renderer.py:463-548 (render_ground), :1079-1111 (ground branch of Renderer.render), :395-451
+ * (blend_output_), novel_light_sphere_tracing.py:69-98,191-212 (per-env-map floor re-shade + blend), cfg.env_lvis
+ * (config.py:135-141), cfg.ground_* (config.py:45,104-107,353).  All maps here are image-sized: F = H*W pixels. */
+typedef struct ra_ground_config {
+    float normal[3];            /* cfg.ground_normal  (0,0,1) */
+    float origin[3];            /* cfg.ground_origin  (0,0,0) */
+    float albedo[3];            /* cfg.ground_albedo  (.05,.05,.05); used when attach_envmap == 0 */
+    int32_t attach_envmap;      /* cfg.ground_attach_envmap (1): floor albedo = env-map colour along the view ray */
+    float shading_multiplier;   /* cfg.ground_shading_multiplier (1.0) */
+    int32_t iter;               /* cfg.env_lvis.iter 16 */
+    float offset, relax, near_offset, dist_th;   /* .01, 0, .02, .005 */
+} ra_ground_config;
+
+typedef struct ra_ground_outputs {  /* every pointer (F, C) fp32; rgb/surf/albedo/lvis/ldot are required, the rest optional */
+    float* rgb_map;        /* (F,3) */
+    float* surf_map;       /* (F,3) */
+    float* albedo_map;     /* (F,3) */
+    float* roughness_map;  /* (F)   all ones */
+    float* spec_map;       /* (F,3) shade / 20 */
+    float* norm_map;       /* (F,3) */
+    float* shade_map;      /* (F,3) */
+    float* depth_map;      /* (F)   */
+    float* lvis_map;       /* (F,512) far-field-blended visibility, kept by the caller for ra_relight_ground */
+    float* ldot_map;       /* (F,512) */
+} ra_ground_outputs;
+
+/* `inds` / ground acc of Renderer.render (:1083-1088): mask_at_box (H*W bytes) + acc_map (P, from ra_render_relight) ->
+ * acc_g (F) = 1 - acc scattered to the mask pixels (1 elsewhere).  Also records the pixel -> ray map used by ra_blend_ground.
+ * The ray order is mask.nonzero() -- what batch_aware_indexing's topk(sorted=False) is relied upon to return. */
+int ra_ground_begin(ra_handle* h, const unsigned char* mask_at_box, int32_t H, int32_t W, const float* acc_map, float* acc_g, void* stream);
+/* render_ground over all F pixels after a ra_render_relight call (continues its per-chunk wbounds growth): ray_o, ray_d (F,3)
+ * from get_rays(H, W, K, R, T) (net_utils.py:403-420); probe (ph,pw,3) lights the floor; albedo image (ih,iw,3) = envmap.image
+ * if present else the probe (ignored when attach_envmap == 0). */
+int ra_render_ground(ra_handle* h, const ra_ground_config* g, const float* ray_o, const float* ray_d, const float* acc_g, int64_t F,
+                     const float* probe, int32_t ph, int32_t pw, const float* albedo_image, int32_t ih, int32_t iw,
+                     const ra_ground_outputs* out, void* stream);
+/* novel_light_sphere_tracing.render_ground for one env-map: re-shade the floor from its stored maps.
+ * albedo_out receives the re-sampled albedo when attach_envmap, else a copy of albedo_in. */
+int ra_relight_ground(ra_handle* h, const ra_ground_config* g, const float* probe, int32_t ph, int32_t pw, const float* albedo_image,
+                      int32_t ih, int32_t iw, const float* ray_d, const float* albedo_in, float* lvis_map, float* ldot_map, int64_t F,
+                      float* rgb, float* albedo_out, float* shade, float* spec, void* stream);
+/* blend_output_ for one key of C channels: out (F,C) = ground * acc_g + scatter(human) * (1 - acc_g).
+ * ground NULL: the acc_map rule (target 0); human NULL: alpha_times.  human_premul != 0: `human` (P,C) is already
+ * multiplied by acc (the maps ra_render_relight returns), so it is added as is. */
+int ra_blend_ground(ra_handle* h, const float* acc_g, const float* ground, const float* human, int32_t human_premul, int32_t C,
+                    int64_t F, float* out, void* stream);
+/* ra_relight_envmaps with raw (not acc-premultiplied) inputs -- what the reference feeds render_human when ground shading
+ * is on (alpha_output_ is skipped, :1109-1113); outputs are multiplied by acc so that ra_blend_ground(human_premul=1) applies. */
+int ra_relight_envmaps_raw(ra_handle* h, const float* probes, int32_t n_env, float* rgb, float* shade, float* spec, void* stream);
+
 /* sphere_tracing_renderer.Renderer.render for the AniSDF network (config 1; raw 16-ch branch :634-635). */
 int ra_render_anisdf_trace(ra_handle* h, const float* ray_o, const float* ray_d, const float* near, const float* far,
                            int64_t P, const ra_outputs* out, void* stream);

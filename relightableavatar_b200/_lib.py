@@ -10,7 +10,8 @@ LIB_PATH = os.environ.get('RA_LIB_PATH') or os.path.join(HERE, 'libra_b200.so') 
 
 EXPORTS = ['ra_create', 'ra_destroy', 'ra_last_error', 'ra_upload_weights', 'ra_set_frame', 'ra_render_relight',
            'ra_relight_envmaps', 'ra_render_anisdf_trace', 'ra_render_anisdf_volume', 'ra_query_sdf', 'ra_query_raw',
-           'ra_get_stats', 'ra_launch_count', 'ra_profile_enable', 'ra_profile_read', 'ra_rotate_probes', 'ra_assemble_image']
+           'ra_get_stats', 'ra_launch_count', 'ra_profile_enable', 'ra_profile_read', 'ra_rotate_probes', 'ra_assemble_image',
+           'ra_ground_begin', 'ra_render_ground', 'ra_relight_ground', 'ra_blend_ground', 'ra_relight_envmaps_raw']
 
 fp = C.POINTER(C.c_float)
 
@@ -47,6 +48,19 @@ class ra_outputs(C.Structure):
     _fields_ = [(n, fp) for n in OUTPUT_MAPS]
 
 
+GROUND_MAPS = ('rgb_map', 'surf_map', 'albedo_map', 'roughness_map', 'spec_map', 'norm_map', 'shade_map', 'depth_map', 'lvis_map', 'ldot_map')
+
+
+class ra_ground_config(C.Structure):
+    _fields_ = [('normal', C.c_float * 3), ('origin', C.c_float * 3), ('albedo', C.c_float * 3), ('attach_envmap', C.c_int32),
+                ('shading_multiplier', C.c_float), ('iter', C.c_int32), ('offset', C.c_float), ('relax', C.c_float),
+                ('near_offset', C.c_float), ('dist_th', C.c_float)]
+
+
+class ra_ground_outputs(C.Structure):
+    _fields_ = [(n, fp) for n in GROUND_MAPS]
+
+
 class ra_stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ('n_rays', 'n_fg', 'n_shadow_rays', 'n_queries', 'n_queries_in_shell', 'n_attr_samples')]
 
@@ -80,6 +94,11 @@ def load():
     lib.ra_launch_count.argtypes = [vp]; lib.ra_launch_count.restype = i64
     lib.ra_assemble_image.argtypes = [vp, vp, vp, vp, i32, i32, f32, vp, vp, vp]
     lib.ra_rotate_probes.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    lib.ra_relight_envmaps_raw.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    lib.ra_ground_begin.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    lib.ra_render_ground.argtypes = [vp, C.POINTER(ra_ground_config), vp, vp, vp, i64, vp, i32, i32, vp, i32, i32, C.POINTER(ra_ground_outputs), vp]
+    lib.ra_relight_ground.argtypes = [vp, C.POINTER(ra_ground_config), vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+    lib.ra_blend_ground.argtypes = [vp, vp, vp, vp, i32, i32, i64, vp, vp]
     lib.ra_profile_enable.argtypes = [vp, i32]
     lib.ra_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]
     _lib = lib

@@ -16,6 +16,7 @@
 #include "hdq.cuh"
 #include "mlp_simt.cuh"
 #include "render.cuh"
+#include "ground.cuh"
 #include "mlp_tc.cuh"
 #include "mlp_tc2.cuh"
 #include "mlp_tc3.cuh"
@@ -88,6 +89,8 @@ struct ra_handle {
     float *pt_smpl = nullptr; int* pt_slot = nullptr;     // ra_query_sdf scratch
     float* bg_spec = nullptr;
     int* blk_cnt = nullptr; int64_t blk_cap = 0;      // image assembly scratch
+    int* pix2ray = nullptr; int64_t pix_cap = 0;      // ground pass: image pixel -> ray (ra_ground_begin)
+    float *g_weight = nullptr, *g_light = nullptr;    // ground pass: far-field blend weight (F), per-light radiance table (L,3)
     // ---- fp32 MLP chunk buffers
     float *Xr0, *ra_[8], *Xr4, *z8, *resd_o, *cpts_o, *Xs0, *sb_[8], *Xs4, *out257, *GA, *GB, *dpe0, *dpes, *gcp, *u4, *gbp, *nrm_o;
     float *hd1, *hd2, *head_a, *head_r, *Xrn, *rn1, *rn2;
@@ -596,7 +599,7 @@ extern "C" int ra_render_anisdf_trace(ra_handle* h, const float* ray_o, const fl
     return render_trace(h, ray_o, ray_d, near_, far_, P, out, (cudaStream_t)stream);
 }
 
-extern "C" int ra_relight_envmaps(ra_handle* h, const float* probes, int32_t n_env, float* rgb, float* shade, float* spec, void* stream) {
+static int relight_envmaps_impl(ra_handle* h, const float* probes, int32_t n_env, float* rgb, float* shade, float* spec, void* stream, int raw) {
     cudaStream_t st = (cudaStream_t)stream;
     const ra_config& c = h->cfg;
     if (!c.relight || h->last_ray_o == nullptr) { h->err = "ra_relight_envmaps needs a preceding ra_render_relight"; return 1; }
@@ -609,7 +612,8 @@ extern "C" int ra_relight_envmaps(ra_handle* h, const float* probes, int32_t n_e
         float* p = spec ? spec + (size_t)e * P * 3 : nullptr;
         if (r) CK(cudaMemsetAsync(r, 0, (size_t)P * 3 * sizeof(float), st));
         if (s) CK(cudaMemsetAsync(s, 0, (size_t)P * 3 * sizeof(float), st));
-        if (p && P) {
+        if (p && P && raw) CK(cudaMemsetAsync(p, 0, (size_t)P * 3 * sizeof(float), st));      // times acc = 0
+        if (p && P && !raw) {
             LAUNCH(h, k_bg_spec, 1, 32, 0, st, h->lxyz, h->larea, L, probe, c.env_h, c.env_w, c.fresnel_f0, h->bg_spec);
             LAUNCH(h, k_fill3, grid_for(h, P * 3), 256, 0, st, p, h->bg_spec, (long long)P);
         }
@@ -619,8 +623,121 @@ extern "C" int ra_relight_envmaps(ra_handle* h, const float* probes, int32_t n_e
         LAUNCH(h, k_shade_multi, grid_for(h, P * 32, 256, 8), 256, 0, st, h->cnt.n_fg, h->fg_ray, h->last_ray_o, h->surf, h->acc, h->fm, h->lvis,
                h->ldot, h->lxyz, h->larea, L, probes + (size_t)e0 * L * 3, ne, c.env_h, c.env_w, c.fresnel_f0, c.shading_albedo,
                rgb ? rgb + (size_t)e0 * P * 3 : nullptr, shade ? shade + (size_t)e0 * P * 3 : nullptr,
-               spec ? spec + (size_t)e0 * P * 3 : nullptr, (long long)P);
+               spec ? spec + (size_t)e0 * P * 3 : nullptr, (long long)P, raw ? 0 : 1, raw ? 1 : 0);
     }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ra_relight_envmaps(ra_handle* h, const float* probes, int32_t n_env, float* rgb, float* shade, float* spec, void* stream) {
+    return relight_envmaps_impl(h, probes, n_env, rgb, shade, spec, stream, 0);
+}
+extern "C" int ra_relight_envmaps_raw(ra_handle* h, const float* probes, int32_t n_env, float* rgb, float* shade, float* spec, void* stream) {
+    return relight_envmaps_impl(h, probes, n_env, rgb, shade, spec, stream, 1);
+}
+
+// ---------------------------------------------------------------------------------------------- ground plane (row f2)
+static GroundCfg ground_cfg(ra_handle* h, const ra_ground_config* g) {
+    GroundCfg c{};
+    for (int i = 0; i < 3; i++) { c.normal[i] = g->normal[i]; c.origin[i] = g->origin[i]; c.albedo[i] = g->albedo[i]; }
+    c.attach_envmap = g->attach_envmap; c.shading_albedo = h->cfg.shading_albedo; c.multiplier = g->shading_multiplier;
+    c.env_r = h->cfg.env_r; c.near_offset = g->near_offset; c.bbox_margin = h->cfg.bbox_margin;
+    return c;
+}
+
+extern "C" int ra_ground_begin(ra_handle* h, const unsigned char* mask_at_box, int32_t H, int32_t W, const float* acc_map, float* acc_g, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int n = H * W, nb = (n + 255) / 256;
+    if (nb > h->blk_cap) { if (h->blk_cnt) cudaFree(h->blk_cnt); CK(dalloc(&h->blk_cnt, (size_t)nb)); h->blk_cap = nb; }
+    if (n > h->pix_cap) {
+        if (h->pix2ray) { cudaFree(h->pix2ray); cudaFree(h->g_weight); }
+        CK(dalloc(&h->pix2ray, (size_t)n)); CK(dalloc(&h->g_weight, (size_t)n)); h->pix_cap = n;
+    }
+    LAUNCH(h, k_mask_count, nb, 256, 0, st, mask_at_box, n, h->blk_cnt);
+    LAUNCH(h, k_scan_blocks, 1, 1024, 0, st, h->blk_cnt, nb);
+    LAUNCH(h, k_ground_pix2ray, nb, 256, 0, st, mask_at_box, n, h->blk_cnt, acc_map, h->pix2ray, acc_g);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ra_render_ground(ra_handle* h, const ra_ground_config* g, const float* ray_o, const float* ray_d, const float* acc_g, int64_t F,
+                                const float* probe, int32_t ph, int32_t pw, const float* albedo_image, int32_t ih, int32_t iw,
+                                const ra_ground_outputs* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const ra_config& c = h->cfg;
+    if (!c.relight || !h->have_frame) { h->err = "ra_render_ground needs a relight handle with a frame set"; return 1; }
+    if (F > h->pix_cap) { h->err = "ra_render_ground: call ra_ground_begin for this image size first"; return 1; }
+    if (!out->rgb_map || !out->surf_map || !out->albedo_map || !out->lvis_map || !out->ldot_map) { h->err = "ra_render_ground: rgb/surf/albedo/lvis/ldot outputs are required"; return 1; }
+    if (F == 0) return 0;
+    const int L = c.env_h * c.env_w, N = c.n_verts;
+    GroundCfg gc = ground_cfg(h, g);
+    if (!h->g_light) CK(dalloc(&h->g_light, (size_t)RA_NLIGHT_MAX * 3));
+    LAUNCH(h, k_ground_light_table, 2, 256, 0, st, h->lxyz, L, probe, ph, pw, h->g_light);
+    const float* img = albedo_image ? albedo_image : probe;
+    if (!albedo_image) { ih = ph; iw = pw; }
+    // reference chunking (only the bbox growth depends on it): human pass chunks so far, equalised floor chunk size
+    const int human_chunks = (int)std::max<int64_t>((h->last_P + c.render_chunk - 1) / c.render_chunk, 1);
+    const int64_t n_chunks = std::max<int64_t>((F + c.render_chunk - 1) / c.render_chunk, 1);
+    const int chunk_actual = (int)((F + n_chunks - 1) / n_chunks);
+    LAUNCH(h, k_ground_setup, grid_for(h, F), 256, 0, st, gc, ray_o, ray_d, 0LL, (long long)F, img, ih, iw, out->surf_map, out->depth_map,
+           out->norm_map, out->albedo_map, out->roughness_map, h->g_weight);
+    TraceCfg sc{g->iter, 1.f, g->relax, g->offset, c.st_eps, c.st_skip, g->dist_th, c.blend_radius};
+    int* n_gshadow = h->counters_blk + 5;
+    // processing granularity: as many pixels as the shadow-ray / query workspaces of this handle hold (256 rays per pixel)
+    const int64_t step = std::max<int64_t>(std::min<int64_t>(h->P_cap, h->q_cap / 256), 1);
+    for (int64_t p0 = 0; p0 < F; p0 += step) {
+        const int64_t n = std::min<int64_t>(step, F - p0);
+        CK(cudaMemsetAsync(n_gshadow, 0, sizeof(int), st));
+        LAUNCH(h, k_ground_rays, grid_for(h, n * L / 4, 256, 16), 256, 0, st, h->fc, gc, out->surf_map, acc_g, (long long)p0, (long long)n, h->ldir, L,
+               human_chunks, chunk_actual, out->lvis_map, h->sr, n_gshadow);
+        const int gs = grid_for(h, n * 64, 256, 8);
+        for (int it = 0; it <= g->iter; it++) {
+            CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
+            LAUNCH(h, k_trace_shadow, gs, 256, 0, st, it, sc, h->fc, h->sv, N, n_gshadow, (const int*)nullptr, out->surf_map, h->ldir, h->lsharp, L,
+                   h->sr, h->q, h->cnt, out->lvis_map, 0, 1);
+            if (it < g->iter && distance_pass(h, st)) return 1;
+        }
+    }
+    LAUNCH(h, k_ground_shade, grid_for(h, F * 32, 256, 8), 256, 0, st, gc, 1, 0LL, (long long)F, h->g_weight, h->ldir, h->larea, L, h->g_light,
+           out->lvis_map, out->ldot_map, out->albedo_map, c.shading_albedo, g->shading_multiplier, out->rgb_map, out->shade_map, out->spec_map);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ra_relight_ground(ra_handle* h, const ra_ground_config* g, const float* probe, int32_t ph, int32_t pw, const float* albedo_image,
+                                 int32_t ih, int32_t iw, const float* ray_d, const float* albedo_in, float* lvis_map, float* ldot_map, int64_t F,
+                                 float* rgb, float* albedo_out, float* shade, float* spec, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const ra_config& c = h->cfg;
+    if (!c.relight) { h->err = "ra_relight_ground needs a relight handle"; return 1; }
+    if (F == 0) return 0;
+    const int L = c.env_h * c.env_w;
+    GroundCfg gc = ground_cfg(h, g);
+    if (!h->g_light) CK(dalloc(&h->g_light, (size_t)RA_NLIGHT_MAX * 3));
+    LAUNCH(h, k_ground_light_table, 2, 256, 0, st, h->lxyz, L, probe, ph, pw, h->g_light);
+    const float* alb = albedo_in;
+    if (g->attach_envmap) {
+        if (!albedo_out) { h->err = "ra_relight_ground: albedo_out required with attach_envmap"; return 1; }
+        const float* img = albedo_image ? albedo_image : probe;
+        if (!albedo_image) { ih = ph; iw = pw; }
+        LAUNCH(h, k_ground_albedo, grid_for(h, F), 256, 0, st, ray_d, (long long)F, img, ih, iw, albedo_out);
+        alb = albedo_out;
+    } else if (albedo_out && albedo_out != albedo_in) {
+        CK(cudaMemcpyAsync(albedo_out, albedo_in, (size_t)F * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    // the novel-light floor shade is sum / pi without shading_albedo and without the multiplier (:93-96)
+    LAUNCH(h, k_ground_shade, grid_for(h, F * 32, 256, 8), 256, 0, st, gc, 0, 0LL, (long long)F, (const float*)nullptr, h->ldir, h->larea, L, h->g_light,
+           lvis_map, ldot_map, alb, 1.f, 1.f, rgb, shade, spec);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ra_blend_ground(ra_handle* h, const float* acc_g, const float* ground, const float* human, int32_t human_premul, int32_t C,
+                               int64_t F, float* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (F > h->pix_cap || !h->pix2ray) { h->err = "ra_blend_ground: call ra_ground_begin first"; return 1; }
+    if (F == 0) return 0;
+    LAUNCH(h, k_ground_blend, grid_for(h, F * C), 256, 0, st, h->pix2ray, acc_g, ground, human, human_premul, C, (long long)F, out);
     CK(cudaGetLastError());
     return 0;
 }

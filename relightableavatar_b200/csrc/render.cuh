@@ -189,7 +189,7 @@ __global__ void k_trace_shadow(int it, TraceCfg cfg, const FrameConst* __restric
         float d_keep = 0.f;
         if (valid) {
             f = sr.fg[i]; l = sr.light[i];
-            int ray = fg_ray[f];
+            int ray = fg_ray ? fg_ray[f] : f;          // floor pass: the ray list indexes image pixels directly
             o = make3(surf[ray * 3], surf[ray * 3 + 1], surf[ray * 3 + 2]);
             d = make3(ldir[l * 3], ldir[l * 3 + 1], ldir[l * 3 + 2]);
             nr = sr.near_[i]; fr = sr.far_[i];
@@ -645,7 +645,7 @@ __global__ void k_shade_multi(const int* __restrict__ n_fg, const int* __restric
                               const float* __restrict__ surf_ray, const float* __restrict__ acc_ray, FgMaps fm,
                               const float* __restrict__ lvis, const float* __restrict__ ldot, const float* __restrict__ lxyz,
                               const float* __restrict__ larea, int L, const float* __restrict__ probes, int n_probe, int eh, int ew,
-                              float f0, float shading_albedo, float* rgb, float* shade, float* spec, long long P) {
+                              float f0, float shading_albedo, float* rgb, float* shade, float* spec, long long P, int premul, int out_premul) {
     const float PI = 3.14159265358979323846f;
     int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -654,8 +654,10 @@ __global__ void k_shade_multi(const int* __restrict__ n_fg, const int* __restric
     const int psz = eh * ew * 3;
     for (int f = warp; f < n; f += nwarps) {
         int ray = fg_ray[f];
-        float a = acc_ray[ray];
-        float3 sp = make3(surf_ray[ray * 3] * a, surf_ray[ray * 3 + 1] * a, surf_ray[ray * 3 + 2] * a);   // premultiplied inputs (a19)
+        const float acc_f = acc_ray[ray];
+        const float a = premul ? acc_f : 1.f;      // premultiplied inputs (a19) unless ground shading is on
+        const float om = out_premul ? acc_f : 1.f;
+        float3 sp = make3(surf_ray[ray * 3] * a, surf_ray[ray * 3 + 1] * a, surf_ray[ray * 3 + 2] * a);
         float3 ro = make3(ray_o[ray * 3], ray_o[ray * 3 + 1], ray_o[ray * 3 + 2]);
         float3 nr = make3(fm.norm[f * 3] * a, fm.norm[f * 3 + 1] * a, fm.norm[f * 3 + 2] * a);
         float al[3] = {fm.albedo[f * 3] * a, fm.albedo[f * 3 + 1] * a, fm.albedo[f * 3 + 2] * a};
@@ -695,9 +697,9 @@ __global__ void k_shade_multi(const int* __restrict__ n_fg, const int* __restric
             if (lane == 0)
                 for (int c = 0; c < 3; c++) {
                     size_t o = ((size_t)e * P + ray) * 3 + c;
-                    if (rgb) rgb[o] = linear2srgb(cr[e][c]);
-                    if (shade) shade[o] = cs[e][c] * shading_albedo / PI;
-                    if (spec) spec[o] = cp[e][c];
+                    if (rgb) rgb[o] = linear2srgb(cr[e][c]) * om;
+                    if (shade) shade[o] = cs[e][c] * shading_albedo / PI * om;
+                    if (spec) spec[o] = cp[e][c] * om;
                 }
         }
     }

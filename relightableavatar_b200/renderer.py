@@ -25,7 +25,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import OUTPUT_MAPS, ra_config, ra_frame, ra_outputs, ra_stats, ra_weights
+from ._lib import GROUND_MAPS, OUTPUT_MAPS, ra_config, ra_frame, ra_ground_config, ra_ground_outputs, ra_outputs, ra_stats, ra_weights
 
 PRECISION = {'fp32': 0, 'tc': 1}
 
@@ -62,6 +62,33 @@ def config_from_reference_cfg(cfg, relight: bool) -> Dict:
         albedo_bias=cfg.albedo_bias, rough_slope=cfg.roughness_slope, rough_bias=cfg.roughness_bias,
         albedo_multiplier=cfg.albedo_multiplier, shading_albedo=cfg.shading_albedo, env_h=cfg.env_h, env_w=cfg.env_w,
         clip_near=cfg.clip_near, clip_far=cfg.clip_far)
+
+
+def default_ground_config(**over) -> Dict:
+    """cfg.ground_* (config.py:45,104-107,353) and cfg.env_lvis (config.py:135-141)."""
+    g = dict(normal=(0.0, 0.0, 1.0), origin=(0.0, 0.0, 0.0), albedo=(0.05, 0.05, 0.05), attach_envmap=1, shading_multiplier=1.0,
+             iter=16, offset=0.01, relax=0.0, near_offset=0.02, dist_th=0.005)
+    g.update(over)
+    return g
+
+
+def ground_config_from_reference_cfg(cfg) -> Dict:
+    e = cfg.env_lvis
+    return default_ground_config(normal=tuple(cfg.ground_normal), origin=tuple(cfg.ground_origin), albedo=tuple(cfg.ground_albedo),
+                                 attach_envmap=int(cfg.ground_attach_envmap), shading_multiplier=cfg.ground_shading_multiplier,
+                                 iter=e.iter, offset=e.offset, relax=e.relax, near_offset=e.near_offset, dist_th=e.dist_th)
+
+
+def get_rays(H: int, W: int, K: torch.Tensor, R: torch.Tensor, T: torch.Tensor):
+    """Every pixel's ray, like net_utils.get_rays (:403-420): K, R (3,3), T (3,1) -> ray_o, ray_d (H*W, 3)."""
+    K, R, T = K.reshape(3, 3), R.reshape(3, 3), T.reshape(3, 1)
+    ray_o = -(R.mT @ T).ravel()
+    i, j = torch.meshgrid(torch.arange(H, dtype=R.dtype, device=R.device), torch.arange(W, dtype=R.dtype, device=R.device), indexing='ij')
+    xy1 = torch.stack([j, i, torch.ones_like(i)], dim=2)
+    pixel_world = (xy1 @ torch.inverse(K).mT - T.ravel()) @ R
+    d = pixel_world - ray_o
+    ray_d = d / (d.norm(dim=-1, keepdim=True) + 1e-8)
+    return ray_o[None, None].expand(pixel_world.shape).reshape(-1, 3).contiguous(), ray_d.reshape(-1, 3).contiguous()
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -217,6 +244,75 @@ class Engine:
                         'ra_relight_envmaps')
         return rgb, shade, spec
 
+    # ------------------------------------------------------------------ ground plane
+    def _gcfg(self, g: Dict) -> ra_ground_config:
+        c = ra_ground_config()
+        for k, v in g.items():
+            if k in ('normal', 'origin', 'albedo'):
+                setattr(c, k, (C.c_float * 3)(*[float(x) for x in v]))
+            else:
+                setattr(c, k, v)
+        return c
+
+    def relight_envmaps_raw(self, probes: torch.Tensor, P: int):
+        """Per-env-map human re-shade from the RAW maps (ground shading on), outputs multiplied by acc."""
+        n = probes.shape[0]
+        rgb = torch.empty(n, P, 3, device=self.device); shade = torch.empty_like(rgb); spec = torch.empty_like(rgb)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_relight_envmaps_raw(self.h, _ptr(probes), n, _ptr(rgb), _ptr(shade), _ptr(spec), self._stream()),
+                        'ra_relight_envmaps_raw')
+        return rgb, shade, spec
+
+    def ground_begin(self, mask_at_box: torch.Tensor, acc_map: torch.Tensor) -> torch.Tensor:
+        mask = torch.as_tensor(mask_at_box).to(self.device).reshape(mask_at_box.shape[-2], mask_at_box.shape[-1]).to(torch.uint8).contiguous()
+        H, W = mask.shape
+        acc_g = torch.empty(H * W, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_ground_begin(self.h, _ptr(mask), H, W, _ptr(acc_map.contiguous()), _ptr(acc_g), self._stream()), 'ra_ground_begin')
+        return acc_g
+
+    def render_ground(self, g: Dict, ray_o: torch.Tensor, ray_d: torch.Tensor, acc_g: torch.Tensor, probe: torch.Tensor,
+                      image: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        Fp = ray_o.shape[0]
+        out = {}
+        for k in GROUND_MAPS:
+            shape = (Fp,) if k in ('roughness_map', 'depth_map') else ((Fp, self.L) if k in ('lvis_map', 'ldot_map') else (Fp, 3))
+            out[k] = torch.empty(*shape, device=self.device)
+        o = ra_ground_outputs()
+        for k in GROUND_MAPS:
+            setattr(o, k, _fptr(out[k]))
+        gc = self._gcfg(g)
+        probe = probe.contiguous()
+        ih, iw = (image.shape[0], image.shape[1]) if image is not None else (0, 0)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_render_ground(self.h, C.byref(gc), _ptr(ray_o), _ptr(ray_d), _ptr(acc_g), Fp, _ptr(probe), probe.shape[0], probe.shape[1],
+                                                  _ptr(image), ih, iw, C.byref(o), self._stream()), 'ra_render_ground')
+        return out
+
+    def relight_ground(self, g: Dict, probe: torch.Tensor, ray_d: torch.Tensor, ground: Dict[str, torch.Tensor], image: Optional[torch.Tensor] = None):
+        Fp = ray_d.shape[0]
+        rgb = torch.empty(Fp, 3, device=self.device); albedo = torch.empty_like(rgb); shade = torch.empty_like(rgb); spec = torch.empty_like(rgb)
+        gc = self._gcfg(g)
+        probe = probe.contiguous()
+        ih, iw = (image.shape[0], image.shape[1]) if image is not None else (0, 0)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_relight_ground(self.h, C.byref(gc), _ptr(probe), probe.shape[0], probe.shape[1], _ptr(image), ih, iw, _ptr(ray_d),
+                                                   _ptr(ground['albedo_map']), _ptr(ground['lvis_map']), _ptr(ground['ldot_map']), Fp,
+                                                   _ptr(rgb), _ptr(albedo), _ptr(shade), _ptr(spec), self._stream()), 'ra_relight_ground')
+        return rgb, albedo, shade, spec
+
+    def blend_ground(self, acc_g: torch.Tensor, ground: Optional[torch.Tensor], human: Optional[torch.Tensor], human_premul: bool = True) -> torch.Tensor:
+        """blend_output_ for one key: (F,C) or (F,) ground / (P,C) or (P,) human -> image-sized map."""
+        ref = ground if ground is not None else human
+        Cn = 1 if ref.ndim == 1 else ref.shape[-1]
+        Fp = acc_g.shape[0]
+        out = torch.empty((Fp,) if ref.ndim == 1 else (Fp, Cn), device=self.device)
+        gt = ground.contiguous() if ground is not None else None
+        ht = human.contiguous() if human is not None else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_blend_ground(self.h, _ptr(acc_g), _ptr(gt), _ptr(ht), int(human_premul), Cn, Fp, _ptr(out), self._stream()), 'ra_blend_ground')
+        return out
+
     def rotate_probes(self, probe: torch.Tensor, repeat: int, j0: int, n_rot: int) -> torch.Tensor:
         """rotate_envmap / shift_image (relight_utils.py:55-103): (eh, ew, 3) -> (n_rot, eh, ew, 3)."""
         probe = probe.to(device=self.device, dtype=torch.float32).reshape(self.config['env_h'], self.config['env_w'], 3).contiguous()
@@ -289,7 +385,8 @@ class Renderer(torch.nn.Module):
     """
 
     def __init__(self, net, mode: str = 'relight', cfg=None, device='cuda:0', precision: str = 'tc', max_rays: int = 1 << 17,
-                 test_light=('main',), return_lvis: bool = False, to_cpu: bool = False, sync_timing: bool = True, **overrides):
+                 test_light=('main',), return_lvis: bool = False, to_cpu: bool = False, sync_timing: bool = True,
+                 ground_shading: Optional[bool] = None, ground: Optional[Dict] = None, **overrides):
         super().__init__()
         self.net = net
         self.mode = mode
@@ -304,6 +401,9 @@ class Renderer(torch.nn.Module):
         self.return_lvis = return_lvis
         self.to_cpu = to_cpu
         self.sync_timing = sync_timing     # reference behaviour: cuda.synchronize + perf_counter around the main pass
+        # cfg.vis_ground_shading (readme.md:64): floor pass over all H*W pixels + blend_output_; outputs become image-sized
+        self.ground_shading = bool(getattr(cfg, 'vis_ground_shading', False)) if ground_shading is None else bool(ground_shading)
+        self.ground = ground_config_from_reference_cfg(cfg) if (cfg is not None and ground is None) else default_ground_config(**(ground or {}))
 
     @torch.no_grad()
     def render(self, batch) -> dotdict:
@@ -327,6 +427,8 @@ class Renderer(torch.nn.Module):
         diff = time.perf_counter() - tick
         relight = dotdict()
         conv = (lambda t: t.cpu()) if self.to_cpu else (lambda t: t)
+        if self.ground_shading:
+            return self._render_with_ground(batch, main, P, diff, conv)
         main_b = dotdict({k: conv(v[None]) for k, v in main.items()})
         main_b.envmap = dotdict(probe=conv(eng.env_main[None]))
         if 'main' in self.test_light:
@@ -343,5 +445,58 @@ class Renderer(torch.nn.Module):
                 human.update(rgb_map=conv(rgb[i][None]), shade_map=conv(shade[i][None]), spec_map=conv(spec[i][None]))
                 human.envmap = dotdict(probe=conv(probes[i][None]))
                 relight[n] = human
+        relight.diff = diff
+        return relight
+
+    _VISUAL = ('rgb_map', 'acc_map', 'norm_map', 'surf_map', 'bpts_map', 'cpts_map', 'spec_map', 'shade_map', 'depth_map', 'albedo_map', 'roughness_map')
+
+    def _render_with_ground(self, batch, main, P, diff, conv) -> dotdict:
+        """The vis_ground_shading + vis_novel_light path (sphere_tracing_renderer.py:1079-1107, novel_light_sphere_tracing.py:157-216):
+        floor pass over every pixel, then per light blend_output_(ground, human) into image-sized maps (mask_at_box becomes all-True)."""
+        eng = self.engine
+        dev = eng.device
+        t = lambda k: torch.as_tensor(batch[k]).to(device=dev, dtype=torch.float32)
+        meta = batch.get('meta') or {}
+        H = int(torch.as_tensor(meta['H'] if 'H' in meta else batch['H']).reshape(-1)[0])
+        W = int(torch.as_tensor(meta['W'] if 'W' in meta else batch['W']).reshape(-1)[0])
+        acc_g = eng.ground_begin(torch.as_tensor(batch['mask_at_box'])[0], main['acc_map'])
+        ray_o, ray_d = get_rays(H, W, t('cam_K'), t('cam_R'), t('cam_T'))
+        ground = eng.render_ground(self.ground, ray_o, ray_d, acc_g, eng.env_main)
+
+        def blend(grd: Dict, human: Dict) -> dotdict:
+            out = dotdict()
+            for k in self._VISUAL + ('lvis_map', 'ldot_map'):
+                if k == 'acc_map' or (k not in grd and k not in human):
+                    continue
+                if k in ('lvis_map', 'ldot_map') and not self.return_lvis:
+                    continue
+                out[k] = conv(eng.blend_ground(acc_g, grd.get(k), human.get(k) if k in self._VISUAL else None, True)[None])
+            out.acc_map = conv(eng.blend_ground(acc_g, None, main['acc_map'], False)[None])
+            return out
+
+        relight = dotdict()
+        human_main = {k: main[k] for k in self._VISUAL if k in main}
+        if 'main' in self.test_light:
+            relight.main = blend(ground, human_main)
+            relight.main.envmap = dotdict(probe=conv(eng.env_main[None]))
+        lights = batch.get('novel_lights') or {}
+        names = [n for n in lights if n in self.test_light or 'all' in self.test_light]
+        if names:
+            get = lambda n, key: (lights[n].get(key) if isinstance(lights[n], dict) else (lights[n] if key == 'probe' else None))
+            probes = torch.stack([torch.as_tensor(get(n, 'probe')).to(device=dev, dtype=torch.float32).reshape(eng.config['env_h'], eng.config['env_w'], 3)
+                                  for n in names]).contiguous()
+            rgb, shade, spec = eng.relight_envmaps_raw(probes, P)
+            for i, n in enumerate(names):
+                human = dict(human_main)
+                human.update(rgb_map=rgb[i], shade_map=shade[i], spec_map=spec[i])
+                img = get(n, 'image')
+                img = torch.as_tensor(img).to(device=dev, dtype=torch.float32)[0].contiguous() if img is not None else None
+                g_rgb, g_alb, g_shade, g_spec = eng.relight_ground(self.ground, probes[i], ray_d, ground, img)
+                grd = {k: ground[k] for k in self._VISUAL if k in ground}
+                grd.update(rgb_map=g_rgb, albedo_map=g_alb, shade_map=g_shade, spec_map=g_spec)
+                relight[n] = blend(grd, human)
+                relight[n].envmap = dotdict(probe=conv(probes[i][None]))
+        if isinstance(batch.get('mask_at_box'), torch.Tensor):
+            batch['mask_at_box'][:] = True           # later used for visualization (:1101)
         relight.diff = diff
         return relight

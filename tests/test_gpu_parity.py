@@ -246,3 +246,31 @@ def test_image_assembly_f3(relight_setup):
     ref = torch.cat([ref_rgb, ref_a], -1)
     assert torch.equal(img_f.cpu(), ref)
     assert torch.equal(img_u8.cpu(), (ref.clip(0, 1) * 255).to(torch.uint8))
+
+
+def test_ground_shading_f2():
+    """SURVEY.md 8 row f2 (cfg.vis_ground_shading): floor pass over all H*W pixels (plane hit, env_lvis soft shadows cast by
+    the body, far-field blend, Lambertian light sum), novel-light floor re-shade and blend_output_, against the oracle's
+    restatement (itself pinned to the reference by tests/golden/relight_ground_24.npz).  fp32 tolerance 1e-3 (q98) relative
+    to 1 + |ref| (plane hits reach 1e2 m near the horizon)."""
+    H = 32
+    b = scene.make_batch(H, H, seed=0, n_env=1)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    probes = {k: v[0] for k, v in b['novel_lights'].items()}
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=8192, test_light=('main', 'all'),
+                 return_lvis=True, ground_shading=True, sync_timing=False)
+    out = r.render(b)
+    ref = O.render_novel_light(b, sd, O.Cfg(), probes, torch.float32, DEV, ground=True)
+    assert out['main']['rgb_map'].shape == (1, H * H, 3)
+    n_shadowed = int((ref['main']['lvis_map'] < 0.999).sum())
+    assert n_shadowed > 1000          # the body does cast a shadow on the floor in this view
+    for name in ['main'] + list(probes):
+        for k in ('rgb_map', 'acc_map', 'surf_map', 'albedo_map', 'shade_map', 'spec_map', 'depth_map', 'norm_map', 'roughness_map'):
+            g, rr = out[name][k][0].double().cpu(), ref[name][k].double().cpu()
+            e = (g - rr).abs() / (1 + rr.abs())
+            assert torch.quantile(e.flatten(), 0.98) <= 1e-3, f'{name}.{k}: q98 {torch.quantile(e.flatten(), 0.98):.3e}'
+    for k in ('lvis_map', 'ldot_map'):
+        e = _err(out['main'][k][0], ref['main'][k])
+        assert torch.quantile(e.flatten()[::7], 0.995) <= 2e-3, f'main.{k}: q99.5 {torch.quantile(e.flatten()[::7], 0.995):.3e}'
+    p = O.psnr(out['main']['rgb_map'][0].cpu().reshape(H, H, 3), ref['main']['rgb_map'].cpu().reshape(H, H, 3))
+    assert p >= 45, f'PSNR {p:.1f} dB'
