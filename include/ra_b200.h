@@ -186,6 +186,39 @@ int ra_blend_ground(ra_handle* h, const float* acc_g, const float* ground, const
  * is on (alpha_output_ is skipped, :1109-1113); outputs are multiplied by acc so that ra_blend_ground(human_premul=1) applies. */
 int ra_relight_envmaps_raw(ra_handle* h, const float* probes, int32_t n_env, float* rgb, float* shade, float* spec, void* stream);
 
+/* ---- per-frame batch preparation on the GPU ------------------------------------------------------
+ * Replaces the CPU work of pose_dataset.__getitem__ (lib/datasets/pose_dataset.py:45-113): get_lbs_params / get_blend
+ * (base_dataset.py:308-397) and get_rays_within_bounds (lib/utils/data_utils.py:925-938).  The body is uploaded once;
+ * per frame only poses / Rh / Th / camera cross PCIe. */
+typedef struct ra_body {        /* "host or device" pointers, copied by the library */
+    const float* tjoints;       /* (J,3) rest joints                      base_dataset.py:205,219 */
+    const int32_t* parents;     /* (J)   kinematic tree, -1 for the root  base_dataset.py:213 */
+    const float* rverts;        /* (N,3) rest-pose vertices */
+    const float* rnorm;         /* (N,3) rest-pose normals, or NULL when `faces` is given */
+    const int32_t* faces;       /* (n_faces,3) or NULL: vertex normals of the posed mesh (pytorch3d verts_normals, base_dataset.py:380-381) */
+    int32_t n_faces;
+    const float* weights;       /* (N,J) skinning weights */
+} ra_body;
+int ra_upload_body(ra_handle* h, const ra_body* body, void* stream);
+
+typedef struct ra_pose_outputs {   /* device pointers; NULL entries are skipped except A, R, pverts, pnorm (needed by ra_set_frame) */
+    float* A;        /* (J,4,4)  get_rigid_transform (net_utils.py:1163-1172) */
+    float* R;        /* (3,3)    cv2.Rodrigues(Rh) */
+    float* pverts;   /* (N,3)    tpose_points_to_pose_points(rverts, weights, A)  blend_utils.py:303-313 */
+    float* pnorm;    /* (N,3) */
+    float* wverts;   /* (N,3)    pose_points_to_world_points                       blend_utils.py:264-273 */
+    float* wnorm;    /* (N,3) */
+    float* pbounds;  /* (2,3)    get_bounds(pverts), +-bounds_pad                  data_utils.py:1241-1248 */
+    float* wbounds;  /* (2,3) */
+} ra_pose_outputs;
+/* poses (J*3 axis-angle), Rh (3), Th (3): DEVICE pointers (the only per-frame upload, < 1 KB). */
+int ra_prepare_pose(ra_handle* h, const float* poses, const float* Rh, const float* Th, float bounds_pad, const ra_pose_outputs* out, void* stream);
+/* get_rays_within_bounds: K, R (3,3), T (3) are HOST pointers (camera, 21 floats); wbounds (2,3) device.  Outputs have capacity
+ * H*W rays; the rays of the pixels whose ray hits the box are written compacted in row-major pixel order, mask_at_box is
+ * H*W bytes, *n_rays (device int) receives P. */
+int ra_prepare_rays(ra_handle* h, const float* K, const float* R, const float* T, int32_t H, int32_t W, const float* wbounds,
+                    float* ray_o, float* ray_d, float* near, float* far, unsigned char* mask_at_box, int32_t* n_rays, void* stream);
+
 /* sphere_tracing_renderer.Renderer.render for the AniSDF network (config 1; raw 16-ch branch :634-635). */
 int ra_render_anisdf_trace(ra_handle* h, const float* ray_o, const float* ray_d, const float* near, const float* far,
                            int64_t P, const ra_outputs* out, void* stream);

@@ -767,6 +767,96 @@ def render_volume(batch: dict, sd: dict, cfg: Cfg, dtype=torch.float32, device='
     return {k: torch.cat([o[k] for o in outs]) for k in outs[0]}
 
 
+# ---------------------------------------------------------------------------------------------- batch preparation (row f1)
+def rodrigues(r: torch.Tensor) -> torch.Tensor:
+    """smplx.lbs.batch_rodrigues (smplx is an unpinned dependency, requirements.txt:19; called at net_utils.py:1163-1172):
+    angle = |r + 1e-8|, axis = r / angle, R = I + sin K + (1 - cos) K K.   (n,3) -> (n,3,3)"""
+    angle = torch.norm(r + 1e-8, dim=1, keepdim=True)
+    d = r / angle
+    cos, sin = torch.cos(angle)[:, None], torch.sin(angle)[:, None]
+    rx, ry, rz = d[:, 0:1], d[:, 1:2], d[:, 2:3]
+    z = torch.zeros_like(rx)
+    K = torch.cat([z, -rz, ry, rz, z, -rx, -ry, rx, z], dim=1).view(-1, 3, 3)
+    return torch.eye(3, dtype=r.dtype)[None] + sin * K + (1 - cos) * torch.bmm(K, K)
+
+
+def rigid_transform(poses: torch.Tensor, joints: torch.Tensor, parents) -> torch.Tensor:
+    """get_rigid_transform (net_utils.py:1163-1172) = smplx.lbs.batch_rigid_transform: chain of [R_j | t_j - t_parent] and
+    A_j = G_j with the rest joint taken out.  poses (J,3), joints (J,3) -> A (J,4,4)."""
+    R = rodrigues(poses.reshape(-1, 3))
+    J = joints.shape[0]
+    G = []
+    for j in range(J):
+        p = int(parents[j])
+        L = torch.eye(4, dtype=poses.dtype)
+        L[:3, :3] = R[j]
+        L[:3, 3] = joints[j] - (joints[p] if p >= 0 else 0.0)
+        G.append(L if p < 0 else G[p] @ L)
+    G = torch.stack(G)
+    A = G.clone()
+    A[:, :3, 3] = G[:, :3, 3] - torch.einsum('jab,jb->ja', G[:, :3, :3], joints)
+    return A
+
+
+def vertex_normals(verts: torch.Tensor, faces: torch.Tensor) -> torch.Tensor:
+    """pytorch3d Meshes.verts_normals_packed (called at base_dataset.py:380-381): area-weighted face normals accumulated
+    per corner, F.normalize(eps=1e-6)."""
+    n = torch.zeros_like(verts)
+    vf = verts[faces]
+    n = n.index_add(0, faces[:, 1], torch.cross(vf[:, 2] - vf[:, 1], vf[:, 0] - vf[:, 1], dim=1))
+    n = n.index_add(0, faces[:, 2], torch.cross(vf[:, 0] - vf[:, 2], vf[:, 1] - vf[:, 2], dim=1))
+    n = n.index_add(0, faces[:, 0], torch.cross(vf[:, 1] - vf[:, 0], vf[:, 2] - vf[:, 0], dim=1))
+    return F.normalize(n, eps=1e-6, dim=1)
+
+
+def prepare_pose(poses, Rh, Th, tjoints, parents, rverts, weights, rnorm=None, faces=None, pad: float = 0.05) -> dict:
+    """get_lbs_params / get_blend (base_dataset.py:308-397, the LBS branch :337-343): float32 torch on the CPU."""
+    t = lambda a: torch.as_tensor(a, dtype=torch.float32)
+    poses, Rh, Th, tjoints, rverts, weights = t(poses).reshape(-1, 3), t(Rh).reshape(1, 3), t(Th).reshape(1, 3), t(tjoints), t(rverts), t(weights)
+    A = rigid_transform(poses, tjoints, parents)
+    R = rodrigues(Rh)[0]
+    A_bw = torch.einsum('nj,jab->nab', weights, A)                                   # blend_transform  blend_utils.py:212-218
+    pverts = torch.sum(A_bw[:, :3, :3] * rverts[:, None], dim=-1) + A_bw[:, :3, 3]   # tpose_points_to_pose_points :303-313
+    wverts = pverts @ R.mT + Th                                                      # pose_points_to_world_points :264-273
+    if faces is not None:
+        pnorm = vertex_normals(pverts, torch.as_tensor(faces, dtype=torch.long))
+        wnorm = vertex_normals(wverts, torch.as_tensor(faces, dtype=torch.long))
+    else:
+        pn = torch.sum(A_bw[:, :3, :3] * t(rnorm)[:, None], dim=-1)
+        pnorm = pn / (pn.norm(dim=-1, keepdim=True) + 1e-12)
+        wnorm = pnorm @ R.mT
+    bounds = lambda x: torch.stack([x.min(0)[0] - pad, x.max(0)[0] + pad])            # get_bounds  data_utils.py:1241-1248
+    return dict(A=A, R=R, pverts=pverts, pnorm=pnorm, wverts=wverts, wnorm=wnorm, pbounds=bounds(pverts), wbounds=bounds(wverts))
+
+
+def rays_within_bounds(H: int, W: int, K, R, T, bounds) -> dict:
+    """get_rays_within_bounds (data_utils.py:925-938) = get_rays (:827-845) + get_near_far / get_full_near_far (:848-875),
+    in numpy float32 like the reference."""
+    import numpy as np
+    K, R, T, bounds = (np.asarray(a, np.float32) for a in (K, R, T, bounds))
+    ray_o = -np.dot(R.T, T).ravel()
+    i, j = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing='ij')
+    xy1 = np.stack([j, i, np.ones_like(i)], axis=2)
+    pixel_camera = np.dot(xy1, np.linalg.inv(K).T)
+    pixel_world = np.dot(pixel_camera - T.ravel(), R)
+    ray_d = pixel_world - ray_o[None, None]
+    ray_d = ray_d / np.linalg.norm(ray_d, axis=2, keepdims=True)
+    ray_o = np.broadcast_to(ray_o, ray_d.shape).reshape(-1, 3).astype(np.float32)
+    ray_d = ray_d.reshape(-1, 3).astype(np.float32)
+    norm_d = np.linalg.norm(ray_d, axis=-1, keepdims=True)
+    viewdir = ray_d / norm_d
+    viewdir[(viewdir < 1e-5) & (viewdir > -1e-10)] = 1e-5
+    viewdir[(viewdir > -1e-5) & (viewdir < 1e-10)] = -1e-5
+    tmin = (bounds[:1] - ray_o[:1]) / viewdir
+    tmax = (bounds[1:2] - ray_o[:1]) / viewdir
+    near = np.max(np.minimum(tmin, tmax), axis=-1)
+    far = np.min(np.maximum(tmin, tmax), axis=-1)
+    mask = near < far
+    near, far = near / norm_d[..., 0], far / norm_d[..., 0]
+    near, far = near[mask] / norm_d[mask, 0], far[mask] / norm_d[mask, 0]
+    return dict(ray_o=ray_o[mask], ray_d=ray_d[mask], near=near.astype(np.float32), far=far.astype(np.float32), mask_at_box=mask.reshape(H, W))
+
+
 def rotate_probe(probe: torch.Tensor, j: int, repeat: int) -> torch.Tensor:
     """rotate_envmap's shift_image applied to the probe (relight_utils.py:55-103): (eH,eW,3) -> (eH,eW,3)."""
     image = probe[None]

@@ -197,6 +197,28 @@ def run(mode: str, H: int, seed: int, n_env: int, fitted: bool, threads: int = 0
     return flat, b
 
 
+def run_prep(H: int, seed: int, frame: int = 2):
+    """Row f1 fixtures: the reference's own in-repo dataset-side functions (numpy / torch, importable under the shims) on the
+    synthetic scene: get_rays_within_bounds, get_bounds (lib/utils/data_utils.py), tpose_points_to_pose_points,
+    pose_points_to_world_points (lib/utils/blend_utils.py).  get_rigid_transform needs smplx (absent): A comes from the scene."""
+    import torch
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, here)
+    root = find_reference()
+    install_shims()
+    sys.path.insert(0, root); sys.argv = ['oracle']; os.chdir(root)
+    from lib.utils import data_utils as DU, blend_utils as BU
+    from relightableavatar_b200 import scene
+    b = scene.make_batch(H, H, frame=frame, n_frames=frame + 1, seed=seed, n_env=0)
+    body = scene.make_body(seed)
+    ro, rd, near, far, mask = DU.get_rays_within_bounds(H, H, b['cam_K'][0], b['cam_R'][0], b['cam_T'][0], b['wbounds'][0])
+    rv = torch.as_tensor(body.rverts, dtype=torch.float32)[None]
+    pp = BU.tpose_points_to_pose_points(rv, torch.as_tensor(b['weights']), torch.as_tensor(b['A']))
+    ww = BU.pose_points_to_world_points(pp, torch.as_tensor(b['R']), torch.as_tensor(b['Th']))
+    return dict(ray_o=ro, ray_d=rd, near=near, far=far, mask_at_box=mask, pverts=pp[0].numpy(), wverts=ww[0].numpy(),
+                wbounds=DU.get_bounds(ww[0].numpy()), pbounds=DU.get_bounds(pp[0].numpy()), _frame=np.int64(frame))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--mode', required=True)
@@ -207,7 +229,10 @@ def main():
     ap.add_argument('--out', required=True)
     a = ap.parse_args()
     out_path = os.path.abspath(a.out)
-    flat, _ = run(a.mode, a.H, a.seed, a.n_env, not a.raw_init)
+    if a.mode == 'prep':
+        flat = run_prep(a.H, a.seed)
+    else:
+        flat, _ = run(a.mode, a.H, a.seed, a.n_env, not a.raw_init)
     np.savez_compressed(out_path, **flat)
     print('wrote', out_path, {k: v.shape for k, v in flat.items()})
 

@@ -11,7 +11,8 @@ LIB_PATH = os.environ.get('RA_LIB_PATH') or os.path.join(HERE, 'libra_b200.so') 
 EXPORTS = ['ra_create', 'ra_destroy', 'ra_last_error', 'ra_upload_weights', 'ra_set_frame', 'ra_render_relight',
            'ra_relight_envmaps', 'ra_render_anisdf_trace', 'ra_render_anisdf_volume', 'ra_query_sdf', 'ra_query_raw',
            'ra_get_stats', 'ra_launch_count', 'ra_profile_enable', 'ra_profile_read', 'ra_rotate_probes', 'ra_assemble_image',
-           'ra_ground_begin', 'ra_render_ground', 'ra_relight_ground', 'ra_blend_ground', 'ra_relight_envmaps_raw']
+           'ra_ground_begin', 'ra_render_ground', 'ra_relight_ground', 'ra_blend_ground', 'ra_relight_envmaps_raw',
+           'ra_upload_body', 'ra_prepare_pose', 'ra_prepare_rays']
 
 fp = C.POINTER(C.c_float)
 
@@ -46,6 +47,18 @@ OUTPUT_MAPS = ('rgb_map', 'acc_map', 'depth_map', 'surf_map', 'norm_map', 'cpts_
 
 class ra_outputs(C.Structure):
     _fields_ = [(n, fp) for n in OUTPUT_MAPS]
+
+
+class ra_body(C.Structure):
+    _fields_ = [('tjoints', fp), ('parents', C.POINTER(C.c_int32)), ('rverts', fp), ('rnorm', fp), ('faces', C.POINTER(C.c_int32)),
+                ('n_faces', C.c_int32), ('weights', fp)]
+
+
+POSE_OUTPUTS = ('A', 'R', 'pverts', 'pnorm', 'wverts', 'wnorm', 'pbounds', 'wbounds')
+
+
+class ra_pose_outputs(C.Structure):
+    _fields_ = [(n, fp) for n in POSE_OUTPUTS]
 
 
 GROUND_MAPS = ('rgb_map', 'surf_map', 'albedo_map', 'roughness_map', 'spec_map', 'norm_map', 'shade_map', 'depth_map', 'lvis_map', 'ldot_map')
@@ -99,6 +112,9 @@ def load():
     lib.ra_render_ground.argtypes = [vp, C.POINTER(ra_ground_config), vp, vp, vp, i64, vp, i32, i32, vp, i32, i32, C.POINTER(ra_ground_outputs), vp]
     lib.ra_relight_ground.argtypes = [vp, C.POINTER(ra_ground_config), vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
     lib.ra_blend_ground.argtypes = [vp, vp, vp, vp, i32, i32, i64, vp, vp]
+    lib.ra_upload_body.argtypes = [vp, C.POINTER(ra_body), vp]
+    lib.ra_prepare_pose.argtypes = [vp, vp, vp, vp, f32, C.POINTER(ra_pose_outputs), vp]
+    lib.ra_prepare_rays.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.ra_profile_enable.argtypes = [vp, i32]
     lib.ra_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]
     _lib = lib

@@ -17,6 +17,7 @@
 #include "mlp_simt.cuh"
 #include "render.cuh"
 #include "ground.cuh"
+#include "prep.cuh"
 #include "mlp_tc.cuh"
 #include "mlp_tc2.cuh"
 #include "mlp_tc3.cuh"
@@ -90,7 +91,8 @@ struct ra_handle {
     float* bg_spec = nullptr;
     int* blk_cnt = nullptr; int64_t blk_cap = 0;      // image assembly scratch
     int* pix2ray = nullptr; int64_t pix_cap = 0;      // ground pass: image pixel -> ray (ra_ground_begin)
-    float *g_weight = nullptr, *g_light = nullptr;    // ground pass: far-field blend weight (F), per-light radiance table (L,3)
+    float *g_weight = nullptr, *g_light = nullptr;
+    BodyDev body; int* prep_mm = nullptr; float* prep_nacc = nullptr;      // f1: uploaded body, bounds scratch, normal accumulator    // ground pass: far-field blend weight (F), per-light radiance table (L,3)
     // ---- fp32 MLP chunk buffers
     float *Xr0, *ra_[8], *Xr4, *z8, *resd_o, *cpts_o, *Xs0, *sb_[8], *Xs4, *out257, *GA, *GB, *dpe0, *dpes, *gcp, *u4, *gbp, *nrm_o;
     float *hd1, *hd2, *head_a, *head_r, *Xrn, *rn1, *rn2;
@@ -634,6 +636,81 @@ extern "C" int ra_relight_envmaps(ra_handle* h, const float* probes, int32_t n_e
 }
 extern "C" int ra_relight_envmaps_raw(ra_handle* h, const float* probes, int32_t n_env, float* rgb, float* shade, float* spec, void* stream) {
     return relight_envmaps_impl(h, probes, n_env, rgb, shade, spec, stream, 1);
+}
+
+// ---------------------------------------------------------------------------------------------- batch preparation (row f1)
+template <typename T>
+static int upload_any(ra_handle* h, T** dst, const T* src, size_t n, cudaStream_t st) {
+    if (*dst) cudaFree(*dst);
+    CK(dalloc(dst, n));
+    CK(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int ra_upload_body(ra_handle* h, const ra_body* b, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->cfg.n_verts, J = h->cfg.n_bones;
+    if (!b->tjoints || !b->parents || !b->rverts || !b->weights || (!b->rnorm && !b->faces)) { h->err = "ra_upload_body: tjoints, parents, rverts, weights and rnorm-or-faces are required"; return 1; }
+    if (upload_any(h, &h->body.tjoints, b->tjoints, (size_t)J * 3, st)) return 1;
+    if (upload_any(h, &h->body.parents, (const int*)b->parents, (size_t)J, st)) return 1;
+    if (upload_any(h, &h->body.rverts, b->rverts, (size_t)N * 3, st)) return 1;
+    if (upload_any(h, &h->body.weights, b->weights, (size_t)N * J, st)) return 1;
+    if (b->rnorm) { if (upload_any(h, &h->body.rnorm, b->rnorm, (size_t)N * 3, st)) return 1; }
+    else if (h->body.rnorm) { cudaFree(h->body.rnorm); h->body.rnorm = nullptr; }
+    h->body.n_faces = 0;
+    if (b->faces && b->n_faces > 0) {
+        if (upload_any(h, &h->body.faces, (const int*)b->faces, (size_t)b->n_faces * 3, st)) return 1;
+        h->body.n_faces = b->n_faces;
+    }
+    if (!h->prep_mm) { CK(dalloc(&h->prep_mm, 16)); CK(dalloc(&h->prep_nacc, (size_t)N * 3)); }
+    h->body.ready = true;
+    return 0;
+}
+
+extern "C" int ra_prepare_pose(ra_handle* h, const float* poses, const float* Rh, const float* Th, float bounds_pad, const ra_pose_outputs* o, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!h->body.ready) { h->err = "ra_prepare_pose before ra_upload_body"; return 1; }
+    if (!o->A || !o->R || !o->pverts || !o->pnorm) { h->err = "ra_prepare_pose: A, R, pverts, pnorm outputs are required"; return 1; }
+    const int N = h->cfg.n_verts, J = h->cfg.n_bones;
+    if (J + 1 > 1024) { h->err = "ra_prepare_pose: too many bones"; return 1; }
+    int threads = ((J + 1 + 31) / 32) * 32;
+    LAUNCH(h, k_prep_pose, 1, threads, (size_t)J * 21 * sizeof(float), st, poses, Rh, h->body.tjoints, h->body.parents, J, o->A, (float*)nullptr, o->R);
+    LAUNCH(h, k_prep_bounds_init, 1, 32, 0, st, h->prep_mm);
+    const bool mesh_normals = h->body.n_faces > 0;
+    LAUNCH(h, k_prep_verts, (N + 127) / 128, 128, 0, st, h->body.rverts, mesh_normals ? (const float*)nullptr : h->body.rnorm, h->body.weights, o->A, N, J,
+           o->R, Th, o->pverts, o->pnorm, o->wverts, o->wnorm, h->prep_mm);
+    if (mesh_normals) {
+        CK(cudaMemsetAsync(h->prep_nacc, 0, (size_t)N * 3 * sizeof(float), st));
+        LAUNCH(h, k_prep_face_normals, (h->body.n_faces + 127) / 128, 128, 0, st, o->pverts, h->body.faces, h->body.n_faces, h->prep_nacc);
+        LAUNCH(h, k_prep_normals_finish, (N + 127) / 128, 128, 0, st, h->prep_nacc, N, o->R, o->pnorm, o->wnorm);
+    }
+    LAUNCH(h, k_prep_bounds_finish, 1, 32, 0, st, h->prep_mm, bounds_pad, o->pbounds, o->wbounds);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ra_prepare_rays(ra_handle* h, const float* K, const float* R, const float* T, int32_t H, int32_t W, const float* wbounds,
+                               float* ray_o, float* ray_d, float* near_, float* far_, unsigned char* mask_at_box, int32_t* n_rays, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (H <= 0 || W <= 0) { h->err = "ra_prepare_rays: bad image size"; return 1; }
+    CamDev c;
+    // inv(K) by the adjugate in double (np.linalg.inv on the host in the reference, data_utils.py:839)
+    double k[9]; for (int i = 0; i < 9; i++) k[i] = K[i];
+    double det = k[0] * (k[4] * k[8] - k[5] * k[7]) - k[1] * (k[3] * k[8] - k[5] * k[6]) + k[2] * (k[3] * k[7] - k[4] * k[6]);
+    if (det == 0.0) { h->err = "ra_prepare_rays: singular K"; return 1; }
+    double inv[9] = {(k[4] * k[8] - k[5] * k[7]), -(k[1] * k[8] - k[2] * k[7]), (k[1] * k[5] - k[2] * k[4]),
+                     -(k[3] * k[8] - k[5] * k[6]), (k[0] * k[8] - k[2] * k[6]), -(k[0] * k[5] - k[2] * k[3]),
+                     (k[3] * k[7] - k[4] * k[6]), -(k[0] * k[7] - k[1] * k[6]), (k[0] * k[4] - k[1] * k[3])};
+    for (int i = 0; i < 9; i++) { c.Kinv[i] = (float)(inv[i] / det); c.R[i] = R[i]; }
+    for (int a = 0; a < 3; a++) { c.T[a] = T[a]; c.o[a] = -(R[a] * T[0] + R[3 + a] * T[1] + R[6 + a] * T[2]); }       // -R^T T
+    int n = H * W, nb = (n + 255) / 256;
+    if (nb > h->blk_cap) { if (h->blk_cnt) cudaFree(h->blk_cnt); CK(dalloc(&h->blk_cnt, (size_t)nb)); h->blk_cap = nb; }
+    LAUNCH(h, k_prep_rays_count, nb, 256, 0, st, c, wbounds, H, W, mask_at_box, h->blk_cnt);
+    LAUNCH(h, k_scan_blocks, 1, 1024, 0, st, h->blk_cnt, nb);
+    LAUNCH(h, k_prep_rays_write, nb, 256, 0, st, c, wbounds, H, W, h->blk_cnt, nb, ray_o, ray_d, near_, far_, (int*)n_rays);
+    CK(cudaGetLastError());
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------- ground plane (row f2)

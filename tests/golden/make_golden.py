@@ -25,6 +25,8 @@ CASES = [
     ('anisdf_volume_24', 'anisdf_volume', 24, 0, None),
     # row f2: vis_ground_shading on (image-sized maps; the CPU harness scrambles `inds`, see oracle.render_ground_pass)
     ('relight_ground_24', 'relight_ground', 24, 1, None),
+    # row f1: the reference's dataset-side numpy / torch functions (rays, AABB, LBS, bounds)
+    ('prep_24', 'prep', 24, 0, None),
 ]
 
 DROP_DUP = ('surf_map', 'depth_map', 'acc_map', 'albedo_map', 'roughness_map', 'norm_map', 'ray_o', 'cpts_map',

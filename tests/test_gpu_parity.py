@@ -274,3 +274,43 @@ def test_ground_shading_f2():
         assert torch.quantile(e.flatten()[::7], 0.995) <= 2e-3, f'main.{k}: q99.5 {torch.quantile(e.flatten()[::7], 0.995):.3e}'
     p = O.psnr(out['main']['rgb_map'][0].cpu().reshape(H, H, 3), ref['main']['rgb_map'].cpu().reshape(H, H, 3))
     assert p >= 45, f'PSNR {p:.1f} dB'
+
+
+def test_batch_preparation_f1():
+    """per-frame batch preparation on the GPU (Rodrigues + kinematic chain, LBS, normals, bounds, rays,
+    AABB near/far, mask compaction) against the oracle restatement (pinned by tests/golden/prep_24.npz), then the frame rendered
+    from the GPU-prepared batch against the frame rendered from the CPU-prepared one."""
+    from relightableavatar_b200.prepare import FramePreparer
+    H, frame = 64, 2
+    b = scene.make_batch(H, H, frame=frame, n_frames=frame + 1, seed=0, n_env=0)
+    body = scene.make_body(0)
+    poses, Rh, _ = scene.make_motion(frame + 1, 1)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=8192, test_light=('main',), sync_timing=False)
+    prep = FramePreparer(r.engine, body.joints, body.parents, body.rverts, body.weights, body.big_A, body.tverts, rnorm=body.rnorm, tnorm=body.tnorm)
+    Th = b['Th'][0, 0]
+    gb = prep.make_batch(poses[frame], Rh[frame], Th, b['cam_K'][0], b['cam_R'][0], b['cam_T'][0], H, H, extra={'train_poses': b['train_poses']})
+    o = O.prepare_pose(poses[frame], Rh[frame], Th, body.joints, body.parents, body.rverts, body.weights, rnorm=body.rnorm)
+    for k in ('A', 'R', 'pverts', 'pnorm', 'wverts', 'wnorm', 'pbounds', 'wbounds'):
+        e = _err(gb[k][0], o[k])
+        assert float(e.max()) <= 5e-6, f'{k}: max {float(e.max()):.3e}'
+    rr = O.rays_within_bounds(H, H, b['cam_K'][0], b['cam_R'][0], b['cam_T'][0], o['wbounds'].numpy())
+    m_g, m_r = gb['mask_at_box'][0].cpu().numpy(), rr['mask_at_box']
+    assert (m_g != m_r).sum() <= 2, f'{(m_g != m_r).sum()} mask flips'            # box-edge rays may flip under fp32 re-association
+    if (m_g == m_r).all():
+        for k in ('ray_o', 'ray_d', 'near', 'far'):
+            e = np.abs(gb[k][0].cpu().numpy() - rr[k])
+            assert e.max() <= 2e-5, f'{k}: max {e.max():.3e}'
+    # mesh normals path: faces given instead of rest normals (pytorch3d verts_normals restated)
+    g = torch.Generator().manual_seed(0)
+    faces = torch.randint(0, body.rverts.shape[0], (9000, 3), generator=g).numpy().astype(np.int32)
+    prep2 = FramePreparer(r.engine, body.joints, body.parents, body.rverts, body.weights, body.big_A, body.tverts, faces=faces)
+    p2 = prep2.pose(poses[frame], Rh[frame], Th)
+    o2 = O.prepare_pose(poses[frame], Rh[frame], Th, body.joints, body.parents, body.rverts, body.weights, faces=faces)
+    assert float(_err(p2['pnorm'], o2['pnorm']).max()) <= 1e-4 and float(_err(p2['wnorm'], o2['wnorm']).max()) <= 1e-4
+    # the render consumes the device-resident batch unchanged
+    out_g = r.render(gb)['main']
+    out_c = r.render(b)['main']
+    if (m_g == m_r).all():
+        p = O.psnr(O.assemble_image(b, out_g['rgb_map'][0].cpu()), O.assemble_image(b, out_c['rgb_map'][0].cpu()))
+        assert p >= 50, f'PSNR {p:.1f} dB'

@@ -69,6 +69,34 @@ def test_relight_ground_matches_reference():
     np.testing.assert_allclose(out['_main_full']['wbounds_after'].numpy(), g['wbounds_after'][0], atol=1e-6)
 
 
+def test_batch_preparation_matches_reference():
+    """Row f1: the oracle's restatement of the dataset-side per-frame work against the reference's own functions
+    (get_rays_within_bounds, get_bounds, tpose_points_to_pose_points, pose_points_to_world_points run under the harness).
+    The kinematic chain (smplx.lbs, absent) is unpinned: checked against the scene's float64 forward kinematics instead."""
+    g = _load('prep_24')
+    H, frame = int(g['_H']), int(g['_frame'])
+    b = scene.make_batch(H, H, frame=frame, n_frames=frame + 1, seed=0, n_env=0)
+    body = scene.make_body(0)
+    poses, Rh, _ = scene.make_motion(frame + 1, 1)
+    o = O.prepare_pose(poses[frame], Rh[frame], b['Th'][0, 0], body.joints, body.parents, body.rverts, body.weights, rnorm=body.rnorm)
+    for k in ('pverts', 'wverts', 'wbounds', 'pbounds'):
+        _close(k, o[k], g[k], 2e-6)
+    for k in ('A', 'R', 'pnorm', 'wnorm'):
+        _close(k + ' (vs scene fp64)', o[k], b[k][0], 2e-6)
+    r = O.rays_within_bounds(H, H, b['cam_K'][0], b['cam_R'][0], b['cam_T'][0], g['wbounds'])
+    assert (r['mask_at_box'] == g['mask_at_box']).all()
+    for k in ('ray_o', 'ray_d', 'near', 'far'):
+        _close(k, r[k], g[k], 2e-6)
+    # vertex normals (pytorch3d, absent): on a closed analytic mesh they must agree with the true normals
+    import numpy as np_
+    t = (1 + 5 ** 0.5) / 2
+    v = torch.tensor([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t], [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], dtype=torch.float32)
+    f = torch.tensor([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2], [10, 7, 6], [7, 1, 8],
+                      [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]])
+    n = O.vertex_normals(v, f)
+    assert torch.allclose(n, torch.nn.functional.normalize(v, dim=1), atol=1e-5)      # icosahedron: vertex normal = radial direction
+
+
 def test_anisdf_trace_matches_reference():
     g = _load('anisdf_trace_48')
     H = int(g['_H'])
