@@ -8,9 +8,15 @@
 #define RA_MAX_GRID_DIM 64
 #define RA_MAX_CELLS (RA_MAX_GRID_DIM * RA_MAX_GRID_DIM * RA_MAX_GRID_DIM)
 #define RA_NLIGHT_MAX 512
+#ifndef RA_KNN_RMAX
 #define RA_KNN_RMAX 2
+#endif
+#ifndef RA_TRACE_MINBLOCKS
+#define RA_TRACE_MINBLOCKS 3      // resident 256-thread blocks per SM the tracing kernels are compiled for (register cap)
+#endif
 #define RA_GRID2_RATIO 3.0f
 #define RA_MAX_OCC 8192
+#define RA_NB_LEVELS 3       // neighbourhood-list levels: certified search radius up to 3 fine cells (>= the 12.5 cm shell at 4 cm cells)
 
 // Per-frame constants living in device memory (written by k_frame_prep, read by every kernel).
 struct FrameConst {
@@ -42,6 +48,11 @@ struct SortedVerts {
     int* cell_start2; // [cells2+1]
     float4* occ_lo;   // occupied coarse cells: tight bbox min xyz, w = first vertex (int bits) in pos2
     float4* occ_hi;   //                        tight bbox max xyz, w = end vertex (int bits)
+    // per-cell neighbourhood lists (rebuilt per frame): level 0 = the 3x3x3 block around the cell, level 1 / 2 = the cube
+    // shells of radius 2 / 3.  nb_pos entries: xyz, w = index into pos/nrm/tv/T (int bits).  A query scans ONE contiguous
+    // list per level instead of walking grid rows -- same candidates, no per-row control flow (warp divergence).
+    int* nb_start[RA_NB_LEVELS];     // [cells+1] each
+    float4* nb_pos[RA_NB_LEVELS];
 };
 
 struct KnnOut {

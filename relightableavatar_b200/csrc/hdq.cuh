@@ -221,7 +221,104 @@ __global__ void k_grid_fill(const FrameConst* fc, const float* __restrict__ pver
     for (int k = 0; k < 24; k++) sv.T[(size_t)dst * 24 + k] = T[k];
 }
 
+// ------------------------------------------------------------------------------------------ neighbourhood lists
+// Enumerate, for the cube shell of radius r around cell (cx,cy,cz) (r == 1: the whole 3x3x3 block), the contiguous
+// runs of the cell-sorted vertex array: full x-runs on the z / y faces, the two end cells on the inner rows.
+template <typename F>
+__device__ __forceinline__ void nb_for_each_run(const GridRef& g, const int* __restrict__ cell_start, int cx, int cy, int cz, int r, F&& f) {
+    const int dx_ = g.dim[0], dy_ = g.dim[1], dz_ = g.dim[2];
+    int z0 = max(cz - r, 0), z1 = min(cz + r, dz_ - 1);
+    int y0 = max(cy - r, 0), y1 = min(cy + r, dy_ - 1);
+    int x0 = max(cx - r, 0), x1 = min(cx + r, dx_ - 1);
+    for (int z = z0; z <= z1; z++) {
+        bool zf = (r == 1) || (z == cz - r) || (z == cz + r);
+        for (int y = y0; y <= y1; y++) {
+            bool yf = zf || (y == cy - r) || (y == cy + r);
+            int row = (z * dy_ + y) * dx_;
+            if (yf) {
+                f(__ldg(&cell_start[row + x0]), __ldg(&cell_start[row + x1 + 1]));
+            } else {
+                if (cx - r >= 0) f(__ldg(&cell_start[row + cx - r]), __ldg(&cell_start[row + cx - r + 1]));
+                if (cx + r < dx_) f(__ldg(&cell_start[row + cx + r]), __ldg(&cell_start[row + cx + r + 1]));
+            }
+        }
+    }
+}
+
+// counts of all levels, one thread per cell: cnt[level * (RA_MAX_CELLS + 1) + cell]
+__global__ void k_nb_count(const FrameConst* fc, const int* __restrict__ cell_start, int* cnt) {
+    GridRef g = grid_ref(fc, 0);
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.cells; c += gridDim.x * blockDim.x) {
+        int cx = c % g.dim[0], cy = (c / g.dim[0]) % g.dim[1], cz = c / (g.dim[0] * g.dim[1]);
+        for (int lv = 0; lv < RA_NB_LEVELS; lv++) {
+            int n = 0;
+            nb_for_each_run(g, cell_start, cx, cy, cz, lv + 1, [&](int s, int e) { n += e - s; });
+            cnt[lv * (RA_MAX_CELLS + 1) + c] = n;
+        }
+    }
+}
+
+// exclusive scans of the RA_NB_LEVELS count arrays (one block per level)
+__global__ void k_nb_scan(const FrameConst* fc, const int* __restrict__ cnt, SortedVerts sv) {
+    __shared__ int carry;
+    __shared__ int wsum[32];
+    const int lv = blockIdx.x;
+    const int n = fc->g_cells;
+    const int* in = cnt + lv * (RA_MAX_CELLS + 1);
+    int* out = sv.nb_start[lv];
+    int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        int i = base + tid;
+        int v = (i < n) ? in[i] : 0, x = v;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int s = (lane < (blockDim.x >> 5)) ? wsum[lane] : 0;
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        int excl = carry + (wid ? wsum[wid - 1] : 0) + x - v;
+        if (i < n) out[i] = excl;
+        __syncthreads();
+        if (tid == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry;
+}
+
+// one warp per (cell, level): copy the runs into the cell's contiguous list
+__global__ void k_nb_fill(const FrameConst* fc, const int* __restrict__ cell_start, const float4* __restrict__ pos, SortedVerts sv) {
+    GridRef g = grid_ref(fc, 0);
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int w = warp; w < g.cells * RA_NB_LEVELS; w += nwarps) {
+        const int c = w / RA_NB_LEVELS, lv = w % RA_NB_LEVELS;
+        int cx = c % g.dim[0], cy = (c / g.dim[0]) % g.dim[1], cz = c / (g.dim[0] * g.dim[1]);
+        int dst = sv.nb_start[lv][c];
+        if (sv.nb_start[lv][c + 1] == dst) continue;
+        float4* out = sv.nb_pos[lv];
+        nb_for_each_run(g, cell_start, cx, cy, cz, lv + 1, [&](int s, int e) {
+            for (int v = s + lane; v < e; v += 32) {
+                float4 q = __ldg(&pos[v]);
+                out[dst + (v - s)] = make_float4(q.x, q.y, q.z, __int_as_float(v));
+            }
+            dst += e - s;
+        });
+    }
+}
+
 // ------------------------------------------------------------------------------------------ exact 3-NN
+#ifdef RA_KNN_STATS
+__device__ unsigned long long g_knn_stats[8];   // [0] near-path queries, [1] far-path queries, [2] far cells scanned, [3] far verts scanned,
+                                                // [4] near verts scanned, [5] near rings visited, [6] near row scans
+#define KNN_STAT(i, v) atomicAdd(&g_knn_stats[i], (unsigned long long)(v))
+#else
+#define KNN_STAT(i, v)
+#endif
 __device__ __forceinline__ void knn_insert(KnnOut& o, float d2, int id) {
     if (d2 < o.d2[2]) {
         if (d2 < o.d2[1]) {
@@ -244,37 +341,37 @@ __device__ __forceinline__ void knn_range(KnnOut& o, float3 p, const float4* __r
     for (int v = s; v < e; v++) knn_insert(o, dist2_ref(p, __ldg(&pos[v])), v);
 }
 
-// One level of the exact ring search: expanding cube shells over a uniform grid until the 3rd best distance is
-// provably inside the explored block.  Returns true when the result is final.
-template <bool ID_FROM_W>
-__device__ __forceinline__ bool knn_rings(const GridRef& g, const int* __restrict__ cell_start, const float4* __restrict__ pos, int rmax,
-                                          float3 p, KnnOut& o) {
+__device__ __forceinline__ float bbox_dist2(float3 p, float4 lo, float4 hi) {
+    float dx = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.f);
+    float dy = fmaxf(fmaxf(lo.y - p.y, p.y - hi.y), 0.f);
+    float dz = fmaxf(fmaxf(lo.z - p.z, p.z - hi.z), 0.f);
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// Exact 3 nearest vertices (K=3 of pytorch3d.ops.knn_points at sample_utils.py:122).
+// Near the body: expanding shells over the fine grid (cell ~4 cm).  Farther away: branch-and-bound over the list of
+// occupied coarse cells (tight vertex bounding boxes): nearest cell first, then every cell whose box is closer than
+// the current 3rd-best distance.  Both are exact; brute force only if the cell list overflowed.
+// near phase: the cell's neighbourhood lists, level by level (3x3x3 block, then the radius-2 and radius-3 shells); after each
+// level the result is final if the 3rd best distance is provably inside the explored block.  Returns true when final
+// (o may hold seed candidates otherwise).
+__device__ __forceinline__ bool knn3_near(const FrameConst* __restrict__ fc, const SortedVerts& sv, float3 p, KnnOut& o) {
+    o.d2[0] = o.d2[1] = o.d2[2] = 3.0e38f;
+    o.id[0] = o.id[1] = o.id[2] = 0;
+    const GridRef g = grid_ref(fc, 0);
     int cx, cy, cz;
-    cell_of(g, p, cx, cy, cz);
+    const int c = cell_of(g, p, cx, cy, cz);
     const int dx_ = g.dim[0], dy_ = g.dim[1], dz_ = g.dim[2];
     const float h = g.h;
-    auto scan = [&](int s, int e) {
+#pragma unroll 1
+    for (int lv = 0; lv < RA_NB_LEVELS; lv++) {
+        const int r = lv + 1;
+        const int s = __ldg(&sv.nb_start[lv][c]), e = __ldg(&sv.nb_start[lv][c + 1]);
+        const float4* __restrict__ lst = sv.nb_pos[lv];
+        KNN_STAT(4, e - s); KNN_STAT(5, 1);
         for (int v = s; v < e; v++) {
-            float4 q = __ldg(&pos[v]);
-            knn_insert(o, dist2_ref(p, q), ID_FROM_W ? __float_as_int(q.w) : v);
-        }
-    };
-    for (int r = 0; r <= rmax; r++) {
-        int z0 = max(cz - r, 0), z1 = min(cz + r, dz_ - 1);
-        int y0 = max(cy - r, 0), y1 = min(cy + r, dy_ - 1);
-        int x0 = max(cx - r, 0), x1 = min(cx + r, dx_ - 1);
-        for (int z = z0; z <= z1; z++) {
-            bool zf = (z == cz - r) || (z == cz + r);
-            for (int y = y0; y <= y1; y++) {
-                bool yf = zf || (y == cy - r) || (y == cy + r);
-                int row = (z * dy_ + y) * dx_;
-                if (yf) {
-                    scan(__ldg(&cell_start[row + x0]), __ldg(&cell_start[row + x1 + 1]));
-                } else {
-                    if (cx - r >= 0) scan(__ldg(&cell_start[row + cx - r]), __ldg(&cell_start[row + cx - r + 1]));
-                    if (cx + r < dx_) scan(__ldg(&cell_start[row + cx + r]), __ldg(&cell_start[row + cx + r + 1]));
-                }
-            }
+            float4 q = __ldg(&lst[v]);
+            knn_insert(o, dist2_ref(p, q), __float_as_int(q.w));
         }
         // distance from p to the nearest face of the explored block that still has unexplored cells behind it
         float bound = 3.0e38f;
@@ -289,30 +386,6 @@ __device__ __forceinline__ bool knn_rings(const GridRef& g, const int* __restric
         if (bound == 3.0e38f) return true;   // whole grid explored
     }
     return false;
-}
-
-__device__ __forceinline__ float bbox_dist2(float3 p, float4 lo, float4 hi) {
-    float dx = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.f);
-    float dy = fmaxf(fmaxf(lo.y - p.y, p.y - hi.y), 0.f);
-    float dz = fmaxf(fmaxf(lo.z - p.z, p.z - hi.z), 0.f);
-    return dx * dx + dy * dy + dz * dz;
-}
-
-// Exact 3 nearest vertices (K=3 of pytorch3d.ops.knn_points at sample_utils.py:122).
-// Near the body: expanding shells over the fine grid (cell ~4 cm).  Farther away: branch-and-bound over the list of
-// occupied coarse cells (tight vertex bounding boxes): nearest cell first, then every cell whose box is closer than
-// the current 3rd-best distance.  Both are exact; brute force only if the cell list overflowed.
-#ifdef RA_KNN_STATS
-__device__ unsigned long long g_knn_stats[8];   // [0] near-path queries, [1] far-path queries, [2] far cells scanned, [3] far verts scanned
-#define KNN_STAT(i, v) atomicAdd(&g_knn_stats[i], (unsigned long long)(v))
-#else
-#define KNN_STAT(i, v)
-#endif
-// near phase: fine-grid shells; returns true when the result is final (o may hold seed candidates otherwise)
-__device__ __forceinline__ bool knn3_near(const FrameConst* __restrict__ fc, const SortedVerts& sv, float3 p, KnnOut& o) {
-    o.d2[0] = o.d2[1] = o.d2[2] = 3.0e38f;
-    o.id[0] = o.id[1] = o.id[2] = 0;
-    return knn_rings<false>(grid_ref(fc, 0), sv.cell_start, sv.pos, RA_KNN_RMAX, p, o);
 }
 
 // far phase: branch-and-bound over the occupied coarse cells, seeded with whatever the near phase found

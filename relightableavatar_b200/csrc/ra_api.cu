@@ -70,6 +70,7 @@ struct ra_handle {
     FrameConst* fc = nullptr;
     SortedVerts sv{};
     int *cell_count = nullptr, *cell_fill = nullptr, *vert_cell = nullptr;
+    int* nb_cnt = nullptr;           // neighbourhood-list counts, RA_NB_LEVELS x (RA_MAX_CELLS + 1)
     ra_frame frame{};
     // ---- per-render workspace
     int64_t P_cap = 0, q_cap = 0, attr_cap = 0, vol_rays = 8192;
@@ -189,6 +190,14 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     CK(dalloc(&h->sv.cell_start, RA_MAX_CELLS + 1));
     CK(dalloc(&h->sv.pos2, N)); CK(dalloc(&h->sv.cell_start2, RA_MAX_CELLS + 1));
     CK(dalloc(&h->sv.occ_lo, RA_MAX_OCC)); CK(dalloc(&h->sv.occ_hi, RA_MAX_OCC));
+    {
+        static const int shell_cells[RA_NB_LEVELS] = {27, 98, 218};     // cells per level: every vertex appears at most that often
+        for (int lv = 0; lv < RA_NB_LEVELS; lv++) {
+            CK(dalloc(&h->sv.nb_start[lv], RA_MAX_CELLS + 1));
+            CK(dalloc(&h->sv.nb_pos[lv], (size_t)shell_cells[lv] * N));
+        }
+        CK(dalloc(&h->nb_cnt, (size_t)RA_NB_LEVELS * (RA_MAX_CELLS + 1)));
+    }
     CK(dalloc(&h->cell_count, RA_MAX_CELLS + 1)); CK(dalloc(&h->cell_fill, RA_MAX_CELLS + 1)); CK(dalloc(&h->vert_cell, N));
     float** ssp[] = {&h->ss.t, &h->ss.occ, &h->ss.d0, &h->ss.cd, &h->ss.dt, &h->ss.st, &h->ss.off, &h->ss.rlx, &h->ss.q_smpl};
     for (auto p : ssp) CK(dalloc(p, P));
@@ -332,6 +341,10 @@ extern "C" int ra_set_frame(ra_handle* h, const ra_frame* f, void* stream) {
     LAUNCH(h, k_grid_scan, 1, 1024, 0, st, h->fc, 0, h->cell_count, h->sv.cell_start, h->cell_fill);
     LAUNCH(h, k_grid_fill, (N + 127) / 128, 128, 0, st, h->fc, f->pverts, f->pnorm, f->tverts, f->weights, f->A, f->big_A, N,
            h->cfg.n_bones, h->vert_cell, h->sv.cell_start, h->cell_fill, h->sv);
+    // per-cell neighbourhood lists (3x3x3 block + radius-2 / radius-3 shells) for the near phase of the 3-NN search
+    LAUNCH(h, k_nb_count, h->sms * 2, 256, 0, st, h->fc, h->sv.cell_start, h->nb_cnt);
+    LAUNCH(h, k_nb_scan, RA_NB_LEVELS, 1024, 0, st, h->fc, h->nb_cnt, h->sv);
+    LAUNCH(h, k_nb_fill, h->sms * 4, 256, 0, st, h->fc, h->sv.cell_start, (const float4*)h->sv.pos, h->sv);
     // coarse second level over the cell-sorted vertices
     LAUNCH(h, k_grid_count, (N + 255) / 256, 256, 0, st, h->fc, 1, f->pverts, (const float4*)h->sv.pos, N, h->cell_count, h->vert_cell);
     LAUNCH(h, k_grid_scan, 1, 1024, 0, st, h->fc, 1, h->cell_count, h->sv.cell_start2, h->cell_fill);

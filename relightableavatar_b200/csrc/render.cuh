@@ -39,7 +39,7 @@ __device__ __forceinline__ void count_queries(const Counters& c, bool valid, boo
 
 // One launch = finish tracing iteration `it-1` with the MLP results, then start iteration `it`
 // (or finalise when it == iters).  Hard (surface) mode of A.4.
-__global__ void k_trace_surface(int it, TraceCfg cfg, const FrameConst* __restrict__ fc, SortedVerts sv, int nverts,
+__global__ void __launch_bounds__(256, RA_TRACE_MINBLOCKS) k_trace_surface(int it, TraceCfg cfg, const FrameConst* __restrict__ fc, SortedVerts sv, int nverts,
                                 const float* __restrict__ ray_o, const float* __restrict__ ray_d,
                                 const float* __restrict__ near_, const float* __restrict__ far_, int P,
                                 SurfState s, QueryList q, Counters cnt,
@@ -171,7 +171,7 @@ __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __res
 }
 
 // Soft-shadow tracing step (A.4 soft + claybook), same finish/start structure as k_trace_surface.
-__global__ void k_trace_shadow(int it, TraceCfg cfg, const FrameConst* __restrict__ fc, SortedVerts sv, int nverts,
+__global__ void __launch_bounds__(256, RA_TRACE_MINBLOCKS) k_trace_shadow(int it, TraceCfg cfg, const FrameConst* __restrict__ fc, SortedVerts sv, int nverts,
                                const int* __restrict__ n_shadow, const int* __restrict__ fg_ray, const float* __restrict__ surf,
                                const float* __restrict__ ldir, const float* __restrict__ lsharp, int L,
                                ShadowRays sr, QueryList q, Counters cnt, float* lvis, int part, int nparts) {

@@ -13,4 +13,6 @@ lib = _lib.load()
 arr = (ctypes.c_ulonglong * 8)()
 r.render(b); lib.ra_debug_knn_stats(arr, 1)
 r.render(b); lib.ra_debug_knn_stats(arr, 1)
-print('frame: near', arr[0], 'far', arr[1], 'far cells/query', arr[2] / max(arr[1], 1), 'far verts/query', arr[3] / max(arr[1], 1), r.engine.stats())
+n = arr[0] + arr[1]
+print('frame: near-finished', arr[0], 'far-phase', arr[1], 'far cells/query', arr[2] / max(arr[1], 1), 'far verts/query', arr[3] / max(arr[1], 1),
+      '| near phase per query: verts', arr[4] / max(n, 1), 'rings', arr[5] / max(n, 1), 'row scans', arr[6] / max(n, 1), r.engine.stats())
