@@ -191,6 +191,112 @@ __global__ void __launch_bounds__(256) k_gemm_tf32x3(GemmArgs a) {
 }
 
 
+// ---- pipelined variant: cp.async multi-stage ring of raw fp32 tiles, hi/lo split at fragment-load time ------------------
+// The kernel above stages 8 K-columns per __syncthreads and converts on the store side; with two CTAs per SM it is bound by
+// that load -> convert -> store -> barrier -> load chain (~107 TFLOP/s of tf32 MMAs).  Here 16 K-columns per stage travel
+// global -> shared with cp.async (zero-filled beyond M / N), 4 stages deep, one barrier per stage; fragments are split into
+// tf32 hi / lo in registers.  Same products in the same order (lo*hi, hi*lo, hi*hi per k8 step, k ascending): bit-identical
+// results.  Row stride 20 floats: 16 B-aligned rows and conflict-free fragment reads (g * 20 mod 32 = {0,20,8,28,16,4,24,12}).
+#define G2K 16
+#define G2LD 20
+#define G2STAGES 4
+#define G2_SMEM_BYTES (G2STAGES * 2 * GBM * G2LD * 4)
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(256, 2) k_gemm_tf32x3_p(GemmArgs a) {
+    int total = *a.count;
+    int M = min(total - a.row0, a.rows_cap);
+    int m0 = blockIdx.x * GBM;
+    if (m0 >= M) return;
+    int n0 = blockIdx.y * GBN;
+    extern __shared__ __align__(16) float g2s[];                 // [stage][X | W][128][G2LD]
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(g2s);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+    const int lrow = tid >> 1, lc = (tid & 1) * 8;              // this thread copies floats [lc, lc + 8) of row lrow of both tiles
+    const bool xok = (m0 + lrow) < M, wok = (n0 + lrow) < a.N;
+    const float* Xp = a.X + (size_t)(xok ? m0 + lrow : 0) * a.ldx + lc;
+    const float* Wp = a.W + (size_t)(wok ? n0 + lrow : 0) * a.ldw + lc;
+    const uint32_t dX = (uint32_t)((lrow * G2LD + lc) * 4), dW = dX + GBM * G2LD * 4;
+    const int nk = a.K / G2K;
+    auto issue = [&](int kt) {
+        const uint32_t sb = s_base + (uint32_t)(kt % G2STAGES) * (2 * GBM * G2LD * 4);
+        cp_async16(sb + dX, Xp + kt * G2K, xok ? 16 : 0);
+        cp_async16(sb + dX + 16, Xp + kt * G2K + 4, xok ? 16 : 0);
+        cp_async16(sb + dW, Wp + kt * G2K, wok ? 16 : 0);
+        cp_async16(sb + dW + 16, Wp + kt * G2K + 4, wok ? 16 : 0);
+    };
+    float acc[4][4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) acc[i][j][r] = 0.f;
+#pragma unroll
+    for (int s = 0; s < G2STAGES - 1; s++) {
+        if (s < nk) issue(s);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int kt = 0; kt < nk; kt++) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(G2STAGES - 2) : "memory");
+        __syncthreads();                                        // stage kt landed for everyone; stage kt-1 is free again
+        if (kt + G2STAGES - 1 < nk) issue(kt + G2STAGES - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const float* Xs = g2s + (size_t)(kt % G2STAGES) * (2 * GBM * G2LD);
+        const float* Ws = Xs + GBM * G2LD;
+#pragma unroll
+        for (int ks = 0; ks < G2K / 8; ks++) {
+            const int kb = ks * 8 + t;
+            uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float* wr = Ws + (wn + j * 8 + g) * G2LD + kb;
+                const float b0 = wr[0], b1 = wr[4];
+                bh[j][0] = f2tf32(b0); bl[j][0] = f2tf32(b0 - __uint_as_float(bh[j][0]));
+                bh[j][1] = f2tf32(b1); bl[j][1] = f2tf32(b1 - __uint_as_float(bh[j][1]));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float* xr = Xs + (wm + i * 16 + g) * G2LD + kb;
+                const float av[4] = {xr[0], xr[8 * G2LD], xr[4], xr[8 * G2LD + 4]};
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) { ah[q] = f2tf32(av[q]); al[q] = f2tf32(av[q] - __uint_as_float(ah[q])); }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    mma_tf32(acc[i][j], al, bh[j]);
+                    mma_tf32(acc[i][j], ah, bl[j]);
+                    mma_tf32(acc[i][j], ah, bh[j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int m = m0 + wm + i * 16 + g + ((r & 2) ? 8 : 0);
+                const int n = n0 + wn + j * 8 + 2 * t + (r & 1);
+                if (m >= M || n >= a.N) continue;
+                float v = acc[i][j][r];
+                if (a.bias) v += __ldg(&a.bias[n]);
+                if (EPI == EPI_RELU) v = fmaxf(v, 0.f);
+                if (EPI == EPI_SOFTPLUS) v = softplus100(v);
+                if (EPI == EPI_MUL_DRELU) v = (a.aux[(size_t)m * a.ldaux + n] > 0.f) ? v : 0.f;
+                if (EPI == EPI_MUL_DSOFTPLUS) v *= dsoftplus100_from_act(a.aux[(size_t)m * a.ldaux + n]);
+                a.Y[(size_t)m * a.ldy + n] = v;
+            }
+}
+
+
 // Y[m, n] for n < N <= 4: one warp per row.
 __global__ void k_skinny(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
                          const float* __restrict__ bias, float* Y, int ldy, const int* count, int row0, int rows_cap,

@@ -64,7 +64,7 @@ struct ra_handle {
     float *lxyz = nullptr, *larea = nullptr, *lsharp = nullptr, *ldir = nullptr;
     TcWeights tc;                    // fp16 UMMA images for the tcgen05 path
     Tc2Weights tc2;                  // ... and for its 2-CTA (cta_group::2) variant
-    int attr_tc = 1;                 // env RA_ATTR_TC: 1 = 3xTF32 tensor-core GEMMs in the fp32 MLP path, 0 = CUDA-core SGEMM
+    int attr_tc = 2;                 // env RA_ATTR_TC: 2 = pipelined 3xTF32 GEMM (cp.async ring), 1 = first 3xTF32 GEMM, 0 = CUDA-core SGEMM
     int tc_variant = 6;              // env RA_TC_VARIANT: 6 = CTA-pair two-slot kernel k_mlp_tc6 (default); 1 = single-CTA kernel; 2-5 = experiments
     // ---- frame
     FrameConst* fc = nullptr;
@@ -160,7 +160,11 @@ static void gemm(ra_handle* h, cudaStream_t st, const float* X, int ldx, const f
                  int ldy, const float* aux, int ldaux, const int* count, int row0, int rows_cap, int N, int K) {
     GemmArgs a{X, ldx, W, ldw, bias, Y, ldy, aux, ldaux, count, row0, rows_cap, N, K};
     dim3 grid((rows_cap + GBM - 1) / GBM, (N + GBN - 1) / GBN);
-    if (h->attr_tc) LAUNCH(h, k_gemm_tf32x3<EPI>, grid, 256, 0, st, a);
+    if (h->attr_tc == 2 && (K % G2K) == 0) {
+        static bool attr_set = false;      // one attribute call per template instance
+        if (!attr_set) { cudaFuncSetAttribute(k_gemm_tf32x3_p<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES); attr_set = true; }
+        LAUNCH(h, k_gemm_tf32x3_p<EPI>, grid, 256, G2_SMEM_BYTES, st, a);
+    } else if (h->attr_tc) LAUNCH(h, k_gemm_tf32x3<EPI>, grid, 256, 0, st, a);
     else LAUNCH(h, k_gemm<EPI>, grid, 256, 0, st, a);
 }
 

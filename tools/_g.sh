@@ -1,0 +1,4 @@
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for v in 2 1; do RA_ATTR_TC=$v timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('attr_tc=$v', round(d['value'],2),'fps', round(d['ms_per_step'],2), {k:round(x,2) for k,x in d['roofline']['stage_ms_per_step'].items()}, 'mlp', round(d['roofline']['kernel_ms_per_step'],2))"; done
