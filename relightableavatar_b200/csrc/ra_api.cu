@@ -24,6 +24,7 @@
 #include "mlp_tc4.cuh"
 #include "mlp_tc5.cuh"
 #include "mlp_tc6.cuh"
+#include "lin_tc.cuh"
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -64,7 +65,8 @@ struct ra_handle {
     float *lxyz = nullptr, *larea = nullptr, *lsharp = nullptr, *ldir = nullptr;
     TcWeights tc;                    // fp16 UMMA images for the tcgen05 path
     Tc2Weights tc2;                  // ... and for its 2-CTA (cta_group::2) variant
-    int attr_tc = 2;                 // env RA_ATTR_TC: 2 = pipelined 3xTF32 GEMM (cp.async ring), 1 = first 3xTF32 GEMM, 0 = CUDA-core SGEMM
+    int attr_tc = 3;                 // env RA_ATTR_TC: 3 = tcgen05 fp16-split GEMM (lin_tc.cuh), 2 = pipelined 3xTF32 mma.sync GEMM, 1 = first 3xTF32 GEMM, 0 = CUDA-core SGEMM
+    LinTcWeights lin_tc;             // packed hi / lo weight images of the attribute-pass GEMMs (built on first use)
     int tc_variant = 6;              // env RA_TC_VARIANT: 6 = CTA-pair two-slot kernel k_mlp_tc6 (default); 1 = single-CTA kernel; 2-5 = experiments
     // ---- frame
     FrameConst* fc = nullptr;
@@ -160,7 +162,18 @@ static void gemm(ra_handle* h, cudaStream_t st, const float* X, int ldx, const f
                  int ldy, const float* aux, int ldaux, const int* count, int row0, int rows_cap, int N, int K) {
     GemmArgs a{X, ldx, W, ldw, bias, Y, ldy, aux, ldaux, count, row0, rows_cap, N, K};
     dim3 grid((rows_cap + GBM - 1) / GBM, (N + GBN - 1) / GBN);
-    if (h->attr_tc == 2 && (K % G2K) == 0) {
+    if (h->attr_tc == 3 && lin_tc_ok(N, K, ldx)) {
+        const int Npad = (N + 31) / 32 * 32;
+        const unsigned char* blob = lin_tc_pack(h->lin_tc, W, ldw, N, K, Npad, st);
+        if (blob) {
+            static bool attr_set = false;
+            if (!attr_set) { cudaFuncSetAttribute(k_lin_tc<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES); attr_set = true; }
+            LinTcArgs la{X, ldx, blob, bias, Y, ldy, aux, ldaux, count, row0, rows_cap, N, Npad, K};
+            LAUNCH(h, k_lin_tc<EPI>, std::min((rows_cap + 127) / 128, h->sms), LT_THREADS, LT_SMEM_BYTES, st, la);
+            return;
+        }
+    }
+    if (h->attr_tc >= 2 && (K % G2K) == 0) {
         static bool attr_set = false;      // one attribute call per template instance
         if (!attr_set) { cudaFuncSetAttribute(k_gemm_tf32x3_p<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES); attr_set = true; }
         LAUNCH(h, k_gemm_tf32x3_p<EPI>, grid, 256, G2_SMEM_BYTES, st, a);
@@ -327,6 +340,7 @@ extern "C" int ra_upload_weights(ra_handle* h, const ra_weights* w, void* stream
         }
         if (upload_raw(h, &h->ldir, dir.data(), dir.size(), st)) return 1;
     }
+    lin_tc_clear(h->lin_tc);         // the packed GEMM images refer to the previous weights
     if (tc_upload(h->tc, w, h->err, st)) return 1;
     if (tc2_upload(h->tc2, w, h->err, st)) return 1;
     h->have_weights = true;
@@ -390,7 +404,11 @@ static void mlp_forward_fp32(ra_handle* h, cudaStream_t st, const float* bpts, c
     for (int l = 5; l < 8; l++)
         gemm<EPI_SOFTPLUS>(h, st, h->sb_[l - 1], 256, h->sdf[l].w, 256, h->sdf[l].b, h->sb_[l], 256, nullptr, 0, count, row0, rows, 256, 256);
     if (full)
-        gemm<EPI_NONE>(h, st, h->sb_[7], 256, h->sdf[8].w, 256, h->sdf[8].b, h->out257, 264, nullptr, 0, count, row0, rows, 257, 256);
+    {   // 257 outputs = 256 feature columns (one tensor-core tile) + the sdf column (rows were permuted to [feat(256), sdf])
+        gemm<EPI_NONE>(h, st, h->sb_[7], 256, h->sdf[8].w, 256, h->sdf[8].b, h->out257, 264, nullptr, 0, count, row0, rows, 256, 256);
+        LAUNCH(h, k_skinny, grid_for(h, (long long)rows * 32), 256, 0, st, h->sb_[7], 256, h->sdf[8].w + 256 * 256, 256, h->sdf[8].b + 256,
+               h->out257 + 256, 264, count, row0, rows, 1, 256);
+    }
     else
         LAUNCH(h, k_skinny, grid_for(h, (long long)rows * 32), 256, 0, st, h->sb_[7], 256, h->sdf[8].w + 256 * 256, 256, h->sdf[8].b + 256,
                net_out, 1, count, row0, rows, 1, 256);
