@@ -169,7 +169,7 @@ static void gemm(ra_handle* h, cudaStream_t st, const float* X, int ldx, const f
             static bool attr_set = false;
             if (!attr_set) { cudaFuncSetAttribute(k_lin_tc<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES); attr_set = true; }
             LinTcArgs la{X, ldx, blob, bias, Y, ldy, aux, ldaux, count, row0, rows_cap, N, Npad, K};
-            LAUNCH(h, k_lin_tc<EPI>, std::min((rows_cap + 127) / 128, h->sms), LT_THREADS, LT_SMEM_BYTES, st, la);
+            LAUNCH(h, k_lin_tc<EPI>, std::min((rows_cap + 127) / 128, 2 * h->sms), LT_THREADS, LT_SMEM_BYTES, st, la);
             return;
         }
     }
