@@ -369,7 +369,16 @@ __device__ __forceinline__ bool knn3_near(const FrameConst* __restrict__ fc, con
         const int s = __ldg(&sv.nb_start[lv][c]), e = __ldg(&sv.nb_start[lv][c + 1]);
         const float4* __restrict__ lst = sv.nb_pos[lv];
         KNN_STAT(4, e - s); KNN_STAT(5, 1);
-        for (int v = s; v < e; v++) {
+        int v = s;
+        for (; v + 4 <= e; v += 4) {          // four independent 16 B loads in flight per lane (the scan is L2-latency bound)
+            const float4 q0 = __ldg(&lst[v]), q1 = __ldg(&lst[v + 1]), q2 = __ldg(&lst[v + 2]), q3 = __ldg(&lst[v + 3]);
+            const float e0 = dist2_ref(p, q0), e1 = dist2_ref(p, q1), e2 = dist2_ref(p, q2), e3 = dist2_ref(p, q3);
+            if (fminf(fminf(e0, e1), fminf(e2, e3)) < o.d2[2]) {
+                knn_insert(o, e0, __float_as_int(q0.w)); knn_insert(o, e1, __float_as_int(q1.w));
+                knn_insert(o, e2, __float_as_int(q2.w)); knn_insert(o, e3, __float_as_int(q3.w));
+            }
+        }
+        for (; v < e; v++) {
             float4 q = __ldg(&lst[v]);
             knn_insert(o, dist2_ref(p, q), __float_as_int(q.w));
         }
