@@ -109,7 +109,7 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'relit 512x512 frames/sec', 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'xuzhen_12v_geo_fix_mat relighting, 1 envmap (main), 512x512', 'sample': sample},
+            'config': {'workload': 'xuzhen_12v_geo_fix_mat relighting, 1 envmap (main), 512x512, 1 frame per GPU per step', 'sample': sample},
             'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
