@@ -25,6 +25,10 @@ def test_ctypes_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.ra_frame) == 11 * 8
     assert ctypes.sizeof(_lib.ra_outputs) == 13 * 8
     assert ctypes.sizeof(_lib.ra_stats) == 6 * 8
+    assert ctypes.sizeof(_lib.ra_ground_config) == 16 * 4
+    assert ctypes.sizeof(_lib.ra_ground_outputs) == 10 * 8
+    assert ctypes.sizeof(_lib.ra_body) == 7 * 8          # 6 pointers + int32 padded to 8
+    assert ctypes.sizeof(_lib.ra_pose_outputs) == 8 * 8
 
 
 def test_product_never_imports_oracle():
