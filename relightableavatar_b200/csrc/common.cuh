@@ -16,7 +16,9 @@
 #endif
 #define RA_GRID2_RATIO 3.0f
 #define RA_MAX_OCC 8192
-#define RA_NB_LEVELS 3       // neighbourhood-list levels: certified search radius up to 3 fine cells (>= the 12.5 cm shell at 4 cm cells)
+#ifndef RA_NB_LEVELS
+#define RA_NB_LEVELS 4       // neighbourhood-list levels: certified search radius up to 4 fine cells (14 cm at 3.5 cm cells >= the 12.5 cm shell)
+#endif
 
 // Per-frame constants living in device memory (written by k_frame_prep, read by every kernel).
 struct FrameConst {

@@ -53,7 +53,7 @@ struct ra_handle {
     std::string err;
     int64_t launches = 0;
     int dev = 0, sms = 148;
-    float cell_h = 0.04f, grid2_ratio = 4.0f;   // tunables (env RA_CELL_H / RA_GRID2_RATIO)
+    float cell_h = 0.035f, grid2_ratio = 4.0f;  // tunables (env RA_CELL_H / RA_GRID2_RATIO); swept on B200 with the list-based 3-NN: .03 / .035 / .04 / .05 -> 23.8 / 23.7 / 24.3 / 24.7 ms per frame
     bool have_weights = false, have_frame = false;
     // ---- weights
     Lin resd[9], sdf[9], rend[5], alb[3], rgh[3];
@@ -208,10 +208,11 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     CK(dalloc(&h->sv.pos2, N)); CK(dalloc(&h->sv.cell_start2, RA_MAX_CELLS + 1));
     CK(dalloc(&h->sv.occ_lo, RA_MAX_OCC)); CK(dalloc(&h->sv.occ_hi, RA_MAX_OCC));
     {
-        static const int shell_cells[RA_NB_LEVELS] = {27, 98, 218};     // cells per level: every vertex appears at most that often
         for (int lv = 0; lv < RA_NB_LEVELS; lv++) {
+            const int r = lv + 1;          // cells per level = how often a vertex can appear: 27, then the shells 98, 218, 386, ...
+            const int shell = (r == 1) ? 27 : (2 * r + 1) * (2 * r + 1) * (2 * r + 1) - (2 * r - 1) * (2 * r - 1) * (2 * r - 1);
             CK(dalloc(&h->sv.nb_start[lv], RA_MAX_CELLS + 1));
-            CK(dalloc(&h->sv.nb_pos[lv], (size_t)shell_cells[lv] * N));
+            CK(dalloc(&h->sv.nb_pos[lv], (size_t)shell * N));
         }
         CK(dalloc(&h->nb_cnt, (size_t)RA_NB_LEVELS * (RA_MAX_CELLS + 1)));
     }
