@@ -314,3 +314,52 @@ def test_batch_preparation_f1():
     if (m_g == m_r).all():
         p = O.psnr(O.assemble_image(b, out_g['rgb_map'][0].cpu()), O.assemble_image(b, out_c['rgb_map'][0].cpu()))
         assert p >= 50, f'PSNR {p:.1f} dB'
+
+
+def test_attribute_gemm_paths_agree(relight_setup, monkeypatch):
+    """The fp32-grade surface-attribute pass on tcgen05 (k_lin_tc: fp16 hi/lo operand split, RA_ATTR_TC=3) against the legacy
+    3xTF32 mma.sync GEMMs (RA_ATTR_TC=1) and the CUDA-core SGEMM (RA_ATTR_TC=0): same raw channels to fp32 rounding."""
+    b, sd = relight_setup
+    x = _sample_points(b, 6000, seed=5, spread=0.03)
+    v = torch.nn.functional.normalize(torch.randn(x.shape[0], 3, generator=torch.Generator().manual_seed(6)), dim=-1)
+    outs = {}
+    for mode in ('3', '1', '0'):
+        monkeypatch.setenv('RA_ATTR_TC', mode)
+        eng = Engine(default_config(True, precision=0, max_rays=8192), DEV)
+        eng.upload_weights(sd); eng.set_frame(b)
+        outs[mode] = eng.query_raw(x, v).clone()
+        eng.close()
+    for mode in ('1', '0'):
+        e = _err(outs['3'], outs[mode])
+        other = [c for c in range(17) if not (13 <= c < 16)]
+        assert float(e[:, other].max()) <= 2e-5, f'mode {mode}: {float(e[:, other].max()):.3e}'
+        assert torch.quantile(e[:, 13:16].flatten(), 0.999) <= 1e-3          # normals: ReLU-kink flips under re-association
+
+
+def test_edge_cases_new_rows():
+    """Empty / ragged inputs of the f1 / f2 entry points: no rays hit the box, image sizes that are not multiples of the block
+    size, a ground pass after an empty human pass."""
+    from relightableavatar_b200.prepare import FramePreparer
+    body = scene.make_body(0)
+    poses, Rh, _ = scene.make_motion(1, 1)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    b = scene.make_batch(37, 37, seed=0, n_env=0)                  # 1369 pixels: not a multiple of 256
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=4096, test_light=('main',),
+                 sync_timing=False, ground_shading=True)
+    out = r.render(b)['main']
+    assert out['rgb_map'].shape == (1, 37 * 37, 3) and torch.isfinite(out['rgb_map']).all()
+    prep = FramePreparer(r.engine, body.joints, body.parents, body.rverts, body.weights, body.big_A, body.tverts, rnorm=body.rnorm)
+    p = prep.pose(poses[0], Rh[0], b['Th'][0, 0])
+    # camera moved 50 m sideways (the slab test treats rays as lines, so merely looking away would still 'hit'): no ray meets the box
+    K, R, T = b['cam_K'][0], b['cam_R'][0].copy(), b['cam_T'][0].copy()
+    T[0] -= 50.0                                                    # c' = c + 50 * camera-x  =>  T' = -R c' = T - 50 e_x
+    rays = prep.rays(K, R, T, 37, 37, p['wbounds'])
+    assert rays['ray_o'].shape[0] == 0 and int(rays['mask_at_box'].sum()) == 0
+    b2 = dict(b)
+    for k in ('ray_o', 'ray_d'):
+        b2[k] = b[k][:, :0]
+    for k in ('near', 'far'):
+        b2[k] = b[k][:, :0]
+    b2['mask_at_box'] = np.zeros_like(b['mask_at_box'])
+    out2 = r.render(b2)['main']                                     # floor only
+    assert out2['rgb_map'].shape == (1, 37 * 37, 3) and float(out2['acc_map'].abs().max()) == 0.0
