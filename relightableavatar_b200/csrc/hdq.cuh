@@ -70,23 +70,26 @@ __global__ void k_frame_prep(FrameConst* fc, const float* __restrict__ R, const 
     }
     // zero the cell counters (max size) for the counting sort that follows
     for (int i = tid; i < RA_MAX_CELLS + 1; i += blockDim.x) cell_count[i] = 0;
-    // folded biases: one output row per thread
-    for (int o = tid; o < 256; o += blockDim.x) {
-        float s0 = resd_b0[o], s4 = resd_b4[o];
+    // folded biases: one output row per WARP (coalesced weight reads, shuffle reduction), rows strided over the block's warps
+    for (int o = wid; o < 256; o += (blockDim.x >> 5)) {
         const float* w0 = resd_w0 + (size_t)o * 219 + 63;
         const float* w4 = resd_w4 + (size_t)o * 475 + 256 + 63;
-        for (int k = 0; k < 156; k++) {
+        const bool rend = rend_w3 != nullptr && mat_cond != nullptr;
+        const float* w3 = rend ? rend_w3 + (size_t)o * 412 + 256 : nullptr;
+        float s0 = 0.f, s4 = 0.f, s3 = 0.f;
+        for (int k = lane; k < 156; k += 32) {
             float c = poses[k];
             s0 += w0[k] * c;
             s4 += w4[k] * c;
+            if (rend) s3 += w3[k] * mat_cond[k];
         }
-        fc->resd_b0[o] = s0;
-        fc->resd_b4[o] = s4;
-        if (rend_w3 != nullptr && mat_cond != nullptr) {
-            float s3 = rend_b3[o];
-            const float* w3 = rend_w3 + (size_t)o * 412 + 256;
-            for (int k = 0; k < 156; k++) s3 += w3[k] * mat_cond[k];
-            fc->rend_b3[o] = s3;
+        for (int m = 16; m; m >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, m); s4 += __shfl_xor_sync(0xffffffffu, s4, m); s3 += __shfl_xor_sync(0xffffffffu, s3, m);
+        }
+        if (lane == 0) {
+            fc->resd_b0[o] = resd_b0[o] + s0;
+            fc->resd_b4[o] = resd_b4[o] + s4;
+            if (rend) fc->rend_b3[o] = rend_b3[o] + s3;
         }
     }
 }
@@ -135,20 +138,28 @@ __global__ void k_grid_fill2(const float4* __restrict__ spos, int nverts, const 
 
 // list of occupied coarse cells with the tight bounding box of their vertices (far-point 3-NN pruning)
 __global__ void k_grid_occ(FrameConst* fc, const int* __restrict__ cell_start2, const float4* __restrict__ pos2, float4* occ_lo, float4* occ_hi) {
-    int n = fc->g2_cells;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
-        int s = cell_start2[c], e = cell_start2[c + 1];
+    const int n = fc->g2_cells;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int c = warp; c < n; c += nwarps) {           // one warp per coarse cell
+        const int s = cell_start2[c], e = cell_start2[c + 1];
         if (e <= s) continue;
         float3 lo = make3(3e38f, 3e38f, 3e38f), hi = make3(-3e38f, -3e38f, -3e38f);
-        for (int v = s; v < e; v++) {
+        for (int v = s + lane; v < e; v += 32) {
             float4 q = pos2[v];
             lo = make3(fminf(lo.x, q.x), fminf(lo.y, q.y), fminf(lo.z, q.z));
             hi = make3(fmaxf(hi.x, q.x), fmaxf(hi.y, q.y), fmaxf(hi.z, q.z));
         }
-        int idx = atomicAdd(&fc->n_occ, 1);
-        if (idx < RA_MAX_OCC) {
-            occ_lo[idx] = make_float4(lo.x, lo.y, lo.z, __int_as_float(s));
-            occ_hi[idx] = make_float4(hi.x, hi.y, hi.z, __int_as_float(e));
+        for (int m = 16; m; m >>= 1) {
+            lo = make3(fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, m)), fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, m)), fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, m)));
+            hi = make3(fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, m)), fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, m)), fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, m)));
+        }
+        if (lane == 0) {
+            int idx = atomicAdd(&fc->n_occ, 1);
+            if (idx < RA_MAX_OCC) {
+                occ_lo[idx] = make_float4(lo.x, lo.y, lo.z, __int_as_float(s));
+                occ_hi[idx] = make_float4(hi.x, hi.y, hi.z, __int_as_float(e));
+            }
         }
     }
 }
