@@ -85,7 +85,8 @@ struct ra_handle {
     QueryList q{}, q2{};             // q2: second work list for the overlapped half of the shadow rays
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int overlap = 0;                 // env RA_OVERLAP=1: split the shadow stage over two streams (experiment: measured 5 % slower)
+    int overlap = 0;                 // env RA_OVERLAP=1: split the shadow stage over two streams (experiment: -0.3..0.5 ms with k_mlp_tc6, but the co-running
+                                     // tracing warps slow the MLP epilogue and blur the per-kernel timing; capping MLP registers for more co-residency lost more than it gained)
     AttrList al{};
     float* raw = nullptr;
     Counters cnt{};
@@ -586,7 +587,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     LAUNCH(h, k_shadow_gen, grid_for(h, P * L / 4, 256, 16), 256, 0, st, h->fc, h->cnt.n_fg, h->fg_ray, h->surf, h->fm.norm, h->ldir, L,
            c.lv_near, c.bbox_margin, h->chunk_actual, h->lvis, h->ldot, h->sr, h->cnt.n_shadow);
     TraceCfg sc{c.lv_iter, 1.f, c.lv_relax, c.lv_offset, c.st_eps, c.st_skip, c.lv_dist_th, c.blend_radius};
-    const bool split = h->overlap && h->cfg.precision == RA_PRECISION_TC && h->tc_variant == 1;
+    const bool split = h->overlap && h->cfg.precision == RA_PRECISION_TC && (h->tc_variant == 1 || h->tc_variant == 6);
     if (!split) {
         int gs = grid_for(h, P * 64, 256, 8);
         for (int it = 0; it <= c.lv_iter; it++) {
