@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <unordered_set>
 #include <cmath>
 
 #include "../../include/ra_b200.h"
@@ -50,6 +51,7 @@ struct Lin {            // one fp32 linear layer, K zero-padded to a multiple of
 
 struct ra_handle {
     ra_config cfg;
+    std::unordered_set<void*> allocs;   // every device block the handle owns through dalloc() -- released by ra_destroy
     std::string err;
     int64_t launches = 0;
     int dev = 0, sms = 148;
@@ -118,10 +120,14 @@ static int grid_for(ra_handle* h, long long n, int block = 256, int per_sm = 8) 
 }
 
 template <typename T>
-static cudaError_t dalloc(T** p, size_t n) {
+static cudaError_t dalloc(ra_handle* h, T** p, size_t n) {
     cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
-    if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(T));
+    if (e == cudaSuccess) { h->allocs.insert((void*)*p); e = cudaMemset(*p, 0, n * sizeof(T)); }
     return e;
+}
+template <typename T>
+static void hfree(ra_handle* h, T*& p) {
+    if (p) { h->allocs.erase((void*)p); cudaFree((void*)p); p = nullptr; }
 }
 
 // copy a (N, K) fp32 matrix (host or device) into a zero-padded (N, Kp) device buffer, optionally selecting columns
@@ -141,8 +147,8 @@ static int upload_lin(ra_handle* h, Lin& L, const float* w, const float* b, int 
     std::vector<float> pt((size_t)Kp * Np8, 0.f);
     for (int n = 0; n < N; n++)
         for (int k = 0; k < Kp; k++) pt[(size_t)k * Np8 + n] = pw[(size_t)n * Kp + k];
-    if (L.w) { cudaFree(L.w); cudaFree(L.b); cudaFree(L.wt); }
-    CK(dalloc(&L.w, pw.size())); CK(dalloc(&L.b, pb.size())); CK(dalloc(&L.wt, pt.size()));
+    hfree(h, L.w); hfree(h, L.b); hfree(h, L.wt);
+    CK(dalloc(h, &L.w, pw.size())); CK(dalloc(h, &L.b, pb.size())); CK(dalloc(h, &L.wt, pt.size()));
     CK(cudaMemcpy(L.w, pw.data(), pw.size() * sizeof(float), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(L.b, pb.data(), pb.size() * sizeof(float), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(L.wt, pt.data(), pt.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -151,8 +157,8 @@ static int upload_lin(ra_handle* h, Lin& L, const float* w, const float* b, int 
 }
 
 static int upload_raw(ra_handle* h, float** dst, const float* src, size_t n, cudaStream_t st) {
-    if (*dst) cudaFree(*dst);
-    CK(dalloc(dst, n));
+    hfree(h, *dst);
+    CK(dalloc(h, dst, n));
     CK(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyDefault, st));
     CK(cudaStreamSynchronize(st));
     return 0;
@@ -203,56 +209,56 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     h->q_cap = std::max<int64_t>(256 * P, 1 << 20);
     h->attr_cap = std::max<int64_t>((int64_t)cfg->n_samples * P, h->vol_rays * cfg->vol_samples);
     int N = cfg->n_verts;
-    CK(dalloc(&h->fc, 1));
-    CK(dalloc(&h->sv.pos, N)); CK(dalloc(&h->sv.nrm, N)); CK(dalloc(&h->sv.tv, N)); CK(dalloc(&h->sv.T, (size_t)N * 24));
-    CK(dalloc(&h->sv.cell_start, RA_MAX_CELLS + 1));
-    CK(dalloc(&h->sv.pos2, N)); CK(dalloc(&h->sv.cell_start2, RA_MAX_CELLS + 1));
-    CK(dalloc(&h->sv.occ_lo, RA_MAX_OCC)); CK(dalloc(&h->sv.occ_hi, RA_MAX_OCC));
+    CK(dalloc(h, &h->fc, 1));
+    CK(dalloc(h, &h->sv.pos, N)); CK(dalloc(h, &h->sv.nrm, N)); CK(dalloc(h, &h->sv.tv, N)); CK(dalloc(h, &h->sv.T, (size_t)N * 24));
+    CK(dalloc(h, &h->sv.cell_start, RA_MAX_CELLS + 1));
+    CK(dalloc(h, &h->sv.pos2, N)); CK(dalloc(h, &h->sv.cell_start2, RA_MAX_CELLS + 1));
+    CK(dalloc(h, &h->sv.occ_lo, RA_MAX_OCC)); CK(dalloc(h, &h->sv.occ_hi, RA_MAX_OCC));
     {
         for (int lv = 0; lv < RA_NB_LEVELS; lv++) {
             const int r = lv + 1;          // cells per level = how often a vertex can appear: 27, then the shells 98, 218, 386, ...
             const int shell = (r == 1) ? 27 : (2 * r + 1) * (2 * r + 1) * (2 * r + 1) - (2 * r - 1) * (2 * r - 1) * (2 * r - 1);
-            CK(dalloc(&h->sv.nb_start[lv], RA_MAX_CELLS + 1));
-            CK(dalloc(&h->sv.nb_pos[lv], (size_t)shell * N));
+            CK(dalloc(h, &h->sv.nb_start[lv], RA_MAX_CELLS + 1));
+            CK(dalloc(h, &h->sv.nb_pos[lv], (size_t)shell * N));
         }
-        CK(dalloc(&h->nb_cnt, (size_t)RA_NB_LEVELS * (RA_MAX_CELLS + 1)));
+        CK(dalloc(h, &h->nb_cnt, (size_t)RA_NB_LEVELS * (RA_MAX_CELLS + 1)));
     }
-    CK(dalloc(&h->cell_count, RA_MAX_CELLS + 1)); CK(dalloc(&h->cell_fill, RA_MAX_CELLS + 1)); CK(dalloc(&h->vert_cell, N));
+    CK(dalloc(h, &h->cell_count, RA_MAX_CELLS + 1)); CK(dalloc(h, &h->cell_fill, RA_MAX_CELLS + 1)); CK(dalloc(h, &h->vert_cell, N));
     float** ssp[] = {&h->ss.t, &h->ss.occ, &h->ss.d0, &h->ss.cd, &h->ss.dt, &h->ss.st, &h->ss.off, &h->ss.rlx, &h->ss.q_smpl};
-    for (auto p : ssp) CK(dalloc(p, P));
-    CK(dalloc(&h->ss.q_slot, P));
-    CK(dalloc(&h->surf, 3 * P)); CK(dalloc(&h->acc, P)); CK(dalloc(&h->depth, P)); CK(dalloc(&h->fg_ray, P));
-    CK(dalloc(&h->fm.norm, 3 * P)); CK(dalloc(&h->fm.albedo, 3 * P)); CK(dalloc(&h->fm.rough, P));
+    for (auto p : ssp) CK(dalloc(h, p, P));
+    CK(dalloc(h, &h->ss.q_slot, P));
+    CK(dalloc(h, &h->surf, 3 * P)); CK(dalloc(h, &h->acc, P)); CK(dalloc(h, &h->depth, P)); CK(dalloc(h, &h->fg_ray, P));
+    CK(dalloc(h, &h->fm.norm, 3 * P)); CK(dalloc(h, &h->fm.albedo, 3 * P)); CK(dalloc(h, &h->fm.rough, P));
     if (cfg->relight) {
-        CK(dalloc(&h->lvis, (size_t)P * L)); CK(dalloc(&h->ldot, (size_t)P * L));
+        CK(dalloc(h, &h->lvis, (size_t)P * L)); CK(dalloc(h, &h->ldot, (size_t)P * L));
         int64_t S = 256 * P;
-        CK(dalloc(&h->sr.fg, S)); CK(dalloc(&h->sr.light, S)); CK(dalloc(&h->sr.near_, S)); CK(dalloc(&h->sr.far_, S));
-        CK(dalloc(&h->sr.t, S)); CK(dalloc(&h->sr.occ, S)); CK(dalloc(&h->sr.d0, S)); CK(dalloc(&h->sr.q_smpl, S)); CK(dalloc(&h->sr.q_slot, S));
+        CK(dalloc(h, &h->sr.fg, S)); CK(dalloc(h, &h->sr.light, S)); CK(dalloc(h, &h->sr.near_, S)); CK(dalloc(h, &h->sr.far_, S));
+        CK(dalloc(h, &h->sr.t, S)); CK(dalloc(h, &h->sr.occ, S)); CK(dalloc(h, &h->sr.d0, S)); CK(dalloc(h, &h->sr.q_smpl, S)); CK(dalloc(h, &h->sr.q_slot, S));
     }
-    CK(dalloc(&h->q.bpts, (size_t)h->q_cap * 3)); CK(dalloc(&h->q.net, (size_t)h->q_cap));
-    if (cfg->relight) { CK(dalloc(&h->q2.bpts, (size_t)h->q_cap * 3 / 2 + 3)); CK(dalloc(&h->q2.net, (size_t)h->q_cap / 2 + 1)); }
+    CK(dalloc(h, &h->q.bpts, (size_t)h->q_cap * 3)); CK(dalloc(h, &h->q.net, (size_t)h->q_cap));
+    if (cfg->relight) { CK(dalloc(h, &h->q2.bpts, (size_t)h->q_cap * 3 / 2 + 3)); CK(dalloc(h, &h->q2.net, (size_t)h->q_cap / 2 + 1)); }
     CK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     if (const char* e = getenv("RA_OVERLAP")) h->overlap = atoi(e);
-    CK(dalloc(&h->al.bpts, (size_t)h->attr_cap * 3)); CK(dalloc(&h->al.mats, (size_t)h->attr_cap * 18));
-    CK(dalloc(&h->al.bvds, (size_t)h->attr_cap * 3)); CK(dalloc(&h->al.src, (size_t)h->attr_cap));
-    CK(dalloc(&h->raw, (size_t)h->attr_cap * 17));
-    CK(dalloc(&h->counters_blk, 16));
+    CK(dalloc(h, &h->al.bpts, (size_t)h->attr_cap * 3)); CK(dalloc(h, &h->al.mats, (size_t)h->attr_cap * 18));
+    CK(dalloc(h, &h->al.bvds, (size_t)h->attr_cap * 3)); CK(dalloc(h, &h->al.src, (size_t)h->attr_cap));
+    CK(dalloc(h, &h->raw, (size_t)h->attr_cap * 17));
+    CK(dalloc(h, &h->counters_blk, 16));
     h->cnt.n_fg = h->counters_blk; h->cnt.n_shadow = h->counters_blk + 1; h->cnt.n_attr = h->counters_blk + 2;
     h->q.count = h->counters_blk + 3; h->al.count = h->cnt.n_attr;
     h->q2.count = h->counters_blk + 4;
     h->cnt.n_queries = (unsigned long long*)(h->counters_blk + 8); h->cnt.n_inshell = (unsigned long long*)(h->counters_blk + 10);
-    CK(dalloc(&h->pt_smpl, (size_t)h->q_cap)); CK(dalloc(&h->pt_slot, (size_t)h->q_cap));
-    CK(dalloc(&h->bg_spec, 4));
+    CK(dalloc(h, &h->pt_smpl, (size_t)h->q_cap)); CK(dalloc(h, &h->pt_slot, (size_t)h->q_cap));
+    CK(dalloc(h, &h->bg_spec, 4));
     size_t R = ATTR_CH;
-    CK(dalloc(&h->Xr0, R * 64)); for (int i = 0; i < 8; i++) CK(dalloc(&h->ra_[i], R * 256));
-    CK(dalloc(&h->Xr4, R * 320)); CK(dalloc(&h->z8, R * 4)); CK(dalloc(&h->resd_o, R * 3)); CK(dalloc(&h->cpts_o, R * 3));
-    CK(dalloc(&h->Xs0, R * 64)); for (int i = 0; i < 8; i++) CK(dalloc(&h->sb_[i], R * 256));
-    CK(dalloc(&h->Xs4, R * 256)); CK(dalloc(&h->out257, R * 264));
-    CK(dalloc(&h->GA, R * 256)); CK(dalloc(&h->GB, R * 256)); CK(dalloc(&h->dpe0, R * 64)); CK(dalloc(&h->dpes, R * 64));
-    CK(dalloc(&h->gcp, R * 3)); CK(dalloc(&h->u4, R * 4)); CK(dalloc(&h->gbp, R * 3)); CK(dalloc(&h->nrm_o, R * 3));
-    CK(dalloc(&h->hd1, R * 128)); CK(dalloc(&h->hd2, R * 128)); CK(dalloc(&h->head_a, R * 4)); CK(dalloc(&h->head_r, R * 4));
-    CK(dalloc(&h->Xrn, R * 288)); CK(dalloc(&h->rn1, R * 256)); CK(dalloc(&h->rn2, R * 256));
+    CK(dalloc(h, &h->Xr0, R * 64)); for (int i = 0; i < 8; i++) CK(dalloc(h, &h->ra_[i], R * 256));
+    CK(dalloc(h, &h->Xr4, R * 320)); CK(dalloc(h, &h->z8, R * 4)); CK(dalloc(h, &h->resd_o, R * 3)); CK(dalloc(h, &h->cpts_o, R * 3));
+    CK(dalloc(h, &h->Xs0, R * 64)); for (int i = 0; i < 8; i++) CK(dalloc(h, &h->sb_[i], R * 256));
+    CK(dalloc(h, &h->Xs4, R * 256)); CK(dalloc(h, &h->out257, R * 264));
+    CK(dalloc(h, &h->GA, R * 256)); CK(dalloc(h, &h->GB, R * 256)); CK(dalloc(h, &h->dpe0, R * 64)); CK(dalloc(h, &h->dpes, R * 64));
+    CK(dalloc(h, &h->gcp, R * 3)); CK(dalloc(h, &h->u4, R * 4)); CK(dalloc(h, &h->gbp, R * 3)); CK(dalloc(h, &h->nrm_o, R * 3));
+    CK(dalloc(h, &h->hd1, R * 128)); CK(dalloc(h, &h->hd2, R * 128)); CK(dalloc(h, &h->head_a, R * 4)); CK(dalloc(h, &h->head_r, R * 4));
+    CK(dalloc(h, &h->Xrn, R * 288)); CK(dalloc(h, &h->rn1, R * 256)); CK(dalloc(h, &h->rn2, R * 256));
     if (tc_init(h->tc, h->err)) return 1;
     if (tc2_init(h->tc2, h->err)) return 1;
     if (tc3_init(h->err)) return 1;
@@ -266,12 +272,17 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
 
 extern "C" void ra_destroy(ra_handle* h) {
     if (!h) return;
-    // device memory is released with the context; explicit frees of the big blocks keep long-lived processes tidy
-    float* bufs[] = {h->lvis, h->ldot, h->q.bpts, h->q.net, h->raw, h->al.bpts, h->al.mats, h->al.bvds, h->Xr4, h->out257};
-    for (float* b : bufs) if (b) cudaFree(b);
-    for (int i = 0; i < 8; i++) { if (h->ra_[i]) cudaFree(h->ra_[i]); if (h->sb_[i]) cudaFree(h->sb_[i]); }
+    for (void* p : h->allocs) cudaFree(p);          // everything allocated through dalloc()
+    h->allocs.clear();
     tc_free(h->tc);
     tc2_free(h->tc2);
+    lin_tc_clear(h->lin_tc);
+    if (h->tc.dbg) cudaFree(h->tc.dbg);
+    if (h->aux) cudaStreamDestroy(h->aux);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    for (cudaEvent_t e : h->ev_mlp) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_stage) cudaEventDestroy(e);
     delete h;
 }
 
@@ -678,8 +689,8 @@ extern "C" int ra_relight_envmaps_raw(ra_handle* h, const float* probes, int32_t
 // ---------------------------------------------------------------------------------------------- batch preparation (row f1)
 template <typename T>
 static int upload_any(ra_handle* h, T** dst, const T* src, size_t n, cudaStream_t st) {
-    if (*dst) cudaFree(*dst);
-    CK(dalloc(dst, n));
+    hfree(h, *dst);
+    CK(dalloc(h, dst, n));
     CK(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyDefault, st));
     CK(cudaStreamSynchronize(st));
     return 0;
@@ -694,13 +705,13 @@ extern "C" int ra_upload_body(ra_handle* h, const ra_body* b, void* stream) {
     if (upload_any(h, &h->body.rverts, b->rverts, (size_t)N * 3, st)) return 1;
     if (upload_any(h, &h->body.weights, b->weights, (size_t)N * J, st)) return 1;
     if (b->rnorm) { if (upload_any(h, &h->body.rnorm, b->rnorm, (size_t)N * 3, st)) return 1; }
-    else if (h->body.rnorm) { cudaFree(h->body.rnorm); h->body.rnorm = nullptr; }
+    else hfree(h, h->body.rnorm);
     h->body.n_faces = 0;
     if (b->faces && b->n_faces > 0) {
         if (upload_any(h, &h->body.faces, (const int*)b->faces, (size_t)b->n_faces * 3, st)) return 1;
         h->body.n_faces = b->n_faces;
     }
-    if (!h->prep_mm) { CK(dalloc(&h->prep_mm, 16)); CK(dalloc(&h->prep_nacc, (size_t)N * 3)); }
+    if (!h->prep_mm) { CK(dalloc(h, &h->prep_mm, 16)); CK(dalloc(h, &h->prep_nacc, (size_t)N * 3)); }
     h->body.ready = true;
     return 0;
 }
@@ -742,7 +753,7 @@ extern "C" int ra_prepare_rays(ra_handle* h, const float* K, const float* R, con
     for (int i = 0; i < 9; i++) { c.Kinv[i] = (float)(inv[i] / det); c.R[i] = R[i]; }
     for (int a = 0; a < 3; a++) { c.T[a] = T[a]; c.o[a] = -(R[a] * T[0] + R[3 + a] * T[1] + R[6 + a] * T[2]); }       // -R^T T
     int n = H * W, nb = (n + 255) / 256;
-    if (nb > h->blk_cap) { if (h->blk_cnt) cudaFree(h->blk_cnt); CK(dalloc(&h->blk_cnt, (size_t)nb)); h->blk_cap = nb; }
+    if (nb > h->blk_cap) { hfree(h, h->blk_cnt); CK(dalloc(h, &h->blk_cnt, (size_t)nb)); h->blk_cap = nb; }
     LAUNCH(h, k_prep_rays_count, nb, 256, 0, st, c, wbounds, H, W, mask_at_box, h->blk_cnt);
     LAUNCH(h, k_scan_blocks, 1, 1024, 0, st, h->blk_cnt, nb);
     LAUNCH(h, k_prep_rays_write, nb, 256, 0, st, c, wbounds, H, W, h->blk_cnt, nb, ray_o, ray_d, near_, far_, (int*)n_rays);
@@ -762,10 +773,10 @@ static GroundCfg ground_cfg(ra_handle* h, const ra_ground_config* g) {
 extern "C" int ra_ground_begin(ra_handle* h, const unsigned char* mask_at_box, int32_t H, int32_t W, const float* acc_map, float* acc_g, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int n = H * W, nb = (n + 255) / 256;
-    if (nb > h->blk_cap) { if (h->blk_cnt) cudaFree(h->blk_cnt); CK(dalloc(&h->blk_cnt, (size_t)nb)); h->blk_cap = nb; }
+    if (nb > h->blk_cap) { hfree(h, h->blk_cnt); CK(dalloc(h, &h->blk_cnt, (size_t)nb)); h->blk_cap = nb; }
     if (n > h->pix_cap) {
-        if (h->pix2ray) { cudaFree(h->pix2ray); cudaFree(h->g_weight); }
-        CK(dalloc(&h->pix2ray, (size_t)n)); CK(dalloc(&h->g_weight, (size_t)n)); h->pix_cap = n;
+        hfree(h, h->pix2ray); hfree(h, h->g_weight);
+        CK(dalloc(h, &h->pix2ray, (size_t)n)); CK(dalloc(h, &h->g_weight, (size_t)n)); h->pix_cap = n;
     }
     LAUNCH(h, k_mask_count, nb, 256, 0, st, mask_at_box, n, h->blk_cnt);
     LAUNCH(h, k_scan_blocks, 1, 1024, 0, st, h->blk_cnt, nb);
@@ -785,7 +796,7 @@ extern "C" int ra_render_ground(ra_handle* h, const ra_ground_config* g, const f
     if (F == 0) return 0;
     const int L = c.env_h * c.env_w, N = c.n_verts;
     GroundCfg gc = ground_cfg(h, g);
-    if (!h->g_light) CK(dalloc(&h->g_light, (size_t)RA_NLIGHT_MAX * 3));
+    if (!h->g_light) CK(dalloc(h, &h->g_light, (size_t)RA_NLIGHT_MAX * 3));
     LAUNCH(h, k_ground_light_table, 2, 256, 0, st, h->lxyz, L, probe, ph, pw, h->g_light);
     const float* img = albedo_image ? albedo_image : probe;
     if (!albedo_image) { ih = ph; iw = pw; }
@@ -827,7 +838,7 @@ extern "C" int ra_relight_ground(ra_handle* h, const ra_ground_config* g, const 
     if (F == 0) return 0;
     const int L = c.env_h * c.env_w;
     GroundCfg gc = ground_cfg(h, g);
-    if (!h->g_light) CK(dalloc(&h->g_light, (size_t)RA_NLIGHT_MAX * 3));
+    if (!h->g_light) CK(dalloc(h, &h->g_light, (size_t)RA_NLIGHT_MAX * 3));
     LAUNCH(h, k_ground_light_table, 2, 256, 0, st, h->lxyz, L, probe, ph, pw, h->g_light);
     const float* alb = albedo_in;
     if (g->attach_envmap) {
@@ -990,7 +1001,7 @@ extern "C" int ra_assemble_image(ra_handle* h, const float* rgb_map, const float
                                  int32_t W, float bg_brightness, float* out_f, unsigned char* out_u8, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int n = H * W, nb = (n + 255) / 256;
-    if (nb > h->blk_cap) { if (h->blk_cnt) cudaFree(h->blk_cnt); CK(dalloc(&h->blk_cnt, (size_t)nb)); h->blk_cap = nb; }
+    if (nb > h->blk_cap) { hfree(h, h->blk_cnt); CK(dalloc(h, &h->blk_cnt, (size_t)nb)); h->blk_cap = nb; }
     LAUNCH(h, k_mask_count, nb, 256, 0, st, mask_at_box, n, h->blk_cnt);
     LAUNCH(h, k_scan_blocks, 1, 1024, 0, st, h->blk_cnt, nb);
     LAUNCH(h, k_assemble, nb, 256, 0, st, mask_at_box, n, h->blk_cnt, rgb_map, acc_map, bg_brightness, out_f, out_u8);

@@ -363,3 +363,21 @@ def test_edge_cases_new_rows():
     b2['mask_at_box'] = np.zeros_like(b['mask_at_box'])
     out2 = r.render(b2)['main']                                     # floor only
     assert out2['rgb_map'].shape == (1, 37 * 37, 3) and float(out2['acc_map'].abs().max()) == 0.0
+
+
+def test_destroy_releases_device_memory(relight_setup):
+    """ra_destroy frees everything the handle allocated (workspaces, neighbourhood lists, packed weights): creating and closing
+    engines repeatedly does not shrink the free device memory."""
+    b, sd = relight_setup
+    free0 = None
+    for i in range(4):
+        eng = Engine(default_config(True, precision=1, max_rays=16384), DEV)
+        eng.upload_weights(sd); eng.set_frame(b)
+        x = _sample_points(b, 2000, seed=9)
+        eng.query_sdf(x, 0.125, True); eng.query_raw(x[:500])
+        eng.close()
+        torch.cuda.synchronize()
+        free = torch.cuda.mem_get_info(0)[0]
+        if i == 0:
+            free0 = free
+    assert free0 - free < 64 << 20, f'leaked {(free0 - free) >> 20} MiB over 3 create/destroy cycles'
