@@ -123,6 +123,12 @@ int ra_set_frame(ra_handle* h, const ra_frame* f, void* stream);
 /* sphere_tracing_renderer.Renderer.render for the relight network (a1-a18, a21). */
 int ra_render_relight(ra_handle* h, const float* ray_o, const float* ray_d, const float* near, const float* far,
                       int64_t P, const ra_outputs* out, void* stream);
+/* Tile sharding (BASELINE config 4): this handle renders only the rays of rank `rank` of `world`, dealt in interleaved blocks of
+ * `block` rays out of the frame's `global_P` in-box rays.  The one place the reference's result depends on a ray's position in
+ * the frame is the per-chunk wbounds growth (sphere_tracing_renderer.py:1020-1022, chunks of cfg.render_chunk_size rays): with the
+ * layout set, the shadow-ray box uses the ray's GLOBAL index, so sharded and unsharded frames agree bit for bit.
+ * world == 1 restores the default. */
+int ra_set_ray_layout(ra_handle* h, int64_t global_P, int32_t block, int32_t world, int32_t rank);
 /* novel_light_sphere_tracing per-env-map re-shade (a19): probes (n_env,16,32,3); rgb/shade/spec (n_env,P,3).
  * Uses the maps of the preceding ra_render_relight call (kept in the workspace). */
 int ra_relight_envmaps(ra_handle* h, const float* probes, int32_t n_env, float* rgb, float* shade, float* spec,

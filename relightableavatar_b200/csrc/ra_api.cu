@@ -110,6 +110,7 @@ struct ra_handle {
     size_t ev_stage_used = 0;
     // last render
     int64_t last_P = 0; const float* last_ray_o = nullptr; int chunk_actual = 1;
+    int64_t lay_global_P = 0; int lay_block = 32, lay_world = 1, lay_rank = 0;     // ra_set_ray_layout (tile sharding)
 };
 
 // ---------------------------------------------------------------------------------------------- helpers
@@ -566,8 +567,9 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     if (zero_outputs(h, out, P, st)) return 1;
     CK(cudaMemsetAsync(h->counters_blk, 0, 16 * sizeof(int), st));
     h->last_P = P; h->last_ray_o = ray_o;
-    int n_chunks = std::max<int64_t>((P + c.render_chunk - 1) / c.render_chunk, 1);
-    h->chunk_actual = P ? (int)((P + n_chunks - 1) / n_chunks) : 1;        // chunkify's equalised size, net_utils.py:323
+    const int64_t Pg = (h->lay_world > 1 && h->lay_global_P > 0) ? h->lay_global_P : P;     // the reference chunks the WHOLE frame's rays
+    int n_chunks = std::max<int64_t>((Pg + c.render_chunk - 1) / c.render_chunk, 1);
+    h->chunk_actual = Pg ? (int)((Pg + n_chunks - 1) / n_chunks) : 1;        // chunkify's equalised size, net_utils.py:323
     if (P == 0) return 0;
     TraceCfg tc{c.st_iter, c.st_tan_i, c.st_relax, c.st_offset, c.st_eps, c.st_skip, c.dist_th, c.blend_radius};
     int N = c.n_verts;
@@ -596,7 +598,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     // light visibility (DFSS)
     int L = c.env_h * c.env_w;
     LAUNCH(h, k_shadow_gen, grid_for(h, P * L / 4, 256, 16), 256, 0, st, h->fc, h->cnt.n_fg, h->fg_ray, h->surf, h->fm.norm, h->ldir, L,
-           c.lv_near, c.bbox_margin, h->chunk_actual, h->lvis, h->ldot, h->sr, h->cnt.n_shadow);
+           c.lv_near, c.bbox_margin, h->chunk_actual, h->lay_block, h->lay_world, h->lay_rank, h->lvis, h->ldot, h->sr, h->cnt.n_shadow);
     TraceCfg sc{c.lv_iter, 1.f, c.lv_relax, c.lv_offset, c.st_eps, c.st_skip, c.lv_dist_th, c.blend_radius};
     const bool split = h->overlap && h->cfg.precision == RA_PRECISION_TC && (h->tc_variant == 1 || h->tc_variant == 6);
     if (!split) {
@@ -676,6 +678,12 @@ static int relight_envmaps_impl(ra_handle* h, const float* probes, int32_t n_env
                spec ? spec + (size_t)e0 * P * 3 : nullptr, (long long)P, raw ? 0 : 1, raw ? 1 : 0);
     }
     CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ra_set_ray_layout(ra_handle* h, int64_t global_P, int32_t block, int32_t world, int32_t rank) {
+    if (world < 1 || rank < 0 || rank >= world || block < 1 || global_P < 0) { h->err = "ra_set_ray_layout: bad arguments"; return 1; }
+    h->lay_global_P = global_P; h->lay_block = block; h->lay_world = world; h->lay_rank = rank;
     return 0;
 }
 

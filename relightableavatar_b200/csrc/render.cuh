@@ -136,6 +136,7 @@ __device__ __forceinline__ void aabb_near_far(const float* bmin, const float* bm
 __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __restrict__ n_fg, const int* __restrict__ fg_ray,
                              const float* __restrict__ surf /*[P][3] by ray*/, const float* __restrict__ f_norm /*[fg][3]*/,
                              const float* __restrict__ ldir /*[L][3]*/, int L, float lv_near, float bbox_margin, int chunk_actual,
+                             int lay_block, int lay_world, int lay_rank,     // tile sharding: local ray -> global ray (identity when world == 1)
                              float* lvis, float* ldot, ShadowRays sr, int* n_shadow) {
     int lane = threadIdx.x & 31;
     long long total = (long long)(*n_fg) * L;
@@ -154,7 +155,9 @@ __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __res
             ldot[idx] = dt;
             float vis = 0.f;
             if (dt > 0.f) {
-                float pad = bbox_margin * (float)(1 + ray / chunk_actual);   // in-place wbounds growth per pixel chunk (:1020-1022)
+                // in-place wbounds growth per pixel chunk (:1020-1022), by the ray's index in the WHOLE frame
+                const int gray = (lay_world > 1) ? ((ray / lay_block) * lay_world + lay_rank) * lay_block + ray % lay_block : ray;
+                float pad = bbox_margin * (float)(1 + gray / chunk_actual);
                 float bmin[3] = {fc->wb[0] - pad, fc->wb[1] - pad, fc->wb[2] - pad};
                 float bmax[3] = {fc->wb[3] + pad, fc->wb[4] + pad, fc->wb[5] + pad};
                 float3 o = make3(surf[ray * 3], surf[ray * 3 + 1], surf[ray * 3 + 2]);

@@ -66,12 +66,20 @@ def deinterleave(gathered: torch.Tensor, P: int, world: int, block: int = BLOCK)
     return out
 
 
-def render_tile_sharded(render_fn, batch: Dict, keys=('rgb_map', 'acc_map'), group=None) -> Dict[str, torch.Tensor]:
-    """`render_fn(batch) -> {key: (1, P_local, C) or (1, P_local)}` on this rank's rays; returns full-frame (1, P, C) maps."""
+def render_tile_sharded(render_fn, batch: Dict, keys=('rgb_map', 'acc_map'), group=None, engine=None) -> Dict[str, torch.Tensor]:
+    """`render_fn(batch) -> {key: (1, P_local, C) or (1, P_local)}` on this rank's rays; returns full-frame (1, P, C) maps.
+    `engine` (the renderer's Engine): told the ray layout, so that the one frame-position dependent quantity of the reference
+    (the per-chunk wbounds growth of frames with more than render_chunk rays) uses global ray indices."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     P = batch['ray_o'].shape[1]
     local_batch, own = shard_batch_rays(batch, rank, world)
-    out = render_fn(local_batch)
+    if engine is not None:
+        engine.set_ray_layout(P, BLOCK, world, rank)
+    try:
+        out = render_fn(local_batch)
+    finally:
+        if engine is not None:
+            engine.set_ray_layout(0, BLOCK, 1, 0)
     cols, widths = [], []
     for k in keys:
         t = out[k][0]

@@ -235,6 +235,10 @@ class Engine:
             self._check(fn(self.h, _ptr(ray_o), _ptr(ray_d), _ptr(near), _ptr(far), P, C.byref(o), self._stream()), mode)
         return out
 
+    def set_ray_layout(self, global_P: int, block: int = 32, world: int = 1, rank: int = 0):
+        """Tile sharding: tell the library which rays of the whole frame this handle renders (see ra_set_ray_layout)."""
+        self._check(self.lib.ra_set_ray_layout(self.h, int(global_P), int(block), int(world), int(rank)), 'ra_set_ray_layout')
+
     def relight_envmaps(self, probes: torch.Tensor, P: int, want_spec=True):
         n = probes.shape[0]
         rgb = torch.empty(n, P, 3, device=self.device); shade = torch.empty_like(rgb)

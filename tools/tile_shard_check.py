@@ -10,14 +10,29 @@ rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int
 dev = torch.device(f'cuda:{local}')
 torch.cuda.set_device(dev)
 dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
-b = scene.make_batch(128, 128, seed=0, n_env=0)
-bt = {k: (torch.from_numpy(v).to(dev) if hasattr(v, 'shape') and getattr(v, 'ndim', 0) > 0 else v) for k, v in b.items() if k != 'novel_lights'}
 sd = scene.make_state_dict(0, relight=True, fitted=True)
-r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=dev, precision='tc', max_rays=8192, test_light=('main',), sync_timing=False)
-full = r.render(bt)['main']
-sharded = parallel.render_tile_sharded(lambda bb: r.render(bb)['main'], bt, keys=('rgb_map', 'acc_map'))
-ok = torch.equal(sharded['rgb_map'], full['rgb_map']) and torch.equal(sharded['acc_map'], full['acc_map'])
-# shadow-ray far distance depends on the reference's per-chunk box growth, which is the constant 0.25 for P <= 65536 rays, so shards agree bit for bit
+ok = True
+# 128^2: one chunk.  512^2: P > 65536 rays = two reference chunks -- the shadow-ray box depends on the ray's chunk
+# (in-place wbounds growth); ra_set_ray_layout makes the shards use global ray indices, so they agree bit for bit as well.
+for H in (128, 512):
+    b = scene.make_batch(H, H, seed=0, n_env=0)
+    bt = {k: (torch.from_numpy(v).to(dev) if hasattr(v, 'shape') and getattr(v, 'ndim', 0) > 0 else v) for k, v in b.items() if k != 'novel_lights'}
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=dev, precision='tc', max_rays=b['ray_o'].shape[1] + 8, test_light=('main',), sync_timing=False)
+    full = r.render(bt)['main']
+    sharded = parallel.render_tile_sharded(lambda bb: r.render(bb)['main'], bt, keys=('rgb_map', 'acc_map'), engine=r.engine)
+    ok = ok and torch.equal(sharded['rgb_map'], full['rgb_map']) and torch.equal(sharded['acc_map'], full['acc_map'])
+    if H == 512:       # strong-scaling timing of the sharded frame (config 4 shape)
+        for _ in range(2):
+            parallel.render_tile_sharded(lambda bb: r.render(bb)['main'], bt, keys=('rgb_map', 'acc_map'), engine=r.engine)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            parallel.render_tile_sharded(lambda bb: r.render(bb)['main'], bt, keys=('rgb_map', 'acc_map'), engine=r.engine)
+        e1.record(); torch.cuda.synchronize()
+        if rank == 0:
+            print(f'TILE_SHARD_TIMING world={world} 512x512 frame: {e0.elapsed_time(e1) / 5:.2f} ms')
+    r.engine.close()
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
