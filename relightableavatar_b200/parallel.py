@@ -24,10 +24,23 @@ def frame_indices(n_frames: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_frames, world))
 
 
-def tile_partition(P: int, rank: int, world: int, block: int = BLOCK) -> torch.Tensor:
-    """Indices (ascending) of the rays owned by `rank`: blocks of `block` consecutive rays dealt round-robin."""
-    idx = torch.arange(P)
-    return idx[(idx // block) % world == rank]
+_PART_CACHE: Dict[tuple, torch.Tensor] = {}
+
+
+def tile_partition(P: int, rank: int, world: int, block: int = BLOCK, device=None) -> torch.Tensor:
+    """Indices (ascending) of the rays owned by `rank`: blocks of `block` consecutive rays dealt round-robin.
+    Cached per (P, rank, world, block, device): a sequence re-uses the same partition every frame."""
+    key = (P, rank, world, block, str(device))
+    t = _PART_CACHE.get(key)
+    if t is None:
+        idx = torch.arange(P)
+        t = idx[(idx // block) % world == rank]
+        if device is not None:
+            t = t.to(device)
+        if len(_PART_CACHE) > 256:
+            _PART_CACHE.clear()
+        _PART_CACHE[key] = t
+    return t
 
 
 def padded_count(P: int, world: int, block: int = BLOCK) -> int:
@@ -39,11 +52,12 @@ def padded_count(P: int, world: int, block: int = BLOCK) -> int:
 def shard_batch_rays(batch: Dict, rank: int, world: int) -> Tuple[Dict, torch.Tensor]:
     """Returns a shallow copy of `batch` whose ray tensors hold only this rank's rays, and the owned indices."""
     P = batch['ray_o'].shape[1]
-    own = tile_partition(P, rank, world)
     b = dict(batch)
+    own = None
     for k in ('ray_o', 'ray_d', 'near', 'far'):
         t = torch.as_tensor(batch[k])
-        b[k] = t[:, own.to(t.device)]
+        own = tile_partition(P, rank, world, device=t.device)
+        b[k] = t[:, own]
     return b, own
 
 
@@ -61,7 +75,7 @@ def deinterleave(gathered: torch.Tensor, P: int, world: int, block: int = BLOCK)
     """(world, n_pad, C) blocks -> (P, C) in original ray order."""
     out = torch.empty(P, gathered.shape[-1], dtype=gathered.dtype, device=gathered.device)
     for r in range(world):
-        own = tile_partition(P, r, world, block).to(gathered.device)
+        own = tile_partition(P, r, world, block, device=gathered.device)
         out[own] = gathered[r, : own.numel()]
     return out
 
