@@ -301,24 +301,53 @@ __global__ void k_nb_scan(const FrameConst* fc, const int* __restrict__ cnt, Sor
     if (tid == 0) out[n] = carry;
 }
 
-// one warp per (cell, level): copy the runs into the cell's contiguous list
+// one warp per (cell, level): copy the runs into the cell's contiguous list.  Lanes enumerate the rows of the (2r+1)^2 square
+// in parallel (most rows of a shell hold no vertex: no serial chain of dependent cell_start loads through them), a warp scan
+// turns the row counts into offsets, and only the non-empty rows are copied (cooperatively).
 __global__ void k_nb_fill(const FrameConst* fc, const int* __restrict__ cell_start, const float4* __restrict__ pos, SortedVerts sv) {
     GridRef g = grid_ref(fc, 0);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int dx_ = g.dim[0], dy_ = g.dim[1], dz_ = g.dim[2];
     for (int w = warp; w < g.cells * RA_NB_LEVELS; w += nwarps) {
         const int c = w / RA_NB_LEVELS, lv = w % RA_NB_LEVELS;
-        int cx = c % g.dim[0], cy = (c / g.dim[0]) % g.dim[1], cz = c / (g.dim[0] * g.dim[1]);
         int dst = sv.nb_start[lv][c];
         if (sv.nb_start[lv][c + 1] == dst) continue;
+        const int cx = c % dx_, cy = (c / dx_) % dy_, cz = c / (dx_ * dy_);
+        const int r = lv + 1, side = 2 * r + 1;
         float4* out = sv.nb_pos[lv];
-        nb_for_each_run(g, cell_start, cx, cy, cz, lv + 1, [&](int s, int e) {
-            for (int v = s + lane; v < e; v += 32) {
-                float4 q = __ldg(&pos[v]);
-                out[dst + (v - s)] = make_float4(q.x, q.y, q.z, __int_as_float(v));
+        for (int j0 = 0; j0 < side * side; j0 += 32) {
+            const int j = j0 + lane;
+            int s0 = 0, e0 = 0, s1 = 0, e1 = 0;          // up to two runs per row
+            if (j < side * side) {
+                const int z = cz - r + j / side, y = cy - r + j % side;
+                if (z >= 0 && z < dz_ && y >= 0 && y < dy_) {
+                    const int row = (z * dy_ + y) * dx_;
+                    const bool face = (r == 1) || z == cz - r || z == cz + r || y == cy - r || y == cy + r;
+                    if (face) {
+                        s0 = __ldg(&cell_start[row + max(cx - r, 0)]); e0 = __ldg(&cell_start[row + min(cx + r, dx_ - 1) + 1]);
+                    } else {
+                        if (cx - r >= 0) { s0 = __ldg(&cell_start[row + cx - r]); e0 = __ldg(&cell_start[row + cx - r + 1]); }
+                        if (cx + r < dx_) { s1 = __ldg(&cell_start[row + cx + r]); e1 = __ldg(&cell_start[row + cx + r + 1]); }
+                    }
+                }
             }
-            dst += e - s;
-        });
+            const int n0 = e0 - s0, n1 = e1 - s1, cnt = n0 + n1;
+            int incl = cnt;
+            for (int o = 1; o < 32; o <<= 1) { int y2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y2; }
+            const int off = dst + incl - cnt;
+            unsigned m = __ballot_sync(0xffffffffu, cnt > 0);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int bs0 = __shfl_sync(0xffffffffu, s0, src), bn0 = __shfl_sync(0xffffffffu, n0, src);
+                const int bs1 = __shfl_sync(0xffffffffu, s1, src), bn1 = __shfl_sync(0xffffffffu, n1, src);
+                const int bo = __shfl_sync(0xffffffffu, off, src);
+                for (int v = lane; v < bn0; v += 32) { float4 q = __ldg(&pos[bs0 + v]); out[bo + v] = make_float4(q.x, q.y, q.z, __int_as_float(bs0 + v)); }
+                for (int v = lane; v < bn1; v += 32) { float4 q = __ldg(&pos[bs1 + v]); out[bo + bn0 + v] = make_float4(q.x, q.y, q.z, __int_as_float(bs1 + v)); }
+            }
+            dst += __shfl_sync(0xffffffffu, incl, 31);
+        }
     }
 }
 
