@@ -136,3 +136,34 @@ def test_analytic_invariants():
     surf, *_ = O.sphere_tracing(o, d, torch.tensor([[0.5]]), torch.tensor([[6.]]), lambda x: x.norm(dim=-1, keepdim=True) - 1,
                                 16, 1000., 0., 0.02, 1e-8, 1, soft=False)
     assert abs(float(surf[0, 2]) + 1) < 2e-2
+
+
+def test_oracle_fp32_vs_fp64_self_consistency():
+    """The ceiling against which 'PSNR within 0.1 dB' is read: the oracle evaluated in fp32 (the reference's
+    precision) against itself in fp64 on the same rays / pose / env-map.  > 100 dB: discontinuity flips aside, fp32 rounding of
+    the path is far below every tolerance used in the GPU parity tests."""
+    b = scene.make_batch(32, 32, seed=0, n_env=1)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    probes = {k: v[0] for k, v in b['novel_lights'].items()}
+    a = O.render_novel_light(b, sd, O.Cfg(), probes, torch.float32)
+    c = O.render_novel_light(b, sd, O.Cfg(), probes, torch.float64)
+    for n in ['main'] + list(probes):
+        p = O.psnr(O.assemble_image(b, a[n]['rgb_map']), O.assemble_image(b, c[n]['rgb_map'].float()))
+        assert p > 90.0, f'{n}: {p:.1f} dB'
+
+
+def test_scene_is_deterministic():
+    """The golden fixtures store only reference OUTPUTS; the inputs are regenerated from the seed, so the generator must be stable."""
+    import hashlib
+    b = scene.make_batch(24, 24, seed=0, n_env=1)
+    h = hashlib.sha256()
+    for k in ('ray_o', 'ray_d', 'near', 'far', 'A', 'pverts', 'pnorm', 'wbounds', 'weights'):
+        h.update(np.ascontiguousarray(b[k]).tobytes())
+    b2 = scene.make_batch(24, 24, seed=0, n_env=1)
+    h2 = hashlib.sha256()
+    for k in ('ray_o', 'ray_d', 'near', 'far', 'A', 'pverts', 'pnorm', 'wbounds', 'weights'):
+        h2.update(np.ascontiguousarray(b2[k]).tobytes())
+    assert h.hexdigest() == h2.hexdigest()
+    g = _load('prep_24')          # and it still produces the rays the prep fixture was generated from
+    b3 = scene.make_batch(24, 24, frame=int(g['_frame']), n_frames=int(g['_frame']) + 1, seed=0, n_env=0)
+    assert b3['ray_o'].shape[1] == g['ray_o'].shape[0] and np.abs(b3['ray_d'][0] - g['ray_d']).max() < 1e-6
