@@ -68,8 +68,7 @@ __global__ void k_frame_prep(FrameConst* fc, const float* __restrict__ R, const 
         for (int i = 0; i < 3; i++) fc->Th[i] = Th[i];
         for (int i = 0; i < 6; i++) fc->wb[i] = wbounds ? wbounds[i] : 0.f;
     }
-    // zero the cell counters (max size) for the counting sort that follows
-    for (int i = tid; i < RA_MAX_CELLS + 1; i += blockDim.x) cell_count[i] = 0;
+    // the cell counters of the counting sort are all zero here: ra_create zero-fills them and k_grid_scan re-zeroes what it consumed
     // folded biases: one output row per WARP (coalesced weight reads, shuffle reduction), rows strided over the block's warps
     for (int o = wid; o < 256; o += (blockDim.x >> 5)) {
         const float* w0 = resd_w0 + (size_t)o * 219 + 63;
@@ -172,10 +171,12 @@ __global__ void k_grid_scan(const FrameConst* fc, int level, int* cell_count, in
     int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += blockDim.x) {
-        int i = base + tid;
-        int v = (i < n) ? cell_count[i] : 0;
-        int x = v;
+    for (int base = 0; base < n; base += 4 * blockDim.x) {        // four consecutive cells per thread
+        const int i0 = base + tid * 4;
+        int v[4], t = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { v[k] = (i0 + k < n) ? cell_count[i0 + k] : 0; t += v[k]; }
+        int x = t;
         for (int o = 1; o < 32; o <<= 1) {
             int y = __shfl_up_sync(0xffffffffu, x, o);
             if (lane >= o) x += y;
@@ -191,10 +192,14 @@ __global__ void k_grid_scan(const FrameConst* fc, int level, int* cell_count, in
             wsum[lane] = s;
         }
         __syncthreads();
-        int excl = carry + (wid ? wsum[wid - 1] : 0) + x - v;
-        if (i < n) { cell_start[i] = excl; cell_fill[i] = 0; cell_count[i] = 0; }
+        int excl = carry + (wid ? wsum[wid - 1] : 0) + x - t;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k < n) { cell_start[i0 + k] = excl; cell_fill[i0 + k] = 0; cell_count[i0 + k] = 0; }
+            excl += v[k];
+        }
         __syncthreads();
-        if (tid == blockDim.x - 1) carry = excl + v;
+        if (tid == blockDim.x - 1) carry = excl;
         __syncthreads();
     }
     if (tid == 0) cell_start[n] = carry;
@@ -280,9 +285,12 @@ __global__ void k_nb_scan(const FrameConst* fc, const int* __restrict__ cnt, Sor
     int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += blockDim.x) {
-        int i = base + tid;
-        int v = (i < n) ? in[i] : 0, x = v;
+    for (int base = 0; base < n; base += 4 * blockDim.x) {        // four consecutive cells per thread
+        const int i0 = base + tid * 4;
+        int v[4], t = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; t += v[k]; }
+        int x = t;
         for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
         if (lane == 31) wsum[wid] = x;
         __syncthreads();
@@ -292,10 +300,11 @@ __global__ void k_nb_scan(const FrameConst* fc, const int* __restrict__ cnt, Sor
             wsum[lane] = s;
         }
         __syncthreads();
-        int excl = carry + (wid ? wsum[wid - 1] : 0) + x - v;
-        if (i < n) out[i] = excl;
+        int excl = carry + (wid ? wsum[wid - 1] : 0) + x - t;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { if (i0 + k < n) out[i0 + k] = excl; excl += v[k]; }
         __syncthreads();
-        if (tid == blockDim.x - 1) carry = excl + v;
+        if (tid == blockDim.x - 1) carry = excl;
         __syncthreads();
     }
     if (tid == 0) out[n] = carry;
