@@ -1,5 +1,6 @@
 """Debug: per-layer clock timeline of CTA 0 (second tile) of k_mlp_tc on a large query batch."""
 import ctypes, os, sys
+os.environ['RA_TC_VARIANT'] = '1'      # this tool reads the single-CTA kernel's 18 x 8 timeline (tools/tc6_timeline.py: the pair kernel)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from relightableavatar_b200 import scene, _lib
