@@ -129,6 +129,11 @@ int ra_render_relight(ra_handle* h, const float* ray_o, const float* ray_d, cons
  * layout set, the shadow-ray box uses the ray's GLOBAL index, so sharded and unsharded frames agree bit for bit.
  * world == 1 restores the default. */
 int ra_set_ray_layout(ra_handle* h, int64_t global_P, int32_t block, int32_t world, int32_t rank);
+/* The single collective of a sharded step: all-gather of every rank's finished, padded pixel block over
+ * NCCL / NVLink.  comm is an `ncclComm_t` (passed as void* so that this header needs no nccl.h); send: n_floats fp32, recv:
+ * world * n_floats.  libnccl.so.2 is resolved at the first call (dlopen), the library has no link-time NCCL dependency; the
+ * Python mirror uses torch.distributed.all_gather_into_tensor for the same exchange (relightableavatar_b200/parallel.py). */
+int ra_allgather(ra_handle* h, void* comm, const float* send, int64_t n_floats, float* recv, void* stream);
 /* novel_light_sphere_tracing per-env-map re-shade (a19): probes (n_env,16,32,3); rgb/shade/spec (n_env,P,3).
  * Uses the maps of the preceding ra_render_relight call (kept in the workspace). */
 int ra_relight_envmaps(ra_handle* h, const float* probes, int32_t n_env, float* rgb, float* shade, float* spec,

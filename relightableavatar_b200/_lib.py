@@ -12,7 +12,7 @@ EXPORTS = ['ra_create', 'ra_destroy', 'ra_last_error', 'ra_upload_weights', 'ra_
            'ra_relight_envmaps', 'ra_render_anisdf_trace', 'ra_render_anisdf_volume', 'ra_query_sdf', 'ra_query_raw',
            'ra_get_stats', 'ra_launch_count', 'ra_profile_enable', 'ra_profile_read', 'ra_rotate_probes', 'ra_assemble_image',
            'ra_ground_begin', 'ra_render_ground', 'ra_relight_ground', 'ra_blend_ground', 'ra_relight_envmaps_raw',
-           'ra_upload_body', 'ra_prepare_pose', 'ra_prepare_rays', 'ra_set_ray_layout']
+           'ra_upload_body', 'ra_prepare_pose', 'ra_prepare_rays', 'ra_set_ray_layout', 'ra_allgather']
 
 fp = C.POINTER(C.c_float)
 
@@ -113,6 +113,7 @@ def load():
     lib.ra_relight_ground.argtypes = [vp, C.POINTER(ra_ground_config), vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
     lib.ra_blend_ground.argtypes = [vp, vp, vp, vp, i32, i32, i64, vp, vp]
     lib.ra_set_ray_layout.argtypes = [vp, i64, i32, i32, i32]
+    lib.ra_allgather.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.ra_upload_body.argtypes = [vp, C.POINTER(ra_body), vp]
     lib.ra_prepare_pose.argtypes = [vp, vp, vp, vp, f32, C.POINTER(ra_pose_outputs), vp]
     lib.ra_prepare_rays.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]

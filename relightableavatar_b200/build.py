@@ -33,7 +33,7 @@ def build(force: bool = False, verbose: bool = True, extra=(), out: str = OUT) -
     if not force and out == OUT and not needs_build():
         return OUT
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ['-lcuda', '-o', out, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ['-lcuda', '-ldl', '-o', out, SRC]
     if verbose:
         print(' '.join(cmd), flush=True)
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

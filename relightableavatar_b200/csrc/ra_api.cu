@@ -10,6 +10,7 @@
 #include <vector>
 #include <algorithm>
 #include <unordered_set>
+#include <dlfcn.h>
 #include <cmath>
 
 #include "../../include/ra_b200.h"
@@ -678,6 +679,22 @@ static int relight_envmaps_impl(ra_handle* h, const float* probes, int32_t n_env
                spec ? spec + (size_t)e0 * P * 3 : nullptr, (long long)P, raw ? 0 : 1, raw ? 1 : 0);
     }
     CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ra_allgather(ra_handle* h, void* comm, const float* send, int64_t n_floats, float* recv, void* stream) {
+    // ncclResult_t ncclAllGather(const void* sendbuff, void* recvbuff, size_t sendcount, ncclDataType_t datatype, ncclComm_t comm, cudaStream_t stream)
+    typedef int (*allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+    static allgather_fn fn = nullptr;
+    if (!fn) {
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);      // the copy already loaded by the host process, if any
+        if (!lib) { h->err = std::string("ra_allgather: dlopen(libnccl.so.2): ") + dlerror(); return 1; }
+        fn = (allgather_fn)dlsym(lib, "ncclAllGather");
+        if (!fn) { h->err = "ra_allgather: ncclAllGather not found"; return 1; }
+    }
+    const int nccl_float32 = 7;      // ncclFloat32 (nccl.h)
+    int rc = fn(send, recv, (size_t)n_floats, nccl_float32, comm, (cudaStream_t)stream);
+    if (rc != 0) { h->err = "ra_allgather: ncclAllGather returned " + std::to_string(rc); return 1; }
     return 0;
 }
 

@@ -33,6 +33,43 @@ for H in (128, 512):
         if rank == 0:
             print(f'TILE_SHARD_TIMING world={world} 512x512 frame: {e0.elapsed_time(e1) / 5:.2f} ms')
     r.engine.close()
+# ra_allgather (the C-ABI's own collective entry point) against torch.distributed on the same buffers: an NCCL communicator
+# is created here through ctypes (unique id from rank 0, shared with a torch broadcast)
+import ctypes
+from relightableavatar_b200 import _lib
+from relightableavatar_b200.renderer import Engine, default_config
+nccl = ctypes.CDLL('libnccl.so.2')
+uid = (ctypes.c_char * 128)()
+if rank == 0:
+    assert nccl.ncclGetUniqueId(ctypes.byref(uid)) == 0
+t_uid = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device=dev)
+dist.broadcast(t_uid, 0)
+uid = (ctypes.c_char * 128).from_buffer_copy(bytes(t_uid.cpu().tolist()))
+comm = ctypes.c_void_p()
+
+
+class _Uid(ctypes.Structure):
+    _fields_ = [('internal', ctypes.c_char * 128)]
+
+
+nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _Uid, ctypes.c_int]
+u = _Uid(); ctypes.memmove(ctypes.byref(u), uid, 128)
+assert nccl.ncclCommInitRank(ctypes.byref(comm), world, u, rank) == 0
+eng = Engine(default_config(True, precision=1, max_rays=1024), dev)
+send = torch.arange(4096, device=dev, dtype=torch.float32) + 10000 * rank
+recv = torch.empty(world * 4096, device=dev)
+lib = _lib.load()
+rc = lib.ra_allgather(eng.h, comm, ctypes.c_void_p(send.data_ptr()), 4096, ctypes.c_void_p(recv.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+torch.cuda.synchronize()
+ref = torch.empty_like(recv)
+dist.all_gather_into_tensor(ref, send)
+ok_ag = rc == 0 and torch.equal(recv, ref)
+if rank == 0:
+    print('RA_ALLGATHER_OK' if ok_ag else f'RA_ALLGATHER_MISMATCH rc={rc}')
+nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+nccl.ncclCommDestroy(comm)
+eng.close()
+ok = ok and ok_ag
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
