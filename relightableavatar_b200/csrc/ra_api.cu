@@ -56,6 +56,7 @@ struct ra_handle {
     std::string err;
     int64_t launches = 0;
     int dev = 0, sms = 148;
+    int tb_surf = 256, tb_shadow = 256;      // tracing-kernel block sizes (env RA_TB_SURF / RA_TB_SHADOW)
     float cell_h = 0.035f, grid2_ratio = 4.0f;  // tunables (env RA_CELL_H / RA_GRID2_RATIO); swept on B200 with the list-based 3-NN: .03 / .035 / .04 / .05 -> 23.8 / 23.7 / 24.3 / 24.7 ms per frame
     bool have_weights = false, have_frame = false;
     // ---- weights
@@ -203,6 +204,8 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     CK(cudaGetDeviceProperties(&prop, h->dev));
     h->sms = prop.multiProcessorCount;
     if (const char* e = getenv("RA_CELL_H")) h->cell_h = (float)atof(e);
+    if (const char* e = getenv("RA_TB_SURF")) h->tb_surf = std::min(256, std::max(32, atoi(e) / 32 * 32));
+    if (const char* e = getenv("RA_TB_SHADOW")) h->tb_shadow = std::min(256, std::max(32, atoi(e) / 32 * 32));
     if (const char* e = getenv("RA_GRID2_RATIO")) h->grid2_ratio = (float)atof(e);
     if (prop.major != 10) { h->err = "ra_b200 requires an sm_100 (B200) device"; return 1; }
     int64_t P = cfg->max_rays;
@@ -574,11 +577,11 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     if (P == 0) return 0;
     TraceCfg tc{c.st_iter, c.st_tan_i, c.st_relax, c.st_offset, c.st_eps, c.st_skip, c.dist_th, c.blend_radius};
     int N = c.n_verts;
-    int g = grid_for(h, P, 256, 8);
+    int g = grid_for(h, P, h->tb_surf, 8 * 256 / h->tb_surf);
     prof_stage(h, st);
     for (int it = 0; it <= c.st_iter; it++) {
         CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
-        LAUNCH(h, k_trace_surface, g, 256, 0, st, it, tc, h->fc, h->sv, N, ray_o, ray_d, near_, far_, (int)P, h->ss, h->q, h->cnt,
+        LAUNCH(h, k_trace_surface, g, h->tb_surf, 0, st, it, tc, h->fc, h->sv, N, ray_o, ray_d, near_, far_, (int)P, h->ss, h->q, h->cnt,
                h->surf, h->acc, h->depth, h->fg_ray);
         if (it < c.st_iter && distance_pass(h, st)) return 1;
     }
@@ -603,10 +606,10 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     TraceCfg sc{c.lv_iter, 1.f, c.lv_relax, c.lv_offset, c.st_eps, c.st_skip, c.lv_dist_th, c.blend_radius};
     const bool split = h->overlap && h->cfg.precision == RA_PRECISION_TC && (h->tc_variant == 1 || h->tc_variant == 6);
     if (!split) {
-        int gs = grid_for(h, P * 64, 256, 8);
+        int gs = grid_for(h, P * 64, h->tb_shadow, 8 * 256 / h->tb_shadow);
         for (int it = 0; it <= c.lv_iter; it++) {
             CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
-            LAUNCH(h, k_trace_shadow, gs, 256, 0, st, it, sc, h->fc, h->sv, N, h->cnt.n_shadow, h->fg_ray, h->surf, h->ldir, h->lsharp, L, h->sr,
+            LAUNCH(h, k_trace_shadow, gs, h->tb_shadow, 0, st, it, sc, h->fc, h->sv, N, h->cnt.n_shadow, h->fg_ray, h->surf, h->ldir, h->lsharp, L, h->sr,
                    h->q, h->cnt, h->lvis, 0, 1);
             if (it < c.lv_iter && distance_pass(h, st)) return 1;
         }
