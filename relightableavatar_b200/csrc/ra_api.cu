@@ -111,7 +111,7 @@ struct ra_handle {
     std::vector<cudaEvent_t> ev_stage;    // 5 marks per render
     size_t ev_stage_used = 0;
     // last render
-    int64_t last_P = 0; const float* last_ray_o = nullptr; int chunk_actual = 1;
+    int64_t last_P = 0; const float* last_ray_o = nullptr; bool have_render = false; int chunk_actual = 1;
     int64_t lay_global_P = 0; int lay_block = 32, lay_world = 1, lay_rank = 0;     // ra_set_ray_layout (tile sharding)
 };
 
@@ -391,7 +391,7 @@ extern "C" int ra_set_frame(ra_handle* h, const ra_frame* f, void* stream) {
         else tc_set_frame(h->tc, h->fc, st, h->launches);
     }
     CK(cudaGetLastError());
-    h->have_frame = true;
+    h->have_frame = true; h->have_render = false;
     return 0;
 }
 
@@ -570,7 +570,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     const ra_config& c = h->cfg;
     if (zero_outputs(h, out, P, st)) return 1;
     CK(cudaMemsetAsync(h->counters_blk, 0, 16 * sizeof(int), st));
-    h->last_P = P; h->last_ray_o = ray_o;
+    h->last_P = P; h->last_ray_o = ray_o; h->have_render = true;      // P == 0 is a valid (empty) render: ray_o may be null
     const int64_t Pg = (h->lay_world > 1 && h->lay_global_P > 0) ? h->lay_global_P : P;     // the reference chunks the WHOLE frame's rays
     int n_chunks = std::max<int64_t>((Pg + c.render_chunk - 1) / c.render_chunk, 1);
     h->chunk_actual = Pg ? (int)((Pg + n_chunks - 1) / n_chunks) : 1;        // chunkify's equalised size, net_utils.py:323
@@ -658,7 +658,7 @@ extern "C" int ra_render_anisdf_trace(ra_handle* h, const float* ray_o, const fl
 static int relight_envmaps_impl(ra_handle* h, const float* probes, int32_t n_env, float* rgb, float* shade, float* spec, void* stream, int raw) {
     cudaStream_t st = (cudaStream_t)stream;
     const ra_config& c = h->cfg;
-    if (!c.relight || h->last_ray_o == nullptr) { h->err = "ra_relight_envmaps needs a preceding ra_render_relight"; return 1; }
+    if (!c.relight || !h->have_render) { h->err = "ra_relight_envmaps needs a preceding ra_render_relight"; return 1; }
     int64_t P = h->last_P;
     int L = c.env_h * c.env_w;
     for (int e = 0; e < n_env; e++) {      // background pixels: rgb = shade = 0, spec = probe-dependent constant (all-zero inputs)

@@ -159,9 +159,14 @@ def test_empty_rays_are_tolerated(relight_setup):
         b2[k] = b[k][:, :0]
     for k in ('near', 'far'):
         b2[k] = b[k][:, :0]
-    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=1024)
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=1024, test_light=('main', 'all'))
     out = r.render(b2)
     assert out['main']['rgb_map'].shape == (1, 0, 3)
+    for name in b['novel_lights']:                      # the re-shade of an empty render is an empty render, not an error
+        assert out[name]['rgb_map'].shape == (1, 0, 3)
+    r.engine.set_frame(b)                               # a new frame invalidates the stored surface / visibility maps
+    with pytest.raises(RuntimeError, match='needs a preceding ra_render_relight'):
+        r.engine.relight_envmaps(torch.as_tensor(next(iter(b['novel_lights'].values()))[0]).to(DEV)[None], 0)
 
 
 def test_two_cta_kernel_variant_matches_single_cta(relight_setup, monkeypatch):

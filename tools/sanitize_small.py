@@ -1,0 +1,74 @@
+"""Walks every kernel of the path once on small inputs, without the oracle: meant to run under
+`compute-sanitizer --tool memcheck --error-exitcode 3 python tools/sanitize_small.py` (gpurun; not a test).
+Prints one line per stage so a report can be attributed to the stage that launched it."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from relightableavatar_b200 import scene
+from relightableavatar_b200.renderer import Renderer
+from relightableavatar_b200.prepare import FramePreparer
+
+DEV = 'cuda:0'
+H = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+
+
+def stage(name):
+    torch.cuda.synchronize()
+    print('STAGE_OK', name, flush=True)
+
+
+b = scene.make_batch(H, H, seed=0, n_env=2)
+sd = scene.make_state_dict(0, relight=True, fitted=True)
+for prec in ('tc', 'fp32'):
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision=prec, max_rays=2048, test_light=('main', 'all'),
+                 return_lvis=True, sync_timing=False)
+    out = r.render(b)
+    assert torch.isfinite(out['main']['rgb_map']).all()
+    stage(f'relight {prec}')
+    if prec == 'fp32':
+        name, probe = next(iter(b['novel_lights'].items()))
+        rot = r.engine.rotate_probes(torch.as_tensor(probe[0]), 4, 0, 5)
+        r.engine.relight_envmaps(rot, b['ray_o'].shape[1])
+        stage('rotation sweep')
+        r.engine.assemble_image(out['main']['rgb_map'][0], out['main']['acc_map'][0], torch.as_tensor(b['mask_at_box'][0]))
+        stage('image assembly')
+        x = torch.as_tensor(b['wverts'][0][::7]).float() + 0.02
+        v = torch.nn.functional.normalize(torch.randn(x.shape[0], 3), dim=-1)
+        r.engine.query_sdf(x, 0.125, True); r.engine.query_raw(x, v)
+        stage('query_sdf / query_raw')
+        body = scene.make_body(0)
+        poses, Rh, _ = scene.make_motion(1, 1)
+        g = torch.Generator().manual_seed(0)
+        faces = torch.randint(0, body.rverts.shape[0], (3000, 3), generator=g).numpy().astype(np.int32)
+        for kw in ({'rnorm': body.rnorm, 'tnorm': body.tnorm}, {'faces': faces}):
+            prep = FramePreparer(r.engine, body.joints, body.parents, body.rverts, body.weights, body.big_A, body.tverts, **kw)
+            gb = prep.make_batch(poses[0], Rh[0], b['Th'][0, 0], b['cam_K'][0], b['cam_R'][0], b['cam_T'][0], H, H, extra={'train_poses': b['train_poses']})
+        r.render(gb)
+        stage('batch preparation + render')
+    r.engine.close()
+
+# fewer rays than one tile, and none at all
+r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='tc', max_rays=2048, test_light=('main', 'all'), sync_timing=False)
+for n in (5, 0):
+    bb = {k: (v[:, :n] if k in ('ray_o', 'ray_d', 'near', 'far') else v) for k, v in b.items()}
+    r.render(bb)
+    stage(f'{n} rays')
+r.engine.close()
+
+r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=2048, test_light=('main', 'all'),
+             ground_shading=True, sync_timing=False)
+r.render(b)
+stage('ground shading')
+r.engine.close()
+
+sd_a = scene.make_state_dict(0, relight=False, fitted=True)
+for mode in ('anisdf_trace', 'anisdf_volume'):
+    try:
+        r = Renderer(scene.SyntheticNet(sd_a, False), mode=mode, device=DEV, precision='fp32', max_rays=2048, sync_timing=False)
+    except Exception as e:                                   # mode names are the renderer's; report, don't hide
+        print('STAGE_SKIPPED', mode, repr(e)); continue
+    r.render(b)
+    stage(mode)
+    r.engine.close()
+print('SANITIZE_DONE')
