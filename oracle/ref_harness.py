@@ -158,7 +158,8 @@ def to_ref_batch(b: dict, device='cpu'):
     return out
 
 
-def run(mode: str, H: int, seed: int, n_env: int, fitted: bool, threads: int = 0):
+def run(mode: str, H: int, seed: int, n_env: int, fitted: bool, threads: int = 0, frame: int = 0, azim_deg: float = 20.0,
+        cam_dist: float = 3.0):
     import torch
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, here)
@@ -178,7 +179,8 @@ def run(mode: str, H: int, seed: int, n_env: int, fitted: bool, threads: int = 0
     assert not missing, missing
     net.eval()
     renderer = make_renderer(cfg, net)
-    b = scene.make_batch(H, H, seed=seed, n_env=n_env if mode.startswith('relight') else 0)
+    b = scene.make_batch(H, H, frame=frame, n_frames=frame + 1, seed=seed, n_env=n_env if mode.startswith('relight') else 0,
+                         cam_dist=cam_dist, azim_deg=azim_deg)
     batch = to_ref_batch(b)
     torch.manual_seed(0)        # compute_ground_tris draws a random tangent (net_utils.py:392-396)
     with torch.no_grad():
@@ -226,13 +228,16 @@ def main():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--n_env', type=int, default=2)
     ap.add_argument('--raw_init', action='store_true', help='geometric-init SDF instead of the fitted one')
+    ap.add_argument('--frame', type=int, default=0, help='pose frame of the synthetic motion')
+    ap.add_argument('--azim', type=float, default=20.0, help='camera azimuth (deg)')
+    ap.add_argument('--cam_dist', type=float, default=3.0)
     ap.add_argument('--out', required=True)
     a = ap.parse_args()
     out_path = os.path.abspath(a.out)
     if a.mode == 'prep':
         flat = run_prep(a.H, a.seed)
     else:
-        flat, _ = run(a.mode, a.H, a.seed, a.n_env, not a.raw_init)
+        flat, _ = run(a.mode, a.H, a.seed, a.n_env, not a.raw_init, frame=a.frame, azim_deg=a.azim, cam_dist=a.cam_dist)
     np.savez_compressed(out_path, **flat)
     print('wrote', out_path, {k: v.shape for k, v in flat.items()})
 

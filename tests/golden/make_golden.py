@@ -27,6 +27,10 @@ CASES = [
     ('relight_ground_24', 'relight_ground', 24, 1, None),
     # row f1: the reference's dataset-side numpy / torch functions (rays, AABB, LBS, bounds)
     ('prep_24', 'prep', 24, 0, None),
+    # a second pose / view / env-map count, and a second set of weights (seed 1, geometric-init SDF instead of the fitted one):
+    # the pins above all share seed 0, frame 0 and one camera
+    ('relight_40_f3_az140', 'relight', 40, 1, dict(frame=3, azim=140.0, cam_dist=2.4)),
+    ('relight_96_seed1_raw', 'relight', 96, 1, dict(seed=1, raw_init=True)),
 ]
 
 DROP_DUP = ('surf_map', 'depth_map', 'acc_map', 'albedo_map', 'roughness_map', 'norm_map', 'ray_o', 'cpts_map',
@@ -35,12 +39,19 @@ DROP_DUP = ('surf_map', 'depth_map', 'acc_map', 'albedo_map', 'roughness_map', '
 
 def main():
     only = set(sys.argv[1:])
-    for name, mode, H, n_env, _ in CASES:
+    for name, mode, H, n_env, view in CASES:
         if only and name not in only:
             continue
+        view = view or {}
         tmp = os.path.join('/tmp', f'golden_{name}.npz')
+        extra = []
+        for k in ('frame', 'azim', 'cam_dist', 'seed'):
+            if k in view:
+                extra += [f'--{k}', str(view[k])]
+        if view.get('raw_init'):
+            extra.append('--raw_init')
         subprocess.check_call([sys.executable, os.path.join(ROOT, 'oracle', 'ref_harness.py'), '--mode', mode,
-                               '--H', str(H), '--n_env', str(n_env), '--out', tmp])
+                               '--H', str(H), '--n_env', str(n_env), '--out', tmp] + extra)
         d = dict(np.load(tmp))
         keep = {}
         seen_lvis = False
@@ -60,7 +71,9 @@ def main():
             keep[k] = v
             if 'lvis_map' in keep and 'ldot_map' in keep:
                 seen_lvis = True
-        keep['_H'] = np.int64(H); keep['_n_env'] = np.int64(n_env); keep['_seed'] = np.int64(0)
+        keep['_H'] = np.int64(H); keep['_n_env'] = np.int64(n_env); keep['_seed'] = np.int64(view.get('seed', 0))
+        keep.setdefault('_frame', np.int64(view.get('frame', 0))); keep['_azim'] = np.float64(view.get('azim', 20.0))
+        keep['_cam_dist'] = np.float64(view.get('cam_dist', 3.0)); keep['_fitted'] = np.int64(0 if view.get('raw_init') else 1)
         out = os.path.join(HERE, f'{name}.npz')
         np.savez_compressed(out, **keep)
         print(name, os.path.getsize(out) / 1e3, 'kB', sorted(keep))

@@ -26,11 +26,13 @@ def _close(name, a, r, atol, q=1.0):
     assert worst <= atol, f'{name}: err {worst:.3e} (q={q}) > {atol:.1e}; max {d.max():.3e}'
 
 
-def test_relight_matches_reference():
-    g = _load('relight_48')
-    H, n_env = int(g['_H']), int(g['_n_env'])
-    b = scene.make_batch(H, H, seed=0, n_env=n_env)
-    sd = scene.make_state_dict(0, relight=True, fitted=True)
+def _check_relight_case(name):
+    g = _load(name)
+    H, n_env, seed = int(g['_H']), int(g['_n_env']), int(g['_seed'])
+    frame, fitted = int(g.get('_frame', 0)), bool(int(g.get('_fitted', 1)))
+    b = scene.make_batch(H, H, frame=frame, n_frames=frame + 1, seed=seed, n_env=n_env, cam_dist=float(g.get('_cam_dist', 3.0)),
+                         azim_deg=float(g.get('_azim', 20.0)))
+    sd = scene.make_state_dict(seed, relight=True, fitted=fitted)
     probes = {k: v[0] for k, v in b['novel_lights'].items()}
     out = O.render_novel_light(b, sd, O.Cfg(), probes)
     assert int((out['main']['acc_map'] > 0).sum()) == int((g['main.acc_map'][0] > 0).sum())
@@ -40,11 +42,26 @@ def test_relight_matches_reference():
     # autograd normals cross ReLU kinks of the residual MLP: isolated fp32 re-ordering flips (SURVEY.md App. A note)
     _close('main.norm_map', out['main']['norm_map'], g['main.norm_map'][0], 2e-3, q=0.99)
     for n in probes:
-        for k in ('rgb_map', 'shade_map', 'spec_map'):
-            _close(f'{n}.{k}', out[n][k], g[f'{n}.{k}'][0], 5e-4)
+        for k in ('rgb_map', 'shade_map', 'spec_map'):       # the few normal-flip pixels carry into the light sum
+            _close(f'{n}.{k}', out[n][k], g[f'{n}.{k}'][0], 5e-4, q=0.998)
+            _close(f'{n}.{k}', out[n][k], g[f'{n}.{k}'][0], 2e-3)
     _close('lvis_map', out['_main_full']['lvis_map'], g['lvis_map'][0], 2e-3, q=0.999)
     _close('ldot_map', out['_main_full']['ldot_map'], g['ldot_map'][0], 2e-3, q=0.999)
     np.testing.assert_allclose(out['_main_full']['wbounds_after'].numpy(), g['wbounds_after'][0], atol=1e-6)
+
+
+def test_relight_matches_reference():
+    _check_relight_case('relight_48')
+
+
+def test_relight_second_pose_and_view_matches_reference():
+    """Pose frame 3 of the synthetic motion, camera at 140 deg azimuth and 2.4 m (the other pins share frame 0 and one camera)."""
+    _check_relight_case('relight_40_f3_az140')
+
+
+def test_relight_second_weight_set_matches_reference():
+    """Seed-1 body, motion, env-map and weights with the geometric-init SDF (not the committed seed-0 fit)."""
+    _check_relight_case('relight_96_seed1_raw')
 
 
 def test_relight_ground_matches_reference():
