@@ -22,9 +22,6 @@
 #include "prep.cuh"
 #include "mlp_tc.cuh"
 #include "mlp_tc2.cuh"
-#include "mlp_tc3.cuh"
-#include "mlp_tc4.cuh"
-#include "mlp_tc5.cuh"
 #include "mlp_tc6.cuh"
 #include "lin_tc.cuh"
 
@@ -71,7 +68,7 @@ struct ra_handle {
     Tc2Weights tc2;                  // ... and for its 2-CTA (cta_group::2) variant
     int attr_tc = 3;                 // env RA_ATTR_TC: 3 = tcgen05 fp16-split GEMM (lin_tc.cuh), 2 = pipelined 3xTF32 mma.sync GEMM, 1 = first 3xTF32 GEMM, 0 = CUDA-core SGEMM
     LinTcWeights lin_tc;             // packed hi / lo weight images of the attribute-pass GEMMs (built on first use)
-    int tc_variant = 6;              // env RA_TC_VARIANT: 6 = CTA-pair two-slot kernel k_mlp_tc6 (default); 1 = single-CTA kernel; 2-5 = experiments
+    int tc_variant = 6;              // env RA_TC_VARIANT: 6 = CTA-pair two-slot kernel k_mlp_tc6 (default); 1 = single-CTA kernel k_mlp_tc; 2 = first CTA-pair kernel k_mlp_tc2 (cross-checks, bit-identical)
     // ---- frame
     FrameConst* fc = nullptr;
     SortedVerts sv{};
@@ -266,11 +263,9 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     CK(dalloc(h, &h->Xrn, R * 288)); CK(dalloc(h, &h->rn1, R * 256)); CK(dalloc(h, &h->rn2, R * 256));
     if (tc_init(h->tc, h->err)) return 1;
     if (tc2_init(h->tc2, h->err)) return 1;
-    if (tc3_init(h->err)) return 1;
-    if (tc4_init(h->err)) return 1;
-    if (tc5_init(h->err)) return 1;
     if (tc6_init(h->err)) return 1;
     if (const char* e = getenv("RA_TC_VARIANT")) h->tc_variant = atoi(e);
+    if (h->tc_variant != 1 && h->tc_variant != 2 && h->tc_variant != 6) { h->err = "RA_TC_VARIANT must be 1, 2 or 6"; return 1; }
     if (const char* e = getenv("RA_ATTR_TC")) h->attr_tc = atoi(e);
     return 0;
 }
@@ -533,9 +528,6 @@ static int distance_pass(ra_handle* h, cudaStream_t st, const QueryList* ql = nu
         if (h->prof) cudaEventRecord(prof_event(h->ev_mlp, h->ev_mlp_used), st);
         if (h->tc_variant == 6) tc6_distance(h->tc2, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         else if (h->tc_variant == 2) tc2_distance(h->tc2, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
-        else if (h->tc_variant == 5) tc5_distance(h->tc, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
-        else if (h->tc_variant == 4) tc4_distance(h->tc, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
-        else if (h->tc_variant == 3) tc3_distance(h->tc, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         else tc_distance(h->tc, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         if (h->prof) cudaEventRecord(prof_event(h->ev_mlp, h->ev_mlp_used), st);
         return 0;
