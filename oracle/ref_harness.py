@@ -221,6 +221,25 @@ def run_prep(H: int, seed: int, frame: int = 2):
                 wbounds=DU.get_bounds(ww[0].numpy()), pbounds=DU.get_bounds(pp[0].numpy()), _frame=np.int64(frame))
 
 
+CFG_KEYS = ('dist_th', 'blend_radius', 'resd_limit', 'env_r', 'render_chunk_size', 'n_samples', 'surf_sample_range', 'fresnel_f0',
+            'albedo_slope', 'albedo_bias', 'roughness_slope', 'roughness_bias', 'albedo_multiplier', 'shading_albedo', 'env_h', 'env_w',
+            'clip_near', 'clip_far', 'ground_normal', 'ground_origin', 'ground_albedo', 'ground_attach_envmap', 'ground_shading_multiplier')
+CFG_GROUPS = {'sphere_tracing': ('iter', 'tan_i', 'relax', 'offset', 'eps', 'shadow_skip_iter'),
+              'obj_lvis': ('iter', 'offset', 'relax', 'near_offset', 'dist_th'),
+              'env_lvis': ('bbox_margin', 'iter', 'offset', 'relax', 'near_offset', 'dist_th')}
+
+
+def dump_cfg(mode: str) -> dict:
+    """The values the reference's renderers read from the global cfg for this path, after its own config cascade
+    (lib/config/config.py + configs/mobile_stage/xuzhen_12v_geo.yaml): pins relightableavatar_b200.renderer.default_config."""
+    cfg = setup_reference(mode)
+    plain = lambda v: list(v) if isinstance(v, (list, tuple)) else (v.item() if hasattr(v, 'item') else v)
+    out = {k: plain(cfg[k]) for k in CFG_KEYS}
+    for g, keys in CFG_GROUPS.items():
+        out[g] = {k: plain(cfg[g][k]) for k in keys}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--mode', required=True)
@@ -234,6 +253,11 @@ def main():
     ap.add_argument('--out', required=True)
     a = ap.parse_args()
     out_path = os.path.abspath(a.out)
+    if a.mode.startswith('cfg_'):
+        import json
+        json.dump(dump_cfg(a.mode[4:]), open(out_path, 'w'), indent=1, sort_keys=True)
+        print('wrote', out_path)
+        return
     if a.mode == 'prep':
         flat = run_prep(a.H, a.seed)
     else:

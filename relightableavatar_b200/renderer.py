@@ -42,7 +42,7 @@ def default_config(relight: bool = True, **over) -> Dict:
     c = dict(relight=int(relight), precision=1, max_rays=1 << 17, n_verts=6890, n_bones=52,
              dist_th=0.125 if relight else 0.1, blend_radius=0.075, resd_limit=0.05,
              st_iter=16, st_tan_i=1000.0, st_relax=0.0, st_offset=0.02, st_eps=1e-8, st_skip=1,
-             lv_iter=4, lv_offset=0.01, lv_relax=0.0, lv_near=0.02, lv_dist_th=0.125,
+             lv_iter=4, lv_offset=0.01, lv_relax=0.0, lv_near=0.02, lv_dist_th=0.125 if relight else 0.05,      # (unused without relighting)
              env_r=10.0, bbox_margin=0.25, render_chunk=65536, n_samples=3, surf_sample_range=0.005,
              fresnel_f0=0.02, albedo_slope=1.0, albedo_bias=0.0, rough_slope=0.9, rough_bias=0.09,
              albedo_multiplier=1.0, shading_albedo=0.8, env_h=16, env_w=32, vol_samples=128, clip_near=0.02, clip_far=10.0)
@@ -50,14 +50,18 @@ def default_config(relight: bool = True, **over) -> Dict:
     return c
 
 
-def config_from_reference_cfg(cfg, relight: bool) -> Dict:
-    """Read the same keys the reference renderer reads from its global `cfg` (once, at construction)."""
+def config_from_reference_cfg(cfg, relight: bool, mode: Optional[str] = None) -> Dict:
+    """Read the same keys the reference renderer reads from its global `cfg` (once, at construction).
+    `cfg.n_samples` is the number of surface samples in the traced modes (3) and of ray samples in the volume renderer (128,
+    base_renderer.py): it lands in `n_samples` or `vol_samples` accordingly."""
     st, lv = cfg.sphere_tracing, cfg.obj_lvis
+    volume = mode == 'anisdf_volume'
     return default_config(
         relight, dist_th=cfg.dist_th, blend_radius=cfg.blend_radius, resd_limit=cfg.resd_limit,
         st_iter=st.iter, st_tan_i=st.tan_i, st_relax=st.relax, st_offset=st.offset, st_eps=st.eps, st_skip=st.shadow_skip_iter,
         lv_iter=lv.iter, lv_offset=lv.offset, lv_relax=lv.relax, lv_near=lv.near_offset, lv_dist_th=lv.dist_th,
-        env_r=cfg.env_r, bbox_margin=cfg.env_lvis.bbox_margin, render_chunk=cfg.render_chunk_size, n_samples=cfg.n_samples,
+        env_r=cfg.env_r, bbox_margin=cfg.env_lvis.bbox_margin, render_chunk=cfg.render_chunk_size,
+        **({'vol_samples': cfg.n_samples} if volume else {'n_samples': cfg.n_samples}),
         surf_sample_range=cfg.surf_sample_range, fresnel_f0=cfg.fresnel_f0, albedo_slope=cfg.albedo_slope,
         albedo_bias=cfg.albedo_bias, rough_slope=cfg.roughness_slope, rough_bias=cfg.roughness_bias,
         albedo_multiplier=cfg.albedo_multiplier, shading_albedo=cfg.shading_albedo, env_h=cfg.env_h, env_w=cfg.env_w,
@@ -395,7 +399,7 @@ class Renderer(torch.nn.Module):
         self.net = net
         self.mode = mode
         relight = mode == 'relight'
-        conf = config_from_reference_cfg(cfg, relight) if cfg is not None else default_config(relight)
+        conf = config_from_reference_cfg(cfg, relight, mode) if cfg is not None else default_config(relight)
         conf.update(precision=PRECISION[precision], max_rays=int(max_rays))
         conf.update(overrides)
         self.engine = Engine(conf, device)

@@ -37,8 +37,22 @@ DROP_DUP = ('surf_map', 'depth_map', 'acc_map', 'albedo_map', 'roughness_map', '
             'bpts_map', 'envmap.probe')
 
 
+def make_cfg_fixture():
+    """cfg_values.json: the reference's effective cfg values for the path (what renderer.default_config must reproduce)."""
+    import json
+    vals = {}
+    for mode in ('relight', 'anisdf_trace', 'anisdf_volume'):
+        tmp = f'/tmp/golden_cfg_{mode}.json'
+        subprocess.check_call([sys.executable, os.path.join(ROOT, 'oracle', 'ref_harness.py'), '--mode', 'cfg_' + mode, '--out', tmp])
+        vals[mode] = json.load(open(tmp))
+    json.dump(vals, open(os.path.join(HERE, 'cfg_values.json'), 'w'), indent=1, sort_keys=True)
+    print('cfg_values.json', sorted(vals))
+
+
 def main():
     only = set(sys.argv[1:])
+    if not only or 'cfg_values' in only:
+        make_cfg_fixture()
     for name, mode, H, n_env, view in CASES:
         if only and name not in only:
             continue

@@ -38,3 +38,32 @@ def test_product_never_imports_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f'{f} imports the oracle'
+
+
+def _dot(d):
+    from relightableavatar_b200.renderer import dotdict
+    return dotdict({k: _dot(v) if isinstance(v, dict) else v for k, v in d.items()})
+
+
+def test_default_config_equals_the_reference_cfg_cascade():
+    """renderer.default_config / default_ground_config restate the EFFECTIVE cfg of xuzhen_12v_geo(_fix_mat); the fixture holds
+    what the reference's own config cascade yields (tests/golden/make_golden.py cfg_values -> oracle/ref_harness.py dump_cfg)."""
+    import json
+    import pytest
+    from relightableavatar_b200 import renderer as R
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'cfg_values.json')
+    if not os.path.exists(p):
+        pytest.skip('cfg fixture missing')
+    vals = json.load(open(p))
+    for mode, relight in (('relight', True), ('anisdf_trace', False), ('anisdf_volume', False)):
+        cfg = _dot(vals[mode])
+        got, want = R.config_from_reference_cfg(cfg, relight, mode), R.default_config(relight)
+        assert set(got) == set(want)
+        if mode == 'anisdf_volume':      # the volume renderer's ray chunk (8192): no effect on results, ra_render_anisdf_volume
+            assert got.pop('render_chunk') == 8192      # streams 8192-ray slabs on its own; the traced modes use 65536
+            want.pop('render_chunk')
+        for k in want:
+            assert got[k] == pytest.approx(want[k], rel=1e-12), (mode, k, got[k], want[k])
+    g, gw = R.ground_config_from_reference_cfg(_dot(vals['relight'])), R.default_ground_config()
+    for k in gw:
+        assert g[k] == pytest.approx(gw[k]), (k, g[k], gw[k])
