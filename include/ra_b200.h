@@ -32,7 +32,8 @@ typedef struct ra_config {
     int32_t relight;            /* 1: relight_network (raw 17 ch), 0: AniSDF base_network (raw 16 ch) */
     int32_t precision;          /* RA_PRECISION_* */
     int32_t max_rays;           /* capacity: max P of any render call */
-    int32_t n_verts, n_bones;   /* 6890, 52 */
+    int32_t n_verts, n_bones;   /* 6890; 52 (SMPL-H, xuzhen_12v_geo) or 24 (SMPL subjects).  The pose-condition width of the residual and
+                                   render MLPs is 3 * n_bones (cfg.cond_dim, config.py:465-466): 156 or 72 */
     float dist_th;              /* net.dist_th: 0.125 relight / 0.1 AniSDF      base_network.py:177 */
     float blend_radius;         /* 0.075                                        config.py:191 */
     float resd_limit;           /* 0.05                                         config.py:224 */
@@ -57,10 +58,11 @@ typedef struct ra_config {
  * (w = g * v / ||v||_row) by the caller.  "host or device" pointers; the library copies them.
  * State-dict keys: SURVEY.md 8b. */
 typedef struct ra_weights {
-    const float* resd_w[9]; const float* resd_b[9];     /* residual_deformation_network.mlp.linears.{l} */
+    const float* resd_w[9]; const float* resd_b[9];     /* residual_deformation_network.mlp.linears.{l}: layer 0 is
+                                                           (256, 63 + 3 n_bones), layer 4 (256, 256 + 63 + 3 n_bones) */
     const float* sdf_w[9];  const float* sdf_b[9];      /* signed_distance_network.mlp.lin{l} (folded)  */
     float sdf_beta;                                     /* clamp(_beta, 1e-9, 1e6) */
-    const float* render_w[5]; const float* render_b[5]; /* render_network.l{l} (folded); NULL if absent  */
+    const float* render_w[5]; const float* render_b[5]; /* render_network.l{l} (folded); NULL if absent; l3 is (256, 256 + 3 n_bones) */
     const float* albedo_w[3]; const float* albedo_b[3]; /* albedo_network.linears.{l}; NULL for AniSDF   */
     const float* rough_w[3];  const float* rough_b[3];  /* roughness_network.linears.{l}                 */
     const float* env_main;  int32_t env_main_h, env_main_w;  /* softplus(global_env_map_) expanded to 3 ch */
@@ -74,15 +76,15 @@ typedef struct ra_weights {
 typedef struct ra_frame {
     const float* R;        /* (3,3)    */
     const float* Th;       /* (3)      */
-    const float* poses;    /* (156)    */
-    const float* A;        /* (52,4,4) */
-    const float* big_A;    /* (52,4,4) */
-    const float* weights;  /* (N,52)   */
+    const float* poses;    /* (3 n_bones) = (156) */
+    const float* A;        /* (n_bones,4,4) */
+    const float* big_A;    /* (n_bones,4,4) */
+    const float* weights;  /* (N,n_bones) */
     const float* pverts;   /* (N,3)    */
     const float* pnorm;    /* (N,3)    */
     const float* tverts;   /* (N,3) big-pose vertices */
     const float* wbounds;  /* (2,3)  world AABB of the posed body (+-0.05); read, not modified */
-    const float* mat_cond; /* (156) train_motion.poses[fix_material]; may be NULL for relight */
+    const float* mat_cond; /* (3 n_bones) train_motion.poses[fix_material]; may be NULL for relight */
 } ra_frame;
 
 /* Per-ray output maps, each (P, C) fp32, premultiplied by acc like the reference's alpha_output_

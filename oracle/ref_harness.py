@@ -109,7 +109,7 @@ def install_shims():
     torch.cuda.synchronize = lambda *a, **k: None
 
 
-def setup_reference(mode: str):
+def setup_reference(mode: str, n_bones: int = 52):
     """Import the reference config and replay the cascade of lib/config/config.py:498-517 by hand."""
     root = find_reference()
     install_shims()
@@ -135,8 +135,8 @@ def setup_reference(mode: str):
         cfg.merge_from_other_cfg(cfg.pose_seq_cfg)
     else:
         raise ValueError(mode)
-    cfg.n_bones = 52
-    cfg.cond_dim = 156
+    cfg.n_bones = n_bones              # what parse_cfg derives from the body model (config.py:441,465-466): 52 SMPL-H, 24 SMPL
+    cfg.cond_dim = 3 * n_bones
     cfg.vis_rendering_map = True
     cfg.probe_size_ratio = 0.0
     cfg.geometry_pretrain = '/nonexistent'
@@ -159,11 +159,11 @@ def to_ref_batch(b: dict, device='cpu'):
 
 
 def run(mode: str, H: int, seed: int, n_env: int, fitted: bool, threads: int = 0, frame: int = 0, azim_deg: float = 20.0,
-        cam_dist: float = 3.0):
+        cam_dist: float = 3.0, n_bones: int = 52):
     import torch
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, here)
-    cfg = setup_reference(mode)
+    cfg = setup_reference(mode, n_bones)
     from relightableavatar_b200 import scene
     if threads:
         torch.set_num_threads(threads)
@@ -172,7 +172,7 @@ def run(mode: str, H: int, seed: int, n_env: int, fitted: bool, threads: int = 0
     from lib.networks.make_network import make_network
     from lib.networks.renderer.make_renderer import make_renderer
     net = make_network(cfg)
-    sd = scene.make_state_dict(seed, relight=mode.startswith('relight'), fitted=fitted)
+    sd = scene.make_state_dict(seed, relight=mode.startswith('relight'), fitted=fitted, n_bones=n_bones)
     missing, unexpected = net.load_state_dict(sd, strict=False)
     missing = [m for m in missing if 'freq_bands' not in m and 'embedder' not in m]
     assert not unexpected, unexpected
@@ -180,7 +180,7 @@ def run(mode: str, H: int, seed: int, n_env: int, fitted: bool, threads: int = 0
     net.eval()
     renderer = make_renderer(cfg, net)
     b = scene.make_batch(H, H, frame=frame, n_frames=frame + 1, seed=seed, n_env=n_env if mode.startswith('relight') else 0,
-                         cam_dist=cam_dist, azim_deg=azim_deg)
+                         cam_dist=cam_dist, azim_deg=azim_deg, n_bones=n_bones)
     batch = to_ref_batch(b)
     torch.manual_seed(0)        # compute_ground_tris draws a random tangent (net_utils.py:392-396)
     with torch.no_grad():
@@ -250,6 +250,7 @@ def main():
     ap.add_argument('--frame', type=int, default=0, help='pose frame of the synthetic motion')
     ap.add_argument('--azim', type=float, default=20.0, help='camera azimuth (deg)')
     ap.add_argument('--cam_dist', type=float, default=3.0)
+    ap.add_argument('--n_bones', type=int, default=52, help='52 = SMPL-H (xuzhen), 24 = SMPL (ZJU-MoCap / synthetic-human configs)')
     ap.add_argument('--out', required=True)
     a = ap.parse_args()
     out_path = os.path.abspath(a.out)
@@ -261,7 +262,7 @@ def main():
     if a.mode == 'prep':
         flat = run_prep(a.H, a.seed)
     else:
-        flat, _ = run(a.mode, a.H, a.seed, a.n_env, not a.raw_init, frame=a.frame, azim_deg=a.azim, cam_dist=a.cam_dist)
+        flat, _ = run(a.mode, a.H, a.seed, a.n_env, not a.raw_init, frame=a.frame, azim_deg=a.azim, cam_dist=a.cam_dist, n_bones=a.n_bones)
     np.savez_compressed(out_path, **flat)
     print('wrote', out_path, {k: v.shape for k, v in flat.items()})
 

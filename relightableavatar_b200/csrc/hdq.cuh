@@ -10,9 +10,10 @@
 __global__ void k_frame_prep(FrameConst* fc, const float* __restrict__ R, const float* __restrict__ Th,
                              const float* __restrict__ pverts, int nverts, const float* __restrict__ wbounds,
                              const float* __restrict__ poses, const float* __restrict__ mat_cond,
-                             const float* __restrict__ resd_w0, const float* __restrict__ resd_b0,   // (256,219)
-                             const float* __restrict__ resd_w4, const float* __restrict__ resd_b4,   // (256,475)
-                             const float* __restrict__ rend_w3, const float* __restrict__ rend_b3,   // (256,412) or null
+                             int cond,                                                               // C = 3 * n_bones
+                             const float* __restrict__ resd_w0, const float* __restrict__ resd_b0,   // (256,63+C)
+                             const float* __restrict__ resd_w4, const float* __restrict__ resd_b4,   // (256,256+63+C)
+                             const float* __restrict__ rend_w3, const float* __restrict__ rend_b3,   // (256,256+C) or null
                              int* cell_count, float cell_h, float grid2_ratio) {
     __shared__ float smin[3][32], smax[3][32];
     int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -71,12 +72,12 @@ __global__ void k_frame_prep(FrameConst* fc, const float* __restrict__ R, const 
     // the cell counters of the counting sort are all zero here: ra_create zero-fills them and k_grid_scan re-zeroes what it consumed
     // folded biases: one output row per WARP (coalesced weight reads, shuffle reduction), rows strided over the block's warps
     for (int o = wid; o < 256; o += (blockDim.x >> 5)) {
-        const float* w0 = resd_w0 + (size_t)o * 219 + 63;
-        const float* w4 = resd_w4 + (size_t)o * 475 + 256 + 63;
+        const float* w0 = resd_w0 + (size_t)o * (63 + cond) + 63;
+        const float* w4 = resd_w4 + (size_t)o * (319 + cond) + 256 + 63;
         const bool rend = rend_w3 != nullptr && mat_cond != nullptr;
-        const float* w3 = rend ? rend_w3 + (size_t)o * 412 + 256 : nullptr;
+        const float* w3 = rend ? rend_w3 + (size_t)o * (256 + cond) + 256 : nullptr;
         float s0 = 0.f, s4 = 0.f, s3 = 0.f;
-        for (int k = lane; k < 156; k += 32) {
+        for (int k = lane; k < cond; k += 32) {
             float c = poses[k];
             s0 += w0[k] * c;
             s4 += w4[k] * c;

@@ -521,12 +521,12 @@ static void tc_pack_bias(std::vector<__half>& blob, const std::vector<float>& b,
     }
 }
 
-static int tc_upload(TcWeights& t, const ra_weights* w, std::string& err, cudaStream_t st) {
+static int tc_upload(TcWeights& t, const ra_weights* w, int cond, std::string& err, cudaStream_t st) {
     auto fetch = [&](const float* src, size_t n, std::vector<float>& dst) -> bool {
         dst.resize(n);
         return cudaMemcpyAsync(dst.data(), src, n * sizeof(float), cudaMemcpyDefault, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
     };
-    static const int rK[9] = {219, 256, 256, 256, 475, 256, 256, 256, 256};
+    const int rK[9] = {63 + cond, 256, 256, 256, 256 + 63 + cond, 256, 256, 256, 256};      // cond = pose condition width (3 * n_bones)
     static const int sN[9] = {256, 256, 256, 205, 256, 256, 256, 256, 257};
     static const int sK[9] = {51, 256, 256, 256, 256, 256, 256, 256, 256};
     std::vector<__half> blob;

@@ -293,8 +293,10 @@ extern "C" int64_t ra_launch_count(ra_handle* h) { return h ? h->launches : 0; }
 extern "C" int ra_upload_weights(ra_handle* h, const ra_weights* w, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const float rs2 = (float)(1.0 / std::sqrt(2.0));
-    // residual deformation MLP: 219 -> 256 x4 -> (256+219) -> 256 x3 -> 3; the 156-d pose condition is folded into biases per frame
-    static const int rK[9] = {219, 256, 256, 256, 475, 256, 256, 256, 256};
+    // residual deformation MLP: (63+C) -> 256 x4 -> (256+63+C) -> 256 x3 -> 3; the C = 3 * n_bones pose condition (156 for SMPL-H,
+    // 72 for SMPL; config.py:465-466) is folded into biases per frame
+    const int C = 3 * h->cfg.n_bones;
+    const int rK[9] = {63 + C, 256, 256, 256, 256 + 63 + C, 256, 256, 256, 256};
     for (int l = 0; l < 9; l++) {
         int N = (l == 8) ? 3 : 256;
         if (l == 0) { if (upload_lin(h, h->resd[l], w->resd_w[l], w->resd_b[l], N, rK[l], 0, 63, 64, 1.f, nullptr, st)) return 1; }
@@ -303,9 +305,9 @@ extern "C" int ra_upload_weights(ra_handle* h, const ra_weights* w, void* stream
             if (upload_lin(h, h->resd[l], w->resd_w[l], w->resd_b[l], N, rK[l], 0, 256 + 63, 320, 1.f, nullptr, st)) return 1;
         } else if (upload_lin(h, h->resd[l], w->resd_w[l], w->resd_b[l], N, rK[l], 0, rK[l], 256, 1.f, nullptr, st)) return 1;
     }
-    if (upload_raw(h, &h->resd_w0_raw, w->resd_w[0], 256 * 219, st)) return 1;
+    if (upload_raw(h, &h->resd_w0_raw, w->resd_w[0], (size_t)256 * rK[0], st)) return 1;
     if (upload_raw(h, &h->resd_b0_raw, w->resd_b[0], 256, st)) return 1;
-    if (upload_raw(h, &h->resd_w4_raw, w->resd_w[4], 256 * 475, st)) return 1;
+    if (upload_raw(h, &h->resd_w4_raw, w->resd_w[4], (size_t)256 * rK[4], st)) return 1;
     if (upload_raw(h, &h->resd_b4_raw, w->resd_b[4], 256, st)) return 1;
     // SDF MLP: 51 -> 256,256,256,205 -> cat(205,51)/sqrt2 -> 256 x3 -> 257 ; rows of the last layer permuted to [feat(256), sdf]
     static const int sN[9] = {256, 256, 256, 205, 256, 256, 256, 256, 257};
@@ -320,14 +322,14 @@ extern "C" int ra_upload_weights(ra_handle* h, const ra_weights* w, void* stream
     }
     h->beta = w->sdf_beta;
     if (w->render_w[0]) {
-        static const int nK[5] = {286, 256, 256, 412, 256};
+        const int nK[5] = {286, 256, 256, 256 + C, 256};
         for (int l = 0; l < 5; l++) {
             int N = (l == 4) ? 3 : 256;
             int use = (l == 3) ? 256 : nK[l];
             int Kp = (l == 0) ? 288 : 256;
             if (upload_lin(h, h->rend[l], w->render_w[l], w->render_b[l], N, nK[l], 0, use, Kp, 1.f, nullptr, st)) return 1;
         }
-        if (upload_raw(h, &h->rend_w3_raw, w->render_w[3], 256 * 412, st)) return 1;
+        if (upload_raw(h, &h->rend_w3_raw, w->render_w[3], (size_t)256 * nK[3], st)) return 1;
         if (upload_raw(h, &h->rend_b3_raw, w->render_b[3], 256, st)) return 1;
     }
     if (h->cfg.relight) {
@@ -354,8 +356,8 @@ extern "C" int ra_upload_weights(ra_handle* h, const ra_weights* w, void* stream
         if (upload_raw(h, &h->ldir, dir.data(), dir.size(), st)) return 1;
     }
     lin_tc_clear(h->lin_tc);         // the packed GEMM images refer to the previous weights
-    if (tc_upload(h->tc, w, h->err, st)) return 1;
-    if (tc2_upload(h->tc2, w, h->err, st)) return 1;
+    if (tc_upload(h->tc, w, C, h->err, st)) return 1;
+    if (tc2_upload(h->tc2, w, C, h->err, st)) return 1;
     h->have_weights = true;
     return 0;
 }
@@ -367,7 +369,7 @@ extern "C" int ra_set_frame(ra_handle* h, const ra_frame* f, void* stream) {
     h->frame = *f;
     int N = h->cfg.n_verts;
     LAUNCH(h, k_frame_prep, 1, 1024, 0, st, h->fc, f->R, f->Th, f->pverts, N, f->wbounds, f->poses, f->mat_cond,
-           h->resd_w0_raw, h->resd_b0_raw, h->resd_w4_raw, h->resd_b4_raw, h->rend_w3_raw, h->rend_b3_raw, h->cell_count, h->cell_h, h->grid2_ratio);
+           3 * h->cfg.n_bones, h->resd_w0_raw, h->resd_b0_raw, h->resd_w4_raw, h->resd_b4_raw, h->rend_w3_raw, h->rend_b3_raw, h->cell_count, h->cell_h, h->grid2_ratio);
     LAUNCH(h, k_grid_count, (N + 255) / 256, 256, 0, st, h->fc, 0, f->pverts, (const float4*)nullptr, N, h->cell_count, h->vert_cell);
     LAUNCH(h, k_grid_scan, 1, 1024, 0, st, h->fc, 0, h->cell_count, h->sv.cell_start, h->cell_fill);
     LAUNCH(h, k_grid_fill, (N + 127) / 128, 128, 0, st, h->fc, f->pverts, f->pnorm, f->tverts, f->weights, f->A, f->big_A, N,

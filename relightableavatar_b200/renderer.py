@@ -149,6 +149,10 @@ class Engine:
         f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
         keep = []
         w = ra_weights()
+        cond = 3 * self.config['n_bones']
+        k0 = sd['residual_deformation_network.mlp.linears.0.weight'].shape[1]
+        if k0 != 63 + cond:          # the C side reads (256, 63 + 3 n_bones) rows: a mismatch would silently shear every row
+            raise ValueError(f'residual MLP input width {k0} != 63 + 3 * n_bones ({63 + cond}): create the Engine with n_bones={(k0 - 63) // 3}')
 
         def put(arr, i, t):
             t = f(t); keep.append(t); arr[i] = _fptr(t)
@@ -194,8 +198,14 @@ class Engine:
 
         fr = ra_frame()
         keep = []
+        J, N = self.config['n_bones'], self.config['n_verts']
+        want = {'poses': 3 * J, 'A': J * 16, 'big_A': J * 16, 'weights': N * J, 'pverts': N * 3, 'pnorm': N * 3, 'tverts': N * 3,
+                'R': 9, 'Th': 3, 'wbounds': 6}
         for name in ('R', 'Th', 'poses', 'A', 'big_A', 'weights', 'pverts', 'pnorm', 'tverts', 'wbounds'):
-            t = g(name); keep.append(t); setattr(fr, name, _fptr(t))
+            t = g(name)
+            if t.numel() != want[name]:
+                raise ValueError(f'batch.{name} has {t.numel()} elements, expected {want[name]} (n_verts={N}, n_bones={J})')
+            keep.append(t); setattr(fr, name, _fptr(t))
         mc = None
         if 'train_motion' in batch and batch['train_motion'] is not None:
             mc = torch.as_tensor(batch['train_motion']['poses'])
@@ -203,6 +213,8 @@ class Engine:
             mc = torch.as_tensor(batch['train_poses'])
         if mc is not None:
             mc = mc.to(device=dev, dtype=torch.float32)[0, max(fix_material, 0)].reshape(-1).contiguous()
+            if mc.numel() != 3 * J:
+                raise ValueError(f'train_motion.poses rows have {mc.numel()} elements, expected {3 * J}')
             keep.append(mc)
         fr.mat_cond = _fptr(mc)
         with torch.cuda.device(self.device):
@@ -400,6 +412,10 @@ class Renderer(torch.nn.Module):
         self.mode = mode
         relight = mode == 'relight'
         conf = config_from_reference_cfg(cfg, relight, mode) if cfg is not None else default_config(relight)
+        # cfg.n_bones / cfg.cond_dim are derived from the body model by the reference (config.py:441,465-466); the network's own
+        # first layer is the authority here: 63 + 3 * n_bones input columns (52 SMPL-H, 24 SMPL)
+        k0 = net.state_dict()['residual_deformation_network.mlp.linears.0.weight'].shape[1]
+        conf.update(n_bones=(k0 - 63) // 3)
         conf.update(precision=PRECISION[precision], max_rays=int(max_rays))
         conf.update(overrides)
         self.engine = Engine(conf, device)

@@ -190,7 +190,26 @@ class Body:
 _BODY_CACHE: Dict[int, Body] = {}
 
 
-def make_body(seed: int = 0) -> Body:
+SMPL_BONES = 24     # the reference's SMPL subjects (configs/my_zju_mocap, configs/synthetic_human): cfg.n_bones 24, cond_dim 72
+
+
+def _reduce_to_smpl24(body: Body) -> Body:
+    """The same body on SMPL's 24-joint skeleton: the 15 finger joints of each hand collapse into one hand joint that
+    follows the wrist.  Rest / big-pose vertices and normals are unchanged (fingers are not posed in the big pose)."""
+    hands = [(22, 37, 20), (37, 52, 21)]                       # (first, end, wrist) of the finger blocks
+    joints = np.concatenate([body.joints[:22]] + [body.joints[a + 6:a + 7] for a, _, _ in hands])       # middle-finger base
+    parents = np.concatenate([body.parents[:22], [20, 21]]).astype(np.int64)
+    w = np.concatenate([body.weights[:, :22]] + [body.weights[:, a:b].sum(1, keepdims=True) for a, b, _ in hands], axis=1)
+    big_A = np.concatenate([body.big_A[:22]] + [body.big_A[wr:wr + 1] for _, _, wr in hands])
+    return Body(joints, parents, body.rverts, body.rnorm, w.astype(np.float32), big_A, body.tverts, body.tnorm, body.big_segs)
+
+
+def make_body(seed: int = 0, n_bones: int = N_BONES) -> Body:
+    if n_bones == SMPL_BONES:
+        if (seed, n_bones) not in _BODY_CACHE:
+            _BODY_CACHE[(seed, n_bones)] = _reduce_to_smpl24(make_body(seed))
+        return _BODY_CACHE[(seed, n_bones)]
+    assert n_bones == N_BONES, 'n_bones must be 52 (SMPL-H) or 24 (SMPL)'
     if seed in _BODY_CACHE:
         return _BODY_CACHE[seed]
     rng = np.random.default_rng(1000 + seed)
@@ -258,8 +277,14 @@ def make_body(seed: int = 0) -> Body:
 
 
 # ----------------------------------------------------------------------------- motion
-def make_motion(n_frames: int, seed: int = 1):
-    """Smooth random-walk SMPL-H motion: poses (T,156), Rh (T,3), Th (T,3) (motion.npz layout)."""
+def make_motion(n_frames: int, seed: int = 1, n_bones: int = N_BONES):
+    """Smooth random-walk SMPL-H motion: poses (T,156), Rh (T,3), Th (T,3) (motion.npz layout).
+    n_bones = 24: the same body motion on SMPL's skeleton, poses (T,72) with the two hand joints at rest."""
+    if n_bones == SMPL_BONES:
+        poses, Rh, Th = make_motion(n_frames, seed)
+        p = poses.reshape(n_frames, N_BONES, 3)[:, :SMPL_BONES].copy()
+        p[:, 22:] = 0
+        return p.reshape(n_frames, -1), Rh, Th
     rng = np.random.default_rng(2000 + seed)
     base = rng.normal(0, 0.2, (N_BONES, 3))
     base[0] = 0                     # root rotation lives in Rh
@@ -348,11 +373,11 @@ def make_envmaps(n: int = 8, seed: int = 10) -> Dict[str, np.ndarray]:
 
 # ----------------------------------------------------------------------------- batch
 def make_batch(H: int = 512, W: int = 512, frame: int = 0, n_frames: int = 1, seed: int = 0,
-               n_env: int = 1, cam_dist: float = 3.0, azim_deg: float = 20.0) -> Dict[str, np.ndarray]:
+               n_env: int = 1, cam_dist: float = 3.0, azim_deg: float = 20.0, n_bones: int = N_BONES) -> Dict[str, np.ndarray]:
     """The `batch` dict of SURVEY.md 8b for one frame, as float32/int numpy arrays with the
     leading B=1 dimension (what DataLoader's default_collate would produce)."""
-    body = make_body(seed)
-    poses, Rh, Th = make_motion(max(n_frames, frame + 1), seed + 1)
+    body = make_body(seed, n_bones)
+    poses, Rh, Th = make_motion(max(n_frames, frame + 1), seed + 1, n_bones)
     pose = poses[frame].reshape(-1, 3)
     _, A = rigid_transform(pose, body.joints, body.parents)
     pverts, pnorm = _lbs(body.rverts, body.rnorm, body.weights.astype(np.float64), A)
@@ -375,7 +400,7 @@ def make_batch(H: int = 512, W: int = 512, frame: int = 0, n_frames: int = 1, se
     ro, rd = f32(ro.reshape(-1, 3)), f32(rd.reshape(-1, 3))
     near, far, mask = get_near_far(wb, ro, rd)
     ro, rd = ro[mask], rd[mask]
-    train_poses, _, _ = make_motion(4, seed + 7)      # "training motion": material condition source
+    train_poses, _, _ = make_motion(4, seed + 7, n_bones)      # "training motion": material condition source
     b = dict(
         ray_o=ro[None], ray_d=rd[None], near=f32(near)[None], far=f32(far)[None],
         mask_at_box=mask.reshape(1, H, W),
@@ -400,7 +425,7 @@ def make_batch(H: int = 512, W: int = 512, frame: int = 0, n_frames: int = 1, se
 _FIT_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'sdf_fit_seed0.npz')
 
 
-def make_state_dict(seed: int = 0, relight: bool = True, fitted: bool = True):
+def make_state_dict(seed: int = 0, relight: bool = True, fitted: bool = True, n_bones: int = N_BONES):
     """Network state-dict with the reference's key names and init schemes.
 
     residual_deformation_network.mlp.linears.{0..8}: nn.Linear default init, last bias 0 (base_network.py:31-32)
@@ -423,8 +448,9 @@ def make_state_dict(seed: int = 0, relight: bool = True, fitted: bool = True):
         return w, b
 
     sd = {}
-    # residual deformation: 219 -> 256 x4 -> (256+219) -> 256 x3 -> 3
-    dims_in = [219, 256, 256, 256, 475, 256, 256, 256, 256]
+    # residual deformation: 219 -> 256 x4 -> (256+219) -> 256 x3 -> 3   (219 = 63 + cond_dim, cond_dim = 3 * n_bones = 156)
+    cond = 3 * n_bones
+    dims_in = [63 + cond, 256, 256, 256, 256 + 63 + cond, 256, 256, 256, 256]
     dims_out = [256] * 8 + [3]
     for l, (i, o) in enumerate(zip(dims_in, dims_out)):
         w, b = linear(i, o)
@@ -457,7 +483,7 @@ def make_state_dict(seed: int = 0, relight: bool = True, fitted: bool = True):
         for k in fit.files:
             sd[k] = torch.from_numpy(fit[k].astype(np.float32))
     # render network (AniSDF colour): 286 -> 256 x3 -> (256+156) -> 256 -> 3
-    for l, (i, o) in enumerate([(286, 256), (256, 256), (256, 256), (412, 256), (256, 3)]):
+    for l, (i, o) in enumerate([(286, 256), (256, 256), (256, 256), (256 + cond, 256), (256, 3)]):
         w, b = linear(i, o)
         sd[f'render_network.l{l}.weight_v'] = w
         sd[f'render_network.l{l}.weight_g'] = w.norm(dim=1, keepdim=True)

@@ -31,6 +31,9 @@ CASES = [
     # the pins above all share seed 0, frame 0 and one camera
     ('relight_40_f3_az140', 'relight', 40, 1, dict(frame=3, azim=140.0, cam_dist=2.4)),
     ('relight_96_seed1_raw', 'relight', 96, 1, dict(seed=1, raw_init=True)),
+    # SMPL skeleton (24 joints, 72-d pose condition): the reference's ZJU-MoCap / synthetic-human configs
+    ('relight_40_smpl24', 'relight', 40, 1, dict(n_bones=24, frame=1)),
+    ('anisdf_trace_40_smpl24', 'anisdf_trace', 40, 0, dict(n_bones=24, frame=1)),
 ]
 
 DROP_DUP = ('surf_map', 'depth_map', 'acc_map', 'albedo_map', 'roughness_map', 'norm_map', 'ray_o', 'cpts_map',
@@ -59,7 +62,7 @@ def main():
         view = view or {}
         tmp = os.path.join('/tmp', f'golden_{name}.npz')
         extra = []
-        for k in ('frame', 'azim', 'cam_dist', 'seed'):
+        for k in ('frame', 'azim', 'cam_dist', 'seed', 'n_bones'):
             if k in view:
                 extra += [f'--{k}', str(view[k])]
         if view.get('raw_init'):
@@ -87,7 +90,7 @@ def main():
                 seen_lvis = True
         keep['_H'] = np.int64(H); keep['_n_env'] = np.int64(n_env); keep['_seed'] = np.int64(view.get('seed', 0))
         keep.setdefault('_frame', np.int64(view.get('frame', 0))); keep['_azim'] = np.float64(view.get('azim', 20.0))
-        keep['_cam_dist'] = np.float64(view.get('cam_dist', 3.0)); keep['_fitted'] = np.int64(0 if view.get('raw_init') else 1)
+        keep['_cam_dist'] = np.float64(view.get('cam_dist', 3.0)); keep['_fitted'] = np.int64(0 if view.get('raw_init') else 1); keep['_n_bones'] = np.int64(view.get('n_bones', 52))
         out = os.path.join(HERE, f'{name}.npz')
         np.savez_compressed(out, **keep)
         print(name, os.path.getsize(out) / 1e3, 'kB', sorted(keep))

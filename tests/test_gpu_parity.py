@@ -132,7 +132,7 @@ def test_render_volume_vs_oracle():
         assert torch.quantile(e.flatten(), 0.98) <= 2e-3, f'{k}: q98 {torch.quantile(e.flatten(), 0.98):.3e}'
 
 
-@pytest.mark.parametrize('fixture', ['relight_48', 'relight_40_f3_az140', 'relight_96_seed1_raw'])
+@pytest.mark.parametrize('fixture', ['relight_48', 'relight_40_f3_az140', 'relight_96_seed1_raw', 'relight_40_smpl24'])
 def test_golden_relight_through_cabi(fixture):
     """The committed reference outputs (tests/golden/*.npz: three poses / views / weight sets) against the CUDA path directly."""
     import os
@@ -140,10 +140,10 @@ def test_golden_relight_through_cabi(fixture):
     if not os.path.exists(p):
         pytest.skip('golden fixture missing')
     g = dict(np.load(p))
-    H, n_env, seed, frame = int(g['_H']), int(g['_n_env']), int(g['_seed']), int(g.get('_frame', 0))
+    H, n_env, seed, frame, n_bones = int(g['_H']), int(g['_n_env']), int(g['_seed']), int(g.get('_frame', 0)), int(g.get('_n_bones', 52))
     b = scene.make_batch(H, H, frame=frame, n_frames=frame + 1, seed=seed, n_env=n_env, cam_dist=float(g.get('_cam_dist', 3.0)),
-                         azim_deg=float(g.get('_azim', 20.0)))
-    sd = scene.make_state_dict(seed, relight=True, fitted=bool(int(g.get('_fitted', 1))))
+                         azim_deg=float(g.get('_azim', 20.0)), n_bones=n_bones)
+    sd = scene.make_state_dict(seed, relight=True, fitted=bool(int(g.get('_fitted', 1))), n_bones=n_bones)
     r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=16384, test_light=('main', 'all'))
     out = r.render(b)
     assert abs(int((out['main']['acc_map'][0] > 0).sum()) - int((g['main.acc_map'][0] > 0).sum())) <= 2
@@ -156,6 +156,44 @@ def test_golden_relight_through_cabi(fixture):
         e = np.abs(out[n]['rgb_map'][0].cpu().numpy() - g[f'{n}.rgb_map'][0])
         assert np.quantile(e, 0.98) <= 1e-3, f'{n}: q98 {np.quantile(e, 0.98):.3e}'
         assert np.quantile(e[fg], 0.95) <= 1e-3, f'{n}: foreground q95 {np.quantile(e[fg], 0.95):.3e}'
+
+
+@pytest.mark.parametrize('precision,tol_q99,tol_max', [('fp32', 2e-5, 2e-3), ('tc', 2e-3, 2e-2)])
+def test_smpl_24_joint_skeleton(precision, tol_q99, tol_max):
+    """cfg.n_bones = 24 / cond_dim = 72 (the reference's SMPL subjects: ZJU-MoCap, synthetic-human configs): distance queries on both
+    precisions against the oracle (same tolerances as test_query_sdf), a mismatching skeleton is refused on the host, and the
+    batch preparation of row f1 runs the 24-joint chain."""
+    from relightableavatar_b200.prepare import FramePreparer
+    nb = scene.SMPL_BONES
+    b = scene.make_batch(48, 48, frame=1, n_frames=2, seed=0, n_env=0, n_bones=nb)
+    sd = scene.make_state_dict(0, relight=True, fitted=True, n_bones=nb)
+    cfg = O.Cfg()
+    eng = Engine(default_config(True, precision={'fp32': 0, 'tc': 1}[precision], max_rays=8192, n_bones=nb), DEV)
+    eng.upload_weights(sd); eng.set_frame(b)
+    x = _sample_points(b, 20000)
+    got = eng.query_sdf(x, 0.125, True)
+    W = O.Weights(sd, torch.float32, DEV); fr = O.Frame.from_batch(b, cfg, torch.float32, DEV)
+    with torch.no_grad():
+        ref = O.hdq_distance(x.to(DEV), fr, W, cfg, 0.125, True)[:, 0]
+    e = _err(got, ref)
+    assert torch.quantile(e, 0.99) <= tol_q99, f'q99 {torch.quantile(e, 0.99):.3e}'
+    assert (e > tol_max).float().mean() < 2e-3, f'outlier fraction {(e > tol_max).float().mean():.3e} max {e.max():.3e}'
+    if precision == 'fp32':
+        with pytest.raises(ValueError, match='n_bones'):
+            eng.upload_weights(scene.make_state_dict(0, relight=True, fitted=True))          # 52-joint weights into a 24-joint handle
+        with pytest.raises(ValueError, match='expected'):
+            eng.set_frame(scene.make_batch(24, 24, seed=0, n_env=0))                           # 52-joint batch
+        eng.upload_weights(sd)
+        body = scene.make_body(0, nb)
+        poses, Rh, _ = scene.make_motion(2, 1, nb)
+        prep = FramePreparer(eng, body.joints, body.parents, body.rverts, body.weights, body.big_A, body.tverts, rnorm=body.rnorm, tnorm=body.tnorm)
+        Th = b['Th'][0, 0]
+        p = prep.pose(poses[1], Rh[1], Th)
+        o = O.prepare_pose(poses[1], Rh[1], Th, body.joints, body.parents, body.rverts, body.weights, rnorm=body.rnorm)
+        for k in ('A', 'pverts', 'pnorm', 'wverts', 'wbounds'):
+            assert float(_err(p[k], o[k]).max()) <= 5e-6, k
+        assert float(_err(p['pverts'], torch.as_tensor(b['pverts'][0])).max()) <= 1e-5          # and equals the scene's own float64 LBS
+    eng.close()
 
 
 def test_empty_rays_are_tolerated(relight_setup):

@@ -29,10 +29,10 @@ def _close(name, a, r, atol, q=1.0):
 def _check_relight_case(name):
     g = _load(name)
     H, n_env, seed = int(g['_H']), int(g['_n_env']), int(g['_seed'])
-    frame, fitted = int(g.get('_frame', 0)), bool(int(g.get('_fitted', 1)))
+    frame, fitted, n_bones = int(g.get('_frame', 0)), bool(int(g.get('_fitted', 1))), int(g.get('_n_bones', 52))
     b = scene.make_batch(H, H, frame=frame, n_frames=frame + 1, seed=seed, n_env=n_env, cam_dist=float(g.get('_cam_dist', 3.0)),
-                         azim_deg=float(g.get('_azim', 20.0)))
-    sd = scene.make_state_dict(seed, relight=True, fitted=fitted)
+                         azim_deg=float(g.get('_azim', 20.0)), n_bones=n_bones)
+    sd = scene.make_state_dict(seed, relight=True, fitted=fitted, n_bones=n_bones)
     probes = {k: v[0] for k, v in b['novel_lights'].items()}
     out = O.render_novel_light(b, sd, O.Cfg(), probes)
     assert int((out['main']['acc_map'] > 0).sum()) == int((g['main.acc_map'][0] > 0).sum())
@@ -57,6 +57,11 @@ def test_relight_matches_reference():
 def test_relight_second_pose_and_view_matches_reference():
     """Pose frame 3 of the synthetic motion, camera at 140 deg azimuth and 2.4 m (the other pins share frame 0 and one camera)."""
     _check_relight_case('relight_40_f3_az140')
+
+
+def test_relight_smpl_24_joint_skeleton_matches_reference():
+    """cfg.n_bones 24 / cond_dim 72 (the reference's ZJU-MoCap and synthetic-human configs) instead of SMPL-H's 52 / 156."""
+    _check_relight_case('relight_40_smpl24')
 
 
 def test_relight_second_weight_set_matches_reference():
@@ -114,11 +119,12 @@ def test_batch_preparation_matches_reference():
     assert torch.allclose(n, torch.nn.functional.normalize(v, dim=1), atol=1e-5)      # icosahedron: vertex normal = radial direction
 
 
-def test_anisdf_trace_matches_reference():
-    g = _load('anisdf_trace_48')
-    H = int(g['_H'])
-    b = scene.make_batch(H, H, seed=0, n_env=0)
-    sd = scene.make_state_dict(0, relight=False, fitted=True)
+@pytest.mark.parametrize('name', ['anisdf_trace_48', 'anisdf_trace_40_smpl24'])
+def test_anisdf_trace_matches_reference(name):
+    g = _load(name)
+    H, frame, n_bones = int(g['_H']), int(g.get('_frame', 0)), int(g.get('_n_bones', 52))
+    b = scene.make_batch(H, H, frame=frame, n_frames=frame + 1, seed=0, n_env=0, n_bones=n_bones)
+    sd = scene.make_state_dict(0, relight=False, fitted=True, n_bones=n_bones)
     out = O.render_sphere_tracing(b, sd, O.anisdf_cfg())
     assert int((g['acc_map'][0] > 0).sum()) > 50
     for k in ('rgb_map', 'acc_map', 'surf_map', 'bpts_map', 'cpts_map', 'depth_map', 'resd_map'):
