@@ -233,10 +233,15 @@ def dump_cfg(mode: str) -> dict:
     """The values the reference's renderers read from the global cfg for this path, after its own config cascade
     (lib/config/config.py + configs/mobile_stage/xuzhen_12v_geo.yaml): pins relightableavatar_b200.renderer.default_config."""
     cfg = setup_reference(mode)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     plain = lambda v: list(v) if isinstance(v, (list, tuple)) else (v.item() if hasattr(v, 'item') else v)
     out = {k: plain(cfg[k]) for k in CFG_KEYS}
     for g, keys in CFG_GROUPS.items():
         out[g] = {k: plain(cfg[g][k]) for k in keys}
+    # the switches the drop-in supports at their default only (renderer.FIXED_SWITCHES): record what the reference has
+    from relightableavatar_b200.renderer import FIXED_ST_SWITCHES, FIXED_SWITCHES
+    out.update({k: plain(cfg[k]) for k in FIXED_SWITCHES})
+    out['sphere_tracing'].update({k: plain(cfg.sphere_tracing[k]) for k in FIXED_ST_SWITCHES})
     return out
 
 

@@ -50,10 +50,40 @@ def default_config(relight: bool = True, **over) -> Dict:
     return c
 
 
+# Switches the reference reads on this path (ablations, debug views, alternative encodings) that the library implements at the
+# reference's DEFAULT value only.  A cfg that sets one of them differently is refused instead of rendered differently.
+# (Defaults: lib/config/config.py; pinned by tests/golden/cfg_values.json.)
+FIXED_SWITCHES = dict(
+    smpl_distance=False, ablate_hdq_mode='hdq', use_geodesic_filter=True, sample_vert_cnt=3, sdf_finite_diff=0,      # HDQ (base_network.py)
+    xyz_res=10, view_res=4, sdf_res=8, feat_dim=256, relight_network_width=128, relight_network_depth=2, lambertian=False,   # network shapes
+    no_visibility=False, local_visibility=False, no_dfss=False, no_claybook=False, only_visibility=False,            # shadow tracing
+    geometry_visibility=False, geometry_normal=False, bruteforce_st=False, check_termination_sdf=False, check_bound_sdf=False,
+    zero_roughness=False, rgb_as_albedo=False, replace_light='', lambert_only=False, glossy_only=False,              # shading
+    bg_brightness=0.0, tonemapping_rendering=True)
+FIXED_ST_SWITCHES = dict(tan_i_multiplier=1)          # cfg.sphere_tracing.*
+
+
+def check_fixed_switches(cfg) -> None:
+    """Raise NotImplementedError when the reference cfg asks for a non-default value of a switch in FIXED_SWITCHES."""
+    def get(node, k):
+        try:
+            return node[k] if k in node else None
+        except TypeError:
+            return getattr(node, k, None)
+    bad = {k: get(cfg, k) for k, d in FIXED_SWITCHES.items() if get(cfg, k) is not None and get(cfg, k) != d}
+    st = get(cfg, 'sphere_tracing')
+    if st is not None:
+        bad.update({'sphere_tracing.' + k: get(st, k) for k, d in FIXED_ST_SWITCHES.items() if get(st, k) is not None and get(st, k) != d})
+    if bad:
+        raise NotImplementedError('relightableavatar_b200 implements these reference switches at their default value only: '
+                                  + ', '.join(f'{k}={v!r} (default {FIXED_SWITCHES.get(k, FIXED_ST_SWITCHES.get(k.split(".")[-1]))!r})' for k, v in bad.items()))
+
+
 def config_from_reference_cfg(cfg, relight: bool, mode: Optional[str] = None) -> Dict:
     """Read the same keys the reference renderer reads from its global `cfg` (once, at construction).
     `cfg.n_samples` is the number of surface samples in the traced modes (3) and of ray samples in the volume renderer (128,
     base_renderer.py): it lands in `n_samples` or `vol_samples` accordingly."""
+    check_fixed_switches(cfg)
     st, lv = cfg.sphere_tracing, cfg.obj_lvis
     volume = mode == 'anisdf_volume'
     return default_config(

@@ -64,6 +64,16 @@ def test_default_config_equals_the_reference_cfg_cascade():
             want.pop('render_chunk')
         for k in want:
             assert got[k] == pytest.approx(want[k], rel=1e-12), (mode, k, got[k], want[k])
+        for k, d in R.FIXED_SWITCHES.items():          # the reference's own defaults are the values the library implements
+            assert vals[mode][k] == d, (mode, k, vals[mode][k], d)
+    cfg = _dot(vals['relight'])
+    cfg['no_dfss'] = True                               # an ablation switch the library does not implement: refused, not ignored
+    with pytest.raises(NotImplementedError, match='no_dfss'):
+        R.config_from_reference_cfg(cfg, True, 'relight')
+    cfg = _dot(vals['relight'])
+    cfg['sphere_tracing']['tan_i_multiplier'] = 2
+    with pytest.raises(NotImplementedError, match='tan_i_multiplier'):
+        R.config_from_reference_cfg(cfg, True, 'relight')
     g, gw = R.ground_config_from_reference_cfg(_dot(vals['relight'])), R.default_ground_config()
     for k in gw:
         assert g[k] == pytest.approx(gw[k]), (k, g[k], gw[k])
