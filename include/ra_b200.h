@@ -52,6 +52,9 @@ typedef struct ra_config {
     int32_t env_h, env_w;       /* 16, 32 */
     int32_t vol_samples;        /* 128: base_renderer uniform samples            base.yaml:78 */
     float clip_near, clip_far;  /* 0.02, 10                                      config.py:79-80 */
+    int32_t tonemapping;        /* 1: the main pass's rgb passes linear2srgb (cfg.tonemapping_rendering, config.py:417); 0 for
+                                   .exr/.hdr output (config.py:446-448)   sphere_tracing_renderer.py:523,731.  The novel-light
+                                   re-shade maps unconditionally, as the reference does (novel_light_sphere_tracing.py:48,94) */
 } ra_config;
 
 /* Network tensors in torch layout (out_features x in_features), weight-norm already folded

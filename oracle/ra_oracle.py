@@ -47,6 +47,7 @@ class Cfg:
     xyz_res: int = 10
     sdf_res: int = 8
     view_res: int = 4
+    tonemapping: bool = True          # cfg.tonemapping_rendering (config.py:417; False for .exr/.hdr output): main pass only
     n_samples: int = 3
     surf_sample_range: float = 0.005
     st_iter: int = 16
@@ -433,8 +434,10 @@ def linear2srgb(x: torch.Tensor) -> torch.Tensor:
     return torch.where(x <= 0.0031308, x * 12.92, 1.055 * torch.pow(x + 1e-7, 1 / 2.4) - 0.055)
 
 
-def shade_pixels(ray_o, surf, norm, albedo, rough, lvis, ldot, probe, W: Weights, cfg: Cfg, chunk: int = 4096):
-    """A.7 + A.8: env fetch, BRDF, 512-light sum.  lvis/ldot (512,S).  Returns rgb(sRGB), shade, spec (S,3)."""
+def shade_pixels(ray_o, surf, norm, albedo, rough, lvis, ldot, probe, W: Weights, cfg: Cfg, chunk: int = 4096, tonemap: bool = True):
+    """A.7 + A.8: env fetch, BRDF, 512-light sum.  lvis/ldot (512,S).  Returns rgb(sRGB), shade, spec (S,3).
+    `tonemap`: the main pass honours cfg.tonemapping_rendering (sphere_tracing_renderer.py:731); the novel-light re-shade applies
+    linear2srgb unconditionally (novel_light_sphere_tracing.py:48)."""
     L = W.light_xyz.reshape(-1, 3)
     area = W.light_area.reshape(-1)
     rgbs, shades, specs = [], [], []
@@ -446,7 +449,7 @@ def shade_pixels(ray_o, surf, norm, albedo, rough, lvis, ldot, probe, W: Weights
         lv, ld = lvis[:, sl].T, ldot[:, sl].T                               # (n,512)
         brdf = microfacet(s2l, s2c, norm[sl], albedo[sl], rough[sl], cfg.fresnel_f0)
         shade = lv[..., None] * 1.0 * area[None, :, None] * light           # ldot := 1 (cancel_cosine)
-        rgbs.append(linear2srgb((brdf * shade).sum(1)))
+        rgbs.append(linear2srgb((brdf * shade).sum(1)) if tonemap else (brdf * shade).sum(1))
         sb = microfacet(s2l, s2c, norm[sl], torch.zeros_like(albedo[sl]), rough[sl], cfg.fresnel_f0)
         # spec: lvis=1, ldot := 1/(|ones|+1e-8)   (sphere_tracing_renderer.py:739-749)
         specs.append((sb * (1.0 / (1.0 + 1e-8)) * area[None, :, None] * light).sum(1))
@@ -541,7 +544,7 @@ def render_human(ray_o, ray_d, near, far, fr: Frame, W: Weights, cfg: Cfg, bbox,
         rough = rough.clip(cfg.rough_bias, cfg.rough_bias + cfg.rough_slope)
         ret.update(albedo_map=albedo, roughness_map=rough[:, 0])
         lvis, ldot = light_visibility(surf, norm, acc, W, fr, cfg, bbox)
-        rgb, shade, _ = shade_pixels(ro, surf, norm, albedo, rough, lvis, ldot, probe, W, cfg)
+        rgb, shade, _ = shade_pixels(ro, surf, norm, albedo, rough, lvis, ldot, probe, W, cfg, tonemap=cfg.tonemapping)
         ret.update(rgb_map=rgb, shade_map=shade)
         if want_lvis:
             ret.update(lvis_map=lvis.T.contiguous(), ldot_map=ldot.T.contiguous())     # (S,512)
@@ -606,7 +609,8 @@ def render_ground(ray_o, ray_d, acc, fr: Frame, W: Weights, cfg: Cfg, bbox, prob
     area = W.light_area.reshape(-1)
     shade = lvis[..., None] * ldot[..., None] * area[:, None, None] * light[:, None]          # evaluate_shade :369-376
     rgb = ((albedo[None] / math.pi) * shade).sum(0)
-    rgb = linear2srgb(rgb)
+    if cfg.tonemapping:                                                                       # sphere_tracing_renderer.py:523
+        rgb = linear2srgb(rgb)
     shade = shade.sum(0) * cfg.shading_albedo / math.pi
     return dict(rgb_map=rgb, surf_map=surf, albedo_map=albedo, roughness_map=torch.ones_like(albedo[:, 0]), spec_map=shade / 20,
                 norm_map=normP.clone(), shade_map=shade * cfg.ground_shading_multiplier, cpts_map=torch.zeros_like(surf),
@@ -621,7 +625,7 @@ def render_ground_novel(ray_d, albedo_map, lvis_map, ldot_map, W: Weights, cfg: 
     albedo = sample_envmap(image if image is not None else probe, ray_d) if cfg.ground_attach_envmap else albedo_map
     area = W.light_area.reshape(-1)
     shade = lvis_map.T[..., None] * ldot_map.T[..., None] * area[:, None, None] * light[:, None]
-    rgb = linear2srgb(((albedo[None] / math.pi) * shade).sum(0))
+    rgb = linear2srgb(((albedo[None] / math.pi) * shade).sum(0))                              # unconditional, :94
     shade = shade.sum(0) / math.pi
     return rgb, albedo, shade, shade / 20
 

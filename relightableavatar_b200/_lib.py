@@ -27,7 +27,7 @@ class ra_config(C.Structure):
                 ('surf_sample_range', C.c_float), ('fresnel_f0', C.c_float), ('albedo_slope', C.c_float),
                 ('albedo_bias', C.c_float), ('rough_slope', C.c_float), ('rough_bias', C.c_float),
                 ('albedo_multiplier', C.c_float), ('shading_albedo', C.c_float), ('env_h', C.c_int32), ('env_w', C.c_int32),
-                ('vol_samples', C.c_int32), ('clip_near', C.c_float), ('clip_far', C.c_float)]
+                ('vol_samples', C.c_int32), ('clip_near', C.c_float), ('clip_far', C.c_float), ('tonemapping', C.c_int32)]
 
 
 class ra_weights(C.Structure):

@@ -11,6 +11,7 @@ struct GroundCfg {
     float normal[3], origin[3], albedo[3];
     int attach_envmap;
     float shading_albedo, multiplier, env_r, near_offset, bbox_margin;
+    int tonemap;
 };
 
 // image pixel -> ray index (or -1): the `inds` of the reference (mask.nonzero() order); also acc_g = 1 - acc_human
@@ -134,7 +135,7 @@ __global__ void k_ground_shade(GroundCfg g, int first_pass, long long p0, long l
         for (int c = 0; c < 3; c++) cs[c] = warp_sum(cs[c]);
         if (lane == 0)
             for (int c = 0; c < 3; c++) {
-                if (rgb) rgb[i * 3 + c] = linear2srgb(albedo[i * 3 + c] / PI * cs[c]);
+                if (rgb) rgb[i * 3 + c] = tone(albedo[i * 3 + c] / PI * cs[c], first_pass ? g.tonemap : 1);      // the re-shade always maps (novel_light_sphere_tracing.py:94)
                 float sh = cs[c] * shade_scale / PI;
                 if (shade) shade[i * 3 + c] = sh * shade_map_mult;
                 if (spec) spec[i * 3 + c] = sh / 20.f;

@@ -628,7 +628,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     }
     prof_stage(h, st);
     LAUNCH(h, k_shade, grid_for(h, P * 32, 256, 8), 256, 0, st, h->cnt.n_fg, h->fg_ray, ray_o, h->surf, h->acc, h->fm, h->lvis, h->ldot,
-           h->lxyz, h->larea, L, h->env_main, h->emh, h->emw, c.fresnel_f0, c.shading_albedo, 0, 1, out->rgb_map, out->shade_map,
+           h->lxyz, h->larea, L, h->env_main, h->emh, h->emw, c.fresnel_f0, c.shading_albedo, 0, 1, c.tonemapping, out->rgb_map, out->shade_map,
            (float*)nullptr);
     if (out->lvis_map || out->ldot_map)
         LAUNCH(h, k_scatter_lmaps, grid_for(h, P * L / 4), 256, 0, st, h->cnt.n_fg, h->fg_ray, h->acc, h->lvis, h->ldot, L, out->lvis_map, out->ldot_map);
@@ -673,7 +673,7 @@ static int relight_envmaps_impl(ra_handle* h, const float* probes, int32_t n_env
         LAUNCH(h, k_shade_multi, grid_for(h, P * 32, 256, 8), 256, 0, st, h->cnt.n_fg, h->fg_ray, h->last_ray_o, h->surf, h->acc, h->fm, h->lvis,
                h->ldot, h->lxyz, h->larea, L, probes + (size_t)e0 * L * 3, ne, c.env_h, c.env_w, c.fresnel_f0, c.shading_albedo,
                rgb ? rgb + (size_t)e0 * P * 3 : nullptr, shade ? shade + (size_t)e0 * P * 3 : nullptr,
-               spec ? spec + (size_t)e0 * P * 3 : nullptr, (long long)P, raw ? 0 : 1, raw ? 1 : 0);
+               spec ? spec + (size_t)e0 * P * 3 : nullptr, (long long)P, raw ? 0 : 1, raw ? 1 : 0, 1);      // the novel-light re-shade maps unconditionally (novel_light_sphere_tracing.py:48)
     }
     CK(cudaGetLastError());
     return 0;
@@ -788,7 +788,7 @@ static GroundCfg ground_cfg(ra_handle* h, const ra_ground_config* g) {
     GroundCfg c{};
     for (int i = 0; i < 3; i++) { c.normal[i] = g->normal[i]; c.origin[i] = g->origin[i]; c.albedo[i] = g->albedo[i]; }
     c.attach_envmap = g->attach_envmap; c.shading_albedo = h->cfg.shading_albedo; c.multiplier = g->shading_multiplier;
-    c.env_r = h->cfg.env_r; c.near_offset = g->near_offset; c.bbox_margin = h->cfg.bbox_margin;
+    c.env_r = h->cfg.env_r; c.near_offset = g->near_offset; c.bbox_margin = h->cfg.bbox_margin; c.tonemap = h->cfg.tonemapping;
     return c;
 }
 

@@ -560,6 +560,9 @@ __device__ __forceinline__ float linear2srgb(float x) {
     return (x <= 0.0031308f) ? x * 12.92f : 1.055f * powf(x + 1e-7f, 1.f / 2.4f) - 0.055f;
 }
 
+// cfg.tonemapping_rendering (config.py:417; switched off for .exr / .hdr output, config.py:446-448)
+__device__ __forceinline__ float tone(float x, int tonemap) { return tonemap ? linear2srgb(x) : x; }
+
 __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -572,7 +575,7 @@ __global__ void k_shade(const int* __restrict__ n_fg, const int* __restrict__ fg
                         const float* __restrict__ surf_ray, const float* __restrict__ acc_ray, FgMaps fm,
                         const float* __restrict__ lvis, const float* __restrict__ ldot, const float* __restrict__ lxyz,
                         const float* __restrict__ larea, int L, const float* __restrict__ probe, int eh, int ew, float f0,
-                        float shading_albedo, int premul, int out_premul, float* rgb, float* shade, float* spec) {
+                        float shading_albedo, int premul, int out_premul, int tonemap, float* rgb, float* shade, float* spec) {
     const float PI = 3.14159265358979323846f;
     int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -611,7 +614,7 @@ __global__ void k_shade(const int* __restrict__ n_fg, const int* __restrict__ fg
         if (lane == 0) {
             float om = out_premul ? a : 1.f;
             for (int c = 0; c < 3; c++) {
-                if (rgb) rgb[ray * 3 + c] = linear2srgb(cr[c]) * om;
+                if (rgb) rgb[ray * 3 + c] = tone(cr[c], tonemap) * om;
                 if (shade) shade[ray * 3 + c] = cs[c] * shading_albedo / PI * om;
                 if (spec) spec[ray * 3 + c] = cp[c];
             }
@@ -648,7 +651,7 @@ __global__ void k_shade_multi(const int* __restrict__ n_fg, const int* __restric
                               const float* __restrict__ surf_ray, const float* __restrict__ acc_ray, FgMaps fm,
                               const float* __restrict__ lvis, const float* __restrict__ ldot, const float* __restrict__ lxyz,
                               const float* __restrict__ larea, int L, const float* __restrict__ probes, int n_probe, int eh, int ew,
-                              float f0, float shading_albedo, float* rgb, float* shade, float* spec, long long P, int premul, int out_premul) {
+                              float f0, float shading_albedo, float* rgb, float* shade, float* spec, long long P, int premul, int out_premul, int tonemap) {
     const float PI = 3.14159265358979323846f;
     int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -700,7 +703,7 @@ __global__ void k_shade_multi(const int* __restrict__ n_fg, const int* __restric
             if (lane == 0)
                 for (int c = 0; c < 3; c++) {
                     size_t o = ((size_t)e * P + ray) * 3 + c;
-                    if (rgb) rgb[o] = linear2srgb(cr[e][c]) * om;
+                    if (rgb) rgb[o] = tone(cr[e][c], tonemap) * om;
                     if (shade) shade[o] = cs[e][c] * shading_albedo / PI * om;
                     if (spec) spec[o] = cp[e][c] * om;
                 }

@@ -45,7 +45,7 @@ def default_config(relight: bool = True, **over) -> Dict:
              lv_iter=4, lv_offset=0.01, lv_relax=0.0, lv_near=0.02, lv_dist_th=0.125 if relight else 0.05,      # (unused without relighting)
              env_r=10.0, bbox_margin=0.25, render_chunk=65536, n_samples=3, surf_sample_range=0.005,
              fresnel_f0=0.02, albedo_slope=1.0, albedo_bias=0.0, rough_slope=0.9, rough_bias=0.09,
-             albedo_multiplier=1.0, shading_albedo=0.8, env_h=16, env_w=32, vol_samples=128, clip_near=0.02, clip_far=10.0)
+             albedo_multiplier=1.0, shading_albedo=0.8, env_h=16, env_w=32, vol_samples=128, clip_near=0.02, clip_far=10.0, tonemapping=1)
     c.update(over)
     return c
 
@@ -59,7 +59,7 @@ FIXED_SWITCHES = dict(
     no_visibility=False, local_visibility=False, no_dfss=False, no_claybook=False, only_visibility=False,            # shadow tracing
     geometry_visibility=False, geometry_normal=False, bruteforce_st=False, check_termination_sdf=False, check_bound_sdf=False,
     zero_roughness=False, rgb_as_albedo=False, replace_light='', lambert_only=False, glossy_only=False,              # shading
-    bg_brightness=0.0, tonemapping_rendering=True)
+    bg_brightness=0.0)
 FIXED_ST_SWITCHES = dict(tan_i_multiplier=1)          # cfg.sphere_tracing.*
 
 
@@ -95,7 +95,7 @@ def config_from_reference_cfg(cfg, relight: bool, mode: Optional[str] = None) ->
         surf_sample_range=cfg.surf_sample_range, fresnel_f0=cfg.fresnel_f0, albedo_slope=cfg.albedo_slope,
         albedo_bias=cfg.albedo_bias, rough_slope=cfg.roughness_slope, rough_bias=cfg.roughness_bias,
         albedo_multiplier=cfg.albedo_multiplier, shading_albedo=cfg.shading_albedo, env_h=cfg.env_h, env_w=cfg.env_w,
-        clip_near=cfg.clip_near, clip_far=cfg.clip_far)
+        clip_near=cfg.clip_near, clip_far=cfg.clip_far, tonemapping=int(bool(cfg.tonemapping_rendering)))
 
 
 def default_ground_config(**over) -> Dict:

@@ -297,7 +297,8 @@ def test_image_assembly_f3(relight_setup):
     assert torch.equal(img_u8.cpu(), (ref.clip(0, 1) * 255).to(torch.uint8))
 
 
-def test_ground_shading_f2():
+@pytest.mark.parametrize('tonemapping', [True, False])
+def test_ground_shading_f2(tonemapping):
     """SURVEY.md 8 row f2 (cfg.vis_ground_shading): floor pass over all H*W pixels (plane hit, env_lvis soft shadows cast by
     the body, far-field blend, Lambertian light sum), novel-light floor re-shade and blend_output_, against the oracle's
     restatement (itself pinned to the reference by tests/golden/relight_ground_24.npz).  fp32 tolerance 1e-3 (q98) relative
@@ -307,9 +308,10 @@ def test_ground_shading_f2():
     sd = scene.make_state_dict(0, relight=True, fitted=True)
     probes = {k: v[0] for k, v in b['novel_lights'].items()}
     r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=8192, test_light=('main', 'all'),
-                 return_lvis=True, ground_shading=True, sync_timing=False)
+                 return_lvis=True, ground_shading=True, sync_timing=False, tonemapping=int(tonemapping))
     out = r.render(b)
-    ref = O.render_novel_light(b, sd, O.Cfg(), probes, torch.float32, DEV, ground=True)
+    # tonemapping False = cfg.tonemapping_rendering off (.exr / .hdr output): linear main pass, tone-mapped novel re-shade
+    ref = O.render_novel_light(b, sd, O.Cfg(tonemapping=tonemapping), probes, torch.float32, DEV, ground=True)
     assert out['main']['rgb_map'].shape == (1, H * H, 3)
     n_shadowed = int((ref['main']['lvis_map'] < 0.999).sum())
     assert n_shadowed > 1000          # the body does cast a shadow on the floor in this view

@@ -69,18 +69,23 @@ def test_relight_second_weight_set_matches_reference():
     _check_relight_case('relight_96_seed1_raw')
 
 
-def test_relight_ground_matches_reference():
+@pytest.mark.parametrize('name', ['relight_ground_24', 'relight_ground_24_linear'])
+def test_relight_ground_matches_reference(name):
     """Row f2 (vis_ground_shading): floor pass over all H*W pixels + blend_output_, main light and one novel probe.
     The reference orders `inds` by topk(sorted=False) of the mask; the fixture was made on CPU torch, so the same call
-    here replays that order (oracle.render_ground_pass explains; the product uses mask.nonzero())."""
-    g = _load('relight_ground_24')
+    here replays that order (oracle.render_ground_pass explains; the product uses mask.nonzero()).
+    `_linear`: cfg.tonemapping_rendering False (.exr / .hdr output) -- the main pass stays linear, the novel re-shade does not."""
+    g = _load(name)
     H, n_env = int(g['_H']), int(g['_n_env'])
+    cfg = O.Cfg(tonemapping=bool(int(g.get('_tonemapping', 1))))
     b = scene.make_batch(H, H, seed=0, n_env=n_env)
     sd = scene.make_state_dict(0, relight=True, fitted=True)
     probes = {k: v[0] for k, v in b['novel_lights'].items()}
     cpu_order = lambda m: m.int().topk(int(m.sum()), dim=-1, sorted=False)[1]
-    out = O.render_novel_light(b, sd, O.Cfg(), probes, ground=True, inds_fn=cpu_order)
+    out = O.render_novel_light(b, sd, cfg, probes, ground=True, inds_fn=cpu_order)
     assert out['main']['rgb_map'].shape[0] == H * H
+    if not cfg.tonemapping:          # the fixture really differs from the tone-mapped one
+        assert np.abs(g['main.rgb_map'] - _load('relight_ground_24')['main.rgb_map']).max() > 0.05
     for k in ('rgb_map', 'acc_map', 'surf_map', 'shade_map', 'spec_map', 'depth_map', 'albedo_map', 'roughness_map', 'bpts_map', 'cpts_map', 'ldot_map'):
         _close('main.' + k, out['main'][k], g['main.' + k][0], 2e-4)
     _close('main.norm_map', out['main']['norm_map'], g['main.norm_map'][0], 2e-3, q=0.99)
