@@ -222,6 +222,27 @@ def run_prep(H: int, seed: int, frame: int = 2):
                 wbounds=DU.get_bounds(ww[0].numpy()), pbounds=DU.get_bounds(pp[0].numpy()), _frame=np.int64(frame))
 
 
+def run_rotate(seed: int = 0, repeat: int = 4):
+    """Row f4 fixture: the reference's own rotate_envmap (lib/utils/relight_utils.py:55-103) on two synthetic probes."""
+    import torch
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, here)
+    setup_reference('relight')
+    from lib.utils.base_utils import dotdict
+    from lib.utils.relight_utils import rotate_envmap
+    from relightableavatar_b200 import scene
+    maps = scene.make_envmaps(2, 10 + seed)
+    novel = dotdict({k: dotdict(probe=torch.from_numpy(v)[None], image=torch.from_numpy(v)[None]) for k, v in maps.items()})
+    eW = next(iter(maps.values())).shape[1]
+    idx = [0, 1, 5, 63, eW * repeat - 1, eW * repeat, eW * repeat + 7, 2 * eW * repeat - 1]
+    out = {'_repeat': np.int64(repeat), '_index': np.asarray(idx, np.int64)}
+    for i in idx:
+        name, env = rotate_envmap(novel, i, repeat, eW, eW)
+        out[f'probe_{i}'] = env.probe[0].numpy()
+        out[f'name_{i}'] = np.asarray(name)
+    return out
+
+
 CFG_KEYS = ('dist_th', 'blend_radius', 'resd_limit', 'env_r', 'render_chunk_size', 'n_samples', 'surf_sample_range', 'fresnel_f0',
             'albedo_slope', 'albedo_bias', 'roughness_slope', 'roughness_bias', 'albedo_multiplier', 'shading_albedo', 'env_h', 'env_w',
             'clip_near', 'clip_far', 'ground_normal', 'ground_origin', 'ground_albedo', 'ground_attach_envmap', 'ground_shading_multiplier')
@@ -266,7 +287,9 @@ def main():
         json.dump(dump_cfg(a.mode[4:]), open(out_path, 'w'), indent=1, sort_keys=True)
         print('wrote', out_path)
         return
-    if a.mode == 'prep':
+    if a.mode == 'rotate':
+        flat = run_rotate(a.seed)
+    elif a.mode == 'prep':
         flat = run_prep(a.H, a.seed)
     else:
         flat, _ = run(a.mode, a.H, a.seed, a.n_env, not a.raw_init, frame=a.frame, azim_deg=a.azim, cam_dist=a.cam_dist, n_bones=a.n_bones, tonemapping=not a.linear)

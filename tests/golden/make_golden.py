@@ -27,6 +27,8 @@ CASES = [
     ('relight_ground_24', 'relight_ground', 24, 1, None),
     # row f1: the reference's dataset-side numpy / torch functions (rays, AABB, LBS, bounds)
     ('prep_24', 'prep', 24, 0, None),
+    # row f4: the reference's rotate_envmap on two synthetic probes
+    ('rotate_envmap', 'rotate', 0, 2, None),
     # a second pose / view / env-map count, and a second set of weights (seed 1, geometric-init SDF instead of the fitted one):
     # the pins above all share seed 0, frame 0 and one camera
     ('relight_40_f3_az140', 'relight', 40, 1, dict(frame=3, azim=140.0, cam_dist=2.4)),

@@ -149,6 +149,24 @@ def test_anisdf_volume_matches_reference():
     _close('norm_map', out['norm_map'], g['norm_map'][0], 3e-3, q=0.99)
 
 
+def test_rotate_envmap_matches_reference():
+    """Row f4: oracle.rotate_probe against the reference's own rotate_envmap (relight_utils.py:55-103): index -> (probe i, step j),
+    name f'{key}-{j:04d}', probe shifted by j / repeat columns with wrap-around bilinear resampling."""
+    g = _load('rotate_envmap')
+    repeat = int(g['_repeat'])
+    maps = scene.make_envmaps(2, 10)
+    keys = list(maps)
+    eW = maps[keys[0]].shape[1]
+    for idx in g['_index']:
+        i, j = int(idx) // (eW * repeat), int(idx) % (eW * repeat)
+        assert str(g[f'name_{idx}']) == f'{keys[i]}-{j:04d}'
+        got = O.rotate_probe(torch.from_numpy(maps[keys[i]]), j, repeat)
+        np.testing.assert_allclose(got.numpy(), g[f'probe_{idx}'], atol=1e-6)
+    # a full turn is the identity (up to the bilinear weights' rounding)
+    full = O.rotate_probe(torch.from_numpy(maps[keys[0]]), eW * repeat, repeat)
+    np.testing.assert_allclose(full.numpy(), maps[keys[0]], rtol=1e-5, atol=1e-5)
+
+
 def test_analytic_invariants():
     """Invariants the reference asserts or implies (SURVEY.md 8c last row)."""
     xyz, area = scene.gen_light_xyz()
