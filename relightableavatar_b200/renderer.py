@@ -215,7 +215,9 @@ class Engine:
         self._wkeep = keep
 
     # ------------------------------------------------------------------ frame
-    def set_frame(self, batch: Dict, fix_material: int = 0):
+    def set_frame(self, batch: Dict, fix_material: int = 0, always_fix_material: bool = True):
+        """Per-frame state.  The colour network's condition follows base_network.py:501-503: train_motion.poses[fix_material]
+        (python indexing: -1 is the LAST training pose) when `fix_material >= 0 or always_fix_material`, else this frame's poses."""
         dev = self.device
 
         def g(key, shape=None):
@@ -237,12 +239,18 @@ class Engine:
                 raise ValueError(f'batch.{name} has {t.numel()} elements, expected {want[name]} (n_verts={N}, n_bones={J})')
             keep.append(t); setattr(fr, name, _fptr(t))
         mc = None
-        if 'train_motion' in batch and batch['train_motion'] is not None:
-            mc = torch.as_tensor(batch['train_motion']['poses'])
-        elif 'train_poses' in batch:
-            mc = torch.as_tensor(batch['train_poses'])
+        if fix_material >= 0 or always_fix_material:
+            if 'train_motion' in batch and batch['train_motion'] is not None:
+                mc = torch.as_tensor(batch['train_motion']['poses'])
+            elif 'train_poses' in batch:
+                mc = torch.as_tensor(batch['train_poses'])
+            if mc is not None:
+                mc = mc.to(device=dev, dtype=torch.float32)[0, int(fix_material)].reshape(-1).contiguous()
+        else:
+            mc = g('poses').reshape(-1)
+        if mc is None and not self.config['relight']:
+            raise KeyError('batch.train_motion.poses (the colour network\'s material condition) is missing')
         if mc is not None:
-            mc = mc.to(device=dev, dtype=torch.float32)[0, max(fix_material, 0)].reshape(-1).contiguous()
             if mc.numel() != 3 * J:
                 raise ValueError(f'train_motion.poses rows have {mc.numel()} elements, expected {3 * J}')
             keep.append(mc)
@@ -436,7 +444,13 @@ class Renderer(torch.nn.Module):
 
     def __init__(self, net, mode: str = 'relight', cfg=None, device='cuda:0', precision: str = 'tc', max_rays: int = 1 << 17,
                  test_light=('main',), return_lvis: bool = False, to_cpu: bool = False, sync_timing: bool = True,
-                 ground_shading: Optional[bool] = None, ground: Optional[Dict] = None, **overrides):
+                 ground_shading: Optional[bool] = None, ground: Optional[Dict] = None, rotate_ratio: Optional[int] = None,
+                 engine=None, **overrides):
+        """`test_light`: 'main' in it keeps the learned-light rendering (cfg.test_light, novel_light_sphere_tracing.py:155).  With a
+        reference `cfg` every env-map of `batch.novel_lights` is rendered, as the reference does (its dataset already filtered them
+        by cfg.test_light, base_dataset.py:141,159); without one, the env-maps named in `test_light` (or all of them for 'all').
+        `rotate_ratio` (cfg.rotate_ratio when cfg.vis_rotate_light): every env-map is rendered at rotate_ratio * env_w rotations.
+        `engine`: an already constructed Engine-like object (tests); otherwise one is created on `device`."""
         super().__init__()
         self.net = net
         self.mode = mode
@@ -448,9 +462,16 @@ class Renderer(torch.nn.Module):
         conf.update(n_bones=(k0 - 63) // 3)
         conf.update(precision=PRECISION[precision], max_rays=int(max_rays))
         conf.update(overrides)
-        self.engine = Engine(conf, device)
-        self.engine.upload_weights(net.state_dict())
+        self.engine = Engine(conf, device) if engine is None else engine
+        if engine is None:
+            self.engine.upload_weights(net.state_dict())
+        self.all_lights = cfg is not None
+        if rotate_ratio is None:
+            rotate_ratio = int(cfg.rotate_ratio) if (cfg is not None and getattr(cfg, 'vis_rotate_light', False)) else -1
+        self.rotate_ratio = int(rotate_ratio)
         self.fix_material = getattr(cfg, 'fix_material', 0) if cfg is not None else 0
+        afm = getattr(cfg, 'always_fix_material', None) if cfg is not None else None
+        self.always_fix_material = True if afm is None else bool(afm)
         self.test_light = tuple(test_light)
         self.return_lvis = return_lvis
         self.to_cpu = to_cpu
@@ -459,10 +480,32 @@ class Renderer(torch.nn.Module):
         self.ground_shading = bool(getattr(cfg, 'vis_ground_shading', False)) if ground_shading is None else bool(ground_shading)
         self.ground = ground_config_from_reference_cfg(cfg) if (cfg is not None and ground is None) else default_ground_config(**(ground or {}))
 
+    def _light_names(self, lights) -> list:
+        return [n for n in lights if self.all_lights or n in self.test_light or 'all' in self.test_light]
+
+    def _probe_of(self, light, key='probe'):
+        return light.get(key) if isinstance(light, dict) else (light if key == 'probe' else None)
+
+    def _light_sweep(self, lights, names):
+        """rotate_envmap's enumeration (relight_utils.py:55-103): yields (name, probe (eh,ew,3) on the device) in the reference's
+        order -- every env-map once, or at rotate_ratio * env_w rotations named f'{key}-{j:04d}' (cfg.vis_rotate_light)."""
+        eng = self.engine
+        eh, ew = eng.config['env_h'], eng.config['env_w']
+        for n in names:
+            probe = torch.as_tensor(self._probe_of(lights[n])).to(device=eng.device, dtype=torch.float32).reshape(eh, ew, 3).contiguous()
+            if self.rotate_ratio <= 0:
+                yield n, probe
+                continue
+            n_rot = ew * self.rotate_ratio
+            for j0 in range(0, n_rot, 16):                      # 16 rotations per call bound the device memory of the sweep
+                rot = eng.rotate_probes(probe, self.rotate_ratio, j0, min(16, n_rot - j0))
+                for k in range(rot.shape[0]):
+                    yield f'{n}-{j0 + k:04d}', rot[k]
+
     @torch.no_grad()
     def render(self, batch) -> dotdict:
         eng = self.engine
-        eng.set_frame(batch, self.fix_material)
+        eng.set_frame(batch, self.fix_material, self.always_fix_material)
         ray_o, ray_d, near, far = eng._rays(batch)
         P = ray_o.shape[0]
         keys = list(_MAIN_KEYS[self.mode])
@@ -488,13 +531,12 @@ class Renderer(torch.nn.Module):
         if 'main' in self.test_light:
             relight.main = main_b
         lights = batch.get('novel_lights') or {}
-        names = [n for n in lights if n in self.test_light or 'all' in self.test_light]
-        if names:
-            probes = torch.stack([torch.as_tensor(lights[n]['probe'] if isinstance(lights[n], dict) else lights[n])
-                                  .to(device=eng.device, dtype=torch.float32).reshape(eng.config['env_h'], eng.config['env_w'], 3)
-                                  for n in names]).contiguous()
+        sweep = list(self._light_sweep(lights, self._light_names(lights)))
+        for c0 in range(0, len(sweep), 16):                     # re-shade in groups: the stored visibility is read once per 4 probes
+            group = sweep[c0:c0 + 16]
+            probes = torch.stack([p for _, p in group]).contiguous()
             rgb, shade, spec = eng.relight_envmaps(probes, P)
-            for i, n in enumerate(names):
+            for i, (n, _) in enumerate(group):
                 human = dotdict(main_b)
                 human.update(rgb_map=conv(rgb[i][None]), shade_map=conv(shade[i][None]), spec_map=conv(spec[i][None]))
                 human.envmap = dotdict(probe=conv(probes[i][None]))
@@ -509,6 +551,9 @@ class Renderer(torch.nn.Module):
         floor pass over every pixel, then per light blend_output_(ground, human) into image-sized maps (mask_at_box becomes all-True)."""
         eng = self.engine
         dev = eng.device
+        if self.rotate_ratio > 0 and self._light_names(batch.get('novel_lights') or {}):
+            raise NotImplementedError('vis_rotate_light together with vis_ground_shading (the floor\'s attached env-map image would '
+                                      'have to be rotated as well, relight_utils.py:74-75,103) is not implemented')
         t = lambda k: torch.as_tensor(batch[k]).to(device=dev, dtype=torch.float32)
         meta = batch.get('meta') or {}
         H = int(torch.as_tensor(meta['H'] if 'H' in meta else batch['H']).reshape(-1)[0])
@@ -534,9 +579,9 @@ class Renderer(torch.nn.Module):
             relight.main = blend(ground, human_main)
             relight.main.envmap = dotdict(probe=conv(eng.env_main[None]))
         lights = batch.get('novel_lights') or {}
-        names = [n for n in lights if n in self.test_light or 'all' in self.test_light]
+        names = self._light_names(lights)
         if names:
-            get = lambda n, key: (lights[n].get(key) if isinstance(lights[n], dict) else (lights[n] if key == 'probe' else None))
+            get = lambda n, key: self._probe_of(lights[n], key)
             probes = torch.stack([torch.as_tensor(get(n, 'probe')).to(device=dev, dtype=torch.float32).reshape(eng.config['env_h'], eng.config['env_w'], 3)
                                   for n in names]).contiguous()
             rgb, shade, spec = eng.relight_envmaps_raw(probes, P)

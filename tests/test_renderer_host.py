@@ -1,0 +1,109 @@
+"""Host logic of the drop-in Renderer (no GPU): light enumeration, the vis_rotate_light sweep, cfg handling and the material
+condition, exercised with a stand-in engine; names / rotated probes are checked against the reference's own rotate_envmap
+(tests/golden/rotate_envmap.npz, made by tests/golden/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ra_oracle as O
+from relightableavatar_b200 import renderer as R
+from relightableavatar_b200 import scene
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+class FakeEngine:
+    """Records what the Renderer asks for; the re-shade returns each probe's mean colour so outputs identify their probe."""
+
+    def __init__(self, relight=True):
+        self.config = R.default_config(relight)
+        self.device = torch.device('cpu')
+        self.env_main = torch.zeros(32, 64, 3)
+        self.frames, self.reshade_calls = [], []
+
+    def set_frame(self, batch, fix_material=0, always_fix_material=True):
+        self.frames.append((fix_material, always_fix_material))
+
+    def _rays(self, batch):
+        c = lambda k: torch.as_tensor(batch[k])[0]
+        return c('ray_o'), c('ray_d'), c('near'), c('far')
+
+    def render(self, mode, ray_o, ray_d, near, far, keys):
+        P = ray_o.shape[0]
+        return {k: (torch.zeros(P) if k in ('acc_map', 'depth_map', 'roughness_map') else torch.zeros(P, 3)) for k in keys}
+
+    def relight_envmaps(self, probes, P, want_spec=True):
+        self.reshade_calls.append(probes.shape[0])
+        rgb = probes.mean(dim=(1, 2))[:, None, :].expand(-1, P, -1).contiguous()
+        return rgb, rgb * 2, rgb * 3
+
+    def rotate_probes(self, probe, repeat, j0, n_rot):
+        return torch.stack([O.rotate_probe(probe, j0 + k, repeat) for k in range(n_rot)])
+
+
+def _dot(d):
+    return R.dotdict({k: _dot(v) if isinstance(v, dict) else v for k, v in d.items()})
+
+
+@pytest.fixture(scope='module')
+def setup():
+    b = scene.make_batch(16, 16, seed=0, n_env=2)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    return b, scene.SyntheticNet(sd, True)
+
+
+def test_rotation_sweep_enumerates_like_rotate_envmap(setup):
+    b, net = setup
+    p = os.path.join(GOLD, 'rotate_envmap.npz')
+    if not os.path.exists(p):
+        pytest.skip('fixture missing')
+    g = dict(np.load(p))
+    repeat = int(g['_repeat'])
+    eng = FakeEngine()
+    r = R.Renderer(net, mode='relight', test_light=('main', 'all'), sync_timing=False, rotate_ratio=repeat, engine=eng)
+    out = r.render(b)
+    names = [k for k in out if k not in ('main', 'diff')]
+    assert list(out)[0] == 'main' and len(names) == 2 * 32 * repeat            # every env-map at rotate_ratio * env_w rotations
+    for idx in g['_index']:                                                     # the reference's index -> (name, probe)
+        assert names[int(idx)] == str(g[f'name_{idx}'])
+        np.testing.assert_allclose(out[names[int(idx)]].envmap.probe[0].numpy(), g[f'probe_{idx}'], atol=1e-6)
+        np.testing.assert_allclose(out[names[int(idx)]].rgb_map[0, 0].numpy(), g[f'probe_{idx}'].mean((0, 1)), atol=1e-5)
+    assert max(eng.reshade_calls) <= 16 and sum(eng.reshade_calls) == len(names)
+
+
+def test_light_selection_follows_the_reference(setup):
+    b, net = setup
+    names = list(b['novel_lights'])
+    # stand-alone use: test_light filters by name
+    out = R.Renderer(net, test_light=('main', names[1]), sync_timing=False, engine=FakeEngine()).render(b)
+    assert [k for k in out if k != 'diff'] == ['main', names[1]]
+    out = R.Renderer(net, test_light=(), sync_timing=False, engine=FakeEngine()).render(b)
+    assert [k for k in out if k != 'diff'] == []
+    # under a reference cfg every env-map of the batch is rendered (the dataset did the filtering, base_dataset.py:141,159) and
+    # 'main' only when cfg.test_light names it (novel_light_sphere_tracing.py:155)
+    vals = json.load(open(os.path.join(GOLD, 'cfg_values.json')))
+    cfg = _dot(vals['relight'])
+    out = R.Renderer(net, cfg=cfg, test_light=(), sync_timing=False, engine=FakeEngine()).render(b)
+    assert [k for k in out if k != 'diff'] == names
+    cfg.vis_rotate_light, cfg.rotate_ratio = True, 1
+    r = R.Renderer(net, cfg=cfg, test_light=('main',), sync_timing=False, engine=FakeEngine())
+    assert r.rotate_ratio == 1
+    out = r.render(b)
+    assert len([k for k in out if k not in ('main', 'diff')]) == 2 * 32 and f'{names[0]}-0031' in out
+    with pytest.raises(NotImplementedError, match='vis_rotate_light'):          # refused before any floor work is launched
+        R.Renderer(net, cfg=cfg, test_light=('main',), sync_timing=False, engine=FakeEngine(), ground_shading=True).render(b)
+
+
+def test_material_condition_follows_fix_material(setup):
+    b, net = setup
+    vals = json.load(open(os.path.join(GOLD, 'cfg_values.json')))
+    cfg = _dot(vals['relight'])
+    cfg.fix_material, cfg.always_fix_material = -1, True
+    eng = FakeEngine()
+    R.Renderer(net, cfg=cfg, sync_timing=False, engine=eng).render(b)
+    assert eng.frames[-1] == (-1, True)
+    r = R.Renderer(net, sync_timing=False, engine=eng)
+    assert (r.fix_material, r.always_fix_material) == (0, True)
