@@ -77,3 +77,24 @@ def test_default_config_equals_the_reference_cfg_cascade():
     g, gw = R.ground_config_from_reference_cfg(_dot(vals['relight'])), R.default_ground_config()
     for k in gw:
         assert g[k] == pytest.approx(gw[k]), (k, g[k], gw[k])
+
+
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """include/ra_b200.h compiles as pedantic C99, a C host links against the library, and without a B200 ra_create refuses
+    loudly (non-zero status + message) instead of falling back to anything."""
+    import shutil
+    import subprocess
+    import pytest
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc missing')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(build.build(verbose=False))
+    exe = str(tmp_path / 'host_minimal')
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Wextra', '-Werror', '-pedantic', '-I' + os.path.join(root, 'include'),
+                           os.path.join(root, 'examples', 'host_minimal.c'), '-L' + libdir, '-lra_b200', '-Wl,-rpath,' + libdir, '-o', exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode in (0, 2), (r.returncode, r.stderr)
+    if r.returncode == 2:
+        assert 'ra_create failed:' in r.stderr and len(r.stderr.strip()) > len('ra_create failed:')
+    else:
+        assert 'handle created' in r.stdout
