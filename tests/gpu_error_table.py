@@ -1,4 +1,4 @@
-"""Prints an error table CUDA-vs-oracle (run under gpurun; not a test)."""
+"""Prints an error table CUDA-vs-oracle (run under gpurun: python tests/gpu_error_table.py [fp32|tc] [H]; a checker, not a collected test)."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
