@@ -106,3 +106,27 @@ def render_tile_sharded(render_fn, batch: Dict, keys=('rgb_map', 'acc_map'), gro
         res[k] = full[:, c0:c0 + w][None] if w > 1 else full[:, c0][None]
         c0 += w
     return res
+
+
+def render_sequence_sharded(render_frame, n_frames: int, n_pad: int, channels: int = 4, group=None, device=None):
+    """Frame sharding (BASELINE config 5): frame f is rendered by rank f % world; every step (world frames) ends with ONE all-gather
+    of the ranks' finished pixel blocks, padded to `n_pad` rows.  `render_frame(f) -> (P_f, channels)` pixels of frame f (P_f <= n_pad,
+    P_f < 2**24).  Yields `(f, pixels (P_f, channels))` in frame order on every rank.  The ray count travels in an extra leading row
+    of the block, so ranks need not know each other's P_f and the step stays a single collective."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    for f0 in range(0, n_frames, world):
+        f = f0 + rank
+        px = render_frame(f) if f < n_frames else None
+        dev = px.device if px is not None else device
+        buf = torch.zeros(n_pad + 1, channels, dtype=torch.float32, device=dev)
+        if px is not None:
+            if px.shape[0] > n_pad:
+                raise ValueError(f'frame {f} has {px.shape[0]} rays, more than n_pad={n_pad}')
+            buf[0, 0] = float(px.shape[0])
+            buf[1:1 + px.shape[0]] = px
+        out = torch.empty(world * (n_pad + 1), channels, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(out, buf, group=group)
+        out = out.view(world, n_pad + 1, channels)
+        for r in range(min(world, n_frames - f0)):
+            n = int(out[r, 0, 0].item())
+            yield f0 + r, out[r, 1:1 + n]

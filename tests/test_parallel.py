@@ -38,3 +38,26 @@ def _worker(rank, world, port, P):
 
 def test_tile_sharded_render_world2_gloo():
     mp.spawn(_worker, args=(2, 29512, 1000), nprocs=2, join=True)
+
+
+def _seq_worker(rank, world, port, n_frames):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    rendered = []
+
+    def render_frame(f):          # frame f has 10 + 3 f rays; pixel values identify (frame, ray)
+        rendered.append(f)
+        n = 10 + 3 * f
+        return torch.arange(n, dtype=torch.float32)[:, None] * torch.ones(1, 4) + 1000 * f
+
+    got = list(parallel.render_sequence_sharded(render_frame, n_frames, n_pad=64, device=torch.device('cpu')))
+    assert rendered == parallel.frame_indices(n_frames, rank, world)          # each rank renders only its own frames
+    assert [f for f, _ in got] == list(range(n_frames))                        # and every rank ends up with all of them, in order
+    for f, px in got:
+        assert px.shape == (10 + 3 * f, 4) and float(px[0, 0]) == 1000 * f and float(px[-1, 3]) == 1000 * f + 9 + 3 * f
+    dist.destroy_process_group()
+
+
+def test_frame_sharded_sequence_world2_gloo():
+    """Config 5 host logic: 5 frames over 2 ranks (the last step has one idle rank), one all-gather per step."""
+    mp.spawn(_seq_worker, args=(2, 29513, 5), nprocs=2, join=True)
