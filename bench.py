@@ -287,7 +287,7 @@ def main():
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': int(d2h_bytes)},
         'gpu_launches': int(launches),
         'roofline': {'kernel': 'k_mlp_tc6 (fused residual+SDF MLP, tcgen05 cta_group::2)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak,
-                     'unit': 'TFLOP/s', 'frac': achieved / peak,
+                     'unit': 'TFLOP/s', 'frac': achieved / peak, 'frac_of_burst_peak': achieved / peaks['bf16_tflops'],
                      'traffic': {'dram_bytes_per_launch': 32.87e6, 'algorithmic_bytes_per_launch': 16 * 2.0e6,
                                  'source': 'profiles/r01_ncu_k_mlp_tc6_summary.txt (ncu --set full, a shadow-iteration launch of ~2 M rows: 12 B in + 4 B out per row; the 1.95 MB weight image is re-read from L2 once per 256-row pair-tile)'}, 'peak_source': f'{which} bf16_tflops_sustained',
                      'algorithmic_flop_per_query': FLOP_PER_QUERY, 'kernel_ms_per_step': prof['mlp_ms'] / args.steps,
