@@ -72,6 +72,7 @@ class Cfg:
     albedo_multiplier: float = 1.0
     shading_albedo: float = 0.8
     fix_material: int = 0
+    always_fix_material: bool = True  # base_network.py:501-503: cond = train_motion.poses[:, fix_material] if fix_material >= 0 or always
     knn_chunk: int = 16384
     # ground-plane shading (row f2): cfg.env_lvis (config.py:135-141), cfg.ground_* (:45, :104-107, :353)
     gl_iter: int = 16
@@ -213,7 +214,8 @@ class Frame:
                      A=t(b['A'][0]), big_A=t(b['big_A'][0]), weights=t(b['weights'][0]),
                      pverts=t(b['pverts'][0]), pnorm=t(b['pnorm'][0]), tverts=t(b['tverts'][0]),
                      wbounds=t(b['wbounds'][0]).clone(),
-                     mat_cond=t(b['train_poses'][0, max(cfg.fix_material, 0)]).reshape(-1))
+                     mat_cond=(t(b['train_poses'][0, cfg.fix_material]) if (cfg.fix_material >= 0 or cfg.always_fix_material)
+                               else t(b['poses'][0])).reshape(-1))      # python indexing: -1 = last training pose
 
 
 def knn3(p: torch.Tensor, verts: torch.Tensor, chunk: int):

@@ -159,11 +159,12 @@ def to_ref_batch(b: dict, device='cpu'):
 
 
 def run(mode: str, H: int, seed: int, n_env: int, fitted: bool, threads: int = 0, frame: int = 0, azim_deg: float = 20.0,
-        cam_dist: float = 3.0, n_bones: int = 52, tonemapping: bool = True):
+        cam_dist: float = 3.0, n_bones: int = 52, tonemapping: bool = True, fix_material: int = 0, always_fix_material: bool = True):
     import torch
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, here)
     cfg = setup_reference(mode, n_bones)
+    cfg.fix_material, cfg.always_fix_material = int(fix_material), bool(always_fix_material)      # base_network.py:501-503
     cfg.tonemapping_rendering = bool(tonemapping)      # False = what parse_cfg sets for vis_ext .exr / .hdr (config.py:446-448)
     from relightableavatar_b200 import scene
     if threads:
@@ -278,6 +279,8 @@ def main():
     ap.add_argument('--azim', type=float, default=20.0, help='camera azimuth (deg)')
     ap.add_argument('--cam_dist', type=float, default=3.0)
     ap.add_argument('--n_bones', type=int, default=52, help='52 = SMPL-H (xuzhen), 24 = SMPL (ZJU-MoCap / synthetic-human configs)')
+    ap.add_argument('--fix_material', type=int, default=0)
+    ap.add_argument('--no_always_fix_material', action='store_true')
     ap.add_argument('--linear', action='store_true', help='cfg.tonemapping_rendering False (HDR output)')
     ap.add_argument('--out', required=True)
     a = ap.parse_args()
@@ -292,7 +295,8 @@ def main():
     elif a.mode == 'prep':
         flat = run_prep(a.H, a.seed)
     else:
-        flat, _ = run(a.mode, a.H, a.seed, a.n_env, not a.raw_init, frame=a.frame, azim_deg=a.azim, cam_dist=a.cam_dist, n_bones=a.n_bones, tonemapping=not a.linear)
+        flat, _ = run(a.mode, a.H, a.seed, a.n_env, not a.raw_init, frame=a.frame, azim_deg=a.azim, cam_dist=a.cam_dist, n_bones=a.n_bones, tonemapping=not a.linear,
+                      fix_material=a.fix_material, always_fix_material=not a.no_always_fix_material)
     np.savez_compressed(out_path, **flat)
     print('wrote', out_path, {k: v.shape for k, v in flat.items()})
 

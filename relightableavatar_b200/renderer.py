@@ -125,6 +125,17 @@ def get_rays(H: int, W: int, K: torch.Tensor, R: torch.Tensor, T: torch.Tensor):
     return ray_o[None, None].expand(pixel_world.shape).reshape(-1, 3).contiguous(), ray_d.reshape(-1, 3).contiguous()
 
 
+def material_condition(batch: Dict, fix_material: int = 0, always_fix_material: bool = True) -> Optional[torch.Tensor]:
+    """The colour network's condition vector (base_network.py:501-503): `train_motion.poses[:, fix_material]` (python indexing, so -1
+    is the LAST training pose) when `fix_material >= 0 or always_fix_material`, otherwise this frame's own poses.  None when the
+    batch carries no training motion (fine for relighting, which never evaluates the colour network)."""
+    if fix_material >= 0 or always_fix_material:
+        tm = batch.get('train_motion') if hasattr(batch, 'get') else None
+        poses = tm['poses'] if tm is not None else batch.get('train_poses')
+        return None if poses is None else torch.as_tensor(poses)[0, int(fix_material)].reshape(-1)
+    return torch.as_tensor(batch['poses']).reshape(-1)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -238,16 +249,9 @@ class Engine:
             if t.numel() != want[name]:
                 raise ValueError(f'batch.{name} has {t.numel()} elements, expected {want[name]} (n_verts={N}, n_bones={J})')
             keep.append(t); setattr(fr, name, _fptr(t))
-        mc = None
-        if fix_material >= 0 or always_fix_material:
-            if 'train_motion' in batch and batch['train_motion'] is not None:
-                mc = torch.as_tensor(batch['train_motion']['poses'])
-            elif 'train_poses' in batch:
-                mc = torch.as_tensor(batch['train_poses'])
-            if mc is not None:
-                mc = mc.to(device=dev, dtype=torch.float32)[0, int(fix_material)].reshape(-1).contiguous()
-        else:
-            mc = g('poses').reshape(-1)
+        mc = material_condition(batch, fix_material, always_fix_material)
+        if mc is not None:
+            mc = mc.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
         if mc is None and not self.config['relight']:
             raise KeyError('batch.train_motion.poses (the colour network\'s material condition) is missing')
         if mc is not None:

@@ -38,6 +38,9 @@ CASES = [
     ('anisdf_trace_40_smpl24', 'anisdf_trace', 40, 0, dict(n_bones=24, frame=1)),
     # cfg.tonemapping_rendering False (.exr / .hdr output): human + floor main pass stay linear, the novel-light re-shade does not
     ('relight_ground_24_linear', 'relight_ground', 24, 1, dict(linear=True)),
+    # colour-network condition: last training pose (fix_material -1 under always_fix_material), and this frame's own pose
+    ('anisdf_trace_40_fixmat_last', 'anisdf_trace', 40, 0, dict(fix_material=-1, frame=1)),
+    ('anisdf_trace_40_fixmat_off', 'anisdf_trace', 40, 0, dict(fix_material=-1, no_always_fix_material=True, frame=1)),
 ]
 
 DROP_DUP = ('surf_map', 'depth_map', 'acc_map', 'albedo_map', 'roughness_map', 'norm_map', 'ray_o', 'cpts_map',
@@ -66,13 +69,15 @@ def main():
         view = view or {}
         tmp = os.path.join('/tmp', f'golden_{name}.npz')
         extra = []
-        for k in ('frame', 'azim', 'cam_dist', 'seed', 'n_bones'):
+        for k in ('frame', 'azim', 'cam_dist', 'seed', 'n_bones', 'fix_material'):
             if k in view:
                 extra += [f'--{k}', str(view[k])]
         if view.get('raw_init'):
             extra.append('--raw_init')
         if view.get('linear'):
             extra.append('--linear')
+        if view.get('no_always_fix_material'):
+            extra.append('--no_always_fix_material')
         subprocess.check_call([sys.executable, os.path.join(ROOT, 'oracle', 'ref_harness.py'), '--mode', mode,
                                '--H', str(H), '--n_env', str(n_env), '--out', tmp] + extra)
         d = dict(np.load(tmp))
@@ -97,6 +102,7 @@ def main():
         keep['_H'] = np.int64(H); keep['_n_env'] = np.int64(n_env); keep['_seed'] = np.int64(view.get('seed', 0))
         keep.setdefault('_frame', np.int64(view.get('frame', 0))); keep['_azim'] = np.float64(view.get('azim', 20.0))
         keep['_cam_dist'] = np.float64(view.get('cam_dist', 3.0)); keep['_fitted'] = np.int64(0 if view.get('raw_init') else 1); keep['_n_bones'] = np.int64(view.get('n_bones', 52)); keep['_tonemapping'] = np.int64(0 if view.get('linear') else 1)
+        keep['_fix_material'] = np.int64(view.get('fix_material', 0)); keep['_always_fix_material'] = np.int64(0 if view.get('no_always_fix_material') else 1)
         out = os.path.join(HERE, f'{name}.npz')
         np.savez_compressed(out, **keep)
         print(name, os.path.getsize(out) / 1e3, 'kB', sorted(keep))

@@ -124,13 +124,16 @@ def test_batch_preparation_matches_reference():
     assert torch.allclose(n, torch.nn.functional.normalize(v, dim=1), atol=1e-5)      # icosahedron: vertex normal = radial direction
 
 
-@pytest.mark.parametrize('name', ['anisdf_trace_48', 'anisdf_trace_40_smpl24'])
+@pytest.mark.parametrize('name', ['anisdf_trace_48', 'anisdf_trace_40_smpl24', 'anisdf_trace_40_fixmat_last', 'anisdf_trace_40_fixmat_off'])
 def test_anisdf_trace_matches_reference(name):
     g = _load(name)
     H, frame, n_bones = int(g['_H']), int(g.get('_frame', 0)), int(g.get('_n_bones', 52))
     b = scene.make_batch(H, H, frame=frame, n_frames=frame + 1, seed=0, n_env=0, n_bones=n_bones)
     sd = scene.make_state_dict(0, relight=False, fitted=True, n_bones=n_bones)
-    out = O.render_sphere_tracing(b, sd, O.anisdf_cfg())
+    cfg = O.anisdf_cfg()
+    # the colour network's condition (base_network.py:501-503): training pose `fix_material` (python index) or this frame's pose
+    cfg.fix_material, cfg.always_fix_material = int(g.get('_fix_material', 0)), bool(int(g.get('_always_fix_material', 1)))
+    out = O.render_sphere_tracing(b, sd, cfg)
     assert int((g['acc_map'][0] > 0).sum()) > 50
     for k in ('rgb_map', 'acc_map', 'surf_map', 'bpts_map', 'cpts_map', 'depth_map', 'resd_map'):
         if k in g:

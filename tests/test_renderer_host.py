@@ -107,3 +107,21 @@ def test_material_condition_follows_fix_material(setup):
     assert eng.frames[-1] == (-1, True)
     r = R.Renderer(net, sync_timing=False, engine=eng)
     assert (r.fix_material, r.always_fix_material) == (0, True)
+
+
+@pytest.mark.parametrize('fix_material,always', [(0, True), (2, False), (-1, True), (-1, False)])
+def test_material_condition_equals_the_oracle_rule(setup, fix_material, always):
+    """renderer.material_condition against the oracle's Frame (itself pinned to the reference for the -1 / always and the
+    per-frame-pose branches by tests/golden/anisdf_trace_40_fixmat_{last,off}.npz)."""
+    b, _ = setup
+    cfg = O.anisdf_cfg()
+    cfg.fix_material, cfg.always_fix_material = fix_material, always
+    want = O.Frame.from_batch(b, cfg, torch.float32, 'cpu').mat_cond
+    got = R.material_condition(b, fix_material, always)
+    assert torch.equal(got.float(), want)
+    # the reference's batch layout: batch.train_motion.poses instead of the flattened synthetic key
+    b2 = {k: v for k, v in b.items() if k != 'train_poses'}
+    b2['train_motion'] = {'poses': torch.as_tensor(b['train_poses'])}
+    assert torch.equal(R.material_condition(b2, fix_material, always).float(), want)
+    if fix_material >= 0 or always:
+        assert R.material_condition({k: v for k, v in b.items() if k != 'train_poses'}, fix_material, always) is None
