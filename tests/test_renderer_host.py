@@ -125,3 +125,16 @@ def test_material_condition_equals_the_oracle_rule(setup, fix_material, always):
     assert torch.equal(R.material_condition(b2, fix_material, always).float(), want)
     if fix_material >= 0 or always:
         assert R.material_condition({k: v for k, v in b.items() if k != 'train_poses'}, fix_material, always) is None
+
+
+def test_every_pixel_rays_match_the_oracle_and_the_scene(setup):
+    """renderer.get_rays (used by the floor pass for all H*W pixels) against the oracle's restatement of net_utils.get_rays and the
+    scene's numpy generator: the in-box subset must be the batch's own rays."""
+    b, _ = setup
+    H = W = 16
+    K, Rm, T = (torch.as_tensor(b[k][0]) for k in ('cam_K', 'cam_R', 'cam_T'))
+    ro, rd = R.get_rays(H, W, K, Rm, T)
+    ro2, rd2 = O.get_rays_full(H, W, K, Rm, T)
+    assert torch.allclose(ro, ro2, atol=1e-6) and torch.allclose(rd, rd2, atol=1e-6)
+    m = torch.as_tensor(b['mask_at_box'][0]).reshape(-1)
+    assert torch.allclose(rd[m], torch.as_tensor(b['ray_d'][0]), atol=2e-6) and torch.allclose(ro[m], torch.as_tensor(b['ray_o'][0]), atol=2e-6)
