@@ -10,6 +10,13 @@ import torch.multiprocessing as mp
 from relightableavatar_b200 import parallel
 
 
+def _free_port() -> int:
+    import socket
+    with socket.socket() as sk:
+        sk.bind(('127.0.0.1', 0))
+        return sk.getsockname()[1]
+
+
 def test_partition_covers_every_ray_once():
     for P in (0, 1, 31, 32, 33, 1000, 69137):
         for world in (1, 2, 4, 8):
@@ -37,7 +44,7 @@ def _worker(rank, world, port, P):
 
 
 def test_tile_sharded_render_world2_gloo():
-    mp.spawn(_worker, args=(2, 29512, 1000), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), 1000), nprocs=2, join=True)
 
 
 def _seq_worker(rank, world, port, n_frames):
@@ -60,4 +67,4 @@ def _seq_worker(rank, world, port, n_frames):
 
 def test_frame_sharded_sequence_world2_gloo():
     """Config 5 host logic: 5 frames over 2 ranks (the last step has one idle rank), one all-gather per step."""
-    mp.spawn(_seq_worker, args=(2, 29513, 5), nprocs=2, join=True)
+    mp.spawn(_seq_worker, args=(2, _free_port(), 5), nprocs=2, join=True)
