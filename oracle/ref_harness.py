@@ -281,6 +281,7 @@ def main():
     ap.add_argument('--n_bones', type=int, default=52, help='52 = SMPL-H (xuzhen), 24 = SMPL (ZJU-MoCap / synthetic-human configs)')
     ap.add_argument('--fix_material', type=int, default=0)
     ap.add_argument('--no_always_fix_material', action='store_true')
+    ap.add_argument('--slim', action='store_true', help='store only the rgb / acc maps (full-size runs: the (P,512) visibility maps are 141 MB each)')
     ap.add_argument('--linear', action='store_true', help='cfg.tonemapping_rendering False (HDR output)')
     ap.add_argument('--out', required=True)
     a = ap.parse_args()
@@ -297,6 +298,8 @@ def main():
     else:
         flat, _ = run(a.mode, a.H, a.seed, a.n_env, not a.raw_init, frame=a.frame, azim_deg=a.azim, cam_dist=a.cam_dist, n_bones=a.n_bones, tonemapping=not a.linear,
                       fix_material=a.fix_material, always_fix_material=not a.no_always_fix_material)
+    if a.slim:
+        flat = {k: v for k, v in flat.items() if k.endswith('rgb_map') or k.endswith('acc_map')}
     np.savez_compressed(out_path, **flat)
     print('wrote', out_path, {k: v.shape for k, v in flat.items()})
 

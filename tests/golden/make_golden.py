@@ -38,6 +38,9 @@ CASES = [
     ('anisdf_trace_40_smpl24', 'anisdf_trace', 40, 0, dict(n_bones=24, frame=1)),
     # cfg.tonemapping_rendering False (.exr / .hdr output): human + floor main pass stay linear, the novel-light re-shade does not
     ('relight_ground_24_linear', 'relight_ground', 24, 1, dict(linear=True)),
+    # the metric's own configuration (BASELINE configs[2]: 512x512, ~69 k rays; ~10 min of the reference on 8 CPU threads): only the
+    # finished pixels are kept, as float16 (quantisation ~70 dB, far above the parity bar of the test that reads it)
+    ('relight_512_pixels', 'relight', 512, 1, dict(keep=('main.rgb_map', 'main.acc_map', 'rgb_map'), f16=True)),
     # colour-network condition: last training pose (fix_material -1 under always_fix_material), and this frame's own pose
     ('anisdf_trace_40_fixmat_last', 'anisdf_trace', 40, 0, dict(fix_material=-1, frame=1)),
     ('anisdf_trace_40_fixmat_off', 'anisdf_trace', 40, 0, dict(fix_material=-1, no_always_fix_material=True, frame=1)),
@@ -78,6 +81,8 @@ def main():
             extra.append('--linear')
         if view.get('no_always_fix_material'):
             extra.append('--no_always_fix_material')
+        if view.get('keep'):
+            extra.append('--slim')
         subprocess.check_call([sys.executable, os.path.join(ROOT, 'oracle', 'ref_harness.py'), '--mode', mode,
                                '--H', str(H), '--n_env', str(n_env), '--out', tmp] + extra)
         d = dict(np.load(tmp))
@@ -99,6 +104,10 @@ def main():
             keep[k] = v
             if 'lvis_map' in keep and 'ldot_map' in keep:
                 seen_lvis = True
+        if view.get('keep'):
+            keep = {k: v for k, v in keep.items() if k in view['keep'] or k.split('.', 1)[-1] in view['keep']}
+        if view.get('f16'):
+            keep = {k: v.astype(np.float16) for k, v in keep.items()}
         keep['_H'] = np.int64(H); keep['_n_env'] = np.int64(n_env); keep['_seed'] = np.int64(view.get('seed', 0))
         keep.setdefault('_frame', np.int64(view.get('frame', 0))); keep['_azim'] = np.float64(view.get('azim', 20.0))
         keep['_cam_dist'] = np.float64(view.get('cam_dist', 3.0)); keep['_fitted'] = np.int64(0 if view.get('raw_init') else 1); keep['_n_bones'] = np.int64(view.get('n_bones', 52)); keep['_tonemapping'] = np.int64(0 if view.get('linear') else 1)
