@@ -41,6 +41,9 @@ CASES = [
     # the metric's own configuration (BASELINE configs[2]: 512x512, ~69 k rays; ~10 min of the reference on 8 CPU threads): only the
     # finished pixels are kept, as float16 (quantisation ~70 dB, far above the parity bar of the test that reads it)
     ('relight_512_pixels', 'relight', 512, 1, dict(keep=('main.rgb_map', 'main.acc_map', 'rgb_map'), f16=True)),
+    # BASELINE configs[0] (AniSDF sphere trace, 128x128: the reference's own CPU-runnable case) and configs[1] (AniSDF volume render, 512x512)
+    ('anisdf_trace_128', 'anisdf_trace', 128, 0, None),
+    ('anisdf_volume_512_pixels', 'anisdf_volume', 512, 0, dict(keep=('rgb_map', 'acc_map'), f16=True)),
     # colour-network condition: last training pose (fix_material -1 under always_fix_material), and this frame's own pose
     ('anisdf_trace_40_fixmat_last', 'anisdf_trace', 40, 0, dict(fix_material=-1, frame=1)),
     ('anisdf_trace_40_fixmat_off', 'anisdf_trace', 40, 0, dict(fix_material=-1, no_always_fix_material=True, frame=1)),

@@ -255,6 +255,30 @@ def test_metric_config_512_against_the_reference_itself(precision, min_psnr):
         assert psnr >= min_psnr, f'{name}: PSNR {psnr:.1f} dB vs the reference'
 
 
+def test_baseline_configs_1_and_2_against_the_reference_itself():
+    """BASELINE configs[0] (AniSDF sphere trace, 128x128) and configs[1] (AniSDF volume render, 512x512, 128 samples per ray) at their
+    real sizes against outputs of the UNMODIFIED reference (tests/golden/anisdf_trace_128.npz; anisdf_volume_512_pixels.npz, float16)."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    sd = scene.make_state_dict(0, relight=False, fitted=True)
+    for fixture, mode, H, keys in (('anisdf_trace_128', 'anisdf_trace', 128, ('rgb_map', 'acc_map', 'surf_map', 'cpts_map', 'bpts_map')),
+                                   ('anisdf_volume_512_pixels', 'anisdf_volume', 512, ('rgb_map', 'acc_map'))):
+        p = os.path.join(gold, fixture + '.npz')
+        if not os.path.exists(p):
+            pytest.skip(f'{fixture} missing')
+        g = dict(np.load(p))
+        b = scene.make_batch(H, H, seed=0, n_env=0)
+        r = Renderer(scene.SyntheticNet(sd, False), mode=mode, device=DEV, precision='fp32', max_rays=b['ray_o'].shape[1] + 8)
+        out = r.render(b)
+        for k in keys:
+            e = np.abs(out[k][0].cpu().numpy() - g[k][0].astype(np.float32))
+            assert np.quantile(e, 0.98) <= 2e-3, f'{fixture}.{k}: q98 {np.quantile(e, 0.98):.3e}'
+        ref = torch.from_numpy(g['rgb_map'][0].astype(np.float32))
+        psnr = O.psnr(O.assemble_image(b, out['rgb_map'][0].cpu()), O.assemble_image(b, ref))
+        assert psnr >= 40.0, f'{fixture}: PSNR {psnr:.1f} dB vs the reference'
+        r.engine.close()
+
+
 def test_relight_1024_config5_properties():
     """BASELINE config 5 size (1024x1024 frame): size-independent properties instead of an oracle run:
     acc in [0,1], maps premultiplied (zero where acc == 0), foreground share plausible, rgb finite and in [0,1],

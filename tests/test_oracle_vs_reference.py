@@ -124,7 +124,7 @@ def test_batch_preparation_matches_reference():
     assert torch.allclose(n, torch.nn.functional.normalize(v, dim=1), atol=1e-5)      # icosahedron: vertex normal = radial direction
 
 
-@pytest.mark.parametrize('name', ['anisdf_trace_48', 'anisdf_trace_40_smpl24', 'anisdf_trace_40_fixmat_last', 'anisdf_trace_40_fixmat_off'])
+@pytest.mark.parametrize('name', ['anisdf_trace_48', 'anisdf_trace_128', 'anisdf_trace_40_smpl24', 'anisdf_trace_40_fixmat_last', 'anisdf_trace_40_fixmat_off'])
 def test_anisdf_trace_matches_reference(name):
     g = _load(name)
     H, frame, n_bones = int(g['_H']), int(g.get('_frame', 0)), int(g.get('_n_bones', 52))
