@@ -43,6 +43,8 @@ CASES = [
     ('relight_512_pixels', 'relight', 512, 1, dict(keep=('main.rgb_map', 'main.acc_map', 'rgb_map'), f16=True)),
     # BASELINE configs[0] (AniSDF sphere trace, 128x128: the reference's own CPU-runnable case) and configs[1] (AniSDF volume render, 512x512)
     ('anisdf_trace_128', 'anisdf_trace', 128, 0, None),
+    # one frame of BASELINE configs[4] (novel-pose sequence, 1024x1024: ~277 k rays = five reference pixel chunks; ~50 min of the reference)
+    ('relight_1024_f5_pixels', 'relight', 1024, 0, dict(frame=5, keep=('main.rgb_map', 'main.acc_map'), f16=True)),
     ('anisdf_volume_512_pixels', 'anisdf_volume', 512, 0, dict(keep=('rgb_map', 'acc_map'), f16=True)),
     # colour-network condition: last training pose (fix_material -1 under always_fix_material), and this frame's own pose
     ('anisdf_trace_40_fixmat_last', 'anisdf_trace', 40, 0, dict(fix_material=-1, frame=1)),
