@@ -228,68 +228,6 @@ def test_two_cta_kernel_variant_matches_single_cta(relight_setup, monkeypatch):
     assert torch.equal(outs[0], outs[2])
 
 
-def _pixels_vs_reference(fixture, precision, min_psnr):
-    import os
-    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', fixture + '.npz')
-    if not os.path.exists(p):
-        pytest.skip('golden fixture missing')
-    g = dict(np.load(p))
-    H, n_env, frame = int(g['_H']), int(g['_n_env']), int(g.get('_frame', 0))
-    b = scene.make_batch(H, H, frame=frame, n_frames=frame + 1, seed=0, n_env=n_env)
-    sd = scene.make_state_dict(0, relight=True, fitted=True)
-    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision=precision, max_rays=b['ray_o'].shape[1] + 8,
-                 test_light=('main', 'all'), sync_timing=False)
-    out = r.render(b)
-    ref_acc = torch.from_numpy(g['main.acc_map'][0].astype(np.float32))
-    fg_ref, fg_got = ref_acc > 0, out['main']['acc_map'][0].cpu() > 0
-    assert int((fg_ref != fg_got).sum()) <= int(1e-2 * int(fg_ref.sum())), f'{int((fg_ref != fg_got).sum())} silhouette flips'      # PSNR below is the bar
-    for name in ['main'] + list(b.get('novel_lights', {})):
-        ref = torch.from_numpy(g[f'{name}.rgb_map'][0].astype(np.float32))
-        psnr = O.psnr(O.assemble_image(b, out[name]['rgb_map'][0].cpu()), O.assemble_image(b, ref))
-        assert psnr >= min_psnr, f'{name}: PSNR {psnr:.1f} dB vs the reference'
-    r.engine.close()
-
-
-def test_config5_frame_1024_against_the_reference_itself():
-    """One frame of BASELINE configs[4] (novel pose, 1024x1024, ~277 k rays = five reference pixel chunks with their cumulative
-    wbounds growth) against the finished pixels of the UNMODIFIED reference (tests/golden/relight_1024_f5_pixels.npz, float16)."""
-    _pixels_vs_reference('relight_1024_f5_pixels', 'tc', 45.0)
-
-
-@pytest.mark.parametrize('precision,min_psnr', [('tc', 45.0), ('fp32', 55.0)])
-def test_metric_config_512_against_the_reference_itself(precision, min_psnr):
-    """BASELINE configs[2] at its real size (512x512, ~69 k rays, two reference pixel chunks): the finished pixels of the UNMODIFIED
-    reference (tests/golden/relight_512_pixels.npz, float16) against the CUDA path.  north_star asks for PSNR within 0.1 dB of the
-    reference on photographs at ~30 dB: an image PSNR >= 45 dB against the reference itself leaves < 0.02 dB of that budget used
-    (measured this round against the oracle: 56-64 dB in tensor-core mode, > 80 dB in fp32 mode; the oracle itself is at 91 dB
-    against this fixture, profiles/r01_oracle_vs_reference_512.txt)."""
-    _pixels_vs_reference('relight_512_pixels', precision, min_psnr)
-
-
-def test_baseline_configs_1_and_2_against_the_reference_itself():
-    """BASELINE configs[0] (AniSDF sphere trace, 128x128) and configs[1] (AniSDF volume render, 512x512, 128 samples per ray) at their
-    real sizes against outputs of the UNMODIFIED reference (tests/golden/anisdf_trace_128.npz; anisdf_volume_512_pixels.npz, float16)."""
-    import os
-    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-    sd = scene.make_state_dict(0, relight=False, fitted=True)
-    for fixture, mode, H, keys in (('anisdf_trace_128', 'anisdf_trace', 128, ('rgb_map', 'acc_map', 'surf_map', 'cpts_map', 'bpts_map')),
-                                   ('anisdf_volume_512_pixels', 'anisdf_volume', 512, ('rgb_map', 'acc_map'))):
-        p = os.path.join(gold, fixture + '.npz')
-        if not os.path.exists(p):
-            pytest.skip(f'{fixture} missing')
-        g = dict(np.load(p))
-        b = scene.make_batch(H, H, seed=0, n_env=0)
-        r = Renderer(scene.SyntheticNet(sd, False), mode=mode, device=DEV, precision='fp32', max_rays=b['ray_o'].shape[1] + 8)
-        out = r.render(b)
-        for k in keys:
-            e = np.abs(out[k][0].cpu().numpy() - g[k][0].astype(np.float32))
-            assert np.quantile(e, 0.98) <= 2e-3, f'{fixture}.{k}: q98 {np.quantile(e, 0.98):.3e}'
-        ref = torch.from_numpy(g['rgb_map'][0].astype(np.float32))
-        psnr = O.psnr(O.assemble_image(b, out['rgb_map'][0].cpu()), O.assemble_image(b, ref))
-        assert psnr >= 40.0, f'{fixture}: PSNR {psnr:.1f} dB vs the reference'
-        r.engine.close()
-
-
 def test_relight_1024_config5_properties():
     """BASELINE config 5 size (1024x1024 frame): size-independent properties instead of an oracle run:
     acc in [0,1], maps premultiplied (zero where acc == 0), foreground share plausible, rgb finite and in [0,1],
@@ -494,3 +432,66 @@ def test_destroy_releases_device_memory(relight_setup):
         if i == 0:
             free0 = free
     assert free0 - free < 64 << 20, f'leaked {(free0 - free) >> 20} MiB over 3 create/destroy cycles'
+
+
+# ---- full-size fixtures of the unmodified reference (BASELINE configs at their real sizes); last in the file on purpose
+def _pixels_vs_reference(fixture, precision, min_psnr):
+    import os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', fixture + '.npz')
+    if not os.path.exists(p):
+        pytest.skip('golden fixture missing')
+    g = dict(np.load(p))
+    H, n_env, frame = int(g['_H']), int(g['_n_env']), int(g.get('_frame', 0))
+    b = scene.make_batch(H, H, frame=frame, n_frames=frame + 1, seed=0, n_env=n_env)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision=precision, max_rays=b['ray_o'].shape[1] + 8,
+                 test_light=('main', 'all'), sync_timing=False)
+    out = r.render(b)
+    ref_acc = torch.from_numpy(g['main.acc_map'][0].astype(np.float32))
+    fg_ref, fg_got = ref_acc > 0, out['main']['acc_map'][0].cpu() > 0
+    assert int((fg_ref != fg_got).sum()) <= int(1e-2 * int(fg_ref.sum())), f'{int((fg_ref != fg_got).sum())} silhouette flips'      # PSNR below is the bar
+    for name in ['main'] + list(b.get('novel_lights', {})):
+        ref = torch.from_numpy(g[f'{name}.rgb_map'][0].astype(np.float32))
+        psnr = O.psnr(O.assemble_image(b, out[name]['rgb_map'][0].cpu()), O.assemble_image(b, ref))
+        assert psnr >= min_psnr, f'{name}: PSNR {psnr:.1f} dB vs the reference'
+    r.engine.close()
+
+
+@pytest.mark.parametrize('precision,min_psnr', [('tc', 45.0), ('fp32', 55.0)])
+def test_metric_config_512_against_the_reference_itself(precision, min_psnr):
+    """BASELINE configs[2] at its real size (512x512, ~69 k rays, two reference pixel chunks): the finished pixels of the UNMODIFIED
+    reference (tests/golden/relight_512_pixels.npz, float16) against the CUDA path.  north_star asks for PSNR within 0.1 dB of the
+    reference on photographs at ~30 dB: an image PSNR >= 45 dB against the reference itself leaves < 0.02 dB of that budget used
+    (measured this round against the oracle: 56-64 dB in tensor-core mode, > 80 dB in fp32 mode; the oracle itself is at 91 dB
+    against this fixture, profiles/r01_oracle_vs_reference_512.txt)."""
+    _pixels_vs_reference('relight_512_pixels', precision, min_psnr)
+
+
+def test_baseline_configs_1_and_2_against_the_reference_itself():
+    """BASELINE configs[0] (AniSDF sphere trace, 128x128) and configs[1] (AniSDF volume render, 512x512, 128 samples per ray) at their
+    real sizes against outputs of the UNMODIFIED reference (tests/golden/anisdf_trace_128.npz; anisdf_volume_512_pixels.npz, float16)."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    sd = scene.make_state_dict(0, relight=False, fitted=True)
+    for fixture, mode, H, keys in (('anisdf_trace_128', 'anisdf_trace', 128, ('rgb_map', 'acc_map', 'surf_map', 'cpts_map', 'bpts_map')),
+                                   ('anisdf_volume_512_pixels', 'anisdf_volume', 512, ('rgb_map', 'acc_map'))):
+        p = os.path.join(gold, fixture + '.npz')
+        if not os.path.exists(p):
+            pytest.skip(f'{fixture} missing')
+        g = dict(np.load(p))
+        b = scene.make_batch(H, H, seed=0, n_env=0)
+        r = Renderer(scene.SyntheticNet(sd, False), mode=mode, device=DEV, precision='fp32', max_rays=b['ray_o'].shape[1] + 8)
+        out = r.render(b)
+        for k in keys:
+            e = np.abs(out[k][0].cpu().numpy() - g[k][0].astype(np.float32))
+            assert np.quantile(e, 0.98) <= 2e-3, f'{fixture}.{k}: q98 {np.quantile(e, 0.98):.3e}'
+        ref = torch.from_numpy(g['rgb_map'][0].astype(np.float32))
+        psnr = O.psnr(O.assemble_image(b, out['rgb_map'][0].cpu()), O.assemble_image(b, ref))
+        assert psnr >= 40.0, f'{fixture}: PSNR {psnr:.1f} dB vs the reference'
+        r.engine.close()
+
+
+def test_config5_frame_1024_against_the_reference_itself():
+    """One frame of BASELINE configs[4] (novel pose, 1024x1024, ~277 k rays = five reference pixel chunks with their cumulative
+    wbounds growth) against the finished pixels of the UNMODIFIED reference (tests/golden/relight_1024_f5_pixels.npz, float16)."""
+    _pixels_vs_reference('relight_1024_f5_pixels', 'tc', 45.0)
