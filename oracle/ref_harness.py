@@ -155,6 +155,8 @@ def to_ref_batch(b: dict, device='cpu'):
         elif isinstance(v, np.ndarray) and v.ndim > 0:
             out[k] = torch.from_numpy(v.copy()).to(device)
     out.meta = dotdict(H=torch.tensor([int(b['H'])]), W=torch.tensor([int(b['W'])]))
+    if 'novel_lights' not in out:
+        out.novel_lights = dotdict()          # the novel-light renderer loops over it unconditionally (novel_light_sphere_tracing.py:165)
     return out
 
 
