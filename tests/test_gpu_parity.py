@@ -463,7 +463,7 @@ def test_metric_config_512_against_the_reference_itself(precision, min_psnr):
     reference (tests/golden/relight_512_pixels.npz, float16) against the CUDA path.  north_star asks for PSNR within 0.1 dB of the
     reference on photographs at ~30 dB: an image PSNR >= 45 dB against the reference itself leaves < 0.02 dB of that budget used
     (measured this round against the oracle: 56-64 dB in tensor-core mode, > 80 dB in fp32 mode; the oracle itself is at 91 dB
-    against this fixture, profiles/r01_oracle_vs_reference_512.txt)."""
+    against this fixture, profiles/r01_oracle_vs_reference_fullsize.txt)."""
     _pixels_vs_reference('relight_512_pixels', precision, min_psnr)
 
 
