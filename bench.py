@@ -10,17 +10,25 @@ sequence / fitted SDF weights; no dataset or checkpoint exists offline).  One st
 `Renderer.render`: per-frame state upload (set_frame), 16-iteration surface trace, 3-sample surface attributes with
 analytic normals, 4-iteration soft-shadow trace over the 16x32 light grid, microfacet light sum.  With N > 1 the
 frames of the sequence are sharded over the ranks (rank r renders frame step*N + r; weak scaling) and every step
-ends with ONE all-gather of the finished pixels (rgb + acc).
+ends with ONE all-gather of the finished pixels (rgb + acc) through the C-ABI's `ra_allgather` on a side stream
+(double-buffered: step s is gathered while step s+1 renders).
 
-`value`  : whole-job frames/s with the frame inputs already resident in HBM.
-`e2e`    : the same through the public plugin call with HOST (pinned) inputs: H2D of the frame + rays and D2H of the
-           finished rgb/acc maps inside the timed region.
-`--impl reference`: the reference's CPU path (the oracle port of oracle/ra_oracle.py, all host threads) on a bounded
-           sample of the same workload (a 32x32 rendering of the same view), scaled to 512x512 frames by ray count.
+`value`    : whole-job frames/s with the frame inputs already resident in HBM.
+`e2e`      : the same through the public plugin call with HOST (pinned) inputs: H2D of the frame + rays and D2H of the
+             finished rgb/acc maps inside the timed region.
+`fp32_mode`: the same frames in the reference-precision mode (every MLP at fp32 accuracy), a few steps.
+`configs`  : the other multi-GPU BASELINE configs on the same ranks -- configs[3]: ONE 512x512 frame with 8 novel env-maps,
+             its rays tile-sharded over the N ranks (strong scaling; `tile_equal`: the gathered frame is bit-identical to the
+             unsharded one); configs[4]: the 1024x1024 novel-pose sequence, frame-sharded (weak scaling).
+`--impl reference`: the reference's own CPU path on the host cores on a bounded sample of the same workload: the UNMODIFIED
+             reference renderer when its tree is present (/root/reference or the mirror baseline/_ref that travels with the
+             snapshot; `cpu_baseline.kind: "reference"`), else the oracle port (`"port"`).
 """
 from __future__ import annotations
 
 import argparse
+import glob
+import hashlib
 import json
 import os
 import statistics
@@ -34,9 +42,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FLOP_PER_QUERY = 2_192_384          # resd MLP 571,648 MAC + SDF MLP 524,544 MAC per in-shell distance query
+BYTES_PER_QUERY = 16                # 12 B big-pose point in + 4 B sdf out per in-shell query (the fused MLP kernel's only HBM traffic)
 H = W = 512
-SAMPLE_H = 32
 SEQ_FRAMES = 8                      # distinct frames of the pose sequence cycled through
+WORKLOAD = 'xuzhen_12v_geo_fix_mat relighting, 1 envmap (main), 512x512, 1 frame per GPU per step'
+SAMPLE_SIZES = (24, 32, 48, 64, 96, 128)
 
 
 def load_peaks():
@@ -44,7 +54,7 @@ def load_peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return d, 'measured'
-    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback (B200_PROFILING.md)'
 
 
 class ClockSampler:
@@ -79,40 +89,118 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def cpu_reference_step(cfg, batch, sd, O, torch):
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        out = O.render_sphere_tracing(batch, sd, cfg, torch.float32, 'cpu', want_lvis=False)
-    return time.perf_counter() - t0, out
+# ------------------------------------------------------------------------------------------------ the reference arm (CPU)
+class CpuReference:
+    """One relight frame of a given size on the host cores: the unmodified reference renderer when its tree is present
+    (oracle/ref_harness.py imports it from where it lies), else the oracle port (oracle/ra_oracle.py)."""
+
+    def __init__(self):
+        import torch
+        from oracle import ref_harness as RH
+        from relightableavatar_b200 import scene
+        self.torch, self.scene, self.RH = torch, scene, RH
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.sd = scene.make_state_dict(0, relight=True, fitted=True)
+        try:
+            self.ref_root = RH.find_reference()
+            self.kind = 'reference'
+        except FileNotFoundError:
+            self.ref_root, self.kind = None, 'port'
+        if self.kind == 'reference':
+            cfg = RH.setup_reference('relight')            # imports the reference's cfg and replays its cascade (chdir into the tree)
+            cfg.test_light = ['main']
+            from lib.networks.make_network import make_network
+            from lib.networks.renderer.make_renderer import make_renderer
+            net = make_network(cfg)
+            missing, unexpected = net.load_state_dict(self.sd, strict=False)
+            assert not unexpected, unexpected
+            net.eval()
+            self.renderer = make_renderer(cfg, net)        # lib.networks.renderer.novel_light_sphere_tracing.Renderer, stock code path
+        else:
+            from oracle import ra_oracle as O
+            self.O = O
+
+    def frame(self, size: int):
+        """-> (seconds, rays) of ONE frame of size x size (same view, body and weights as the GPU workload)."""
+        torch = self.torch
+        b = self.scene.make_batch(size, size, seed=0, n_env=0)
+        if self.kind == 'reference':
+            batch = self.RH.to_ref_batch(b)                # fresh every time: the reference grows batch.wbounds in place
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                self.renderer.render(batch)
+            return time.perf_counter() - t0, b['ray_o'].shape[1]
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            self.O.render_sphere_tracing(b, self.sd, self.O.Cfg(), torch.float32, 'cpu', want_lvis=False)
+        return time.perf_counter() - t0, b['ray_o'].shape[1]
+
+    def pick_size(self, n_frames: int, budget_s: float):
+        """Largest sample size whose n_frames frames fit the time budget, from the per-ray cost of a 24x24 probe frame."""
+        t, rays = self.frame(SAMPLE_SIZES[0])
+        per_ray = t / max(rays, 1)
+        best = SAMPLE_SIZES[0]
+        for s in SAMPLE_SIZES[1:]:
+            est_rays = rays * (s / SAMPLE_SIZES[0]) ** 2
+            if per_ray * est_rays * n_frames <= budget_s:
+                best = s
+        return best
 
 
 def run_reference(args):
-    """The reference's CPU path (oracle port) on the host cores; rank 0 only."""
-    rank = int(os.environ.get('RANK', 0))
-    if rank != 0:
+    """`--impl reference`: rank 0 only; W warm-up + K timed frames of a bounded sample, scaled to 512x512 frames by ray count."""
+    if int(os.environ.get('RANK', 0)) != 0:
         return
-    import torch
-    from oracle import ra_oracle as O
-    from relightableavatar_b200 import scene
-    torch.set_num_threads(os.cpu_count())
-    b = scene.make_batch(SAMPLE_H, SAMPLE_H, seed=0, n_env=0)
-    P_full = scene.make_batch(H, W, seed=0, n_env=0)['ray_o'].shape[1]
-    P_s = b['ray_o'].shape[1]
-    sd = scene.make_state_dict(0, relight=True, fitted=True)
-    cfg = O.Cfg()
-    for _ in range(max(args.warmup, 0)):
-        cpu_reference_step(cfg, b, sd, O, torch)
-    ts = [cpu_reference_step(cfg, b, sd, O, torch)[0] for _ in range(max(args.steps, 1))]
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):        # the reference logs to stdout; the JSON line must stay alone there
+        cpu = CpuReference()
+        P_full = cpu.scene.make_batch(H, W, seed=0, n_env=0)['ray_o'].shape[1]
+        size = cpu.pick_size(max(args.steps, 1) + max(args.warmup, 0), args.cpu_budget)
+        for _ in range(max(args.warmup, 0)):
+            cpu.frame(size)
+        ts, P_s = [], 0
+        for _ in range(max(args.steps, 1)):
+            t, P_s = cpu.frame(size)
+            ts.append(t)
     t = sum(ts) / len(ts)
     fps = (P_s / P_full) / t
-    sample = f'{SAMPLE_H}x{SAMPLE_H} relight rendering of the same view ({P_s} of {P_full} rays), scaled by ray count'
+    what = ('the UNMODIFIED reference renderer (lib.networks.renderer.novel_light_sphere_tracing, stock code path)' if cpu.kind == 'reference'
+            else 'the oracle port of the reference path (oracle/ra_oracle.py; no reference tree on this box)')
+    sample = f'{size}x{size} relight rendering of the same view by {what}: {P_s} of {P_full} rays, {t:.2f} s per frame, scaled by ray count'
     line = {'impl': 'reference', 'metric': 'relit 512x512 frames/sec', 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'xuzhen_12v_geo_fix_mat relighting, 1 envmap (main), 512x512, 1 frame per GPU per step', 'sample': sample},
-            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
+            'config': {'workload': WORKLOAD, 'sample': sample},
+            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cpu.torch.get_num_threads(), 'kind': cpu.kind, 'sample': sample},
             'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(budget_s: float):
+    """The `cpu_baseline` leg of the N=1 line: the reference arm in its own process (its import shims and chdir stay out of
+    this one), one warm-up + two timed frames of a sample sized for ~budget_s of CPU work."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '2', '--warmup', '1',
+                            '--cpu-budget', str(budget_s)], capture_output=True, text=True, timeout=600,
+                           env={**os.environ, 'CUDA_VISIBLE_DEVICES': ''})
+        line = [l for l in r.stdout.splitlines() if l.startswith('{')]
+        return json.loads(line[-1])['cpu_baseline'] if line else {'error': (r.stderr or r.stdout)[-300:]}
+    except Exception as e:      # the baseline is a reported extra: never let it take the bench line down
+        return {'error': repr(e)[:300]}
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the fused MLP kernel from the committed ncu capture of this bench command
+    (profiles/r*_ncu_k_mlp_tc6_dram.json, written by tools/ncu_dram_per_launch.py; cited with its sha256)."""
+    cands = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_ncu_k_mlp_tc6_dram.json')))
+    if not cands:
+        return None
+    p = cands[-1]
+    d = json.load(open(p))
+    d['source'] = os.path.relpath(p, ROOT)
+    d['sha256'] = hashlib.sha256(open(p, 'rb').read()).hexdigest()
+    return d
 
 
 def main():
@@ -123,6 +211,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default='tc', choices=['tc', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the fp32_mode and configs[3]/[4] measurements')
+    ap.add_argument('--cpu-budget', type=float, default=150.0, help='seconds of CPU work the reference arm may spend in total')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
@@ -130,7 +220,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from relightableavatar_b200 import scene
+    from relightableavatar_b200 import parallel, scene
     from relightableavatar_b200.renderer import Renderer
 
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -143,77 +233,31 @@ def main():
 
     # ---- workload: a short pose sequence, host (pinned) and device copies
     sd = scene.make_state_dict(0, relight=True, fitted=True)
-    frames_host, frames_dev = [], []
+    net = scene.SyntheticNet(sd, True)
     tensor_keys = ('ray_o', 'ray_d', 'near', 'far', 'R', 'Th', 'poses', 'A', 'big_A', 'weights', 'pverts', 'pnorm', 'tverts', 'wbounds', 'train_poses')
-    P_max = 0
-    for f in range(SEQ_FRAMES):
-        b = scene.make_batch(H, W, frame=f, n_frames=SEQ_FRAMES, seed=0, n_env=0)
-        hb = {k: torch.from_numpy(b[k]).pin_memory() for k in tensor_keys}
-        hb['mask_at_box'] = torch.from_numpy(b['mask_at_box'])
-        frames_host.append(hb)
-        frames_dev.append({k: v.to(dev) for k, v in hb.items() if k in tensor_keys})
-        P_max = max(P_max, b['ray_o'].shape[1])
-    h2d_bytes = int(statistics.mean(sum(v.numel() * v.element_size() for k, v in hb.items() if k in tensor_keys) for hb in frames_host))
-    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=dev, precision=args.precision, max_rays=P_max + 1024, test_light=('main',), sync_timing=False)
+
+    def load_frames(size, n):
+        host, devs, p_max = [], [], 0
+        for f in range(n):
+            b = scene.make_batch(size, size, frame=f, n_frames=SEQ_FRAMES, seed=0, n_env=0)
+            hb = {k: torch.from_numpy(b[k]).pin_memory() for k in tensor_keys}
+            host.append(hb)
+            devs.append({k: v.to(dev) for k, v in hb.items()})
+            p_max = max(p_max, b['ray_o'].shape[1])
+        return host, devs, p_max
+
+    frames_host, frames_dev, P_max = load_frames(H, SEQ_FRAMES)
+    h2d_bytes = int(statistics.mean(sum(v.numel() * v.element_size() for v in hb.values()) for hb in frames_host))
+    r = Renderer(net, mode='relight', device=dev, precision=args.precision, max_rays=P_max + 1024, test_light=('main',), sync_timing=False)
     eng = r.engine
     pad = P_max
-    out_host = torch.empty(pad, 4).pin_memory()
-
-    def frame_of(step):
-        return (step * world + rank) % SEQ_FRAMES
-
-    def step_device(step):
-        out = r.render(frames_dev[frame_of(step)])['main']
-        px = torch.cat([out['rgb_map'][0], out['acc_map'][0][:, None]], dim=1)
-        if world > 1:
-            buf = torch.zeros(pad, 4, device=dev)
-            buf[: px.shape[0]] = px
-            g = torch.empty(world * pad, 4, device=dev)
-            dist.all_gather_into_tensor(g, buf)          # the single collective of the step
-            return g
-        return px
-
-    # end-to-end: every step copies its frame from pinned host memory and returns its pixels to pinned host memory.
-    # Two side streams keep the PCIe transfers of step s+1 (H2D) and step s-1 (D2H) under the rendering of step s.
-    h2d_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    out_hosts = [torch.empty(pad, 4).pin_memory() for _ in range(2)]
-    pipe = {'next': None, 'd2h_ev': [None, None], 'keep': []}
-
-    def prefetch(step):
-        hb = frames_host[frame_of(step)]
-        with torch.cuda.stream(h2d_stream):
-            db = {k: v.to(dev, non_blocking=True) for k, v in hb.items() if k in tensor_keys}
-            ev = torch.cuda.Event(); ev.record(h2d_stream)
-        return db, ev
-
-    def step_e2e(step):
-        if pipe['next'] is None or pipe['next'][0] != step:
-            pipe['next'] = (step,) + prefetch(step)
-        _, db, ev = pipe['next']
-        torch.cuda.current_stream().wait_event(ev)
-        pipe['next'] = (step + 1,) + prefetch(step + 1)          # H2D of the next frame overlaps this frame's kernels
-        out = r.render(db)['main']
-        px = torch.cat([out['rgb_map'][0], out['acc_map'][0][:, None]], dim=1)
-        if world > 1:
-            buf = torch.zeros(pad, 4, device=dev)
-            buf[: px.shape[0]] = px
-            g = torch.empty(world * pad, 4, device=dev)
-            dist.all_gather_into_tensor(g, buf)
-        done = torch.cuda.Event(); done.record()
-        slot = step & 1
-        if pipe['d2h_ev'][slot] is not None:
-            pipe['d2h_ev'][slot].synchronize()                    # the host consumed that buffer two steps ago
-        with torch.cuda.stream(d2h_stream):
-            d2h_stream.wait_event(done)
-            out_hosts[slot][: px.shape[0]].copy_(px, non_blocking=True)
-            e2 = torch.cuda.Event(); e2.record(d2h_stream)
-        pipe['d2h_ev'][slot] = e2
-        pipe['keep'] = [pipe['keep'][-1] if pipe['keep'] else None, (db, px)]   # keep tensors alive until their copies ran
-        return px.shape[0] * 16
+    gather = parallel.PixelGather(eng, pad, 4) if world > 1 else None
 
     def timed(fn, steps, warmup, finish=None):
         for s in range(warmup):
             fn(s)
+        if finish is not None:
+            finish()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -235,36 +279,89 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), ret
 
+    def make_steps(rr, fdev, fhost, n_frames, gat, n_pad):
+        """-> (step_device, step_e2e, finish) for renderer rr over the given frame lists."""
+        def frame_of(step):
+            return (step * world + rank) % n_frames
+
+        def pixels(out):
+            return torch.cat([out['rgb_map'][0], out['acc_map'][0][:, None]], dim=1)
+
+        def step_device(step):
+            px = pixels(rr.render(fdev[frame_of(step)])['main'])
+            if gat is not None:
+                gat.submit(px)            # the single collective of the step, on the side stream (ra_allgather)
+            return px
+
+        # end-to-end: every step copies its frame from pinned host memory and returns its pixels to pinned host memory.
+        # Two side streams keep the PCIe transfers of step s+1 (H2D) and step s-1 (D2H) under the rendering of step s.
+        h2d_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        out_hosts = [torch.empty(n_pad, 4).pin_memory() for _ in range(2)]
+        pipe = {'next': None, 'd2h_ev': [None, None], 'keep': []}
+
+        def prefetch(step):
+            hb = fhost[frame_of(step)]
+            with torch.cuda.stream(h2d_stream):
+                db = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+                ev = torch.cuda.Event(); ev.record(h2d_stream)
+            return db, ev
+
+        def step_e2e(step):
+            if pipe['next'] is None or pipe['next'][0] != step:
+                pipe['next'] = (step,) + prefetch(step)
+            _, db, ev = pipe['next']
+            torch.cuda.current_stream().wait_event(ev)
+            pipe['next'] = (step + 1,) + prefetch(step + 1)          # H2D of the next frame overlaps this frame's kernels
+            px = pixels(rr.render(db)['main'])
+            if gat is not None:
+                gat.submit(px)
+            done = torch.cuda.Event(); done.record()
+            slot = step & 1
+            if pipe['d2h_ev'][slot] is not None:
+                pipe['d2h_ev'][slot].synchronize()                    # the host consumed that buffer two steps ago
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done)
+                out_hosts[slot][: px.shape[0]].copy_(px, non_blocking=True)
+                e2 = torch.cuda.Event(); e2.record(d2h_stream)
+            pipe['d2h_ev'][slot] = e2
+            pipe['keep'] = [pipe['keep'][-1] if pipe['keep'] else None, (db, px)]   # keep tensors alive until their copies ran
+            return px.shape[0] * 16
+
+        def finish():      # the last gathers / the last frames' pixels must have landed before the clock stops
+            if gat is not None:
+                gat.drain()
+            for ev in pipe['d2h_ev']:
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
+
+        return step_device, step_e2e, finish
+
+    step_device, step_e2e, finish = make_steps(r, frames_dev, frames_host, SEQ_FRAMES, gather, pad)
+
     # ---- device-resident throughput (+ per-kernel timing of the fused MLP kernel + clocks)
     sampler = ClockSampler(local)
     eng.profile_enable(True)
-    l0 = eng.launch_count()
     for s in range(args.warmup):
         step_device(s)
+    finish()
     eng.profile_read()
     l0 = eng.launch_count()
     sampler.start()
-    ms_dev, _ = timed(step_device, args.steps, 0)
+    ms_dev, _ = timed(step_device, args.steps, 0, finish)
     clocks = sampler.stop()
     prof = eng.profile_read()
     launches = eng.launch_count() - l0
     eng.profile_enable(False)
     stats = eng.stats()
-    # in-shell queries summed over the timed steps are not kept per step; the last frame's count x steps is
-    # exact only for a 1-frame sequence, so accumulate from a dedicated pass:
-    inshell = 0
-    nq = 0
+    # in-shell queries per timed step (the counters hold the last render only): a dedicated pass over the same frames
+    inshell = nq = 0
     for s in range(args.steps):
         step_device(args.warmup + s)
         st = eng.stats()
         inshell += st['n_queries_in_shell']; nq += st['n_queries']
+    finish()
     # ---- end-to-end (host buffers in, host pixels out)
-    def e2e_finish():      # the last frames' pixels must have landed in host memory before the clock stops
-        for ev in pipe['d2h_ev']:
-            if ev is not None:
-                torch.cuda.current_stream().wait_event(ev)
-
-    ms_e2e, d2h_bytes = timed(step_e2e, args.steps, args.warmup, e2e_finish)
+    ms_e2e, d2h_bytes = timed(step_e2e, args.steps, args.warmup, finish)
 
     frames = args.steps * world
     value = frames / (ms_dev / 1e3)
@@ -272,42 +369,119 @@ def main():
     peaks, which = load_peaks()
     mlp_s = prof['mlp_ms'] / 1e3
     achieved = inshell * FLOP_PER_QUERY / max(mlp_s, 1e-9) / 1e12
-    peak = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
+    peak = peaks['bf16_tflops']            # burst: the kernel is timed launch by launch inside a 20 ms step, not in a seconds-long loop
+    n_launch = max(prof['mlp_launches'], 1)
+    traffic = ncu_traffic()
     line = {
         'metric': 'relit 512x512 frames/sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f16 tensor-core operands, f32 accumulate (distance MLPs); f32 elsewhere' if args.precision == 'tc' else 'f32',
         'data': 'synthetic',
-        'config': {'workload': 'xuzhen_12v_geo_fix_mat relighting, 1 envmap (main), 512x512, 1 frame per GPU per step',
+        'config': {'workload': WORKLOAD,
                    'P_rays': stats['n_rays'], 'S_fg': stats['n_fg'], 'shadow_rays': stats['n_shadow_rays'],
                    'queries_per_frame': nq // max(args.steps, 1), 'in_shell_fraction': round(inshell / max(nq, 1), 4),
-                   'parallelism': f'frame-sharded x{world}, one all-gather of pixels per step' if world > 1 else 'single GPU',
+                   'parallelism': (f'frame-sharded x{world}; one all-gather of pixels per step through ra_allgather on a side stream, double-buffered'
+                                   if world > 1 else 'single GPU'),
                    'l2': 'per-frame workspace (query lists + 2x141 MB visibility maps) exceeds the 126 MB L2; no explicit flush; the 1.95 MB fp16 weight image is L2-resident by design'},
         'clocks': clocks,
         'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': int(d2h_bytes)},
         'gpu_launches': int(launches),
         'roofline': {'kernel': 'k_mlp_tc6 (fused residual+SDF MLP, tcgen05 cta_group::2)', 'bound': 'tensor', 'achieved': achieved, 'peak': peak,
-                     'unit': 'TFLOP/s', 'frac': achieved / peak, 'frac_of_burst_peak': achieved / peaks['bf16_tflops'],
-                     'traffic': {'dram_bytes_per_launch': 32.87e6, 'algorithmic_bytes_per_launch': 16 * 2.0e6,
-                                 'source': 'profiles/r01_ncu_k_mlp_tc6_summary.txt (ncu --set full, a shadow-iteration launch of ~2 M rows: 12 B in + 4 B out per row; the 1.95 MB weight image is re-read from L2 once per 256-row pair-tile)'}, 'peak_source': f'{which} bf16_tflops_sustained',
+                     'unit': 'TFLOP/s', 'frac': achieved / peak, 'peak_source': f'{which} bf16_tflops (burst)',
+                     'frac_of_sustained_peak': achieved / peaks.get('bf16_tflops_sustained', peak),
+                     'traffic': (traffic or {}).get('dram_bytes_per_launch'), 'traffic_detail': traffic,
+                     'algorithmic_bytes_per_launch': BYTES_PER_QUERY * inshell / n_launch,
                      'algorithmic_flop_per_query': FLOP_PER_QUERY, 'kernel_ms_per_step': prof['mlp_ms'] / args.steps,
                      'kernel_launches_per_step': prof['mlp_launches'] / args.steps,
                      'kernel_share_of_step': prof['mlp_ms'] / ms_dev, 'stage_ms_per_step': {k: v / args.steps for k, v in prof['stage_ms'].items()}},
     }
+
+    if not args.no_extras:
+        line['fp32_mode'] = bench_fp32(args, net, dev, frames_dev, P_max, world, rank, timed, make_steps, Renderer)
+        line['configs'] = bench_configs(args, net, dev, eng, world, rank, timed, make_steps, load_frames, Renderer, parallel, scene, torch, dist)
+    if gather is not None:
+        gather.close()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import ra_oracle as O
-        torch.set_num_threads(os.cpu_count())
-        b = scene.make_batch(SAMPLE_H, SAMPLE_H, seed=0, n_env=0)
-        t, _ = cpu_reference_step(O.Cfg(), b, sd, O, torch)      # warm
-        ts = [cpu_reference_step(O.Cfg(), b, sd, O, torch)[0] for _ in range(3)]
-        t = statistics.median(ts)
-        P_s = b['ray_o'].shape[1]
-        line['cpu_baseline'] = {'value': (P_s / stats['n_rays']) / t, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-                                'sample': f'{SAMPLE_H}x{SAMPLE_H} relight rendering of the same view ({P_s} of {stats["n_rays"]} rays, {t:.2f} s), scaled by ray count'}
+        line['cpu_baseline'] = cpu_baseline_subprocess(25.0)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_fp32(args, net, dev, frames_dev, P_max, world, rank, timed, make_steps, Renderer):
+    """The same frames in reference-precision mode (precision='fp32': every MLP at fp32 accuracy on the fp16-split tensor GEMMs)."""
+    r32 = Renderer(net, mode='relight', device=dev, precision='fp32', max_rays=P_max + 1024, test_light=('main',), sync_timing=False)
+    step_device, _, finish = make_steps(r32, frames_dev, None, len(frames_dev), None, P_max)
+    steps = max(2, min(args.steps, 4))
+    ms, _ = timed(step_device, steps, 2, finish)
+    r32.engine.close()
+    return {'value': steps * world / (ms / 1e3), 'unit': 'frames/s', 'ms_per_step': ms / steps, 'steps': steps,
+            'note': 'device-resident inputs; one host read of the shadow-ray count per frame (chunking of the fp32 GEMM chain)'}
+
+
+def bench_configs(args, net, dev, eng, world, rank, timed, make_steps, load_frames, Renderer, parallel, scene, torch, dist):
+    """BASELINE.json configs[3] and configs[4] on the ranks of this run."""
+    res = {}
+    # ---- configs[3]: relighting, 8 env-maps, 512x512, rays tile-sharded over the ranks (strong scaling)
+    b = scene.make_batch(H, W, frame=0, n_frames=SEQ_FRAMES, seed=0, n_env=8)
+    names = list(b['novel_lights'].keys())
+    bd = {k: torch.from_numpy(v).to(dev) for k, v in b.items() if hasattr(v, 'ndim') and getattr(v, 'ndim', 0) > 0 and k != 'novel_lights'}
+    bd['novel_lights'] = {n: torch.from_numpy(p).to(dev) for n, p in b['novel_lights'].items()}
+    P = b['ray_o'].shape[1]
+    r8 = Renderer(net, mode='relight', device=dev, engine=eng, test_light=('main', 'all'), sync_timing=False)
+    C = 4 + 3 * len(names)
+
+    def pack(out):
+        return torch.cat([out['main']['rgb_map'][0], out['main']['acc_map'][0][:, None]] + [out[n]['rgb_map'][0] for n in names], dim=1)
+
+    n_pad = parallel.padded_count(P, world)
+    gat = parallel.PixelGather(eng, n_pad, C) if world > 1 else None
+    state = {}
+
+    def step_tile(step):
+        if world == 1:
+            state['full'] = pack(r8.render(bd))
+            return
+        local, own = parallel.shard_batch_rays(bd, rank, world)
+        eng.set_ray_layout(P, parallel.BLOCK, world, rank)
+        px = pack(r8.render(local))
+        eng.set_ray_layout(0, parallel.BLOCK, 1, 0)
+        slot = gat.submit(px)
+        state['full'] = parallel.deinterleave(gat.result(slot), P, world)       # every rank holds the whole frame
+
+    steps = max(3, min(args.steps, 10))
+    ms, _ = timed(step_tile, steps, 3)
+    res['tile_8env_ms'] = ms / steps
+    res['tile_8env'] = {'workload': 'xuzhen_12v_geo_fix_mat relighting, main + 8 novel envmaps, 512x512, ONE frame per step, rays tile-sharded in '
+                                    f'interleaved 32-ray blocks over {world} GPU(s); one all-gather of {C} channels per ray', 'scaling': 'strong',
+                        'ms_per_frame': ms / steps, 'frames_per_s': 1e3 * steps / ms, 'rays': int(P), 'steps': steps}
+    if world > 1:
+        unsharded = pack(r8.render(bd))
+        eq = torch.tensor([1 if torch.equal(state['full'], unsharded) else 0], device=dev)
+        dist.all_reduce(eq, op=dist.ReduceOp.MIN)
+        res['tile_equal'] = bool(eq.item())
+        res['tile_8env']['max_abs_diff_vs_unsharded'] = float((state['full'] - unsharded).abs().max())
+        gat.close()
+    else:
+        res['tile_equal'] = None          # nothing is sharded on one GPU
+    # ---- configs[4]: novel-pose sequence at 1024x1024, frame-sharded (weak scaling)
+    n_seq = 2
+    host, devs, p_max = load_frames(1024, n_seq)
+    r1k = Renderer(net, mode='relight', device=dev, precision=args.precision, max_rays=p_max + 1024, test_light=('main',), sync_timing=False)
+    gat = parallel.PixelGather(r1k.engine, p_max, 4) if world > 1 else None
+    step_device, step_e2e, finish = make_steps(r1k, devs, host, n_seq, gat, p_max)
+    steps = max(3, min(args.steps, 8))
+    ms, _ = timed(step_device, steps, 3, finish)
+    ms_e, _ = timed(step_e2e, steps, 3, finish)
+    res['seq1024_fps'] = steps * world / (ms / 1e3)
+    res['seq1024'] = {'workload': f'xuzhen_12v_geo_fix_mat novel-pose sequence, 1024x1024, frame-sharded over {world} GPU(s), one all-gather of pixels per step',
+                      'scaling': 'weak', 'frames_per_s': steps * world / (ms / 1e3), 'ms_per_step': ms / steps,
+                      'e2e_frames_per_s': steps * world / (ms_e / 1e3), 'rays_per_frame': int(p_max), 'steps': steps}
+    if gat is not None:
+        gat.close()
+    r1k.engine.close()
+    return res
 
 
 if __name__ == '__main__':

@@ -106,6 +106,7 @@ typedef struct ra_outputs {
     float* shade_map;      /* (P,3) relight only */
     float* lvis_map;       /* (P,512) optional */
     float* ldot_map;       /* (P,512) optional */
+    float* spec_map;       /* (P,3) relight only, optional: the main pass's specular view (cfg.vis_specular_map, sphere_tracing_renderer.py:739-748) */
 } ra_outputs;
 
 /* Work counters of the last render call (device-side counts read back on request; forces a sync). */
@@ -116,6 +117,8 @@ typedef struct ra_stats {
     int64_t n_queries;         /* HDQ distance queries issued (all iterations) */
     int64_t n_queries_in_shell;/* ... of which went through the MLPs */
     int64_t n_attr_samples;    /* in-shell surface/volume samples (fwd + input-gradient) */
+    int64_t n_dropped_shadow_rays; /* shadow rays beyond the workspace (256 per ray of max_rays): 0 for the reference's 16x32 light grid,
+                                      whose antipodal symmetry puts at most L/2 lights in front of a pixel; non-zero = lvis incomplete */
 } ra_stats;
 
 int  ra_create(ra_handle** out, const ra_config* cfg);
@@ -151,6 +154,43 @@ int ra_rotate_probes(ra_handle* h, const float* probe, int32_t repeat, int32_t j
  * mask_at_box: H*W bytes; out_f (H,W,4) fp32 and/or out_u8 (H,W,4) = clip(.,0,1)*255; either may be NULL. */
 int ra_assemble_image(ra_handle* h, const float* rgb_map, const float* acc_map, const unsigned char* mask_at_box, int32_t H, int32_t W,
                       float bg_brightness, float* out_f, unsigned char* out_u8, void* stream);
+/* ---- Visualizer.generate_image on the device ---------------------------------------------------------
+ * Reference: lib/visualizers/base_visualizer.py:55-231 (generate_image: the per-type map transforms, the ray -> image scatter,
+ * the light-probe overlay, the alpha channel), lib/utils/relight_utils.py:38-52 (add_light_probe), lib/utils/data_utils.py:689-709
+ * (save_image: BGR order, 16-bit png / 8-bit jpg quantisation).  A frame leaves the device as finished pixels. */
+enum { RA_VIS_RENDERING = 0, RA_VIS_NORMAL = 1, RA_VIS_ALPHA = 2, RA_VIS_DEPTH = 3, RA_VIS_SHADING = 4, RA_VIS_ALBEDO = 5,
+       RA_VIS_ROUGHNESS = 6, RA_VIS_SURFACE = 7, RA_VIS_RESIDUAL = 8, RA_VIS_SPECULAR = 9 };     /* Output (lib/config/config.py:364-378) */
+typedef struct ra_visual_inputs {   /* one light's maps in ray order, (n,3) or (n); only what the requested type reads must be non-NULL */
+    const float *rgb_map, *acc_map, *norm_map, *depth_map, *shade_map, *albedo_map, *roughness_map, *cpts_map, *bpts_map, *surf_map, *spec_map;
+    const float* cam_R;      /* (3,3) batch.cam_R, device (Normal) */
+    const float* tbounds;    /* (2,3) batch.tbounds, device (Surface) */
+} ra_visual_inputs;
+typedef struct ra_visual_config {
+    float min_clip;              /* cfg.min_clip 1.0              config.py:46 */
+    int32_t normalize_shading;   /* cfg.normalize_shading False   config.py:41 */
+    int32_t normalize_specular;  /* cfg.normalize_specular True   config.py:42 */
+    int32_t tonemapping_albedo;  /* cfg.tonemapping_albedo True   config.py:416 */
+} ra_visual_config;
+/* generate_image's rgb_map for one Output type: out (n,3) in ray order.  The percentiles of Depth / Residual / normalised
+ * Shading / Specular are exact k-th order statistics (the reference's topk(k)[0].max() / .min()) selected on the device. */
+int ra_visual_map(ra_handle* h, int32_t type, const ra_visual_inputs* in, int64_t n, const ra_visual_config* vc, float* out, void* stream);
+typedef struct ra_image_config {
+    float bg_brightness;         /* cfg.bg_brightness */
+    int32_t channels;            /* 4 with cfg.store_alpha_channel, else 3 */
+    int32_t bgr;                 /* save_image's RGB -> BGR swap for cv2 */
+    const float* probe;          /* (eh,ew,3) env-map shown in the top-left corner (cfg.probe_size_ratio > 0), or NULL */
+    int32_t eh, ew;
+    const float* probe_dirs;     /* (uH,uW,3) world-space directions of the overlay pixels = gen_light_dir(uH, uW, cam_R)  relight_utils.py:9-35 */
+    int32_t uH, uW;              /* uW = int(W * probe_size_ratio), uH = int(uW * eh / ew) */
+} ra_image_config;
+/* img = bg; img[mask_at_box] = map; overlay; alpha[mask_at_box] = acc_map -> (H,W,channels) as fp32 and / or
+ * (v*255).clip(0,255) uint8 and / or (v*65535).clip(0,65535) uint16 (any of the three outputs may be NULL). */
+int ra_assemble_visual(ra_handle* h, const float* map, const float* acc_map, const unsigned char* mask_at_box, int32_t H, int32_t W,
+                       const ra_image_config* ic, float* out_f, unsigned char* out_u8, unsigned short* out_u16, void* stream);
+/* rotate_envmap's shift_image for an image of any size (the env-map image attached to the floor rotates with the probe,
+ * relight_utils.py:74-75,103): out (n_rot,H,W,3) = image shifted by step * (j0 .. j0+n_rot-1) texels, step = iW / (env_w * repeat). */
+int ra_rotate_image(ra_handle* h, const float* image, int32_t H, int32_t W, double step, int32_t j0, int32_t n_rot, float* out, void* stream);
+
 /* ---- ground-plane shading (cfg.vis_ground_shading) -------------------------------------------------
  * Reference: sphere_tracing_renderer.py:463-548 (render_ground), :1079-1111 (ground branch of Renderer.render), :395-451
  * (blend_output_), novel_light_sphere_tracing.py:69-98,191-212 (per-env-map floor re-shade + blend), cfg.env_lvis

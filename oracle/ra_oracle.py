@@ -70,6 +70,7 @@ class Cfg:
     rough_slope: float = 0.9
     rough_bias: float = 0.09
     albedo_multiplier: float = 1.0
+    vis_specular_map: bool = False      # main pass also returns spec_map (sphere_tracing_renderer.py:739-748)
     shading_albedo: float = 0.8
     fix_material: int = 0
     always_fix_material: bool = True  # base_network.py:501-503: cond = train_motion.poses[:, fix_material] if fix_material >= 0 or always
@@ -542,12 +543,16 @@ def render_human(ray_o, ray_d, near, far, fr: Frame, W: Weights, cfg: Cfg, bbox,
     norm = normalize(norm)
     ret.update(cpts_map=cpts, bpts_map=bpts, resd_map=resd, norm_map=norm)
     if cfg.relight:
-        albedo = albedo.clip(cfg.albedo_bias, cfg.albedo_bias + cfg.albedo_slope) * cfg.albedo_multiplier
+        albedo = albedo.clip(cfg.albedo_bias, cfg.albedo_bias + cfg.albedo_slope)
+        if cfg.albedo_multiplier > 0:          # sphere_tracing_renderer.py:653-655: a non-positive multiplier means 'off'
+            albedo = albedo * cfg.albedo_multiplier
         rough = rough.clip(cfg.rough_bias, cfg.rough_bias + cfg.rough_slope)
         ret.update(albedo_map=albedo, roughness_map=rough[:, 0])
         lvis, ldot = light_visibility(surf, norm, acc, W, fr, cfg, bbox)
-        rgb, shade, _ = shade_pixels(ro, surf, norm, albedo, rough, lvis, ldot, probe, W, cfg, tonemap=cfg.tonemapping)
+        rgb, shade, spec = shade_pixels(ro, surf, norm, albedo, rough, lvis, ldot, probe, W, cfg, tonemap=cfg.tonemapping)
         ret.update(rgb_map=rgb, shade_map=shade)
+        if cfg.vis_specular_map:
+            ret.update(spec_map=spec)
         if want_lvis:
             ret.update(lvis_map=lvis.T.contiguous(), ldot_map=ldot.T.contiguous())     # (S,512)
     else:
@@ -863,11 +868,12 @@ def rays_within_bounds(H: int, W: int, K, R, T, bounds) -> dict:
     return dict(ray_o=ray_o[mask], ray_d=ray_d[mask], near=near.astype(np.float32), far=far.astype(np.float32), mask_at_box=mask.reshape(H, W))
 
 
-def rotate_probe(probe: torch.Tensor, j: int, repeat: int) -> torch.Tensor:
-    """rotate_envmap's shift_image applied to the probe (relight_utils.py:55-103): (eH,eW,3) -> (eH,eW,3)."""
+def rotate_probe(probe: torch.Tensor, j: int, repeat: int, probe_width: Optional[int] = None) -> torch.Tensor:
+    """rotate_envmap's shift_image applied to the probe (relight_utils.py:55-103): (eH,eW,3) -> (eH,eW,3); with `probe_width` = eW it
+    is the shift of the attached env-map IMAGE (iH,iW,3): image_shift = iW / (eW * repeat) * j  (:74-75)."""
     image = probe[None]
     B, H, W = image.shape[:3]
-    shift = W / (W * repeat) * j
+    shift = W / ((probe_width or W) * repeat) * j
     i, jj = torch.meshgrid(torch.arange(0, H, device=image.device), torch.arange(0, W, device=image.device), indexing='ij')
     grid = torch.stack([jj, i], dim=-1)[None].expand(B, H, W, 2).float() + 0.5
     grid = grid.clone()
@@ -890,3 +896,112 @@ def psnr(a: torch.Tensor, b: torch.Tensor) -> float:
     """base_evaluator.py:26-29."""
     mse = torch.mean((a.double() - b.double()) ** 2).item()
     return float('inf') if mse == 0 else -10 * math.log10(mse)
+
+
+# ---------------------------------------------------------------------------------------------- row f3: image assembly
+@dataclass
+class VisCfg:
+    """cfg values Visualizer.generate_image reads (lib/config/config.py:41-46,92,354,395-398,416)."""
+    bg_brightness: float = 0.0
+    store_alpha_channel: bool = True
+    probe_size_ratio: float = 0.2
+    min_clip: float = 1.0
+    normalize_shading: bool = False
+    normalize_specular: bool = True
+    tonemapping_albedo: bool = True
+    env_h: int = 16
+    env_w: int = 32
+
+
+def gen_light_xyz_dirs(h: int, w: int, r: float = 1e2) -> torch.Tensor:
+    """gen_light_xyz (relight_utils.py:423-452), positions only."""
+    lat_half, lng_half = torch.pi / h / 2, 2 * torch.pi / w / 2
+    lats = torch.linspace(torch.pi / 2 - lat_half, -torch.pi / 2 + lat_half, h)
+    lngs = torch.linspace(torch.pi - lng_half, -torch.pi + lng_half, w)
+    lngs, lats = torch.meshgrid(lngs, lats, indexing='xy')
+    return torch.stack([r * torch.cos(lats) * torch.cos(lngs), r * torch.cos(lats) * torch.sin(lngs), r * torch.sin(lats)], -1)
+
+
+def gen_light_dir(H: int, W: int, cam_R: torch.Tensor) -> torch.Tensor:
+    """relight_utils.py:9-35: overlay pixel -> world direction; cam_R (3,3) world -> camera."""
+    R = cam_R.reshape(3, 3).clone().mT.clone()
+    front = R[:, 2]
+    down = torch.zeros_like(R[:, 1])
+    down[2] = torch.sign(R[:, 1][2])
+    right = normalize(torch.linalg.cross(down, front))
+    front = normalize(torch.linalg.cross(right, down))
+    R[:, 0], R[:, 1], R[:, 2] = right, down, front
+    R[:, 1], R[:, 2] = -R[:, 2].clone(), -R[:, 1].clone()
+    return normalize(gen_light_xyz_dirs(H, W)) @ R.mT
+
+
+def kth_percentile(x: torch.Tensor, k: int, largest: bool) -> torch.Tensor:
+    """The reference's "simple version of percentile": topk(k)[0].max() / .min()   base_visualizer.py:107-108."""
+    v = x.ravel().topk(k, largest=largest)[0]
+    return v.min() if largest else v.max()
+
+
+def generate_image(output: dict, batch: dict, vtype: str, vc: VisCfg) -> torch.Tensor:
+    """Visualizer.generate_image (base_visualizer.py:55-231) for one light's maps ((P,C) tensors, B squeezed): (H,W,3|4) float32.
+    `output['envmap']` (eh,ew,3) or None; batch: mask_at_box (1,H,W), cam_R (1,3,3), tbounds (1,2,3)."""
+    mask = torch.as_tensor(batch['mask_at_box'][0]).bool()
+    H, W = mask.shape
+    g = lambda k: torch.as_tensor(output[k]).float().cpu()
+    acc = g('acc_map')
+    t = vtype.lower()
+    if t == 'normal':
+        n = normalize(g('norm_map')) @ torch.as_tensor(batch['cam_R'][0]).float().mT
+        n = n * torch.tensor([1.0, -1.0, -1.0])
+        rgb = (n * 0.5 + 0.5) * acc[:, None]
+    elif t == 'alpha':
+        rgb = acc[:, None].expand(-1, 3)
+    elif t == 'depth':
+        d = g('depth_map')
+        k = int(0.01 * d.numel())
+        lo = kth_percentile(d[acc.bool()], k, False).clip(None, vc.min_clip)
+        hi = kth_percentile(d[acc.bool()], k, True)
+        rgb = ((d - lo) / (hi - lo)).clip(0, 1)[:, None].expand(-1, 3)
+    elif t in ('shading', 'specular'):
+        rgb = g('shade_map' if t == 'shading' else 'spec_map')
+        if vc.normalize_shading if t == 'shading' else vc.normalize_specular:
+            rgb = rgb / kth_percentile(rgb, int(0.005 * rgb.numel()), True)
+    elif t == 'albedo':
+        rgb = linear2srgb(g('albedo_map')) if vc.tonemapping_albedo else g('albedo_map')
+    elif t == 'roughness':
+        rgb = g('roughness_map')[:, None].expand(-1, 3)
+    elif t == 'surface':
+        tb = torch.as_tensor(batch['tbounds'][0]).float()
+        rgb = g('cpts_map') if 'cpts_map' in output else g('surf_map')
+        rgb = acc[:, None] * ((rgb - tb[0:1]) / (tb[1:2] - tb[0:1]))
+    elif t == 'residual':
+        d = g('cpts_map') - g('bpts_map')
+        rgb = acc[:, None] * (d / kth_percentile(d, int(0.005 * d.numel()), True))
+    elif t == 'rendering':
+        rgb = g('rgb_map')
+    else:
+        raise NotImplementedError(vtype)
+    img = torch.ones(H, W, 3) * vc.bg_brightness
+    img[mask] = rgb
+    env = output.get('envmap')
+    if vc.probe_size_ratio > 0 and env is not None:                      # add_light_probe (relight_utils.py:38-52)
+        uW = int(W * vc.probe_size_ratio)
+        uH = int(uW * vc.env_h / vc.env_w)
+        dirs = gen_light_dir(uH, uW, torch.as_tensor(batch['cam_R'][0]).float())
+        img[:uH, :uW] = sample_envmap(torch.as_tensor(env).float().cpu(), dirs.reshape(-1, 3)).reshape(uH, uW, 3)
+    if vc.store_alpha_channel:
+        alpha = torch.zeros(H, W, 1)
+        alpha[mask] = acc[:, None]
+        img = torch.cat([img, alpha], -1)
+    return img
+
+
+def save_image_pixels(img: torch.Tensor, ext: str):
+    """What save_image (data_utils.py:689-709) hands to cv2.imwrite: BGR order; .png -> uint16, .jpg -> 3-channel uint8."""
+    import numpy as np
+    a = img.numpy().copy()
+    a[..., :3] = a[..., [2, 1, 0]]
+    if ext == '.png':
+        return (a * 65535).clip(0, 65535).astype(np.uint16)
+    if ext == '.jpg':
+        return (a[..., :3] * 255).clip(0, 255).astype(np.uint8)
+    return a[..., :3] if ext == '.hdr' else a

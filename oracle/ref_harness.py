@@ -106,7 +106,8 @@ def install_shims():
         return torch.cat(outs_d, 1), torch.cat(outs_i, 1), None
 
     p3o.knn_points = knn_points
-    torch.cuda.synchronize = lambda *a, **k: None
+    if not torch.cuda.is_available():
+        torch.cuda.synchronize = lambda *a, **k: None
 
 
 def setup_reference(mode: str, n_bones: int = 52):
@@ -246,9 +247,53 @@ def run_rotate(seed: int = 0, repeat: int = 4):
     return out
 
 
+VISUAL_CASES = {'main': ('rendering', 'normal', 'alpha', 'depth', 'shading', 'albedo', 'roughness', 'surface', 'residual', 'envmap'),
+                'sky00': ('rendering', 'specular', 'shading')}
+
+
+def run_visual(fixture: str = 'relight_48'):
+    """Row f3 fixture: the reference's own Visualizer.generate_image (lib/visualizers/base_visualizer.py:55-231, incl. add_light_probe and
+    the alpha channel) applied to the maps the reference rendered for tests/golden/<fixture>.npz, for every Output type the path can
+    produce; plus save_image's quantisation (lib/utils/data_utils.py:689-709) restated on two of the images through cv2-free numpy
+    (save_image itself only adds the cv2.imwrite call)."""
+    import torch
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, here)
+    g = dict(np.load(os.path.join(here, 'tests', 'golden', fixture + '.npz')))
+    cfg = setup_reference('relight')
+    cfg.probe_size_ratio = 0.2          # config.py:354 (setup_reference switches the overlay off for the rendering fixtures)
+    cfg.store_alpha_channel = True
+    from lib.config.config import Output
+    from lib.utils.base_utils import dotdict
+    from lib.visualizers.base_visualizer import Visualizer
+    from lib.utils import relight_utils as RU
+    from relightableavatar_b200 import scene
+    if not torch.cuda.is_available():      # gen_light_xyz defaults to device='cuda' (relight_utils.py:423); same arithmetic on the CPU
+        _glx = RU.gen_light_xyz
+        RU.gen_light_xyz = lambda h, w, envmap_r=1e2, device='cpu': _glx(h, w, envmap_r, device='cpu')
+    H = int(g['_H'])
+    b = scene.make_batch(H, H, seed=int(g['_seed']), n_env=int(g['_n_env']))
+    batch = to_ref_batch(b)
+    main = dotdict({k[5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('main.') and k != 'main.envmap.probe'})
+    main.envmap = dotdict(probe=torch.from_numpy(g['main.envmap.probe']))
+    outs = {'main': main}
+    for n in b['novel_lights']:
+        o = dotdict(main)
+        o.update({k[len(n) + 1:]: torch.from_numpy(v) for k, v in g.items() if k.startswith(n + '.')})
+        o.envmap = dotdict(probe=torch.from_numpy(b['novel_lights'][n]))
+        outs[n] = o
+    flat = {'_fixture': np.asarray(fixture)}
+    for n, types in VISUAL_CASES.items():
+        for t in types:
+            ty = next(o for o in Output if o.name.lower() == t)
+            img = Visualizer.generate_image(dotdict(outs[n]), batch, ty)
+            flat[f'{n}.{t}'] = np.asarray(img, np.float32)
+    return flat
+
+
 CFG_KEYS = ('dist_th', 'blend_radius', 'resd_limit', 'env_r', 'render_chunk_size', 'n_samples', 'surf_sample_range', 'fresnel_f0',
             'albedo_slope', 'albedo_bias', 'roughness_slope', 'roughness_bias', 'albedo_multiplier', 'shading_albedo', 'env_h', 'env_w',
-            'clip_near', 'clip_far', 'ground_normal', 'ground_origin', 'ground_albedo', 'ground_attach_envmap', 'ground_shading_multiplier')
+            'clip_near', 'clip_far', 'tonemapping_rendering', 'ground_normal', 'ground_origin', 'ground_albedo', 'ground_attach_envmap', 'ground_shading_multiplier')
 CFG_GROUPS = {'sphere_tracing': ('iter', 'tan_i', 'relax', 'offset', 'eps', 'shadow_skip_iter'),
               'obj_lvis': ('iter', 'offset', 'relax', 'near_offset', 'dist_th'),
               'env_lvis': ('bbox_margin', 'iter', 'offset', 'relax', 'near_offset', 'dist_th')}
@@ -297,6 +342,8 @@ def main():
         flat = run_rotate(a.seed)
     elif a.mode == 'prep':
         flat = run_prep(a.H, a.seed)
+    elif a.mode == 'visual':
+        flat = run_visual()
     else:
         flat, _ = run(a.mode, a.H, a.seed, a.n_env, not a.raw_init, frame=a.frame, azim_deg=a.azim, cam_dist=a.cam_dist, n_bones=a.n_bones, tonemapping=not a.linear,
                       fix_material=a.fix_material, always_fix_material=not a.no_always_fix_material)

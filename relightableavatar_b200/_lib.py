@@ -12,7 +12,8 @@ EXPORTS = ['ra_create', 'ra_destroy', 'ra_last_error', 'ra_upload_weights', 'ra_
            'ra_relight_envmaps', 'ra_render_anisdf_trace', 'ra_render_anisdf_volume', 'ra_query_sdf', 'ra_query_raw',
            'ra_get_stats', 'ra_launch_count', 'ra_profile_enable', 'ra_profile_read', 'ra_rotate_probes', 'ra_assemble_image',
            'ra_ground_begin', 'ra_render_ground', 'ra_relight_ground', 'ra_blend_ground', 'ra_relight_envmaps_raw',
-           'ra_upload_body', 'ra_prepare_pose', 'ra_prepare_rays', 'ra_set_ray_layout', 'ra_allgather']
+           'ra_upload_body', 'ra_prepare_pose', 'ra_prepare_rays', 'ra_set_ray_layout', 'ra_allgather', 'ra_visual_map', 'ra_assemble_visual',
+           'ra_rotate_image']
 
 fp = C.POINTER(C.c_float)
 
@@ -42,7 +43,7 @@ class ra_frame(C.Structure):
 
 
 OUTPUT_MAPS = ('rgb_map', 'acc_map', 'depth_map', 'surf_map', 'norm_map', 'cpts_map', 'bpts_map', 'resd_map', 'albedo_map',
-               'roughness_map', 'shade_map', 'lvis_map', 'ldot_map')
+               'roughness_map', 'shade_map', 'lvis_map', 'ldot_map', 'spec_map')
 
 
 class ra_outputs(C.Structure):
@@ -74,8 +75,26 @@ class ra_ground_outputs(C.Structure):
     _fields_ = [(n, fp) for n in GROUND_MAPS]
 
 
+VISUAL_INPUTS = ('rgb_map', 'acc_map', 'norm_map', 'depth_map', 'shade_map', 'albedo_map', 'roughness_map', 'cpts_map', 'bpts_map', 'surf_map',
+                 'spec_map', 'cam_R', 'tbounds')
+VIS_TYPES = {'rendering': 0, 'normal': 1, 'alpha': 2, 'depth': 3, 'shading': 4, 'albedo': 5, 'roughness': 6, 'surface': 7, 'residual': 8, 'specular': 9}
+
+
+class ra_visual_inputs(C.Structure):
+    _fields_ = [(n, fp) for n in VISUAL_INPUTS]
+
+
+class ra_visual_config(C.Structure):
+    _fields_ = [('min_clip', C.c_float), ('normalize_shading', C.c_int32), ('normalize_specular', C.c_int32), ('tonemapping_albedo', C.c_int32)]
+
+
+class ra_image_config(C.Structure):
+    _fields_ = [('bg_brightness', C.c_float), ('channels', C.c_int32), ('bgr', C.c_int32), ('probe', fp), ('eh', C.c_int32), ('ew', C.c_int32),
+                ('probe_dirs', fp), ('uH', C.c_int32), ('uW', C.c_int32)]
+
+
 class ra_stats(C.Structure):
-    _fields_ = [(n, C.c_int64) for n in ('n_rays', 'n_fg', 'n_shadow_rays', 'n_queries', 'n_queries_in_shell', 'n_attr_samples')]
+    _fields_ = [(n, C.c_int64) for n in ('n_rays', 'n_fg', 'n_shadow_rays', 'n_queries', 'n_queries_in_shell', 'n_attr_samples', 'n_dropped_shadow_rays')]
 
 
 _lib = None
@@ -117,6 +136,9 @@ def load():
     lib.ra_upload_body.argtypes = [vp, C.POINTER(ra_body), vp]
     lib.ra_prepare_pose.argtypes = [vp, vp, vp, vp, f32, C.POINTER(ra_pose_outputs), vp]
     lib.ra_prepare_rays.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.ra_visual_map.argtypes = [vp, i32, C.POINTER(ra_visual_inputs), i64, C.POINTER(ra_visual_config), vp, vp]
+    lib.ra_assemble_visual.argtypes = [vp, vp, vp, vp, i32, i32, C.POINTER(ra_image_config), vp, vp, vp, vp]
+    lib.ra_rotate_image.argtypes = [vp, vp, i32, i32, C.c_double, i32, i32, vp, vp]
     lib.ra_profile_enable.argtypes = [vp, i32]
     lib.ra_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]
     _lib = lib

@@ -101,7 +101,7 @@ __global__ void k_ground_rays(const FrameConst* __restrict__ fc, GroundCfg g, co
             lvis[(size_t)pix * L + l] = vis;
         }
         int slot = warp_append(n_shadow, trace);
-        if (trace) { sr.fg[slot] = (int)pix; sr.light[slot] = (unsigned short)l; sr.near_[slot] = nr; sr.far_[slot] = fr; }
+        if (shadow_slot_ok(sr, trace, slot)) { sr.fg[slot] = (int)pix; sr.light[slot] = (unsigned short)l; sr.near_[slot] = nr; sr.far_[slot] = fr; }
     }
 }
 

@@ -407,7 +407,7 @@ __device__ __forceinline__ float bbox_dist2(float3 p, float4 lo, float4 hi) {
 // (o may hold seed candidates otherwise).
 __device__ __forceinline__ bool knn3_near(const FrameConst* __restrict__ fc, const SortedVerts& sv, float3 p, KnnOut& o) {
     o.d2[0] = o.d2[1] = o.d2[2] = 3.0e38f;
-    o.id[0] = o.id[1] = o.id[2] = 0;
+    o.id[0] = o.id[1] = o.id[2] = -1;      // empty slots: never equal to a real sorted-vertex id (knn3_far de-duplicates against them)
     const GridRef g = grid_ref(fc, 0);
     int cx, cy, cz;
     const int c = cell_of(g, p, cx, cy, cz);

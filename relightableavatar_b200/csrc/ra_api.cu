@@ -24,6 +24,7 @@
 #include "mlp_tc2.cuh"
 #include "mlp_tc6.cuh"
 #include "lin_tc.cuh"
+#include "visual.cuh"
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -97,6 +98,7 @@ struct ra_handle {
     int* blk_cnt = nullptr; int64_t blk_cap = 0;      // image assembly scratch
     int* pix2ray = nullptr; int64_t pix_cap = 0;      // ground pass: image pixel -> ray (ra_ground_begin)
     float *g_weight = nullptr, *g_light = nullptr;
+    KthState* kth = nullptr;          // two order-statistic states (f3: Depth / Shading / Specular / Residual percentiles)
     BodyDev body; int* prep_mm = nullptr; float* prep_nacc = nullptr;      // f1: uploaded body, bounds scratch, normal accumulator    // ground pass: far-field blend weight (F), per-light radiance table (L,3)
     // ---- fp32 MLP chunk buffers
     float *Xr0, *ra_[8], *Xr4, *z8, *resd_o, *cpts_o, *Xs0, *sb_[8], *Xs4, *out257, *GA, *GB, *dpe0, *dpes, *gcp, *u4, *gbp, *nrm_o;
@@ -173,19 +175,33 @@ static void gemm(ra_handle* h, cudaStream_t st, const float* X, int ldx, const f
         const int Npad = (N + 31) / 32 * 32;
         const unsigned char* blob = lin_tc_pack(h->lin_tc, W, ldw, N, K, Npad, st);
         if (blob) {
-            static bool attr_set = false;
-            if (!attr_set) { cudaFuncSetAttribute(k_lin_tc<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES); attr_set = true; }
             LinTcArgs la{X, ldx, blob, bias, Y, ldy, aux, ldaux, count, row0, rows_cap, N, Npad, K};
             LAUNCH(h, k_lin_tc<EPI>, std::min((rows_cap + 127) / 128, 2 * h->sms), LT_THREADS, LT_SMEM_BYTES, st, la);
             return;
         }
     }
     if (h->attr_tc >= 2 && (K % G2K) == 0) {
-        static bool attr_set = false;      // one attribute call per template instance
-        if (!attr_set) { cudaFuncSetAttribute(k_gemm_tf32x3_p<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES); attr_set = true; }
         LAUNCH(h, k_gemm_tf32x3_p<EPI>, grid, 256, G2_SMEM_BYTES, st, a);
     } else if (h->attr_tc) LAUNCH(h, k_gemm_tf32x3<EPI>, grid, 256, 0, st, a);
     else LAUNCH(h, k_gemm<EPI>, grid, 256, 0, st, a);
+}
+
+// Dynamic shared-memory opt-in of every GEMM instantiation.  cudaFuncSetAttribute applies to the CURRENT device only, so this runs in
+// every ra_create (one handle per device; a process may hold handles on several GPUs), like tc_init / tc2_init / tc6_init.
+template <int EPI>
+static cudaError_t gemm_attr_one() {
+    cudaError_t e = cudaFuncSetAttribute(k_lin_tc<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_gemm_tf32x3_p<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES);
+}
+static int gemm_init(std::string& err) {
+    cudaError_t e = gemm_attr_one<EPI_NONE>();
+    if (e == cudaSuccess) e = gemm_attr_one<EPI_RELU>();
+    if (e == cudaSuccess) e = gemm_attr_one<EPI_SOFTPLUS>();
+    if (e == cudaSuccess) e = gemm_attr_one<EPI_MUL_DRELU>();
+    if (e == cudaSuccess) e = gemm_attr_one<EPI_MUL_DSOFTPLUS>();
+    if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute(attribute GEMMs): ") + cudaGetErrorString(e); return 1; }
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------- create / destroy
@@ -235,6 +251,7 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
         CK(dalloc(h, &h->lvis, (size_t)P * L)); CK(dalloc(h, &h->ldot, (size_t)P * L));
         int64_t S = 256 * P;
         CK(dalloc(h, &h->sr.fg, S)); CK(dalloc(h, &h->sr.light, S)); CK(dalloc(h, &h->sr.near_, S)); CK(dalloc(h, &h->sr.far_, S));
+        h->sr.cap = (int)std::min<int64_t>(S, 0x7fffffff);
         CK(dalloc(h, &h->sr.t, S)); CK(dalloc(h, &h->sr.occ, S)); CK(dalloc(h, &h->sr.d0, S)); CK(dalloc(h, &h->sr.q_smpl, S)); CK(dalloc(h, &h->sr.q_slot, S));
     }
     CK(dalloc(h, &h->q.bpts, (size_t)h->q_cap * 3)); CK(dalloc(h, &h->q.net, (size_t)h->q_cap));
@@ -249,6 +266,7 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     h->cnt.n_fg = h->counters_blk; h->cnt.n_shadow = h->counters_blk + 1; h->cnt.n_attr = h->counters_blk + 2;
     h->q.count = h->counters_blk + 3; h->al.count = h->cnt.n_attr;
     h->q2.count = h->counters_blk + 4;
+    h->sr.dropped = h->counters_blk + 6;          // (+5: shadow-ray counter of the floor pass)
     h->cnt.n_queries = (unsigned long long*)(h->counters_blk + 8); h->cnt.n_inshell = (unsigned long long*)(h->counters_blk + 10);
     CK(dalloc(h, &h->pt_smpl, (size_t)h->q_cap)); CK(dalloc(h, &h->pt_slot, (size_t)h->q_cap));
     CK(dalloc(h, &h->bg_spec, 4));
@@ -264,6 +282,7 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     if (tc_init(h->tc, h->err)) return 1;
     if (tc2_init(h->tc2, h->err)) return 1;
     if (tc6_init(h->err)) return 1;
+    if (gemm_init(h->err)) return 1;
     if (const char* e = getenv("RA_TC_VARIANT")) h->tc_variant = atoi(e);
     if (h->tc_variant != 1 && h->tc_variant != 2 && h->tc_variant != 6) { h->err = "RA_TC_VARIANT must be 1, 2 or 6"; return 1; }
     if (const char* e = getenv("RA_ATTR_TC")) h->attr_tc = atoi(e);
@@ -524,7 +543,10 @@ static void prof_stage(ra_handle* h, cudaStream_t st) {
     if (h->prof) cudaEventRecord(prof_event(h->ev_stage, h->ev_stage_used), st);
 }
 
-static int distance_pass(ra_handle* h, cudaStream_t st, const QueryList* ql = nullptr) {
+// `rows_bound` (fp32 mode only): a host-side upper bound of the work list's length.  The GEMM chain runs chunk by chunk over
+// [0, rows_bound); every kernel reads the true count on the device and returns early past it, so no counter is read back per
+// tracing iteration (the surface stage is bounded by P, the shadow stages by the shadow-ray count read ONCE per stage).
+static int distance_pass(ra_handle* h, cudaStream_t st, int64_t rows_bound, const QueryList* ql = nullptr) {
     const QueryList& q = ql ? *ql : h->q;
     if (h->cfg.precision == RA_PRECISION_TC) {
         if (h->prof) cudaEventRecord(prof_event(h->ev_mlp, h->ev_mlp_used), st);
@@ -534,13 +556,20 @@ static int distance_pass(ra_handle* h, cudaStream_t st, const QueryList* ql = nu
         if (h->prof) cudaEventRecord(prof_event(h->ev_mlp, h->ev_mlp_used), st);
         return 0;
     }
-    int c = 0;
-    CK(cudaMemcpyAsync(&c, q.count, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    const int64_t c = std::min<int64_t>(rows_bound, h->q_cap);
     for (int64_t row0 = 0; row0 < c; row0 += ATTR_CH) {
         int rows = (int)std::min<int64_t>(ATTR_CH, c - row0);
         mlp_forward_fp32(h, st, q.bpts + row0 * 3, q.count, (int)row0, rows, false, q.net + row0);
     }
+    return 0;
+}
+
+// one device counter -> host (fp32 mode: once per shadow stage; never on the tensor-core product path)
+static int read_counter(ra_handle* h, const int* dev, cudaStream_t st, int64_t* out) {
+    int c = 0;
+    CK(cudaMemcpyAsync(&c, dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *out = c;
     return 0;
 }
 
@@ -551,7 +580,7 @@ static int zero_outputs(ra_handle* h, const ra_outputs* o, int64_t P, cudaStream
     int L = h->cfg.env_h * h->cfg.env_w;
     struct { float* p; size_t n; } m[] = {{o->rgb_map, 3}, {o->acc_map, 1}, {o->depth_map, 1}, {o->surf_map, 3}, {o->norm_map, 3},
                                           {o->cpts_map, 3}, {o->bpts_map, 3}, {o->resd_map, 3}, {o->albedo_map, 3}, {o->roughness_map, 1},
-                                          {o->shade_map, 3}, {o->lvis_map, (size_t)L}, {o->ldot_map, (size_t)L}};
+                                          {o->shade_map, 3}, {o->lvis_map, (size_t)L}, {o->ldot_map, (size_t)L}, {o->spec_map, 3}};
     for (auto& e : m)
         if (e.p) CK(cudaMemsetAsync(e.p, 0, e.n * P * sizeof(float), st));
     return 0;
@@ -577,7 +606,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
         CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
         LAUNCH(h, k_trace_surface, g, h->tb_surf, 0, st, it, tc, h->fc, h->sv, N, ray_o, ray_d, near_, far_, (int)P, h->ss, h->q, h->cnt,
                h->surf, h->acc, h->depth, h->fg_ray);
-        if (it < c.st_iter && distance_pass(h, st)) return 1;
+        if (it < c.st_iter && distance_pass(h, st, P)) return 1;
     }
     prof_stage(h, st);
     // surface samples -> attributes
@@ -590,7 +619,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     OutMaps om{out->rgb_map, out->acc_map, out->depth_map, out->surf_map, out->norm_map, out->cpts_map, out->bpts_map, out->resd_map,
                out->albedo_map, out->roughness_map, out->shade_map};
     LAUNCH(h, k_surface_blend, grid_for(h, P), 256, 0, st, c.relight, h->cnt.n_fg, h->fg_ray, h->raw, c.n_samples, h->acc, h->surf, h->depth,
-           c.albedo_slope, c.albedo_bias, c.rough_slope, c.rough_bias, c.albedo_multiplier, h->fm, om);
+           c.albedo_slope, c.albedo_bias, c.rough_slope, c.rough_bias, c.albedo_multiplier > 0.f ? c.albedo_multiplier : 1.f /* <= 0 means 'off' (sphere_tracing_renderer.py:653) */, h->fm, om);
     if (!c.relight) { CK(cudaGetLastError()); return 0; }
     prof_stage(h, st);
     // light visibility (DFSS)
@@ -599,13 +628,15 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
            c.lv_near, c.bbox_margin, h->chunk_actual, h->lay_block, h->lay_world, h->lay_rank, h->lvis, h->ldot, h->sr, h->cnt.n_shadow);
     TraceCfg sc{c.lv_iter, 1.f, c.lv_relax, c.lv_offset, c.st_eps, c.st_skip, c.lv_dist_th, c.blend_radius};
     const bool split = h->overlap && h->cfg.precision == RA_PRECISION_TC && (h->tc_variant == 1 || h->tc_variant == 6);
+    int64_t n_sh = h->sr.cap;
+    if (h->cfg.precision == RA_PRECISION_FP32 && read_counter(h, h->cnt.n_shadow, st, &n_sh)) return 1;
     if (!split) {
         int gs = grid_for(h, P * 64, h->tb_shadow, 8 * 256 / h->tb_shadow);
         for (int it = 0; it <= c.lv_iter; it++) {
             CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
             LAUNCH(h, k_trace_shadow, gs, h->tb_shadow, 0, st, it, sc, h->fc, h->sv, N, h->cnt.n_shadow, h->fg_ray, h->surf, h->ldir, h->lsharp, L, h->sr,
                    h->q, h->cnt, h->lvis, 0, 1);
-            if (it < c.lv_iter && distance_pass(h, st)) return 1;
+            if (it < c.lv_iter && distance_pass(h, st, n_sh)) return 1;
         }
     } else {
         // Two halves of the shadow rays on two streams: while the fused MLP kernel (tensor pipe, 2 CTAs x 80 regs per SM)
@@ -620,7 +651,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
                 CK(cudaMemsetAsync(ql.count, 0, sizeof(int), ps));
                 LAUNCH(h, k_trace_shadow, gs, 128, 0, ps, it, sc, h->fc, h->sv, N, h->cnt.n_shadow, h->fg_ray, h->surf, h->ldir, h->lsharp, L,
                        h->sr, ql, h->cnt, h->lvis, part, 2);
-                if (it < c.lv_iter && distance_pass(h, ps, &ql)) return 1;
+                if (it < c.lv_iter && distance_pass(h, ps, n_sh, &ql)) return 1;
             }
         }
         CK(cudaEventRecord(h->ev_join, h->aux));
@@ -629,7 +660,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     prof_stage(h, st);
     LAUNCH(h, k_shade, grid_for(h, P * 32, 256, 8), 256, 0, st, h->cnt.n_fg, h->fg_ray, ray_o, h->surf, h->acc, h->fm, h->lvis, h->ldot,
            h->lxyz, h->larea, L, h->env_main, h->emh, h->emw, c.fresnel_f0, c.shading_albedo, 0, 1, c.tonemapping, out->rgb_map, out->shade_map,
-           (float*)nullptr);
+           out->spec_map);
     if (out->lvis_map || out->ldot_map)
         LAUNCH(h, k_scatter_lmaps, grid_for(h, P * L / 4), 256, 0, st, h->cnt.n_fg, h->fg_ray, h->acc, h->lvis, h->ldot, L, out->lvis_map, out->ldot_map);
     prof_stage(h, st);
@@ -838,11 +869,13 @@ extern "C" int ra_render_ground(ra_handle* h, const ra_ground_config* g, const f
         LAUNCH(h, k_ground_rays, grid_for(h, n * L / 4, 256, 16), 256, 0, st, h->fc, gc, out->surf_map, acc_g, (long long)p0, (long long)n, h->ldir, L,
                human_chunks, chunk_actual, out->lvis_map, h->sr, n_gshadow);
         const int gs = grid_for(h, n * 64, 256, 8);
+        int64_t n_sh = h->sr.cap;
+        if (h->cfg.precision == RA_PRECISION_FP32 && read_counter(h, n_gshadow, st, &n_sh)) return 1;
         for (int it = 0; it <= g->iter; it++) {
             CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
             LAUNCH(h, k_trace_shadow, gs, 256, 0, st, it, sc, h->fc, h->sv, N, n_gshadow, (const int*)nullptr, out->surf_map, h->ldir, h->lsharp, L,
                    h->sr, h->q, h->cnt, out->lvis_map, 0, 1);
-            if (it < g->iter && distance_pass(h, st)) return 1;
+            if (it < g->iter && distance_pass(h, st, n_sh)) return 1;
         }
     }
     LAUNCH(h, k_ground_shade, grid_for(h, F * 32, 256, 8), 256, 0, st, gc, 1, 0LL, (long long)F, h->g_weight, h->ldir, h->larea, L, h->g_light,
@@ -923,7 +956,7 @@ extern "C" int ra_query_sdf(ra_handle* h, const float* x, int64_t n, float dist_
     CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
     LAUNCH(h, k_points_front, grid_for(h, n, 256, 8), 256, 0, st, h->fc, h->sv, h->cfg.n_verts, x, (int)n, dist_th, h->cfg.blend_radius,
            h->pt_smpl, h->pt_slot, h->q, h->cnt);
-    if (distance_pass(h, st)) return 1;
+    if (distance_pass(h, st, n)) return 1;
     LAUNCH(h, k_points_finish, grid_for(h, n), 256, 0, st, h->pt_smpl, h->pt_slot, h->q.net, (int)n, dist_th, smooth, sdf);
     CK(cudaGetLastError());
     return 0;
@@ -954,6 +987,7 @@ extern "C" int ra_get_stats(ra_handle* h, ra_stats* out) {
     unsigned long long q[2];
     memcpy(q, &c[8], 16);
     out->n_queries = (int64_t)q[0]; out->n_queries_in_shell = (int64_t)q[1];
+    out->n_dropped_shadow_rays = c[6];
     return 0;
 }
 
@@ -1027,6 +1061,82 @@ extern "C" int ra_assemble_image(ra_handle* h, const float* rgb_map, const float
     LAUNCH(h, k_mask_count, nb, 256, 0, st, mask_at_box, n, h->blk_cnt);
     LAUNCH(h, k_scan_blocks, 1, 1024, 0, st, h->blk_cnt, nb);
     LAUNCH(h, k_assemble, nb, 256, 0, st, mask_at_box, n, h->blk_cnt, rgb_map, acc_map, bg_brightness, out_f, out_u8);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+/* ---- row f3 (remainder): Visualizer.generate_image on the device ------------------------------------------------------------ */
+/* rotate_envmap's shift_image for an image of any size (the env-map image attached to the floor, relight_utils.py:74-75,103) */
+extern "C" int ra_rotate_image(ra_handle* h, const float* image, int32_t H, int32_t W, double step, int32_t j0, int32_t n_rot, float* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (H <= 0 || W <= 0 || n_rot <= 0) { h->err = "ra_rotate_image: bad arguments"; return 1; }
+    LAUNCH(h, k_shift_image, grid_for(h, (long long)n_rot * H * W), 256, 0, st, image, H, W, step, j0, n_rot, out);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// k-th smallest (largest == 0) / largest element of the selection domain -> h->kth[slot].result (stays on the device)
+static int kth_select(ra_handle* h, int slot, int mode, int largest, const float* a, const float* b, long long n, long long k, cudaStream_t st) {
+    if (!h->kth) CK(dalloc(h, &h->kth, 2));
+    if (k <= 0 || k > n) { h->err = "percentile of too few elements (the reference's topk(0).max() raises as well)"; return 1; }
+    KthState* s = h->kth + slot;
+    LAUNCH(h, k_kth_init, 1, 256, 0, st, s, (unsigned)k);
+    for (int pass = 0; pass < 4; pass++) {
+        LAUNCH(h, k_kth_hist, grid_for(h, n, 256, 4), 256, 0, st, s, pass, mode, largest, a, b, n);
+        LAUNCH(h, k_kth_pick, 1, 32, 0, st, s, pass, largest);
+    }
+    return 0;
+}
+
+extern "C" int ra_visual_map(ra_handle* h, int32_t type, const ra_visual_inputs* in, int64_t n, const ra_visual_config* vc, float* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!in || !vc || !out) { h->err = "ra_visual_map: null argument"; return 1; }
+    if (n == 0) return 0;
+    VisualIn v{in->rgb_map, in->acc_map, in->norm_map, in->depth_map, in->shade_map, in->albedo_map, in->roughness_map, in->cpts_map, in->bpts_map,
+               in->surf_map, in->spec_map, in->cam_R, in->tbounds, nullptr, nullptr, vc->min_clip, 0, vc->tonemapping_albedo};
+    auto need = [&](const void* p, const char* what) { if (!p) { h->err = std::string("ra_visual_map: ") + what + " is required for this output type"; return true; } return false; };
+    switch (type) {
+    case RA_VIS_RENDERING: if (need(in->rgb_map, "rgb_map")) return 1; break;
+    case RA_VIS_NORMAL: if (need(in->norm_map, "norm_map") || need(in->acc_map, "acc_map") || need(in->cam_R, "cam_R")) return 1; break;
+    case RA_VIS_ALPHA: if (need(in->acc_map, "acc_map")) return 1; break;
+    case RA_VIS_DEPTH: {
+        if (need(in->depth_map, "depth_map") || need(in->acc_map, "acc_map")) return 1;
+        const long long k = (long long)(0.01 * (double)n);         // int(percentile * depth_map.numel())   :106
+        if (kth_select(h, 0, 2, 0, in->depth_map, in->acc_map, n, k, st) || kth_select(h, 1, 2, 1, in->depth_map, in->acc_map, n, k, st)) return 1;
+    } break;
+    case RA_VIS_SHADING: case RA_VIS_SPECULAR: {
+        const float* m = type == RA_VIS_SHADING ? in->shade_map : in->spec_map;
+        if (need(m, type == RA_VIS_SHADING ? "shade_map" : "spec_map")) return 1;
+        v.normalize = type == RA_VIS_SHADING ? vc->normalize_shading : vc->normalize_specular;
+        if (v.normalize && kth_select(h, 1, 0, 1, m, nullptr, n * 3, (long long)(0.005 * (double)(n * 3)), st)) return 1;
+    } break;
+    case RA_VIS_ALBEDO: if (need(in->albedo_map, "albedo_map")) return 1; break;
+    case RA_VIS_ROUGHNESS: if (need(in->roughness_map, "roughness_map")) return 1; break;
+    case RA_VIS_SURFACE: if (need(in->cpts_map ? in->cpts_map : in->surf_map, "cpts_map or surf_map") || need(in->acc_map, "acc_map") || need(in->tbounds, "tbounds")) return 1; break;
+    case RA_VIS_RESIDUAL:
+        if (need(in->cpts_map, "cpts_map") || need(in->bpts_map, "bpts_map") || need(in->acc_map, "acc_map")) return 1;
+        if (kth_select(h, 1, 1, 1, in->cpts_map, in->bpts_map, n * 3, (long long)(0.005 * (double)(n * 3)), st)) return 1;
+        break;
+    default: h->err = "ra_visual_map: unknown output type"; return 1;
+    }
+    v.lo = h->kth; v.hi = h->kth ? h->kth + 1 : nullptr;
+    LAUNCH(h, k_visual_map, grid_for(h, n), 256, 0, st, type, v, (long long)n, out);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ra_assemble_visual(ra_handle* h, const float* map, const float* acc_map, const unsigned char* mask_at_box, int32_t H, int32_t W,
+                                  const ra_image_config* ic, float* out_f, unsigned char* out_u8, unsigned short* out_u16, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!ic || (ic->channels != 3 && ic->channels != 4)) { h->err = "ra_assemble_visual: channels must be 3 or 4"; return 1; }
+    if (ic->probe && (!ic->probe_dirs || ic->uH > H || ic->uW > W)) { h->err = "ra_assemble_visual: probe overlay needs probe_dirs and uH <= H, uW <= W"; return 1; }
+    int n = H * W, nb = (n + 255) / 256;
+    if (nb > h->blk_cap) { hfree(h, h->blk_cnt); CK(dalloc(h, &h->blk_cnt, (size_t)nb)); h->blk_cap = nb; }
+    LAUNCH(h, k_mask_count, nb, 256, 0, st, mask_at_box, n, h->blk_cnt);
+    LAUNCH(h, k_scan_blocks, 1, 1024, 0, st, h->blk_cnt, nb);
+    AssembleArgs a{mask_at_box, n, W, h->blk_cnt, map, acc_map, ic->bg_brightness, ic->channels, ic->bgr, ic->probe, ic->eh, ic->ew,
+                   ic->probe_dirs, ic->probe ? ic->uH : 0, ic->probe ? ic->uW : 0, out_f, out_u8, out_u16};
+    LAUNCH(h, k_assemble2, nb, 256, 0, st, a);
     CK(cudaGetLastError());
     return 0;
 }

@@ -116,7 +116,15 @@ struct ShadowRays {      // SoA over traced (pixel, light) pairs
     int* fg; unsigned short* light;
     float *near_, *far_, *t, *occ, *d0, *q_smpl;
     int* q_slot;
+    int cap;             // entries the arrays hold (256 per ray of ra_config.max_rays)
+    int* dropped;        // device counter: rays that did not fit (reported by ra_get_stats; their light stays 'visible')
 };
+// append guard: a light layout with more than 256 front-facing lights per pixel (not the antipodally symmetric 16x32 grid of
+// gen_light_xyz) could generate more shadow rays than the workspace holds -- drop and count instead of writing out of bounds
+__device__ __forceinline__ bool shadow_slot_ok(const ShadowRays& sr, bool trace, int slot) {
+    if (trace && slot >= sr.cap) { atomicAdd(sr.dropped, 1); return false; }
+    return trace;
+}
 
 __device__ __forceinline__ void aabb_near_far(const float* bmin, const float* bmax, float3 o, float3 d, float& near_, float& far_) {
     // get_near_far_aabb(return_raw=True), net_utils.py:1683-1712
@@ -169,7 +177,7 @@ __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __res
             lvis[idx] = vis;
         }
         int slot = warp_append(n_shadow, trace);
-        if (trace) { sr.fg[slot] = f; sr.light[slot] = (unsigned short)l; sr.near_[slot] = nr; sr.far_[slot] = fr; }
+        if (shadow_slot_ok(sr, trace, slot)) { sr.fg[slot] = f; sr.light[slot] = (unsigned short)l; sr.near_[slot] = nr; sr.far_[slot] = fr; }
     }
 }
 
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(256, RA_TRACE_MINBLOCKS) k_trace_shadow(int it
                                ShadowRays sr, QueryList q, Counters cnt, float* lvis, int part, int nparts) {
     // rays [lo, hi) of the list: the host runs the parts on different streams so that one part's CUDA-core work overlaps
     // the other part's tensor-core MLP kernel
-    const long long Nall = *n_shadow;
+    const long long Nall = min(*n_shadow, sr.cap);
     const int lo = (int)(Nall * part / nparts), N = (int)(Nall * (part + 1) / nparts);
     for (int base = lo + blockIdx.x * blockDim.x; base < N; base += gridDim.x * blockDim.x) {      // block-uniform trip count
         int i = base + threadIdx.x;
@@ -616,7 +624,7 @@ __global__ void k_shade(const int* __restrict__ n_fg, const int* __restrict__ fg
             for (int c = 0; c < 3; c++) {
                 if (rgb) rgb[ray * 3 + c] = tone(cr[c], tonemap) * om;
                 if (shade) shade[ray * 3 + c] = cs[c] * shading_albedo / PI * om;
-                if (spec) spec[ray * 3 + c] = cp[c];
+                if (spec) spec[ray * 3 + c] = cp[c] * om;       // cfg.vis_specular_map (:739-748): spec brdf x unshadowed light, in blend_keys
             }
         }
     }

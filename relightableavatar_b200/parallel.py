@@ -118,6 +118,8 @@ def render_sequence_sharded(render_frame, n_frames: int, n_pad: int, channels: i
         f = f0 + rank
         px = render_frame(f) if f < n_frames else None
         dev = px.device if px is not None else device
+        if dev is None:        # an idle rank of the ragged last step still joins the collective: NCCL needs a CUDA buffer
+            dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend(group) == 'nccl' else torch.device('cpu')
         buf = torch.zeros(n_pad + 1, channels, dtype=torch.float32, device=dev)
         if px is not None:
             if px.shape[0] > n_pad:
@@ -130,3 +132,84 @@ def render_sequence_sharded(render_frame, n_frames: int, n_pad: int, channels: i
         for r in range(min(world, n_frames - f0)):
             n = int(out[r, 0, 0].item())
             yield f0 + r, out[r, 1:1 + n]
+
+
+class PixelGather:
+    """The one collective of a sharded step, taken off the rendering stream.
+
+    Every rank's finished, padded pixel block (n_pad x channels fp32) is all-gathered through the C-ABI's own entry point
+    `ra_allgather` (NCCL over NVLink; the communicator is created here through ctypes from a unique id that travels over
+    torch.distributed) on a SIDE stream into pre-allocated, double-buffered device memory: step s is gathered while step s+1
+    renders, so a rank never stalls on the slowest frame of the current step and no per-step allocation / zero-fill / concat
+    kernels run.  `submit(px)` -> slot; `result(slot)` -> (world, n_pad, channels) view, valid until the slot is reused two
+    submits later.  Unused rows of a block keep whatever an earlier step left there: callers slice by their own ray counts."""
+
+    def __init__(self, engine, n_pad: int, channels: int = 4, group=None, slots: int = 2):
+        import ctypes as C
+        self.C = C
+        self.engine, self.n_pad, self.channels = engine, int(n_pad), int(channels)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        dev = engine.device
+        self.dev = dev
+        self.stream = torch.cuda.Stream(dev)
+        self.send = [torch.zeros(self.n_pad, channels, device=dev) for _ in range(slots)]
+        self.recv = [torch.zeros(self.world * self.n_pad, channels, device=dev) for _ in range(slots)]
+        self.done = [None] * slots
+        self.step = 0
+        self.nccl = C.CDLL('libnccl.so.2')                 # the copy torch already loaded into this process
+        uid = (C.c_char * 128)()
+        if self.rank == 0:
+            rc = self.nccl.ncclGetUniqueId(C.byref(uid))
+            if rc != 0:
+                raise RuntimeError(f'ncclGetUniqueId returned {rc}')
+        t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0, group=group)
+
+        class _Uid(C.Structure):
+            _fields_ = [('internal', C.c_char * 128)]
+
+        u = _Uid()
+        C.memmove(C.byref(u), bytes(t.cpu().tolist()), 128)
+        self.comm = C.c_void_p()
+        self.nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, _Uid, C.c_int]
+        with torch.cuda.device(dev):
+            rc = self.nccl.ncclCommInitRank(C.byref(self.comm), self.world, u, self.rank)
+        if rc != 0:
+            raise RuntimeError(f'ncclCommInitRank returned {rc}')
+
+    def submit(self, px: torch.Tensor) -> int:
+        """px (n <= n_pad, channels) on the engine's device, produced on the current stream."""
+        C = self.C
+        slot = self.step % len(self.send)
+        self.step += 1
+        if self.done[slot] is not None:
+            torch.cuda.current_stream(self.dev).wait_event(self.done[slot])       # the slot's previous gather has drained
+        self.send[slot][: px.shape[0]].copy_(px, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.dev))
+        self.stream.wait_event(ready)
+        eng = self.engine
+        with torch.cuda.device(self.dev):
+            eng._check(eng.lib.ra_allgather(eng.h, self.comm, C.c_void_p(self.send[slot].data_ptr()), self.n_pad * self.channels,
+                                            C.c_void_p(self.recv[slot].data_ptr()), C.c_void_p(self.stream.cuda_stream)), 'ra_allgather')
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        self.done[slot] = ev
+        return slot
+
+    def result(self, slot: int) -> torch.Tensor:
+        """Makes the current stream wait for the slot's gather and returns (world, n_pad, channels)."""
+        torch.cuda.current_stream(self.dev).wait_event(self.done[slot])
+        return self.recv[slot].view(self.world, self.n_pad, self.channels)
+
+    def drain(self) -> None:
+        for ev in self.done:
+            if ev is not None:
+                torch.cuda.current_stream(self.dev).wait_event(ev)
+
+    def close(self) -> None:
+        if getattr(self, 'comm', None):
+            torch.cuda.synchronize(self.dev)
+            self.nccl.ncclCommDestroy.argtypes = [self.C.c_void_p]
+            self.nccl.ncclCommDestroy(self.comm)
+            self.comm = None

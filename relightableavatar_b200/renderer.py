@@ -59,6 +59,7 @@ FIXED_SWITCHES = dict(
     no_visibility=False, local_visibility=False, no_dfss=False, no_claybook=False, only_visibility=False,            # shadow tracing
     geometry_visibility=False, geometry_normal=False, bruteforce_st=False, check_termination_sdf=False, check_bound_sdf=False,
     zero_roughness=False, rgb_as_albedo=False, replace_light='', lambert_only=False, glossy_only=False,              # shading
+    vis_lvis_map=False, vis_ldot_map=False,             # debug views that overwrite shade_map with a visibility / cosine mean (:756-757)
     bg_brightness=0.0)
 FIXED_ST_SWITCHES = dict(tan_i_multiplier=1)          # cfg.sphere_tracing.*
 
@@ -159,6 +160,9 @@ class Engine:
             rc = self.lib.ra_create(C.byref(self.h), C.byref(cfg))
         if rc:
             msg = self.lib.ra_last_error(self.h).decode() if self.h else 'ra_create failed'
+            if self.h:
+                self.lib.ra_destroy(self.h)          # releases the partially built handle and every device block it allocated
+                self.h = None
             raise RuntimeError(f'ra_create: {msg}')
         self._keep = []          # tensors borrowed by the library until the next set_frame
         self._wkeep = []
@@ -383,6 +387,17 @@ class Engine:
             self._check(self.lib.ra_rotate_probes(self.h, _ptr(probe), int(repeat), int(j0), int(n_rot), _ptr(out), self._stream()), 'ra_rotate_probes')
         return out
 
+    def rotate_image(self, image: torch.Tensor, repeat: int, j0: int, n_rot: int) -> torch.Tensor:
+        """rotate_envmap's shift_image on the env-map IMAGE attached to the floor (relight_utils.py:74-75,103): (iH,iW,3) ->
+        (n_rot,iH,iW,3), rotation j shifts by iW / (env_w * repeat) * j texels."""
+        image = image.to(device=self.device, dtype=torch.float32).contiguous()
+        iH, iW = int(image.shape[0]), int(image.shape[1])
+        out = torch.empty(n_rot, iH, iW, 3, device=self.device)
+        step = iW / (self.config['env_w'] * repeat)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_rotate_image(self.h, _ptr(image), iH, iW, C.c_double(step), int(j0), int(n_rot), _ptr(out), self._stream()), 'ra_rotate_image')
+        return out
+
     def assemble_image(self, rgb_map: torch.Tensor, acc_map: torch.Tensor, mask_at_box: torch.Tensor, bg_brightness: float = 0.0):
         """Visualizer.generate_image's scatter (base_visualizer.py:182-202): -> (H,W,4) float RGBA and (H,W,4) uint8."""
         mask = torch.as_tensor(mask_at_box).to(self.device).reshape(mask_at_box.shape[-2], mask_at_box.shape[-1]).to(torch.uint8).contiguous()
@@ -447,10 +462,11 @@ class Renderer(torch.nn.Module):
     """
 
     def __init__(self, net, mode: str = 'relight', cfg=None, device='cuda:0', precision: str = 'tc', max_rays: int = 1 << 17,
-                 test_light=('main',), return_lvis: bool = False, to_cpu: bool = False, sync_timing: bool = True,
+                 test_light=None, return_lvis: bool = False, to_cpu: bool = False, sync_timing: bool = True,
                  ground_shading: Optional[bool] = None, ground: Optional[Dict] = None, rotate_ratio: Optional[int] = None,
                  engine=None, **overrides):
-        """`test_light`: 'main' in it keeps the learned-light rendering (cfg.test_light, novel_light_sphere_tracing.py:155).  With a
+        """`test_light` (default: cfg.test_light under a reference cfg, else ('main',)): 'main' in it keeps the learned-light
+        rendering (novel_light_sphere_tracing.py:155).  With a
         reference `cfg` every env-map of `batch.novel_lights` is rendered, as the reference does (its dataset already filtered them
         by cfg.test_light, base_dataset.py:141,159); without one, the env-maps named in `test_light` (or all of them for 'all').
         `rotate_ratio` (cfg.rotate_ratio when cfg.vis_rotate_light): every env-map is rendered at rotate_ratio * env_w rotations.
@@ -465,6 +481,8 @@ class Renderer(torch.nn.Module):
         k0 = net.state_dict()['residual_deformation_network.mlp.linears.0.weight'].shape[1]
         conf.update(n_bones=(k0 - 63) // 3)
         conf.update(precision=PRECISION[precision], max_rays=int(max_rays))
+        # cfg.vis_specular_map: the main pass also returns its specular view (sphere_tracing_renderer.py:739-748)
+        self.main_spec = bool(overrides.pop('vis_specular_map', getattr(cfg, 'vis_specular_map', False) if cfg is not None else False))
         conf.update(overrides)
         self.engine = Engine(conf, device) if engine is None else engine
         if engine is None:
@@ -476,6 +494,8 @@ class Renderer(torch.nn.Module):
         self.fix_material = getattr(cfg, 'fix_material', 0) if cfg is not None else 0
         afm = getattr(cfg, 'always_fix_material', None) if cfg is not None else None
         self.always_fix_material = True if afm is None else bool(afm)
+        if test_light is None:
+            test_light = tuple(getattr(cfg, 'test_light', None) or ()) if cfg is not None else ('main',)
         self.test_light = tuple(test_light)
         self.return_lvis = return_lvis
         self.to_cpu = to_cpu
@@ -490,24 +510,47 @@ class Renderer(torch.nn.Module):
     def _probe_of(self, light, key='probe'):
         return light.get(key) if isinstance(light, dict) else (light if key == 'probe' else None)
 
-    def _light_sweep(self, lights, names):
+    def _light_sweep(self, lights, names, with_image: bool = False):
         """rotate_envmap's enumeration (relight_utils.py:55-103): yields (name, probe (eh,ew,3) on the device) in the reference's
-        order -- every env-map once, or at rotate_ratio * env_w rotations named f'{key}-{j:04d}' (cfg.vis_rotate_light)."""
+        order -- every env-map once, or at rotate_ratio * env_w rotations named f'{key}-{j:04d}' (cfg.vis_rotate_light).
+        `with_image`: yields (name, probe, image) -- the env-map image attached to the floor rotates with the probe (:74-75,103);
+        None when the light carries no image (the floor then samples the probe)."""
         eng = self.engine
         eh, ew = eng.config['env_h'], eng.config['env_w']
         for n in names:
             probe = torch.as_tensor(self._probe_of(lights[n])).to(device=eng.device, dtype=torch.float32).reshape(eh, ew, 3).contiguous()
+            image = self._probe_of(lights[n], 'image') if with_image else None
+            if image is not None:
+                image = torch.as_tensor(image).to(device=eng.device, dtype=torch.float32)
+                image = (image[0] if image.ndim == 4 else image).contiguous()
             if self.rotate_ratio <= 0:
-                yield n, probe
+                yield (n, probe, image) if with_image else (n, probe)
                 continue
             n_rot = ew * self.rotate_ratio
-            for j0 in range(0, n_rot, 16):                      # 16 rotations per call bound the device memory of the sweep
-                rot = eng.rotate_probes(probe, self.rotate_ratio, j0, min(16, n_rot - j0))
+            # rotations per call: bounded device memory of the sweep (an 8k env-map image is 400 MB per rotation)
+            step = 16 if image is None else max(1, min(16, (1 << 28) // max(image.numel(), 1)))
+            for j0 in range(0, n_rot, step):
+                rot = eng.rotate_probes(probe, self.rotate_ratio, j0, min(step, n_rot - j0))
+                rimg = eng.rotate_image(image, self.rotate_ratio, j0, rot.shape[0]) if image is not None else None
                 for k in range(rot.shape[0]):
-                    yield f'{n}-{j0 + k:04d}', rot[k]
+                    name = f'{n}-{j0 + k:04d}'
+                    yield (name, rot[k], rimg[k] if rimg is not None else None) if with_image else (name, rot[k])
+
+    def _ensure_capacity(self, P: int) -> None:
+        """A frame with more rays than the handle was created for (e.g. the first 1024^2 frame under a cfg that carries no image
+        size) gets a larger handle: workspaces are sized by ra_config.max_rays at ra_create."""
+        eng = self.engine
+        if P <= eng.config['max_rays'] or not isinstance(eng, Engine):
+            return
+        conf = dict(eng.config, max_rays=int(P * 1.25) + 1024)
+        dev = eng.device
+        eng.close()
+        self.engine = Engine(conf, dev)
+        self.engine.upload_weights(self.net.state_dict())
 
     @torch.no_grad()
     def render(self, batch) -> dotdict:
+        self._ensure_capacity(int(torch.as_tensor(batch['ray_o']).shape[-2]))
         eng = self.engine
         eng.set_frame(batch, self.fix_material, self.always_fix_material)
         ray_o, ray_d, near, far = eng._rays(batch)
@@ -515,6 +558,8 @@ class Renderer(torch.nn.Module):
         keys = list(_MAIN_KEYS[self.mode])
         if self.mode == 'relight' and self.return_lvis:
             keys += ['lvis_map', 'ldot_map']
+        if self.mode == 'relight' and self.main_spec:
+            keys += ['spec_map']
         if self.mode != 'relight':
             out = eng.render(self.mode, ray_o, ray_d, near, far, keys)
             return dotdict({k: v[None] for k, v in out.items()})
@@ -530,18 +575,24 @@ class Renderer(torch.nn.Module):
         conv = (lambda t: t.cpu()) if self.to_cpu else (lambda t: t)
         if self.ground_shading:
             return self._render_with_ground(batch, main, P, diff, conv)
-        main_b = dotdict({k: conv(v[None]) for k, v in main.items()})
-        main_b.envmap = dotdict(probe=conv(eng.env_main[None]))
+        # `main` of the reference (:126-158): the learned-light entry keeps the `visual` keys and stays on the device; every novel light
+        # gets `{**main, **human}` (so also ray_o and, when kept, the (P,512) lvis / ldot maps) moved to the host by to_cpu (:216).
+        # The main maps are moved once and shared by all lights instead of once per light.
         if 'main' in self.test_light:
-            relight.main = main_b
+            relight.main = dotdict({k: v[None] for k, v in main.items() if k not in ('lvis_map', 'ldot_map')})
+            relight.main.envmap = dotdict(probe=eng.env_main[None])
         lights = batch.get('novel_lights') or {}
         sweep = list(self._light_sweep(lights, self._light_names(lights)))
+        shared = None
         for c0 in range(0, len(sweep), 16):                     # re-shade in groups: the stored visibility is read once per 4 probes
             group = sweep[c0:c0 + 16]
             probes = torch.stack([p for _, p in group]).contiguous()
             rgb, shade, spec = eng.relight_envmaps(probes, P)
+            if shared is None:
+                shared = dotdict({k: conv(v[None]) for k, v in main.items()})
+                shared.ray_o = conv(ray_o[None])
             for i, (n, _) in enumerate(group):
-                human = dotdict(main_b)
+                human = dotdict(shared)
                 human.update(rgb_map=conv(rgb[i][None]), shade_map=conv(shade[i][None]), spec_map=conv(spec[i][None]))
                 human.envmap = dotdict(probe=conv(probes[i][None]))
                 relight[n] = human
@@ -555,9 +606,6 @@ class Renderer(torch.nn.Module):
         floor pass over every pixel, then per light blend_output_(ground, human) into image-sized maps (mask_at_box becomes all-True)."""
         eng = self.engine
         dev = eng.device
-        if self.rotate_ratio > 0 and self._light_names(batch.get('novel_lights') or {}):
-            raise NotImplementedError('vis_rotate_light together with vis_ground_shading (the floor\'s attached env-map image would '
-                                      'have to be rotated as well, relight_utils.py:74-75,103) is not implemented')
         t = lambda k: torch.as_tensor(batch[k]).to(device=dev, dtype=torch.float32)
         meta = batch.get('meta') or {}
         H = int(torch.as_tensor(meta['H'] if 'H' in meta else batch['H']).reshape(-1)[0])
@@ -566,7 +614,7 @@ class Renderer(torch.nn.Module):
         ray_o, ray_d = get_rays(H, W, t('cam_K'), t('cam_R'), t('cam_T'))
         ground = eng.render_ground(self.ground, ray_o, ray_d, acc_g, eng.env_main)
 
-        def blend(grd: Dict, human: Dict) -> dotdict:
+        def blend(grd: Dict, human: Dict, conv=conv) -> dotdict:
             out = dotdict()
             for k in self._VISUAL + ('lvis_map', 'ldot_map'):
                 if k == 'acc_map' or (k not in grd and k not in human):
@@ -580,25 +628,32 @@ class Renderer(torch.nn.Module):
         relight = dotdict()
         human_main = {k: main[k] for k in self._VISUAL if k in main}
         if 'main' in self.test_light:
-            relight.main = blend(ground, human_main)
-            relight.main.envmap = dotdict(probe=conv(eng.env_main[None]))
+            relight.main = blend(ground, human_main, conv=lambda t: t)          # the learned-light entry stays on the device (:155-158)
+            relight.main.envmap = dotdict(probe=eng.env_main[None])
         lights = batch.get('novel_lights') or {}
-        names = self._light_names(lights)
-        if names:
-            get = lambda n, key: self._probe_of(lights[n], key)
-            probes = torch.stack([torch.as_tensor(get(n, 'probe')).to(device=dev, dtype=torch.float32).reshape(eng.config['env_h'], eng.config['env_w'], 3)
-                                  for n in names]).contiguous()
+        # every env-map once, or (cfg.vis_rotate_light) at rotate_ratio * env_w rotations of probe AND attached image
+        group = []
+
+        def flush():
+            if not group:
+                return
+            probes = torch.stack([p for _, p, _ in group]).contiguous()
             rgb, shade, spec = eng.relight_envmaps_raw(probes, P)
-            for i, n in enumerate(names):
+            for i, (n, _, img) in enumerate(group):
                 human = dict(human_main)
                 human.update(rgb_map=rgb[i], shade_map=shade[i], spec_map=spec[i])
-                img = get(n, 'image')
-                img = torch.as_tensor(img).to(device=dev, dtype=torch.float32)[0].contiguous() if img is not None else None
                 g_rgb, g_alb, g_shade, g_spec = eng.relight_ground(self.ground, probes[i], ray_d, ground, img)
                 grd = {k: ground[k] for k in self._VISUAL if k in ground}
                 grd.update(rgb_map=g_rgb, albedo_map=g_alb, shade_map=g_shade, spec_map=g_spec)
                 relight[n] = blend(grd, human)
                 relight[n].envmap = dotdict(probe=conv(probes[i][None]))
+            group.clear()
+
+        for item in self._light_sweep(lights, self._light_names(lights), with_image=True):
+            group.append(item)
+            if len(group) == 4:              # the human re-shade reads the stored visibility once per 4 probes
+                flush()
+        flush()
         if isinstance(batch.get('mask_at_box'), torch.Tensor):
             batch['mask_at_box'][:] = True           # later used for visualization (:1101)
         relight.diff = diff

@@ -29,6 +29,8 @@ CASES = [
     ('prep_24', 'prep', 24, 0, None),
     # row f4: the reference's rotate_envmap on two synthetic probes
     ('rotate_envmap', 'rotate', 0, 2, None),
+    # row f3: the reference's own Visualizer.generate_image on the maps of relight_48 (every Output type, light-probe overlay, alpha)
+    ('visual_48', 'visual', 48, 2, None),
     # a second pose / view / env-map count, and a second set of weights (seed 1, geometric-init SDF instead of the fitted one):
     # the pins above all share seed 0, frame 0 and one camera
     ('relight_40_f3_az140', 'relight', 40, 1, dict(frame=3, azim=140.0, cam_dist=2.4)),

@@ -23,8 +23,8 @@ def test_ctypes_struct_sizes_match_header():
     # 37 4-byte fields in ra_config; pointers are 8 bytes
     assert ctypes.sizeof(_lib.ra_config) == 37 * 4
     assert ctypes.sizeof(_lib.ra_frame) == 11 * 8
-    assert ctypes.sizeof(_lib.ra_outputs) == 13 * 8
-    assert ctypes.sizeof(_lib.ra_stats) == 6 * 8
+    assert ctypes.sizeof(_lib.ra_outputs) == 14 * 8
+    assert ctypes.sizeof(_lib.ra_stats) == 7 * 8
     assert ctypes.sizeof(_lib.ra_ground_config) == 16 * 4
     assert ctypes.sizeof(_lib.ra_ground_outputs) == 10 * 8
     assert ctypes.sizeof(_lib.ra_body) == 7 * 8          # 6 pointers + int32 padded to 8

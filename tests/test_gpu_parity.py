@@ -495,3 +495,113 @@ def test_config5_frame_1024_against_the_reference_itself():
     """One frame of BASELINE configs[4] (novel pose, 1024x1024, ~277 k rays = five reference pixel chunks with their cumulative
     wbounds growth) against the finished pixels of the UNMODIFIED reference (tests/golden/relight_1024_f5_pixels.npz, float16)."""
     _pixels_vs_reference('relight_1024_f5_pixels', 'tc', 45.0)
+
+
+# ---- round 2: row f3 remainder (Visualizer.generate_image on the device), rotation sweep with ground shading, main-pass spec view
+def test_generate_image_f3_every_output_type():
+    """Row f3: every Output type of Visualizer.generate_image (base_visualizer.py:55-231) incl. the light-probe overlay
+    (add_light_probe) and the alpha channel, computed by ra_visual_map + ra_assemble_visual from the maps the REFERENCE rendered
+    (tests/golden/relight_48.npz), against the reference's own generate_image output on them (tests/golden/visual_48.npz).
+    The percentiles (Depth / Residual / normalised Specular) are exact order statistics, so the tolerance is fp32 rounding."""
+    from tests.test_oracle_vs_reference import _load, _visual_inputs
+    from relightableavatar_b200.visualizer import Visualizer
+    v = _load('visual_48')
+    b, outs = _visual_inputs()
+    eng = Engine(default_config(True, precision=0, max_rays=4096), DEV)
+    vis = Visualizer(eng)
+    dev_outs = {}
+    for n, o in outs.items():
+        d = {k: t[None].to(DEV) for k, t in o.items() if k != 'envmap'}
+        d['envmap'] = {'probe': o['envmap'][None].to(DEV)}
+        dev_outs[n] = d
+    n_checked = 0
+    for key, want in v.items():
+        if key.startswith('_'):
+            continue
+        name, vtype = key.split('.')
+        got = vis.generate_image(dev_outs[name], b, vtype)
+        assert got.shape == want.shape and got.dtype == np.float32, key
+        assert np.abs(got - want).max() <= 3e-6, f'{key}: {np.abs(got - want).max():.3e}'
+        n_checked += 1
+    assert n_checked == 13
+    # save_image's pixels: BGR, uint16 png / 3-channel uint8 jpg; truncation of v*65535 may differ by one step where fp32 rounding
+    # of v crosses an integer
+    ref_img = torch.from_numpy(v['main.rendering'])
+    png = vis.encode(dev_outs['main'], b, 'rendering', '.png').cpu().numpy().view(np.uint16)
+    jpg = vis.encode(dev_outs['main'], b, 'rendering', '.jpg').cpu().numpy()
+    want_png, want_jpg = O.save_image_pixels(ref_img, '.png'), O.save_image_pixels(ref_img, '.jpg')
+    assert png.shape == want_png.shape and jpg.shape == want_jpg.shape and jpg.dtype == np.uint8
+    assert np.abs(png.astype(np.int64) - want_png.astype(np.int64)).max() <= 1 and (png != want_png).mean() < 1e-3
+    assert np.abs(jpg.astype(np.int64) - want_jpg.astype(np.int64)).max() <= 1 and (jpg != want_jpg).mean() < 1e-3
+    # one batched device -> host copy for every light x type of the frame
+    frame = vis.encode_frame(dev_outs, b, types=('rendering', 'shading'), ext='.png')
+    assert set(frame) == {(n, t) for n in dev_outs for t in ('rendering', 'shading')}
+    assert np.array_equal(frame[('main', 'rendering')], png)
+    assert vis.d2h_bytes == sum(a.nbytes for a in frame.values())
+    with pytest.raises(NotImplementedError):
+        vis.generate_image(dev_outs['main'], b, 'semantic')
+    with pytest.raises(RuntimeError, match='spec_map'):
+        vis.generate_image(dev_outs['main'], b, 'specular')          # the learned-light entry has no spec_map unless cfg.vis_specular_map
+    eng.close()
+
+
+def test_kth_order_statistic_is_exact():
+    """The device radix select behind the percentile views equals torch.topk on adversarial inputs (ties, negatives, zeros)."""
+    from relightableavatar_b200.visualizer import Visualizer
+    eng = Engine(default_config(True, precision=0, max_rays=4096), DEV)
+    vis = Visualizer(eng, normalize_shading=True, store_alpha_channel=False, probe_size_ratio=0.0)
+    g = torch.Generator().manual_seed(4)
+    for n in (700, 5000, 70001):
+        x = torch.randn(n, 3, generator=g)
+        x[::7] = 0.0; x[1::11] = x[0]; x[2::13] = -x[2::13].abs()
+        out = {'shade_map': x[None].to(DEV), 'acc_map': torch.ones(1, n, device=DEV)}
+        got = vis.visual_map(out, {}, 'shading').cpu()
+        k = int(0.005 * x.numel())
+        want = x / x.ravel().topk(k, largest=True)[0].min()
+        assert torch.equal(got, want), n
+    eng.close()
+
+
+def test_rotation_sweep_with_ground_shading():
+    """vis_rotate_light together with vis_ground_shading (relight_utils.py:55-103: probe AND the env-map image attached to the floor
+    rotate): entry f'{name}-{j:04d}' of the sweep equals the frame rendered with the pre-rotated probe / image as a plain novel light,
+    and the pre-rotation is the oracle's restatement of shift_image."""
+    H = 24
+    b = scene.make_batch(H, H, seed=0, n_env=1)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    name, probe = next(iter(b['novel_lights'].items()))
+    probe = torch.as_tensor(probe[0])
+    image = torch.nn.functional.interpolate(probe.permute(2, 0, 1)[None], size=(32, 96), mode='bilinear', align_corners=False)[0].permute(1, 2, 0).contiguous()
+    b['novel_lights'] = {name: {'probe': probe[None].numpy(), 'image': image[None].numpy()}}
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=8192, test_light=('all',),
+                 ground_shading=True, sync_timing=False, rotate_ratio=1)
+    sweep = r.render(dict(b))
+    assert len([k for k in sweep if k != 'diff']) == 32 and f'{name}-0000' in sweep and f'{name}-0031' in sweep
+    j = 5
+    rot_p, rot_i = O.rotate_probe(probe, j, 1), O.rotate_probe(image, j, 1, probe_width=32)
+    got_i = r.engine.rotate_image(image, 1, j, 1)[0].cpu()
+    assert float((got_i - rot_i).abs().max()) < 1e-5
+    b2 = dict(b); b2['novel_lights'] = {'pre': {'probe': rot_p[None].numpy(), 'image': rot_i[None].numpy()}}
+    b2['mask_at_box'] = scene.make_batch(H, H, seed=0, n_env=0)['mask_at_box']        # the ground pass sets the mask to all-True in place
+    r2 = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=8192, test_light=('all',),
+                  ground_shading=True, sync_timing=False)
+    one = r2.render(b2)['pre']
+    for k in ('rgb_map', 'albedo_map', 'shade_map', 'spec_map'):
+        e = _err(sweep[f'{name}-{j:04d}'][k], one[k])
+        assert float(e.max()) <= 2e-5, f'{k}: {float(e.max()):.3e}'
+
+
+def test_main_pass_specular_view_and_capacity_growth():
+    """cfg.vis_specular_map (sphere_tracing_renderer.py:739-748): the main pass returns spec_map (acc-premultiplied like every
+    blend key) -- against the oracle; and a frame with more rays than the handle was created for gets a larger handle."""
+    b = scene.make_batch(48, 48, seed=0, n_env=0)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=64, test_light=('main',),
+                 sync_timing=False, vis_specular_map=True)
+    out = r.render(b)['main']
+    assert r.engine.config['max_rays'] >= b['ray_o'].shape[1]
+    ref = O.render_sphere_tracing(b, sd, O.Cfg(vis_specular_map=True), torch.float32, DEV)
+    e = _err(out['spec_map'][0], ref['spec_map'])
+    assert torch.quantile(e.flatten(), 0.99) <= 1e-4 and float(out['spec_map'].abs().max()) > 0
+    st = r.engine.stats()
+    assert st['n_dropped_shadow_rays'] == 0

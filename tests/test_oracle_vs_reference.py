@@ -9,7 +9,8 @@ import torch
 from oracle import ra_oracle as O
 from relightableavatar_b200 import scene
 
-GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _load(name):
@@ -216,3 +217,64 @@ def test_scene_is_deterministic():
     g = _load('prep_24')          # and it still produces the rays the prep fixture was generated from
     b3 = scene.make_batch(24, 24, frame=int(g['_frame']), n_frames=int(g['_frame']) + 1, seed=0, n_env=0)
     assert b3['ray_o'].shape[1] == g['ray_o'].shape[0] and np.abs(b3['ray_d'][0] - g['ray_d']).max() < 1e-6
+
+
+def _visual_inputs():
+    """The maps of tests/golden/relight_48.npz (reference outputs) as generate_image inputs, B squeezed."""
+    g = _load('relight_48')
+    b = scene.make_batch(int(g['_H']), int(g['_H']), seed=int(g['_seed']), n_env=int(g['_n_env']))
+    main = {k[5:]: torch.from_numpy(v[0]) for k, v in g.items() if k.startswith('main.') and k != 'main.envmap.probe'}
+    main['envmap'] = torch.from_numpy(g['main.envmap.probe'][0])
+    outs = {'main': main}
+    for n in b['novel_lights']:
+        o = dict(main)
+        o.update({k[len(n) + 1:]: torch.from_numpy(v[0]) for k, v in g.items() if k.startswith(n + '.')})
+        o['envmap'] = torch.from_numpy(b['novel_lights'][n][0])
+        outs[n] = o
+    return b, outs
+
+
+def test_generate_image_matches_reference():
+    """Row f3: the oracle's restatement of Visualizer.generate_image (every Output type of the path, add_light_probe, alpha channel)
+    against the reference's own function run on the same maps (tests/golden/visual_48.npz)."""
+    v = _load('visual_48')
+    b, outs = _visual_inputs()
+    vc = O.VisCfg()
+    n_checked = 0
+    for key, want in v.items():
+        if key.startswith('_'):
+            continue
+        name, vtype = key.split('.')
+        if vtype == 'envmap':
+            got = outs[name]['envmap'].numpy()
+        else:
+            got = O.generate_image(outs[name], b, vtype, vc).numpy()
+        assert got.shape == want.shape, key
+        assert np.abs(got - want).max() <= 2e-6, f'{key}: {np.abs(got - want).max():.3e}'
+        n_checked += 1
+    assert n_checked == 13
+    # save_image's quantisation (data_utils.py:689-709): BGR order, uint16 png / 3-channel uint8 jpg
+    img = torch.from_numpy(v['main.rendering'])
+    png, jpg = O.save_image_pixels(img, '.png'), O.save_image_pixels(img, '.jpg')
+    assert png.dtype == np.uint16 and png.shape == (48, 48, 4) and jpg.dtype == np.uint8 and jpg.shape == (48, 48, 3)
+    assert int(png[..., 0].max()) == int((img[..., 2] * 65535).clip(0, 65535).max())
+
+
+def test_scene_light_grid_equals_the_reference_gen_light_xyz():
+    """Row a15: the light grid the synthetic state-dict carries (scene.gen_light_xyz -> light_xyz_ / light_area buffers) is what the
+    reference's own gen_light_xyz (lib/utils/relight_utils.py:423-465) produces; checked live when the reference tree is present, and
+    against the reference-rendered fixture otherwise (the harness loads the scene's buffers over the reference's, so the fixture alone
+    would not pin them)."""
+    import subprocess, sys
+    xyz, area = scene.gen_light_xyz(16, 32, 10.0)
+    try:
+        from oracle import ref_harness as RH
+        RH.find_reference()
+    except FileNotFoundError:
+        pytest.skip('reference tree not present')
+    code = ('import sys, numpy as np; sys.path.insert(0, %r); from oracle import ref_harness as RH; RH.setup_reference("relight"); '
+            'from lib.utils.relight_utils import gen_light_xyz; x, a = gen_light_xyz(16, 32, 10.0, device="cpu"); '
+            'np.savez("/tmp/_ref_light_grid.npz", xyz=x.numpy(), area=a.numpy())' % ROOT)
+    subprocess.check_call([sys.executable, '-c', code], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    ref = np.load('/tmp/_ref_light_grid.npz')
+    assert np.array_equal(ref['xyz'], xyz) and np.array_equal(ref['area'], area)

@@ -93,8 +93,20 @@ def test_light_selection_follows_the_reference(setup):
     assert r.rotate_ratio == 1
     out = r.render(b)
     assert len([k for k in out if k not in ('main', 'diff')]) == 2 * 32 and f'{names[0]}-0031' in out
-    with pytest.raises(NotImplementedError, match='vis_rotate_light'):          # refused before any floor work is launched
-        R.Renderer(net, cfg=cfg, test_light=('main',), sync_timing=False, engine=FakeEngine(), ground_shading=True).render(b)
+    # no explicit test_light under a cfg: cfg.test_light decides about 'main' (novel_light_sphere_tracing.py:155)
+    cfg.vis_rotate_light = False
+    cfg.test_light = ['main', names[0]]
+    out = R.Renderer(net, cfg=cfg, sync_timing=False, engine=FakeEngine()).render(b)
+    assert [k for k in out if k != 'diff'] == ['main'] + names
+    cfg.test_light = [names[0]]
+    out = R.Renderer(net, cfg=cfg, sync_timing=False, engine=FakeEngine()).render(b)
+    assert [k for k in out if k != 'diff'] == names
+    # the per-light dicts carry {**main, **human} like the reference's (:189): main's maps + ray_o + rgb / shade / spec + envmap
+    assert {'ray_o', 'rgb_map', 'shade_map', 'spec_map', 'acc_map', 'surf_map', 'envmap'} <= set(out[names[0]])
+    # debug views the library does not produce are refused, not ignored
+    cfg.vis_lvis_map = True
+    with pytest.raises(NotImplementedError, match='vis_lvis_map'):
+        R.Renderer(net, cfg=cfg, sync_timing=False, engine=FakeEngine())
 
 
 def test_material_condition_follows_fix_material(setup):
