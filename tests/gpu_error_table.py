@@ -50,7 +50,7 @@ print('fg', fg_g.sum().item(), fg_r.sum().item(), 'mismatch', (fg_g != fg_r).sum
 for k in ('rgb_map', 'acc_map', 'surf_map', 'albedo_map', 'roughness_map', 'shade_map', 'norm_map', 'depth_map', 'cpts_map'):
     ee = (out['main'][k][0] - ref['main'][k]).abs().flatten()
     print(f'   main.{k:14s} q50 {ee.median():.3e} q98 {torch.quantile(ee, .98):.3e} max {ee.max():.3e}')
-ee = (out['main']['lvis_map'][0] - ref['_main_full']['lvis_map']).abs().flatten()
+ee = (out[next(iter(probes))]['lvis_map'][0] - ref['_main_full']['lvis_map']).abs().flatten()      # per-light dicts carry the maps (:189)
 print(f'   lvis q98 {torch.quantile(ee[:2000000], .98):.3e} max {ee.max():.3e}')
 for n in probes:
     for k in ('rgb_map', 'shade_map', 'spec_map'):

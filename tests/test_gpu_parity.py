@@ -99,15 +99,30 @@ def test_render_relight_vs_oracle(relight_setup, precision):
     fg_g, fg_r = (main['acc_map'][0] > 0).cpu(), (ref['main']['acc_map'] > 0).cpu()
     assert fg_r.sum() > 100
     assert (fg_g != fg_r).sum() <= max(2, 0.01 * fg_r.sum())
-    tol = 1e-3 if precision == 'fp32' else 1e-2
-    for k in ('rgb_map', 'acc_map', 'surf_map', 'albedo_map', 'roughness_map', 'shade_map', 'norm_map'):
+    # Bounds = measured (profiles/r02_parity_report.log) with headroom: q98 <= 3.7e-5 / 3.3e-3, q99.8 <= 5.5e-4 / 1.9e-2, max over the
+    # pixels both sides call foreground <= 1.3e-3 / 5.7e-2 (fp32 / tensor-core mode); PSNR 79.5-97.5 / 60.3-66.3 dB.
+    q98, q998, cap, min_psnr = (2e-4, 2e-3, 1e-2, 73.0) if precision == 'fp32' else (8e-3, 4e-2, 0.15, 54.0)
+    both = (fg_g & fg_r)
+    for k in ('rgb_map', 'acc_map', 'surf_map', 'albedo_map', 'roughness_map', 'shade_map', 'norm_map', 'cpts_map', 'bpts_map'):
         e = _err(main[k][0], ref['main'][k])
-        assert torch.quantile(e.flatten(), 0.98) <= tol, f'{k}: q98 {torch.quantile(e.flatten(), 0.98):.3e}'
+        assert torch.quantile(e.flatten(), 0.98) <= q98, f'{k}: q98 {torch.quantile(e.flatten(), 0.98):.3e}'
+        assert torch.quantile(e.flatten(), 0.998) <= q998, f'{k}: q99.8 {torch.quantile(e.flatten(), 0.998):.3e}'
+        assert float(e[both].max()) <= cap, f'{k}: max over agreeing foreground pixels {float(e[both].max()):.3e}'
+    # the human visibility / cosine maps themselves (P,512), acc-premultiplied like every blend key: single shadow rays flip at
+    # grazing occluders (max error 0.34 / 1.0), so the bar is the mean and the share of entries off by more than 0.05
+    # (measured: mean 3.1e-6 / 3.0e-4, share 9e-6 / 5.7e-4; ldot q99.9 6.9e-4 / 2.7e-2)
+    any_light = next(iter(probes))
+    e = _err(out[any_light]['lvis_map'][0], ref['_main_full']['lvis_map'])
+    assert float(e.mean()) <= (5e-5 if precision == 'fp32' else 2e-3), f'lvis_map: mean {float(e.mean()):.3e}'
+    assert float((e > 0.05).float().mean()) <= (1e-4 if precision == 'fp32' else 3e-3), f'lvis_map: share > 0.05 {float((e > 0.05).float().mean()):.3e}'
+    e = _err(out[any_light]['ldot_map'][0], ref['_main_full']['ldot_map'])
+    assert torch.quantile(e.flatten()[::5], 0.999) <= (5e-3 if precision == 'fp32' else 0.1), f'ldot_map: q99.9 {torch.quantile(e.flatten()[::5], 0.999):.3e}'
+    assert 'lvis_map' not in main                       # the learned-light entry keeps the `visual` keys only (novel_light_sphere_tracing.py:142-158)
     for n in probes:
         img_g = O.assemble_image(b, out[n]['rgb_map'][0].cpu())
         img_r = O.assemble_image(b, ref[n]['rgb_map'].cpu())
         p = O.psnr(img_g, img_r)
-        assert p >= (45 if precision == 'fp32' else 35), f'{n}: PSNR {p:.1f} dB'
+        assert p >= min_psnr, f'{n}: PSNR {p:.1f} dB'
     st = r.engine.stats()
     assert st['n_fg'] == int(fg_g.sum()) and st['n_shadow_rays'] > 0 and st['n_queries_in_shell'] > 0
 
@@ -435,7 +450,7 @@ def test_destroy_releases_device_memory(relight_setup):
 
 
 # ---- full-size fixtures of the unmodified reference (BASELINE configs at their real sizes); last in the file on purpose
-def _pixels_vs_reference(fixture, precision, min_psnr):
+def _pixels_vs_reference(fixture, precision, min_psnr, min_psnr_novel=None):
     import os
     p = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', fixture + '.npz')
     if not os.path.exists(p):
@@ -453,18 +468,19 @@ def _pixels_vs_reference(fixture, precision, min_psnr):
     for name in ['main'] + list(b.get('novel_lights', {})):
         ref = torch.from_numpy(g[f'{name}.rgb_map'][0].astype(np.float32))
         psnr = O.psnr(O.assemble_image(b, out[name]['rgb_map'][0].cpu()), O.assemble_image(b, ref))
-        assert psnr >= min_psnr, f'{name}: PSNR {psnr:.1f} dB vs the reference'
+        bar = min_psnr if name == 'main' or min_psnr_novel is None else min_psnr_novel
+        assert psnr >= bar, f'{name}: PSNR {psnr:.1f} dB vs the reference (bar {bar})'
     r.engine.close()
 
 
-@pytest.mark.parametrize('precision,min_psnr', [('tc', 45.0), ('fp32', 55.0)])
-def test_metric_config_512_against_the_reference_itself(precision, min_psnr):
+@pytest.mark.parametrize('precision,min_psnr,min_psnr_novel', [('tc', 52.0, 46.0), ('fp32', 74.0, 73.0)])
+def test_metric_config_512_against_the_reference_itself(precision, min_psnr, min_psnr_novel):
     """BASELINE configs[2] at its real size (512x512, ~69 k rays, two reference pixel chunks): the finished pixels of the UNMODIFIED
     reference (tests/golden/relight_512_pixels.npz, float16) against the CUDA path.  north_star asks for PSNR within 0.1 dB of the
-    reference on photographs at ~30 dB: an image PSNR >= 45 dB against the reference itself leaves < 0.02 dB of that budget used
-    (measured this round against the oracle: 56-64 dB in tensor-core mode, > 80 dB in fp32 mode; the oracle itself is at 91 dB
-    against this fixture, profiles/r01_oracle_vs_reference_fullsize.txt)."""
-    _pixels_vs_reference('relight_512_pixels', precision, min_psnr)
+    reference on photographs at ~30 dB: an image PSNR >= 46 dB against the reference itself leaves < 0.02 dB of that budget used.
+    Bars = measured - 6 dB (profiles/r02_parity_report.log: tensor-core mode 57.7 dB learned light / 51.3 dB novel env-map, fp32 mode
+    80.5 / 79.3 dB; the oracle itself is at 91 dB against this fixture, profiles/r01_oracle_vs_reference_fullsize.txt)."""
+    _pixels_vs_reference('relight_512_pixels', precision, min_psnr, min_psnr_novel)
 
 
 def test_baseline_configs_1_and_2_against_the_reference_itself():
@@ -487,14 +503,14 @@ def test_baseline_configs_1_and_2_against_the_reference_itself():
             assert np.quantile(e, 0.98) <= 2e-3, f'{fixture}.{k}: q98 {np.quantile(e, 0.98):.3e}'
         ref = torch.from_numpy(g['rgb_map'][0].astype(np.float32))
         psnr = O.psnr(O.assemble_image(b, out['rgb_map'][0].cpu()), O.assemble_image(b, ref))
-        assert psnr >= 40.0, f'{fixture}: PSNR {psnr:.1f} dB vs the reference'
+        assert psnr >= (100.0 if mode == 'anisdf_trace' else 88.0), f'{fixture}: PSNR {psnr:.1f} dB vs the reference'      # measured 109.0 / 94.6 dB
         r.engine.close()
 
 
 def test_config5_frame_1024_against_the_reference_itself():
     """One frame of BASELINE configs[4] (novel pose, 1024x1024, ~277 k rays = five reference pixel chunks with their cumulative
     wbounds growth) against the finished pixels of the UNMODIFIED reference (tests/golden/relight_1024_f5_pixels.npz, float16)."""
-    _pixels_vs_reference('relight_1024_f5_pixels', 'tc', 45.0)
+    _pixels_vs_reference('relight_1024_f5_pixels', 'tc', 51.0)          # measured 56.9 dB
 
 
 # ---- round 2: row f3 remainder (Visualizer.generate_image on the device), rotation sweep with ground shading, main-pass spec view
@@ -503,7 +519,7 @@ def test_generate_image_f3_every_output_type():
     (add_light_probe) and the alpha channel, computed by ra_visual_map + ra_assemble_visual from the maps the REFERENCE rendered
     (tests/golden/relight_48.npz), against the reference's own generate_image output on them (tests/golden/visual_48.npz).
     The percentiles (Depth / Residual / normalised Specular) are exact order statistics, so the tolerance is fp32 rounding."""
-    from tests.test_oracle_vs_reference import _load, _visual_inputs
+    from test_oracle_vs_reference import _load, _visual_inputs          # tests/ is on sys.path (pytest rootdir-less import mode)
     from relightableavatar_b200.visualizer import Visualizer
     v = _load('visual_48')
     b, outs = _visual_inputs()
