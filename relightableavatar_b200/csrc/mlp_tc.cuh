@@ -201,47 +201,44 @@ __device__ __forceinline__ void put8(uint32_t buf, int row, int k0, const float*
 }
 
 // Positional encoding [x, sin(2^l x), cos(2^l x)]_l (embedder.py:26-37) of this thread's point into chunks [ch0, ch1)
-// of a 64-wide K-major buffer.  An accurate sincosf anchors every 4th octave; the octaves in between come from the
-// double-angle recurrence (3 doublings: error <= 8 ulp-ish, far below fp16 quantisation).
+// of a 64-wide K-major buffer.  Every feature is evaluated directly: the argument 2^l x (exact in fp32) is reduced to
+// [-pi, pi] with a two-constant Cody-Waite step (|error| < 3e-7 for |2^l x| < 2^10) and goes through the MUFU sine / cosine
+// (|error| < 1e-6 on that interval) -- ~7 instructions per (axis, octave) and far below the fp16 rounding (2.4e-4) the value
+// receives as a tensor-core operand.  (The first version anchored a double-angle recurrence on accurate sincosf calls: ~2000 clk
+// per 128 x 64 encode, every column-group warp recomputing all octaves -- the largest non-MMA item of the kernel's timeline.)
+__device__ __forceinline__ float pe_reduce(float t) {
+    const float k = rintf(t * 0.15915494309189535f);
+    float r = fmaf(k, -6.2831854820251465f, t);
+    return fmaf(k, 1.7484556000744883e-7f, r);
+}
+// feature `idx` (compile-time after unrolling) of the L-octave encoding of x; idx >= 3 + 6 L: zero padding
+template <int L>
+__device__ __forceinline__ float pe_feat(const float3& x, int idx) {
+    if (idx < 3) return idx == 0 ? x.x : (idx == 1 ? x.y : x.z);
+    if (idx >= 3 + 6 * L) return 0.f;
+    const int j = idx - 3, l = j / 6, r = j % 6, c = r % 3;
+    const float t = pe_reduce((c == 0 ? x.x : (c == 1 ? x.y : x.z)) * (float)(1 << l));
+    return (r < 3) ? __sinf(t) : __cosf(t);
+}
+template <int L, int CH>
+__device__ __forceinline__ void write_pe_chunk(uint32_t buf, int row, const float3& x) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = pe_feat<L>(x, CH * 8 + j);
+    put8(buf, row, CH * 8, v);
+}
+// chunks [ch0, ch1) with ch0 = 2 cg (four column-group warps, two chunks each) or ch0 = 4 half (two warps, four chunks each)
 template <int L>
 __device__ __forceinline__ void write_pe(uint32_t buf, int row, float3 x, int ch0, int ch1) {
-    float v[8];
-    int n = 0, ch = 0;
-    auto push = [&](float f) {
-        v[n++] = f;
-        if (n == 8) {
-            if (ch >= ch0 && ch < ch1) put8(buf, row, ch * 8, v);
-            ch++; n = 0;
-        }
-    };
-    push(x.x); push(x.y); push(x.z);
-    float s[3], c[3];
-    const float xs[3] = {x.x, x.y, x.z};
-#pragma unroll
-    for (int l = 0; l < L; l++) {
-        if ((l & 3) == 0) {
-#pragma unroll
-            for (int a = 0; a < 3; a++) sincosf(xs[a] * (float)(1 << l), &s[a], &c[a]);
-        } else {
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-                float s2 = 2.f * s[a] * c[a];
-                float c2 = (c[a] - s[a]) * (c[a] + s[a]);
-                s[a] = s2; c[a] = c2;
-            }
-        }
-        push(s[0]); push(s[1]); push(s[2]); push(c[0]); push(c[1]); push(c[2]);
+    switch (ch0) {
+    case 0: write_pe_chunk<L, 0>(buf, row, x); write_pe_chunk<L, 1>(buf, row, x); if (ch1 > 2) { write_pe_chunk<L, 2>(buf, row, x); write_pe_chunk<L, 3>(buf, row, x); } break;
+    case 2: write_pe_chunk<L, 2>(buf, row, x); write_pe_chunk<L, 3>(buf, row, x); break;
+    case 4: write_pe_chunk<L, 4>(buf, row, x); write_pe_chunk<L, 5>(buf, row, x); if (ch1 > 6) { write_pe_chunk<L, 6>(buf, row, x); write_pe_chunk<L, 7>(buf, row, x); } break;
+    default: write_pe_chunk<L, 6>(buf, row, x); write_pe_chunk<L, 7>(buf, row, x); break;
     }
-#pragma unroll
-    for (int k = 3 + 6 * L; k < 64; k++) push(0.f);
 }
-// one PE8 feature by index (used for the three features that land in a mixed chunk of the S4 skip input)
-__device__ __forceinline__ float pe_feature(float3 x, int idx) {
-    if (idx < 3) return idx == 0 ? x.x : (idx == 1 ? x.y : x.z);
-    int j = idx - 3, l = j / 6, r = j % 6, c = r % 3;
-    float v = (c == 0 ? x.x : (c == 1 ? x.y : x.z)) * (float)(1 << l);
-    return (r < 3) ? sinf(v) : cosf(v);
-}
+// one PE8 feature by index (the three features that land in a mixed chunk of the S4 skip input)
+__device__ __forceinline__ float pe_feature(float3 x, int idx) { return pe_feat<8>(x, idx); }
 
 // hidden-layer epilogue: 128 accumulator columns of this warp's rows -> activation -> fp16 A operand of the next layer.
 // Biases are already inside the accumulator (added by a K=16 rank-2 MMA step, see the MMA issuer).

@@ -30,9 +30,11 @@ struct Tc2Params {
     const int* count;
     float resd_limit;
     unsigned long long* dbg;   // optional timeline (debug builds, tools/tc6_timeline.py)
+    int skew;                  // k_mlp_tc7: layers slot 1 runs behind slot 0 (env RA_TC_SKEW, default 4)
 };
 struct Tc2Weights {
     unsigned char* blob = nullptr;
+    int skew = 4;                      // env RA_TC_SKEW (read in ra_create)
     Tc2Params p{};
     bool ready = false;
     unsigned long long* dbg = nullptr;

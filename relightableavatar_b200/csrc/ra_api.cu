@@ -23,6 +23,7 @@
 #include "mlp_tc.cuh"
 #include "mlp_tc2.cuh"
 #include "mlp_tc6.cuh"
+#include "mlp_tc7.cuh"
 #include "lin_tc.cuh"
 #include "visual.cuh"
 
@@ -69,7 +70,7 @@ struct ra_handle {
     Tc2Weights tc2;                  // ... and for its 2-CTA (cta_group::2) variant
     int attr_tc = 3;                 // env RA_ATTR_TC: 3 = tcgen05 fp16-split GEMM (lin_tc.cuh), 2 = pipelined 3xTF32 mma.sync GEMM, 1 = first 3xTF32 GEMM, 0 = CUDA-core SGEMM
     LinTcWeights lin_tc;             // packed hi / lo weight images of the attribute-pass GEMMs (built on first use)
-    int tc_variant = 6;              // env RA_TC_VARIANT: 6 = CTA-pair two-slot kernel k_mlp_tc6 (default); 1 = single-CTA kernel k_mlp_tc; 2 = first CTA-pair kernel k_mlp_tc2 (cross-checks, bit-identical)
+    int tc_variant = 6;              // env RA_TC_VARIANT: 6 = CTA-pair two-slot kernel k_mlp_tc6 (default); 7 = k_mlp_tc7 (tc6 + output layers with A in tensor memory + skewed slots: measured no faster, kept as the tcgen05.st / TS-MMA cross-check); 1 = single-CTA kernel k_mlp_tc; 2 = first CTA-pair kernel k_mlp_tc2 (all bit-identical)
     // ---- frame
     FrameConst* fc = nullptr;
     SortedVerts sv{};
@@ -282,9 +283,11 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     if (tc_init(h->tc, h->err)) return 1;
     if (tc2_init(h->tc2, h->err)) return 1;
     if (tc6_init(h->err)) return 1;
+    if (tc7_init(h->err)) return 1;
     if (gemm_init(h->err)) return 1;
     if (const char* e = getenv("RA_TC_VARIANT")) h->tc_variant = atoi(e);
-    if (h->tc_variant != 1 && h->tc_variant != 2 && h->tc_variant != 6) { h->err = "RA_TC_VARIANT must be 1, 2 or 6"; return 1; }
+    if (const char* e = getenv("RA_TC_SKEW")) h->tc2.skew = std::max(0, std::min(17, atoi(e)));
+    if (h->tc_variant != 1 && h->tc_variant != 2 && h->tc_variant != 6 && h->tc_variant != 7) { h->err = "RA_TC_VARIANT must be 1, 2, 6 or 7"; return 1; }
     if (const char* e = getenv("RA_ATTR_TC")) h->attr_tc = atoi(e);
     return 0;
 }
@@ -403,7 +406,7 @@ extern "C" int ra_set_frame(ra_handle* h, const ra_frame* f, void* stream) {
     LAUNCH(h, k_grid_fill2, (N + 255) / 256, 256, 0, st, (const float4*)h->sv.pos, N, h->vert_cell, h->sv.cell_start2, h->cell_fill, h->sv.pos2);
     LAUNCH(h, k_grid_occ, 64, 256, 0, st, h->fc, h->sv.cell_start2, (const float4*)h->sv.pos2, h->sv.occ_lo, h->sv.occ_hi);
     if (h->cfg.precision == RA_PRECISION_TC) {
-        if (h->tc_variant == 2 || h->tc_variant == 6) tc2_set_frame(h->tc2, h->fc, st, h->launches);
+        if (h->tc_variant == 2 || h->tc_variant >= 6) tc2_set_frame(h->tc2, h->fc, st, h->launches);
         else tc_set_frame(h->tc, h->fc, st, h->launches);
     }
     CK(cudaGetLastError());
@@ -550,7 +553,8 @@ static int distance_pass(ra_handle* h, cudaStream_t st, int64_t rows_bound, cons
     const QueryList& q = ql ? *ql : h->q;
     if (h->cfg.precision == RA_PRECISION_TC) {
         if (h->prof) cudaEventRecord(prof_event(h->ev_mlp, h->ev_mlp_used), st);
-        if (h->tc_variant == 6) tc6_distance(h->tc2, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
+        if (h->tc_variant == 7) tc7_distance(h->tc2, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
+        else if (h->tc_variant == 6) tc6_distance(h->tc2, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         else if (h->tc_variant == 2) tc2_distance(h->tc2, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         else tc_distance(h->tc, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         if (h->prof) cudaEventRecord(prof_event(h->ev_mlp, h->ev_mlp_used), st);
@@ -627,7 +631,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     LAUNCH(h, k_shadow_gen, grid_for(h, P * L / 4, 256, 16), 256, 0, st, h->fc, h->cnt.n_fg, h->fg_ray, h->surf, h->fm.norm, h->ldir, L,
            c.lv_near, c.bbox_margin, h->chunk_actual, h->lay_block, h->lay_world, h->lay_rank, h->lvis, h->ldot, h->sr, h->cnt.n_shadow);
     TraceCfg sc{c.lv_iter, 1.f, c.lv_relax, c.lv_offset, c.st_eps, c.st_skip, c.lv_dist_th, c.blend_radius};
-    const bool split = h->overlap && h->cfg.precision == RA_PRECISION_TC && (h->tc_variant == 1 || h->tc_variant == 6);
+    const bool split = h->overlap && h->cfg.precision == RA_PRECISION_TC && (h->tc_variant == 1 || h->tc_variant >= 6);
     int64_t n_sh = h->sr.cap;
     if (h->cfg.precision == RA_PRECISION_FP32 && read_counter(h, h->cnt.n_shadow, st, &n_sh)) return 1;
     if (!split) {
@@ -1038,7 +1042,7 @@ extern "C" int ra_debug_tc_timeline(ra_handle* h, unsigned long long* out, int e
     }
     CK(cudaDeviceSynchronize());
     // 18 x 8 entries for the single-CTA kernel; 36 x 8 ((layer, slot) x 8) for the pair kernel k_mlp_tc6
-    if (h->tc.dbg && out) CK(cudaMemcpy(out, h->tc.dbg, (h->tc_variant == 6 ? 512 : 18 * 8) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (h->tc.dbg && out) CK(cudaMemcpy(out, h->tc.dbg, (h->tc_variant >= 6 ? 512 : 18 * 8) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return 0;
 }
 
