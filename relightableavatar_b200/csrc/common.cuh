@@ -16,6 +16,7 @@
 #endif
 #define RA_GRID2_RATIO 3.0f
 #define RA_MAX_OCC 8192
+#define RA_MAX_SUP 512       // super cells (blocks of coarse cells) of the far-field 3-NN hierarchy
 #ifndef RA_NB_LEVELS
 #define RA_NB_LEVELS 4       // neighbourhood-list levels: certified search radius up to 4 fine cells (14 cm at 3.5 cm cells >= the 12.5 cm shell)
 #endif
@@ -32,7 +33,8 @@ struct FrameConst {
     float g2_h, g2_inv_h;
     int g2_dim[3];
     int g2_cells;
-    int n_occ;             // occupied coarse cells (list in SortedVerts::occ_lo/occ_hi)
+    int n_occ;             // occupied coarse cells (list in SortedVerts::occ_lo/occ_hi, grouped by super cell)
+    int n_sup;             // occupied super cells (SortedVerts::sup_lo/sup_hi)
     float wb[6];           // wbounds (2,3) as given (unpadded)
     float resd_b0[256];    // layer-0 bias + W0[:,63:219] . poses      (cond folded, base_network.py:34-40)
     float resd_b4[256];    // layer-4 bias + W4[:,256+63:475] . poses
@@ -50,6 +52,10 @@ struct SortedVerts {
     int* cell_start2; // [cells2+1]
     float4* occ_lo;   // occupied coarse cells: tight bbox min xyz, w = first vertex (int bits) in pos2
     float4* occ_hi;   //                        tight bbox max xyz, w = end vertex (int bits)
+    float4* sup_lo;   // occupied super cells (blocks of coarse cells): bbox min xyz, w = first entry (int bits) of occ_lo/occ_hi
+    float4* sup_hi;   //                                                  bbox max xyz, w = end entry
+    float4* occ_tmp;  // [2 * RA_MAX_OCC] scratch of the per-frame build
+    int* occ_sup;     // [RA_MAX_OCC] scratch: super cell of every occupied coarse cell
     // per-cell neighbourhood lists (rebuilt per frame): level 0 = the 3x3x3 block around the cell, level 1 / 2 = the cube
     // shells of radius 2 / 3.  nb_pos entries: xyz, w = index into pos/nrm/tv/T (int bits).  A query scans ONE contiguous
     // list per level instead of walking grid rows -- same candidates, no per-row control flow (warp divergence).

@@ -233,6 +233,8 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     CK(dalloc(h, &h->sv.cell_start, RA_MAX_CELLS + 1));
     CK(dalloc(h, &h->sv.pos2, N)); CK(dalloc(h, &h->sv.cell_start2, RA_MAX_CELLS + 1));
     CK(dalloc(h, &h->sv.occ_lo, RA_MAX_OCC)); CK(dalloc(h, &h->sv.occ_hi, RA_MAX_OCC));
+    CK(dalloc(h, &h->sv.sup_lo, RA_MAX_SUP)); CK(dalloc(h, &h->sv.sup_hi, RA_MAX_SUP));
+    CK(dalloc(h, &h->sv.occ_tmp, 2 * RA_MAX_OCC)); CK(dalloc(h, &h->sv.occ_sup, RA_MAX_OCC));
     {
         for (int lv = 0; lv < RA_NB_LEVELS; lv++) {
             const int r = lv + 1;          // cells per level = how often a vertex can appear: 27, then the shells 98, 218, 386, ...
@@ -404,7 +406,7 @@ extern "C" int ra_set_frame(ra_handle* h, const ra_frame* f, void* stream) {
     LAUNCH(h, k_grid_count, (N + 255) / 256, 256, 0, st, h->fc, 1, f->pverts, (const float4*)h->sv.pos, N, h->cell_count, h->vert_cell);
     LAUNCH(h, k_grid_scan, 1, 1024, 0, st, h->fc, 1, h->cell_count, h->sv.cell_start2, h->cell_fill);
     LAUNCH(h, k_grid_fill2, (N + 255) / 256, 256, 0, st, (const float4*)h->sv.pos, N, h->vert_cell, h->sv.cell_start2, h->cell_fill, h->sv.pos2);
-    LAUNCH(h, k_grid_occ, 64, 256, 0, st, h->fc, h->sv.cell_start2, (const float4*)h->sv.pos2, h->sv.occ_lo, h->sv.occ_hi);
+    LAUNCH(h, k_grid_occ, 1, 1024, 0, st, h->fc, h->sv.cell_start2, (const float4*)h->sv.pos2, h->sv);
     if (h->cfg.precision == RA_PRECISION_TC) {
         if (h->tc_variant == 2 || h->tc_variant >= 6) tc2_set_frame(h->tc2, h->fc, st, h->launches);
         else tc_set_frame(h->tc, h->fc, st, h->launches);

@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256, RA_TRACE_MINBLOCKS) k_trace_shadow(int it
         if (it < cfg.iters) {
             HdqFront hf; hf.in_shell = false; hf.smpl = 0.f;
             const bool ask = alive && !parked;
-            hdq_front<false>(fc, sv, nverts, o + d * t, ask, cfg.th, cfg.blend_radius, hf);
+            hdq_front<false>(fc, sv, nverts, o + d * t, ask, cfg.th, cfg.blend_radius, hf, 32);      // shadow rays: far lanes are served by the whole warp
             bool ins = ask && hf.in_shell;
             count_queries(cnt, ask, ins);
             int slot = warp_append(q.count, ins);

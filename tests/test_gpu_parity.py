@@ -622,3 +622,32 @@ def test_main_pass_specular_view_and_capacity_growth():
     assert torch.quantile(e.flatten(), 0.99) <= 1e-4 and float(out['spec_map'].abs().max()) > 0
     st = r.engine.stats()
     assert st['n_dropped_shadow_rays'] == 0
+
+
+def test_far_field_knn_is_exact():
+    """Far-field branch of the exact 3-NN (two-level box hierarchy: super cells -> occupied coarse cells -> vertices): points 0.2-3 m
+    away from the body, among them points beyond every corner of the body's bounding box (the nearest vertices of the minimum corner
+    are the first entries of the cell-sorted vertex array: sorted vertex 0 must be found like any other).  Out of the shell the
+    distance is the mean signed distance to the three nearest vertices: any wrong neighbour shows at the 1e-3 level, fp32 rounding
+    at 1e-6."""
+    b = scene.make_batch(32, 32, seed=0, n_env=0)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    cfg = O.Cfg()
+    eng = Engine(default_config(True, precision=0, max_rays=8192), DEV)
+    eng.upload_weights(sd); eng.set_frame(b)
+    g = torch.Generator().manual_seed(11)
+    wv = torch.as_tensor(b['wverts'][0])
+    lo, hi = wv.min(0)[0], wv.max(0)[0]
+    corners = torch.stack([torch.where(torch.tensor([(i >> k) & 1 for k in range(3)]).bool(), hi, lo) for i in range(8)])
+    out_dir = torch.nn.functional.normalize(corners - (lo + hi) / 2, dim=-1)
+    pts = [corners[i] + out_dir[i] * r + torch.randn(200, 3, generator=g) * 0.05 for i in range(8) for r in (0.2, 0.6, 2.0)]
+    idx = torch.randint(0, wv.shape[0], (6000,), generator=g)
+    pts.append(wv[idx] + torch.nn.functional.normalize(torch.randn(6000, 3, generator=g), dim=-1) * (0.2 + 2.8 * torch.rand(6000, 1, generator=g)))
+    x = torch.cat(pts).float()
+    got = eng.query_sdf(x, 0.125, True)
+    W = O.Weights(sd, torch.float32, DEV); fr = O.Frame.from_batch(b, cfg, torch.float32, DEV)
+    with torch.no_grad():
+        ref = O.hdq_distance(x.to(DEV), fr, W, cfg, 0.125, True)[:, 0]
+    e = _err(got, ref)
+    assert float(e.max()) <= 2e-5, f'max {float(e.max()):.3e} at {x[e.argmax()].tolist()}'
+    eng.close()
