@@ -52,6 +52,9 @@ typedef struct ra_config {
     int32_t env_h, env_w;       /* 16, 32 */
     int32_t vol_samples;        /* 128: base_renderer uniform samples            base.yaml:78 */
     float clip_near, clip_far;  /* 0.02, 10                                      config.py:79-80 */
+    int32_t visibility_mode;    /* 0: DFSS soft-shadow tracing; 1: cfg.local_visibility (lvis = n.l > 0); 2: cfg.no_visibility (lvis = 1)
+                                   sphere_tracing_renderer.py:296-301 */
+    int32_t brdf_mode;          /* 0: glossy + Lambert; 1: cfg.lambert_only; 2: cfg.glossy_only     relight_utils.py:563-568 */
     int32_t tonemapping;        /* 1: the main pass's rgb passes linear2srgb (cfg.tonemapping_rendering, config.py:417); 0 for
                                    .exr/.hdr output (config.py:446-448)   sphere_tracing_renderer.py:523,731.  The novel-light
                                    re-shade maps unconditionally, as the reference does (novel_light_sphere_tracing.py:48,94) */
@@ -142,6 +145,9 @@ int ra_set_ray_layout(ra_handle* h, int64_t global_P, int32_t block, int32_t wor
  * world * n_floats.  libnccl.so.2 is resolved at the first call (dlopen), the library has no link-time NCCL dependency; the
  * Python mirror uses torch.distributed.all_gather_into_tensor for the same exchange (relightableavatar_b200/parallel.py). */
 int ra_allgather(ra_handle* h, void* comm, const float* send, int64_t n_floats, float* recv, void* stream);
+/* cfg.replace_light (sphere_tracing_renderer.py:1068-1069): `probe` (ph,pw,3, device, copied) lights the main pass of the following
+ * ra_render_relight calls instead of the learned env-map; NULL restores the learned one. */
+int ra_set_main_light(ra_handle* h, const float* probe, int32_t ph, int32_t pw, void* stream);
 /* novel_light_sphere_tracing per-env-map re-shade (a19): probes (n_env,16,32,3); rgb/shade/spec (n_env,P,3).
  * Uses the maps of the preceding ra_render_relight call (kept in the workspace). */
 int ra_relight_envmaps(ra_handle* h, const float* probes, int32_t n_env, float* rgb, float* shade, float* spec,
@@ -287,6 +293,10 @@ int ra_render_anisdf_volume(ra_handle* h, const float* ray_o, const float* ray_d
 int ra_query_sdf(ra_handle* h, const float* x, int64_t n, float dist_th, int32_t smooth, float* sdf, void* stream);
 /* net(x, v, d, batch).raw (eval): x,v (n,3) -> raw (n, 17 | 16), zero rows out of shell */
 int ra_query_raw(ra_handle* h, const float* x, const float* v, int64_t n, float* raw, void* stream);
+
+/* exact K=3 nearest posed vertices (pytorch3d.ops.knn_points at sample_utils.py:122): x (n,3) world -> ids (n,3) vertex indices,
+ * nearest first, d2 (n,3) squared distances in pose space */
+int ra_query_knn(ra_handle* h, const float* x, int64_t n, int32_t* ids, float* d2, void* stream);
 
 int ra_get_stats(ra_handle* h, ra_stats* out);   /* synchronises the device */
 /* Device-side timing for bench.py's roofline line: when enabled, every launch of the fused MLP kernel and every

@@ -71,6 +71,10 @@ class Cfg:
     rough_bias: float = 0.09
     albedo_multiplier: float = 1.0
     vis_specular_map: bool = False      # main pass also returns spec_map (sphere_tracing_renderer.py:739-748)
+    no_visibility: bool = False         # lvis = 1                      sphere_tracing_renderer.py:296-298
+    local_visibility: bool = False      # lvis = (n.l > 0)              :299-301
+    lambert_only: bool = False          # relight_utils.py:563-568
+    glossy_only: bool = False
     shading_albedo: float = 0.8
     fix_material: int = 0
     always_fix_material: bool = True  # base_network.py:501-503: cond = train_motion.poses[:, fix_material] if fix_material >= 0 or always
@@ -350,6 +354,10 @@ def light_visibility(surf, norm, acc, W: Weights, fr: Frame, cfg: Cfg, bbox: tor
     L = W.light_xyz.reshape(-1, 3)
     ldir = normalize(L)                                                     # (512,3)
     ldot = (ldir[:, None] * norm[None]).sum(-1)                             # (512,S)
+    if cfg.no_visibility:
+        return torch.ones_like(ldot), ldot
+    if cfg.local_visibility:
+        return (ldot > 0).to(ldot), ldot
     lfrt = (ldot > 0) & (acc[None] > 0)
     li, pi = lfrt.nonzero(as_tuple=True)
     ro, rd = surf[pi], ldir[li]
@@ -402,7 +410,7 @@ def safe_divide(a: torch.Tensor, b: torch.Tensor, eps: float = 1e-8) -> torch.Te
     return div.clip(-1e10, 1e10)
 
 
-def microfacet(pts2l, pts2c, normal, albedo, rough, f0: float):
+def microfacet(pts2l, pts2c, normal, albedo, rough, f0: float, lambert_only: bool = False, glossy_only: bool = False):
     """relight_utils.py:484-615 with cancel_cosine=True.  pts2l (N,L,3), others (N,3)/(N,1) -> (N,L,3)."""
     pts2l = F.normalize(pts2l, p=2, dim=-1, eps=1e-7)
     pts2c = F.normalize(pts2c, p=2, dim=-1, eps=1e-7)
@@ -429,6 +437,10 @@ def microfacet(pts2l, pts2c, normal, albedo, rough, f0: float):
     g = safe_divide(chi_g * 2, 1 + torch.sqrt(1 + alpha ** 2 * tv2[:, None]))
     denom = 4 * torch.abs(torch.ones_like(l_dot_n)) * torch.abs(v_dot_n)[:, None]
     spec = safe_divide(f * g * d, denom)
+    if lambert_only:
+        return lambert
+    if glossy_only:
+        return spec[:, :, None].repeat(1, 1, 3)
     return spec[:, :, None].repeat(1, 1, 3) + lambert
 
 
@@ -450,10 +462,10 @@ def shade_pixels(ray_o, surf, norm, albedo, rough, lvis, ldot, probe, W: Weights
         s2c = normalize(ray_o[sl] - surf[sl])
         light = sample_envmap(probe, s2l)                                   # (n,512,3)
         lv, ld = lvis[:, sl].T, ldot[:, sl].T                               # (n,512)
-        brdf = microfacet(s2l, s2c, norm[sl], albedo[sl], rough[sl], cfg.fresnel_f0)
+        brdf = microfacet(s2l, s2c, norm[sl], albedo[sl], rough[sl], cfg.fresnel_f0, cfg.lambert_only, cfg.glossy_only)
         shade = lv[..., None] * 1.0 * area[None, :, None] * light           # ldot := 1 (cancel_cosine)
         rgbs.append(linear2srgb((brdf * shade).sum(1)) if tonemap else (brdf * shade).sum(1))
-        sb = microfacet(s2l, s2c, norm[sl], torch.zeros_like(albedo[sl]), rough[sl], cfg.fresnel_f0)
+        sb = microfacet(s2l, s2c, norm[sl], torch.zeros_like(albedo[sl]), rough[sl], cfg.fresnel_f0, cfg.lambert_only, cfg.glossy_only)
         # spec: lvis=1, ldot := 1/(|ones|+1e-8)   (sphere_tracing_renderer.py:739-749)
         specs.append((sb * (1.0 / (1.0 + 1e-8)) * area[None, :, None] * light).sum(1))
         shades.append((lv[..., None] * ld[..., None] * area[None, :, None] * light).sum(1) * cfg.shading_albedo / math.pi)
@@ -686,7 +698,7 @@ def render_ground_pass(batch: dict, ret: dict, fr: Frame, W: Weights, cfg: Cfg, 
 
 
 def render_sphere_tracing(batch: dict, sd: dict, cfg: Cfg, dtype=torch.float32, device='cpu', want_lvis=True, ground=False,
-                          tangent_scale: float = 1.0, inds_fn=None) -> dict:
+                          tangent_scale: float = 1.0, inds_fn=None, main_probe=None) -> dict:
     """sphere_tracing_renderer.Renderer.render (:1066-1115): chunked get_pixel_value with the in-place wbounds growth, then
     alpha_output_ -- or, with ground=True (cfg.vis_ground_shading, vis_novel_light on), the UN-premultiplied human maps plus
     ret['ground'] (the floor pass over all H*W pixels)."""
@@ -696,6 +708,8 @@ def render_sphere_tracing(batch: dict, sd: dict, cfg: Cfg, dtype=torch.float32, 
     ray_o, ray_d, near, far = t(batch['ray_o'][0]), t(batch['ray_d'][0]), t(batch['near'][0]), t(batch['far'][0])
     P = ray_o.shape[0]
     probe = W.env_main if cfg.relight else None
+    if main_probe is not None:                                                # cfg.replace_light (:1068-1069)
+        probe = torch.as_tensor(main_probe).to(device=device, dtype=dtype)
     n_chunks = max(math.ceil(P / cfg.render_chunk), 1)
     actual = math.ceil(P / n_chunks) if P else 1                              # net_utils.py:323
     rets = []

@@ -13,7 +13,7 @@ EXPORTS = ['ra_create', 'ra_destroy', 'ra_last_error', 'ra_upload_weights', 'ra_
            'ra_get_stats', 'ra_launch_count', 'ra_profile_enable', 'ra_profile_read', 'ra_rotate_probes', 'ra_assemble_image',
            'ra_ground_begin', 'ra_render_ground', 'ra_relight_ground', 'ra_blend_ground', 'ra_relight_envmaps_raw',
            'ra_upload_body', 'ra_prepare_pose', 'ra_prepare_rays', 'ra_set_ray_layout', 'ra_allgather', 'ra_visual_map', 'ra_assemble_visual',
-           'ra_rotate_image']
+           'ra_rotate_image', 'ra_set_main_light', 'ra_query_knn']
 
 fp = C.POINTER(C.c_float)
 
@@ -28,7 +28,8 @@ class ra_config(C.Structure):
                 ('surf_sample_range', C.c_float), ('fresnel_f0', C.c_float), ('albedo_slope', C.c_float),
                 ('albedo_bias', C.c_float), ('rough_slope', C.c_float), ('rough_bias', C.c_float),
                 ('albedo_multiplier', C.c_float), ('shading_albedo', C.c_float), ('env_h', C.c_int32), ('env_w', C.c_int32),
-                ('vol_samples', C.c_int32), ('clip_near', C.c_float), ('clip_far', C.c_float), ('tonemapping', C.c_int32)]
+                ('vol_samples', C.c_int32), ('clip_near', C.c_float), ('clip_far', C.c_float), ('visibility_mode', C.c_int32), ('brdf_mode', C.c_int32),
+                ('tonemapping', C.c_int32)]
 
 
 class ra_weights(C.Structure):
@@ -139,6 +140,8 @@ def load():
     lib.ra_visual_map.argtypes = [vp, i32, C.POINTER(ra_visual_inputs), i64, C.POINTER(ra_visual_config), vp, vp]
     lib.ra_assemble_visual.argtypes = [vp, vp, vp, vp, i32, i32, C.POINTER(ra_image_config), vp, vp, vp, vp]
     lib.ra_rotate_image.argtypes = [vp, vp, i32, i32, C.c_double, i32, i32, vp, vp]
+    lib.ra_set_main_light.argtypes = [vp, vp, i32, i32, vp]
+    lib.ra_query_knn.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.ra_profile_enable.argtypes = [vp, i32]
     lib.ra_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]
     _lib = lib

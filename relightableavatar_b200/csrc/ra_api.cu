@@ -65,6 +65,7 @@ struct ra_handle {
     float* w4_skipT = nullptr;       // resd WT4 rows 256..319 live inside resd[4].wt; helper pointers below
     float beta = 0.1f;
     float *env_main = nullptr; int emh = 0, emw = 0;
+    float* main_light = nullptr; int mlh = 0, mlw = 0;      // cfg.replace_light: env-map that lights the main pass instead of the learned one (ra_set_main_light)
     float *lxyz = nullptr, *larea = nullptr, *lsharp = nullptr, *ldir = nullptr;
     TcWeights tc;                    // fp16 UMMA images for the tcgen05 path
     Tc2Weights tc2;                  // ... and for its 2-CTA (cta_group::2) variant
@@ -631,12 +632,14 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     // light visibility (DFSS)
     int L = c.env_h * c.env_w;
     LAUNCH(h, k_shadow_gen, grid_for(h, P * L / 4, 256, 16), 256, 0, st, h->fc, h->cnt.n_fg, h->fg_ray, h->surf, h->fm.norm, h->ldir, L,
-           c.lv_near, c.bbox_margin, h->chunk_actual, h->lay_block, h->lay_world, h->lay_rank, h->lvis, h->ldot, h->sr, h->cnt.n_shadow);
+           c.lv_near, c.bbox_margin, h->chunk_actual, h->lay_block, h->lay_world, h->lay_rank, c.visibility_mode, h->lvis, h->ldot, h->sr, h->cnt.n_shadow);
     TraceCfg sc{c.lv_iter, 1.f, c.lv_relax, c.lv_offset, c.st_eps, c.st_skip, c.lv_dist_th, c.blend_radius};
     const bool split = h->overlap && h->cfg.precision == RA_PRECISION_TC && (h->tc_variant == 1 || h->tc_variant >= 6);
     int64_t n_sh = h->sr.cap;
-    if (h->cfg.precision == RA_PRECISION_FP32 && read_counter(h, h->cnt.n_shadow, st, &n_sh)) return 1;
-    if (!split) {
+    if (c.visibility_mode) n_sh = 0;          // cfg.local_visibility / cfg.no_visibility: k_shadow_gen already wrote the final lvis, nothing to trace
+    else if (h->cfg.precision == RA_PRECISION_FP32 && read_counter(h, h->cnt.n_shadow, st, &n_sh)) return 1;
+    if (c.visibility_mode) {
+    } else if (!split) {
         int gs = grid_for(h, P * 64, h->tb_shadow, 8 * 256 / h->tb_shadow);
         for (int it = 0; it <= c.lv_iter; it++) {
             CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
@@ -665,8 +668,8 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     }
     prof_stage(h, st);
     LAUNCH(h, k_shade, grid_for(h, P * 32, 256, 8), 256, 0, st, h->cnt.n_fg, h->fg_ray, ray_o, h->surf, h->acc, h->fm, h->lvis, h->ldot,
-           h->lxyz, h->larea, L, h->env_main, h->emh, h->emw, c.fresnel_f0, c.shading_albedo, 0, 1, c.tonemapping, out->rgb_map, out->shade_map,
-           out->spec_map);
+           h->lxyz, h->larea, L, h->main_light ? h->main_light : h->env_main, h->main_light ? h->mlh : h->emh, h->main_light ? h->mlw : h->emw,
+           c.fresnel_f0, c.shading_albedo, 0, 1, c.tonemapping, c.brdf_mode, out->rgb_map, out->shade_map, out->spec_map);
     if (out->lvis_map || out->ldot_map)
         LAUNCH(h, k_scatter_lmaps, grid_for(h, P * L / 4), 256, 0, st, h->cnt.n_fg, h->fg_ray, h->acc, h->lvis, h->ldot, L, out->lvis_map, out->ldot_map);
     prof_stage(h, st);
@@ -701,7 +704,7 @@ static int relight_envmaps_impl(ra_handle* h, const float* probes, int32_t n_env
         if (s) CK(cudaMemsetAsync(s, 0, (size_t)P * 3 * sizeof(float), st));
         if (p && P && raw) CK(cudaMemsetAsync(p, 0, (size_t)P * 3 * sizeof(float), st));      // times acc = 0
         if (p && P && !raw) {
-            LAUNCH(h, k_bg_spec, 1, 32, 0, st, h->lxyz, h->larea, L, probe, c.env_h, c.env_w, c.fresnel_f0, h->bg_spec);
+            LAUNCH(h, k_bg_spec, 1, 32, 0, st, h->lxyz, h->larea, L, probe, c.env_h, c.env_w, c.fresnel_f0, c.brdf_mode, h->bg_spec);
             LAUNCH(h, k_fill3, grid_for(h, P * 3), 256, 0, st, p, h->bg_spec, (long long)P);
         }
     }
@@ -710,7 +713,7 @@ static int relight_envmaps_impl(ra_handle* h, const float* probes, int32_t n_env
         LAUNCH(h, k_shade_multi, grid_for(h, P * 32, 256, 8), 256, 0, st, h->cnt.n_fg, h->fg_ray, h->last_ray_o, h->surf, h->acc, h->fm, h->lvis,
                h->ldot, h->lxyz, h->larea, L, probes + (size_t)e0 * L * 3, ne, c.env_h, c.env_w, c.fresnel_f0, c.shading_albedo,
                rgb ? rgb + (size_t)e0 * P * 3 : nullptr, shade ? shade + (size_t)e0 * P * 3 : nullptr,
-               spec ? spec + (size_t)e0 * P * 3 : nullptr, (long long)P, raw ? 0 : 1, raw ? 1 : 0, 1);      // the novel-light re-shade maps unconditionally (novel_light_sphere_tracing.py:48)
+               spec ? spec + (size_t)e0 * P * 3 : nullptr, (long long)P, raw ? 0 : 1, raw ? 1 : 0, 1, c.brdf_mode);      // the novel-light re-shade maps unconditionally (novel_light_sphere_tracing.py:48)
     }
     CK(cudaGetLastError());
     return 0;
@@ -1143,6 +1146,33 @@ extern "C" int ra_assemble_visual(ra_handle* h, const float* map, const float* a
     AssembleArgs a{mask_at_box, n, W, h->blk_cnt, map, acc_map, ic->bg_brightness, ic->channels, ic->bgr, ic->probe, ic->eh, ic->ew,
                    ic->probe_dirs, ic->probe ? ic->uH : 0, ic->probe ? ic->uW : 0, out_f, out_u8, out_u16};
     LAUNCH(h, k_assemble2, nb, 256, 0, st, a);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+/* cfg.replace_light (sphere_tracing_renderer.py:1068-1069): the main pass is lit by this env-map instead of the learned one.
+ * probe: device pointer (ph,pw,3), copied; NULL restores the learned light. */
+extern "C" int ra_set_main_light(ra_handle* h, const float* probe, int32_t ph, int32_t pw, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!probe) { h->main_light = nullptr; return 0; }
+    if (ph <= 0 || pw <= 0) { h->err = "ra_set_main_light: bad probe size"; return 1; }
+    static_assert(sizeof(float) == 4, "");
+    float* buf = nullptr;
+    CK(dalloc(h, &buf, (size_t)ph * pw * 3));
+    CK(cudaMemcpyAsync(buf, probe, (size_t)ph * pw * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    float* old = h->main_light;
+    h->main_light = buf; h->mlh = ph; h->mlw = pw;
+    if (old) { CK(cudaStreamSynchronize(st)); hfree(h, old); }
+    return 0;
+}
+
+/* The exact 3-NN of row a4 on its own (pytorch3d.ops.knn_points, K=3; sample_utils.py:122): x (n,3) world points ->
+ * ids (n,3) original vertex indices nearest first, d2 (n,3) squared pose-space distances.  Same search the renderers use. */
+extern "C" int ra_query_knn(ra_handle* h, const float* x, int64_t n, int32_t* ids, float* d2, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!h->have_frame) { h->err = "query before ra_set_frame"; return 1; }
+    if (n == 0) return 0;
+    LAUNCH(h, k_points_knn, grid_for(h, n, 256, 8), 256, 0, st, h->fc, h->sv, h->cfg.n_verts, x, (int)n, (int*)ids, d2);
     CK(cudaGetLastError());
     return 0;
 }

@@ -145,6 +145,7 @@ __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __res
                              const float* __restrict__ surf /*[P][3] by ray*/, const float* __restrict__ f_norm /*[fg][3]*/,
                              const float* __restrict__ ldir /*[L][3]*/, int L, float lv_near, float bbox_margin, int chunk_actual,
                              int lay_block, int lay_world, int lay_rank,     // tile sharding: local ray -> global ray (identity when world == 1)
+                             int vis_mode,       // 0: DFSS tracing; 1: cfg.local_visibility (lvis = ldot > 0); 2: cfg.no_visibility (lvis = 1)   :296-301
                              float* lvis, float* ldot, ShadowRays sr, int* n_shadow) {
     int lane = threadIdx.x & 31;
     long long total = (long long)(*n_fg) * L;
@@ -162,7 +163,8 @@ __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __res
             float dt = dl.x * n.x + dl.y * n.y + dl.z * n.z;
             ldot[idx] = dt;
             float vis = 0.f;
-            if (dt > 0.f) {
+            if (vis_mode) vis = (vis_mode == 2 || dt > 0.f) ? 1.f : 0.f;
+            else if (dt > 0.f) {
                 // in-place wbounds growth per pixel chunk (:1020-1022), by the ray's index in the WHOLE frame
                 const int gray = (lay_world > 1) ? ((ray / lay_block) * lay_world + lay_rank) * lay_block + ray % lay_block : ray;
                 float pad = bbox_margin * (float)(1 + gray / chunk_actual);
@@ -269,6 +271,25 @@ __global__ void k_points_front(const FrameConst* __restrict__ fc, SortedVerts sv
         int slot = warp_append(q.count, ins);
         if (ins) { q.bpts[(size_t)slot * 3] = f.bpts.x; q.bpts[(size_t)slot * 3 + 1] = f.bpts.y; q.bpts[(size_t)slot * 3 + 2] = f.bpts.z; }
         if (valid) { smpl[i] = f.smpl; slot_out[i] = slot; }
+    }
+}
+
+// The exact 3-NN on its own (row a4: pytorch3d.ops.knn_points K=3 at sample_utils.py:122): world points -> pose space -> the three
+// nearest posed vertices as ORIGINAL vertex indices, nearest first, with their squared distances.
+__global__ void k_points_knn(const FrameConst* __restrict__ fc, SortedVerts sv, int nverts, const float* __restrict__ x, int n, int* ids, float* d2) {
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {      // block-uniform trip count
+        const int i = base + threadIdx.x;
+        const bool valid = i < n;
+        float3 p = make3(0, 0, 0);
+        if (valid) {
+            const float3 q = make3(x[i * 3] - fc->Th[0], x[i * 3 + 1] - fc->Th[1], x[i * 3 + 2] - fc->Th[2]);
+            p = make3(q.x * fc->R[0] + q.y * fc->R[3] + q.z * fc->R[6], q.x * fc->R[1] + q.y * fc->R[4] + q.z * fc->R[7],
+                      q.x * fc->R[2] + q.y * fc->R[5] + q.z * fc->R[8]);
+        }
+        KnnOut nn;
+        knn3_warp(fc, sv, nverts, p, valid, nn);
+        if (valid)
+            for (int k = 0; k < 3; k++) { ids[i * 3 + k] = __float_as_int(__ldg(&sv.pos[nn.id[k]]).w); d2[i * 3 + k] = nn.d2[k]; }
     }
 }
 
@@ -531,6 +552,11 @@ __device__ __forceinline__ float3 envmap_fetch(const float* __restrict__ img, in
 }
 
 // Microfacet (cancel_cosine=True): returns the scalar specular term and the lambert cosine factor l.n / pi
+// brdf_mode: 0 glossy + lambert, 1 cfg.lambert_only, 2 cfg.glossy_only (relight_utils.py:563-568)
+__device__ __forceinline__ void brdf_mode_apply(int brdf_mode, float& spec, float& lambert_k) {
+    if (brdf_mode == 1) spec = 0.f;
+    if (brdf_mode == 2) lambert_k = 0.f;
+}
 __device__ __forceinline__ void microfacet_eval(float3 s2l, float3 s2c, float3 nrm, float rough, float f0, float& spec, float& lambert_k) {
     const float PI = 3.14159265358979323846f;
     float3 l = normalize_f(s2l), v = normalize_f(s2c), n = normalize_f(nrm);
@@ -583,7 +609,7 @@ __global__ void k_shade(const int* __restrict__ n_fg, const int* __restrict__ fg
                         const float* __restrict__ surf_ray, const float* __restrict__ acc_ray, FgMaps fm,
                         const float* __restrict__ lvis, const float* __restrict__ ldot, const float* __restrict__ lxyz,
                         const float* __restrict__ larea, int L, const float* __restrict__ probe, int eh, int ew, float f0,
-                        float shading_albedo, int premul, int out_premul, int tonemap, float* rgb, float* shade, float* spec) {
+                        float shading_albedo, int premul, int out_premul, int tonemap, int brdf_mode, float* rgb, float* shade, float* spec) {
     const float PI = 3.14159265358979323846f;
     int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -605,6 +631,7 @@ __global__ void k_shade(const int* __restrict__ n_fg, const int* __restrict__ fg
             float3 li = envmap_fetch(probe, eh, ew, s2l);
             float sp_term, lk;
             microfacet_eval(s2l, s2c, nr, rough, f0, sp_term, lk);
+            brdf_mode_apply(brdf_mode, sp_term, lk);
             float lv = lvis[(size_t)f * L + l] * pm, ld = ldot[(size_t)f * L + l] * pm;
             float ar = larea[l];
             float lic[3] = {li.x, li.y, li.z};
@@ -659,7 +686,8 @@ __global__ void k_shade_multi(const int* __restrict__ n_fg, const int* __restric
                               const float* __restrict__ surf_ray, const float* __restrict__ acc_ray, FgMaps fm,
                               const float* __restrict__ lvis, const float* __restrict__ ldot, const float* __restrict__ lxyz,
                               const float* __restrict__ larea, int L, const float* __restrict__ probes, int n_probe, int eh, int ew,
-                              float f0, float shading_albedo, float* rgb, float* shade, float* spec, long long P, int premul, int out_premul, int tonemap) {
+                              float f0, float shading_albedo, float* rgb, float* shade, float* spec, long long P, int premul, int out_premul, int tonemap,
+                              int brdf_mode) {
     const float PI = 3.14159265358979323846f;
     int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -685,6 +713,7 @@ __global__ void k_shade_multi(const int* __restrict__ n_fg, const int* __restric
             float3 s2l = normalize_ref(make3(lxyz[l * 3] - sp.x, lxyz[l * 3 + 1] - sp.y, lxyz[l * 3 + 2] - sp.z));
             float sp_term, lk;
             microfacet_eval(s2l, s2c, nr, rough, f0, sp_term, lk);
+            brdf_mode_apply(brdf_mode, sp_term, lk);
             float lv = lvis[(size_t)f * L + l] * a, ld = ldot[(size_t)f * L + l] * a;
             float ar = larea[l];
             const EnvTap tap = envmap_tap(eh, ew, s2l);
@@ -721,7 +750,7 @@ __global__ void k_shade_multi(const int* __restrict__ n_fg, const int* __restric
 
 // background pixels in the novel-light pass: all inputs are zero, spec is a probe-dependent constant
 __global__ void k_bg_spec(const float* __restrict__ lxyz, const float* __restrict__ larea, int L, const float* __restrict__ probe,
-                          int eh, int ew, float f0, float* out3) {
+                          int eh, int ew, float f0, int brdf_mode, float* out3) {
     int lane = threadIdx.x & 31;
     float cp[3] = {0, 0, 0};
     float3 z = make3(0, 0, 0);
@@ -731,6 +760,7 @@ __global__ void k_bg_spec(const float* __restrict__ lxyz, const float* __restric
         float3 li = envmap_fetch(probe, eh, ew, s2l);
         float sp_term, lk;
         microfacet_eval(s2l, s2c, z, 0.f, f0, sp_term, lk);
+        brdf_mode_apply(brdf_mode, sp_term, lk);
         cp[0] += sp_term * (larea[l] * li.x); cp[1] += sp_term * (larea[l] * li.y); cp[2] += sp_term * (larea[l] * li.z);
     }
     for (int c = 0; c < 3; c++) cp[c] = warp_sum(cp[c]);

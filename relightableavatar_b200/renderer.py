@@ -45,7 +45,8 @@ def default_config(relight: bool = True, **over) -> Dict:
              lv_iter=4, lv_offset=0.01, lv_relax=0.0, lv_near=0.02, lv_dist_th=0.125 if relight else 0.05,      # (unused without relighting)
              env_r=10.0, bbox_margin=0.25, render_chunk=65536, n_samples=3, surf_sample_range=0.005,
              fresnel_f0=0.02, albedo_slope=1.0, albedo_bias=0.0, rough_slope=0.9, rough_bias=0.09,
-             albedo_multiplier=1.0, shading_albedo=0.8, env_h=16, env_w=32, vol_samples=128, clip_near=0.02, clip_far=10.0, tonemapping=1)
+             albedo_multiplier=1.0, shading_albedo=0.8, env_h=16, env_w=32, vol_samples=128, clip_near=0.02, clip_far=10.0,
+             visibility_mode=0, brdf_mode=0, tonemapping=1)
     c.update(over)
     return c
 
@@ -56,9 +57,9 @@ def default_config(relight: bool = True, **over) -> Dict:
 FIXED_SWITCHES = dict(
     smpl_distance=False, ablate_hdq_mode='hdq', use_geodesic_filter=True, sample_vert_cnt=3, sdf_finite_diff=0,      # HDQ (base_network.py)
     xyz_res=10, view_res=4, sdf_res=8, feat_dim=256, relight_network_width=128, relight_network_depth=2, lambertian=False,   # network shapes
-    no_visibility=False, local_visibility=False, no_dfss=False, no_claybook=False, only_visibility=False,            # shadow tracing
+    no_dfss=False, no_claybook=False, only_visibility=False,            # shadow tracing (no_visibility / local_visibility: ra_config.visibility_mode)
     geometry_visibility=False, geometry_normal=False, bruteforce_st=False, check_termination_sdf=False, check_bound_sdf=False,
-    zero_roughness=False, rgb_as_albedo=False, replace_light='', lambert_only=False, glossy_only=False,              # shading
+    zero_roughness=False, rgb_as_albedo=False,              # shading (lambert_only / glossy_only: ra_config.brdf_mode; replace_light: ra_set_main_light)
     vis_lvis_map=False, vis_ldot_map=False,             # debug views that overwrite shade_map with a visibility / cosine mean (:756-757)
     bg_brightness=0.0)
 FIXED_ST_SWITCHES = dict(tan_i_multiplier=1)          # cfg.sphere_tracing.*
@@ -96,7 +97,17 @@ def config_from_reference_cfg(cfg, relight: bool, mode: Optional[str] = None) ->
         surf_sample_range=cfg.surf_sample_range, fresnel_f0=cfg.fresnel_f0, albedo_slope=cfg.albedo_slope,
         albedo_bias=cfg.albedo_bias, rough_slope=cfg.roughness_slope, rough_bias=cfg.roughness_bias,
         albedo_multiplier=cfg.albedo_multiplier, shading_albedo=cfg.shading_albedo, env_h=cfg.env_h, env_w=cfg.env_w,
-        clip_near=cfg.clip_near, clip_far=cfg.clip_far, tonemapping=int(bool(cfg.tonemapping_rendering)))
+        clip_near=cfg.clip_near, clip_far=cfg.clip_far, tonemapping=int(bool(cfg.tonemapping_rendering)),
+        # ablation switches of light_visibility (sphere_tracing_renderer.py:296-301) and Microfacet (relight_utils.py:563-568)
+        visibility_mode=2 if _flag(cfg, 'no_visibility') else (1 if _flag(cfg, 'local_visibility') else 0),
+        brdf_mode=1 if _flag(cfg, 'lambert_only') else (2 if _flag(cfg, 'glossy_only') else 0))
+
+
+def _flag(cfg, name) -> bool:
+    try:
+        return bool(cfg[name]) if name in cfg else False
+    except TypeError:
+        return bool(getattr(cfg, name, False))
 
 
 def default_ground_config(**over) -> Dict:
@@ -297,6 +308,17 @@ class Engine:
             self._check(fn(self.h, _ptr(ray_o), _ptr(ray_d), _ptr(near), _ptr(far), P, C.byref(o), self._stream()), mode)
         return out
 
+    def set_main_light(self, probe: Optional[torch.Tensor]):
+        """cfg.replace_light (sphere_tracing_renderer.py:1068-1069): env-map (ph,pw,3) that lights the main pass instead of the learned
+        one; None restores the learned light."""
+        if probe is None:
+            self._check(self.lib.ra_set_main_light(self.h, _ptr(None), 0, 0, self._stream()), 'ra_set_main_light')
+            return
+        probe = probe.to(device=self.device, dtype=torch.float32)
+        probe = (probe[0] if probe.ndim == 4 else probe).contiguous()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_set_main_light(self.h, _ptr(probe), probe.shape[0], probe.shape[1], self._stream()), 'ra_set_main_light')
+
     def set_ray_layout(self, global_P: int, block: int = 32, world: int = 1, rank: int = 0):
         """Tile sharding: tell the library which rays of the whole frame this handle renders (see ra_set_ray_layout)."""
         self._check(self.lib.ra_set_ray_layout(self.h, int(global_P), int(block), int(world), int(rank)), 'ra_set_ray_layout')
@@ -419,6 +441,15 @@ class Engine:
             self._check(self.lib.ra_query_sdf(self.h, _ptr(x), x.shape[0], th, int(smooth), _ptr(out), self._stream()), 'ra_query_sdf')
         return out
 
+    def query_knn(self, x: torch.Tensor):
+        """Exact 3 nearest posed vertices of world points (sample_utils.py:122): -> ids (n,3) int32 vertex indices, d2 (n,3)."""
+        x = x.to(device=self.device, dtype=torch.float32).reshape(-1, 3).contiguous()
+        ids = torch.empty(x.shape[0], 3, device=self.device, dtype=torch.int32)
+        d2 = torch.empty(x.shape[0], 3, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ra_query_knn(self.h, _ptr(x), x.shape[0], _ptr(ids), _ptr(d2), self._stream()), 'ra_query_knn')
+        return ids, d2
+
     def query_raw(self, x: torch.Tensor, v: Optional[torch.Tensor] = None) -> torch.Tensor:
         x = x.to(device=self.device, dtype=torch.float32).reshape(-1, 3).contiguous()
         v = v.to(device=self.device, dtype=torch.float32).reshape(-1, 3).contiguous() if v is not None else None
@@ -483,6 +514,8 @@ class Renderer(torch.nn.Module):
         conf.update(precision=PRECISION[precision], max_rays=int(max_rays))
         # cfg.vis_specular_map: the main pass also returns its specular view (sphere_tracing_renderer.py:739-748)
         self.main_spec = bool(overrides.pop('vis_specular_map', getattr(cfg, 'vis_specular_map', False) if cfg is not None else False))
+        # cfg.replace_light: name of the batch env-map that lights the main pass instead of the learned one (:1068-1069)
+        self.replace_light = overrides.pop('replace_light', None) or (getattr(cfg, 'replace_light', '') if cfg is not None else '') or ''
         conf.update(overrides)
         self.engine = Engine(conf, device) if engine is None else engine
         if engine is None:
@@ -564,6 +597,11 @@ class Renderer(torch.nn.Module):
             out = eng.render(self.mode, ray_o, ray_d, near, far, keys)
             return dotdict({k: v[None] for k, v in out.items()})
         # novel_light_sphere_tracing.Renderer.render (:101-221): main pass, then one cheap re-shade per env-map
+        main_probe = eng.env_main
+        if self.replace_light:
+            main_probe = torch.as_tensor(self._probe_of((batch.get('novel_lights') or {})[self.replace_light])).to(device=eng.device, dtype=torch.float32)
+            main_probe = (main_probe[0] if main_probe.ndim == 4 else main_probe).contiguous()
+            eng.set_main_light(main_probe)
         if self.sync_timing:
             torch.cuda.synchronize(eng.device)
         tick = time.perf_counter()
@@ -574,13 +612,15 @@ class Renderer(torch.nn.Module):
         relight = dotdict()
         conv = (lambda t: t.cpu()) if self.to_cpu else (lambda t: t)
         if self.ground_shading:
+            if eng.config.get('visibility_mode') or self.replace_light:
+                raise NotImplementedError('vis_ground_shading together with no_visibility / local_visibility / replace_light is not implemented')
             return self._render_with_ground(batch, main, P, diff, conv)
         # `main` of the reference (:126-158): the learned-light entry keeps the `visual` keys and stays on the device; every novel light
         # gets `{**main, **human}` (so also ray_o and, when kept, the (P,512) lvis / ldot maps) moved to the host by to_cpu (:216).
         # The main maps are moved once and shared by all lights instead of once per light.
         if 'main' in self.test_light:
             relight.main = dotdict({k: v[None] for k, v in main.items() if k not in ('lvis_map', 'ldot_map')})
-            relight.main.envmap = dotdict(probe=eng.env_main[None])
+            relight.main.envmap = dotdict(probe=main_probe[None])
         lights = batch.get('novel_lights') or {}
         sweep = list(self._light_sweep(lights, self._light_names(lights)))
         shared = None

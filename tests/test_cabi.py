@@ -20,8 +20,8 @@ def test_library_builds_and_exports_header_symbols():
 
 
 def test_ctypes_struct_sizes_match_header():
-    # 37 4-byte fields in ra_config; pointers are 8 bytes
-    assert ctypes.sizeof(_lib.ra_config) == 37 * 4
+    # 39 4-byte fields in ra_config; pointers are 8 bytes
+    assert ctypes.sizeof(_lib.ra_config) == 39 * 4
     assert ctypes.sizeof(_lib.ra_frame) == 11 * 8
     assert ctypes.sizeof(_lib.ra_outputs) == 14 * 8
     assert ctypes.sizeof(_lib.ra_stats) == 7 * 8

@@ -651,3 +651,73 @@ def test_far_field_knn_is_exact():
     e = _err(got, ref)
     assert float(e.max()) <= 2e-5, f'max {float(e.max()):.3e} at {x[e.argmax()].tolist()}'
     eng.close()
+
+
+@pytest.mark.parametrize('switch', ['local_visibility', 'no_visibility', 'lambert_only', 'glossy_only', 'replace_light'])
+def test_reference_ablation_switches(relight_setup, switch):
+    """cfg.local_visibility / cfg.no_visibility (light_visibility, sphere_tracing_renderer.py:296-301), cfg.lambert_only / cfg.glossy_only
+    (Microfacet, relight_utils.py:563-568) and cfg.replace_light (:1068-1069) against the oracle's restatement of the same branches."""
+    b, sd = relight_setup
+    probes = {k: v[0] for k, v in b['novel_lights'].items()}
+    name = next(iter(probes))
+    over = {'local_visibility': dict(visibility_mode=1), 'no_visibility': dict(visibility_mode=2), 'lambert_only': dict(brdf_mode=1),
+            'glossy_only': dict(brdf_mode=2), 'replace_light': dict(replace_light=name)}[switch]
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=8192, test_light=('main', 'all'),
+                 sync_timing=False, **over)
+    out = r.render(b)
+    cfg = O.Cfg(**({switch: True} if switch != 'replace_light' else {}))
+    main_probe = torch.as_tensor(probes[name]) if switch == 'replace_light' else None
+    W = O.Weights(sd, torch.float32, DEV)
+    ref_main = O.render_sphere_tracing(b, sd, cfg, torch.float32, DEV, main_probe=main_probe)
+    for k in ('rgb_map', 'shade_map', 'albedo_map'):
+        e = _err(out['main'][k][0], ref_main[k])
+        assert torch.quantile(e.flatten(), 0.99) <= 2e-4, f'main.{k}: q99 {torch.quantile(e.flatten(), 0.99):.3e}'
+    if switch == 'replace_light':
+        assert torch.equal(out['main']['envmap']['probe'][0].cpu(), torch.as_tensor(probes[name]).reshape(16, 32, 3))
+        plain = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='fp32', max_rays=8192, test_light=('main',), sync_timing=False).render(b)
+        assert float((plain['main']['rgb_map'] - out['main']['rgb_map']).abs().max()) > 1e-2          # the light did change
+    else:
+        ref = O.render_novel_light(b, sd, cfg, probes, torch.float32, DEV)
+        for k in ('rgb_map', 'shade_map', 'spec_map'):
+            e = _err(out[name][k][0], ref[name][k])
+            assert torch.quantile(e.flatten(), 0.99) <= 2e-4, f'{name}.{k}: q99 {torch.quantile(e.flatten(), 0.99):.3e}'
+    if switch in ('local_visibility', 'no_visibility'):
+        assert r.engine.stats()['n_shadow_rays'] == 0          # nothing was traced
+
+
+def test_knn3_indices_are_exact():
+    """Row a4 on its own: the three nearest posed vertices (pytorch3d.ops.knn_points K=3, sample_utils.py:122) of 60 k points -- on the
+    surface, in the shell, a few cells out (neighbourhood-list levels 1-3) and far away (box hierarchy) -- against brute force with the
+    same squared-L2 arithmetic: identical distances, and identical indices wherever the gaps between the four nearest distances exceed
+    the rounding of the world -> pose transform (torch's matmul here, explicit FMAs in the kernel)."""
+    b = scene.make_batch(32, 32, frame=2, n_frames=3, seed=0, n_env=0)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    eng = Engine(default_config(True, precision=0, max_rays=8192), DEV)
+    eng.upload_weights(sd); eng.set_frame(b)
+    g = torch.Generator().manual_seed(21)
+    wv = torch.as_tensor(b['wverts'][0])
+    parts = []
+    for n, spread in ((15000, 0.0), (15000, 0.01), (10000, 0.05), (10000, 0.12), (5000, 0.4), (5000, 2.0)):
+        idx = torch.randint(0, wv.shape[0], (n,), generator=g)
+        parts.append(wv[idx] + torch.randn(n, 3, generator=g) * spread)
+    x = torch.cat(parts).float().to(DEV)
+    ids, d2 = eng.query_knn(x)
+    R = torch.as_tensor(b['R'][0]).to(DEV); Th = torch.as_tensor(b['Th'][0]).reshape(1, 3).to(DEV)
+    pv = torch.as_tensor(b['pverts'][0]).to(DEV)
+    p = (x - Th) @ R
+    ref_d, ref_i = [], []
+    for s in range(0, x.shape[0], 4096):
+        q = p[s:s + 4096]
+        dd = (q[:, None, 0] - pv[None, :, 0]) ** 2
+        dd = dd + (q[:, None, 1] - pv[None, :, 1]) ** 2
+        dd = dd + (q[:, None, 2] - pv[None, :, 2]) ** 2
+        v, i = torch.topk(dd, 4, dim=-1, largest=False, sorted=True)
+        ref_d.append(v); ref_i.append(i)
+    ref_d, ref_i = torch.cat(ref_d), torch.cat(ref_i)
+    tol = 1e-5 * ref_d[:, :3] + 1e-9                                   # |d2| * (rounding of p) per entry
+    assert bool(((d2 - ref_d[:, :3]).abs() <= tol).all()), float(((d2 - ref_d[:, :3]).abs() - tol).max())
+    gaps = ref_d[:, 1:] - ref_d[:, :-1]
+    distinct = (gaps > 4 * tol[:, :1].expand(-1, 3) + 4e-5 * ref_d[:, 3:]).all(dim=1)
+    assert distinct.float().mean() > 0.8, float(distinct.float().mean())
+    assert torch.equal(ids[distinct].long(), ref_i[distinct, :3])
+    eng.close()
