@@ -12,8 +12,11 @@
 #define RA_KNN_RMAX 2
 #endif
 #ifndef RA_TRACE_MINBLOCKS
-#define RA_TRACE_MINBLOCKS 3      // resident 256-thread blocks per SM the tracing kernels are compiled for (register cap)
+#define RA_TRACE_MINBLOCKS 3      // resident 256-thread blocks per SM the surface tracing kernel is compiled for (register cap: 80)
 #endif
+#ifndef RA_SHADOW_MINBLOCKS
+#define RA_SHADOW_MINBLOCKS 4     // ... the shadow tracing kernel: 64 registers (32 B of spills) -> 32 instead of 24 resident warps; measured on the
+#endif                            // 512^2 frame: visibility stage 19.1 / 18.2 / 17.4 ms at 2 / 3 / 4 blocks (the kernel is L2-latency bound: more warps win)
 #define RA_GRID2_RATIO 3.0f
 #define RA_MAX_OCC 8192
 #define RA_MAX_SUP 512       // super cells (blocks of coarse cells) of the far-field 3-NN hierarchy

@@ -184,7 +184,7 @@ __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __res
 }
 
 // Soft-shadow tracing step (A.4 soft + claybook), same finish/start structure as k_trace_surface.
-__global__ void __launch_bounds__(256, RA_TRACE_MINBLOCKS) k_trace_shadow(int it, TraceCfg cfg, const FrameConst* __restrict__ fc, SortedVerts sv, int nverts,
+__global__ void __launch_bounds__(256, RA_SHADOW_MINBLOCKS) k_trace_shadow(int it, TraceCfg cfg, const FrameConst* __restrict__ fc, SortedVerts sv, int nverts,
                                const int* __restrict__ n_shadow, const int* __restrict__ fg_ray, const float* __restrict__ surf,
                                const float* __restrict__ ldir, const float* __restrict__ lsharp, int L,
                                ShadowRays sr, QueryList q, Counters cnt, float* lvis, int part, int nparts) {

@@ -538,7 +538,8 @@ def test_generate_image_f3_every_output_type():
         name, vtype = key.split('.')
         got = vis.generate_image(dev_outs[name], b, vtype)
         assert got.shape == want.shape and got.dtype == np.float32, key
-        assert np.abs(got - want).max() <= 3e-6, f'{key}: {np.abs(got - want).max():.3e}'
+        # relative to the image's range: the overlay of a novel env-map shows HDR probe values (up to ~10 for the synthetic sky maps)
+        assert np.abs(got - want).max() <= 3e-6 * max(1.0, float(np.abs(want).max())), f'{key}: {np.abs(got - want).max():.3e}'
         n_checked += 1
     assert n_checked == 13
     # save_image's pixels: BGR, uint16 png / 3-channel uint8 jpg; truncation of v*65535 may differ by one step where fp32 rounding
@@ -714,7 +715,7 @@ def test_knn3_indices_are_exact():
         v, i = torch.topk(dd, 4, dim=-1, largest=False, sorted=True)
         ref_d.append(v); ref_i.append(i)
     ref_d, ref_i = torch.cat(ref_d), torch.cat(ref_i)
-    tol = 1e-5 * ref_d[:, :3] + 1e-9                                   # |d2| * (rounding of p) per entry
+    tol = 1e-6 * ref_d[:, :3].sqrt() + 1e-5 * ref_d[:, :3] + 1e-9      # 2 |dx| ulp(p) + relative rounding, per entry
     assert bool(((d2 - ref_d[:, :3]).abs() <= tol).all()), float(((d2 - ref_d[:, :3]).abs() - tol).max())
     gaps = ref_d[:, 1:] - ref_d[:, :-1]
     distinct = (gaps > 4 * tol[:, :1].expand(-1, 3) + 4e-5 * ref_d[:, 3:]).all(dim=1)
