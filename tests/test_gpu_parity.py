@@ -722,3 +722,4 @@ def test_knn3_indices_are_exact():
     assert distinct.float().mean() > 0.8, float(distinct.float().mean())
     assert torch.equal(ids[distinct].long(), ref_i[distinct, :3])
     eng.close()
+
