@@ -638,7 +638,7 @@ __device__ void knn3_warp(const FrameConst* __restrict__ fc, const SortedVerts& 
                             const int cc = cb + __ffs(qm) - 1;
                             qm &= qm - 1;
                             const int s = __float_as_int(__ldg(&sv.occ_lo[cc]).w), e = __float_as_int(__ldg(&sv.occ_hi[cc]).w);
-                            KNN_STAT(2, 1); KNN_STAT(3, e - s);
+                            if (lane == 0) { KNN_STAT(2, 1); KNN_STAT(3, e - s); }      // (one count per query, not per lane)
                             for (int v = s + lane; v < e; v += 32) {
                                 float4 t = __ldg(&sv.pos2[v]);
                                 knn_insert(w, dist2_ref(q, t), __float_as_int(t.w));

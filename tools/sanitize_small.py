@@ -71,4 +71,39 @@ for mode in ('anisdf_trace', 'anisdf_volume'):
     r.render(b)
     stage(mode)
     r.engine.close()
+# round-2 entry points: image side (every Output type, overlay, 16-bit), rotation sweep with the floor, ablation switches,
+# replaced main light, the 3-NN query, the tensor-memory MLP variant
+from relightableavatar_b200.visualizer import Visualizer
+from relightableavatar_b200.renderer import Engine, default_config
+r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='tc', max_rays=2048, test_light=('main', 'all'), sync_timing=False,
+             vis_specular_map=True)
+out = r.render(b)
+vis = Visualizer(r.engine)
+bb = dict(b); bb['tbounds'] = b['tbounds']
+for t in ('rendering', 'normal', 'alpha', 'depth', 'shading', 'albedo', 'roughness', 'surface', 'residual', 'specular', 'envmap'):
+    vis.generate_image(out['main'], bb, t)
+vis.encode_frame(out, bb, types=('rendering', 'normal'), ext='.png')
+vis.encode_frame(out, bb, types=('rendering',), ext='.jpg')
+stage('visualizer')
+ids, d2 = r.engine.query_knn(torch.as_tensor(b['wverts'][0][::5]).float() + 0.3)
+stage('query_knn')
+r.engine.close()
+name = next(iter(b['novel_lights']))
+for over in (dict(visibility_mode=1), dict(visibility_mode=2), dict(brdf_mode=1), dict(brdf_mode=2), dict(replace_light=name)):
+    r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='tc', max_rays=2048, test_light=('main', 'all'), sync_timing=False, **over)
+    r.render(b)
+    r.engine.close()
+stage('ablation switches')
+r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='tc', max_rays=2048, test_light=('all',), ground_shading=True,
+             sync_timing=False, rotate_ratio=1)
+bl = dict(b); bl['novel_lights'] = {name: {'probe': b['novel_lights'][name], 'image': np.repeat(b['novel_lights'][name], 2, axis=2)}}
+r.render(bl)
+stage('rotation sweep with ground shading')
+r.engine.close()
+os.environ['RA_TC_VARIANT'] = '7'
+eng = Engine(default_config(True, precision=1, max_rays=2048), DEV)
+eng.upload_weights(sd); eng.set_frame(b)
+eng.query_sdf(torch.as_tensor(b['wverts'][0][::3]).float() + 0.01, 0.125, True)
+stage('k_mlp_tc7')
+eng.close()
 print('SANITIZE_DONE')
