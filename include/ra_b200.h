@@ -122,6 +122,7 @@ typedef struct ra_stats {
     int64_t n_attr_samples;    /* in-shell surface/volume samples (fwd + input-gradient) */
     int64_t n_dropped_shadow_rays; /* shadow rays beyond the workspace (256 per ray of max_rays): 0 for the reference's 16x32 light grid,
                                       whose antipodal symmetry puts at most L/2 lights in front of a pixel; non-zero = lvis incomplete */
+    int64_t n_shadow_slots;    /* entries of the shadow-ray list incl. the padding of partly filled 32-ray packets (human pass + last floor batch) */
 } ra_stats;
 
 int  ra_create(ra_handle** out, const ra_config* cfg);
@@ -297,6 +298,9 @@ int ra_query_raw(ra_handle* h, const float* x, const float* v, int64_t n, float*
 /* exact K=3 nearest posed vertices (pytorch3d.ops.knn_points at sample_utils.py:122): x (n,3) world -> ids (n,3) vertex indices,
  * nearest first, d2 (n,3) squared distances in pose space */
 int ra_query_knn(ra_handle* h, const float* x, int64_t n, int32_t* ids, float* d2, void* stream);
+/* the same search as the shadow tracer runs it: every 32 consecutive points form a packet (parallel rays of neighbouring pixels)
+ * whose far-field lanes walk the box hierarchy together.  Exact for any input; the grouping only decides which search runs. */
+int ra_query_knn_packets(ra_handle* h, const float* x, int64_t n, int32_t* ids, float* d2, void* stream);
 
 int ra_get_stats(ra_handle* h, ra_stats* out);   /* synchronises the device */
 /* Device-side timing for bench.py's roofline line: when enabled, every launch of the fused MLP kernel and every

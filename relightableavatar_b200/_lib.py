@@ -13,7 +13,7 @@ EXPORTS = ['ra_create', 'ra_destroy', 'ra_last_error', 'ra_upload_weights', 'ra_
            'ra_get_stats', 'ra_launch_count', 'ra_profile_enable', 'ra_profile_read', 'ra_rotate_probes', 'ra_assemble_image',
            'ra_ground_begin', 'ra_render_ground', 'ra_relight_ground', 'ra_blend_ground', 'ra_relight_envmaps_raw',
            'ra_upload_body', 'ra_prepare_pose', 'ra_prepare_rays', 'ra_set_ray_layout', 'ra_allgather', 'ra_visual_map', 'ra_assemble_visual',
-           'ra_rotate_image', 'ra_set_main_light', 'ra_query_knn']
+           'ra_rotate_image', 'ra_set_main_light', 'ra_query_knn', 'ra_query_knn_packets']
 
 fp = C.POINTER(C.c_float)
 
@@ -95,7 +95,7 @@ class ra_image_config(C.Structure):
 
 
 class ra_stats(C.Structure):
-    _fields_ = [(n, C.c_int64) for n in ('n_rays', 'n_fg', 'n_shadow_rays', 'n_queries', 'n_queries_in_shell', 'n_attr_samples', 'n_dropped_shadow_rays')]
+    _fields_ = [(n, C.c_int64) for n in ('n_rays', 'n_fg', 'n_shadow_rays', 'n_queries', 'n_queries_in_shell', 'n_attr_samples', 'n_dropped_shadow_rays', 'n_shadow_slots')]
 
 
 _lib = None
@@ -142,6 +142,7 @@ def load():
     lib.ra_rotate_image.argtypes = [vp, vp, i32, i32, C.c_double, i32, i32, vp, vp]
     lib.ra_set_main_light.argtypes = [vp, vp, i32, i32, vp]
     lib.ra_query_knn.argtypes = [vp, vp, i64, vp, vp, vp]
+    lib.ra_query_knn_packets.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.ra_profile_enable.argtypes = [vp, i32]
     lib.ra_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]
     _lib = lib

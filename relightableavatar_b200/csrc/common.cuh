@@ -17,6 +17,12 @@
 #ifndef RA_SHADOW_MINBLOCKS
 #define RA_SHADOW_MINBLOCKS 4     // ... the shadow tracing kernel: 64 registers (32 B of spills) -> 32 instead of 24 resident warps; measured on the
 #endif                            // 512^2 frame: visibility stage 19.1 / 18.2 / 17.4 ms at 2 / 3 / 4 blocks (the kernel is L2-latency bound: more warps win)
+#ifndef RA_PKT_MIN
+#define RA_PKT_MIN 2         // far lanes a warp needs before its far-field 3-NN runs as ONE packet search (hdq.cuh: knn3_packet; measured flat from 2 to 6)
+#endif
+#ifndef RA_PKT_RHO
+#define RA_PKT_RHO 1.0e9f    // largest packet radius (metres) served that way: no limit -- with per-lane box tests a wide packet only scans the union
+#endif                       // of its lanes' candidate cells (floor pass at 512^2: 162 / 148 / 134 / 124 / 108 / 106 ms at 0.1 / 0.15 / 0.25 / 0.4 / 1 m / no limit)
 #define RA_GRID2_RATIO 3.0f
 #define RA_MAX_OCC 8192
 #define RA_MAX_SUP 512       // super cells (blocks of coarse cells) of the far-field 3-NN hierarchy
@@ -62,6 +68,7 @@ struct SortedVerts {
     // per-cell neighbourhood lists (rebuilt per frame): level 0 = the 3x3x3 block around the cell, level 1 / 2 = the cube
     // shells of radius 2 / 3.  nb_pos entries: xyz, w = index into pos/nrm/tv/T (int bits).  A query scans ONE contiguous
     // list per level instead of walking grid rows -- same candidates, no per-row control flow (warp divergence).
+    unsigned char* nb_mask;          // [cells] bit lv set: the cell's level-lv list holds vertices (a far query skips the empty levels: 0 = straight to the far phase)
     int* nb_start[RA_NB_LEVELS];     // [cells+1] each
     float4* nb_pos[RA_NB_LEVELS];
 };

@@ -73,18 +73,26 @@ __global__ void k_ground_setup(GroundCfg g, const float* __restrict__ ray_o, con
 // pixel index (`chunk_actual` = the reference's equalised chunk size over the H*W pixels).
 __global__ void k_ground_rays(const FrameConst* __restrict__ fc, GroundCfg g, const float* __restrict__ surf, const float* __restrict__ acc_g,
                               long long p0, long long n, const float* __restrict__ ldir, int L, int pad_chunks0, int chunk_actual,
-                              float* lvis, ShadowRays sr, int* n_shadow) {
+                              float* lvis, ShadowRays sr, int* n_shadow, int packets,
+                              int tile_w /* image width when a packet is an 8 x 4 pixel tile (batch = whole groups of 4 rows), 0: 32 consecutive pixels */) {
+    // one warp = one packet: the same light for 32 consecutive pixels (see k_shadow_gen); always a whole aligned block of the ray list
     int lane = threadIdx.x & 31;
-    long long total = n * L;
+    const long long ntile = (n + 31) >> 5;
+    long long total = packets ? ntile * L * 32 : n * L;
     float3 nn = normalize_ref(make3(g.normal[0], g.normal[1], g.normal[2]));
     for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += (long long)gridDim.x * blockDim.x) {
-        long long idx = base + lane;
-        bool valid = idx < total;
+        const long long w = base >> 5;
+        const int l = packets ? (int)(w % L) : (int)((base + lane) % L);
+        long long k = packets ? (w / L) * 32 + lane : (base + lane) / L;
+        if (packets && tile_w) {
+            const long long tile = w / L, per_row = tile_w >> 3;
+            k = ((tile / per_row) * 4 + (lane >> 3)) * tile_w + (tile % per_row) * 8 + (lane & 7);
+        }
+        bool valid = packets ? k < n : base + lane < total;
         bool trace = false;
-        long long pix = 0; int l = 0;
+        long long pix = p0 + k;
         float nr = 0.f, fr = 0.f;
         if (valid) {
-            pix = p0 + idx / L; l = (int)(idx % L);
             float3 dl = make3(ldir[l * 3], ldir[l * 3 + 1], ldir[l * 3 + 2]);
             float dt = dl.x * nn.x + dl.y * nn.y + dl.z * nn.z;
             float vis = 0.f;
@@ -100,8 +108,7 @@ __global__ void k_ground_rays(const FrameConst* __restrict__ fc, GroundCfg g, co
             }
             lvis[(size_t)pix * L + l] = vis;
         }
-        int slot = warp_append(n_shadow, trace);
-        if (shadow_slot_ok(sr, trace, slot)) { sr.fg[slot] = (int)pix; sr.light[slot] = (unsigned short)l; sr.near_[slot] = nr; sr.far_[slot] = fr; }
+        shadow_append(sr, n_shadow, packets != 0, trace, (int)pix, l, nr, fr);
     }
 }
 

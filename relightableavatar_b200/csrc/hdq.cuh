@@ -126,12 +126,28 @@ __global__ void k_grid_count(const FrameConst* fc, int level, const float* __res
     atomicAdd(&cell_count[c], 1);
 }
 
-__global__ void k_grid_fill2(const float4* __restrict__ spos, int nverts, const int* __restrict__ vert_cell,
-                             const int* __restrict__ cell_start, int* cell_fill, float4* pos2) {
+// Counting sort, scatter step, made DETERMINISTIC: k_grid_order drops the vertex ids of a cell into its run in whatever order the
+// atomics retire; the fill kernels then place vertex i at the rank of i among the ids of its run.  The order of the vertices inside a
+// cell decides which of two exactly equidistant vertices the 3-NN keeps -- without this a frame could differ from the same frame
+// rendered by another handle in one visibility entry out of millions (observed: the first handle of a process vs. the later ones).
+__global__ void k_grid_order(int nverts, const int* __restrict__ vert_cell, const int* __restrict__ cell_start, int* cell_fill, int* order) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nverts) return;
     int c = vert_cell[i];
-    int dst = cell_start[c] + atomicAdd(&cell_fill[c], 1);
+    order[cell_start[c] + atomicAdd(&cell_fill[c], 1)] = i;
+}
+__device__ __forceinline__ int grid_rank_slot(int i, const int* __restrict__ vert_cell, const int* __restrict__ cell_start, const int* __restrict__ order) {
+    const int c = vert_cell[i];
+    const int s = cell_start[c], e = cell_start[c + 1];
+    int rank = 0;
+    for (int k = s; k < e; k++) rank += (order[k] < i);
+    return s + rank;
+}
+__global__ void k_grid_fill2(const float4* __restrict__ spos, int nverts, const int* __restrict__ vert_cell,
+                             const int* __restrict__ cell_start, const int* __restrict__ order, float4* pos2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nverts) return;
+    int dst = grid_rank_slot(i, vert_cell, cell_start, order);
     float4 v = spos[i];
     pos2[dst] = make_float4(v.x, v.y, v.z, __int_as_float(i));
 }
@@ -263,12 +279,11 @@ __global__ void k_grid_scan(const FrameConst* fc, int level, int* cell_count, in
 __global__ void k_grid_fill(const FrameConst* fc, const float* __restrict__ pverts, const float* __restrict__ pnorm,
                             const float* __restrict__ tverts, const float* __restrict__ weights,
                             const float* __restrict__ A, const float* __restrict__ bigA, int nverts, int nbones,
-                            const int* __restrict__ vert_cell, const int* __restrict__ cell_start, int* cell_fill,
+                            const int* __restrict__ vert_cell, const int* __restrict__ cell_start, const int* __restrict__ order,
                             SortedVerts sv) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nverts) return;
-    int c = vert_cell[i];
-    int dst = cell_start[c] + atomicAdd(&cell_fill[c], 1);
+    int dst = grid_rank_slot(i, vert_cell, cell_start, order);
     sv.pos[dst] = make_float4(pverts[i * 3], pverts[i * 3 + 1], pverts[i * 3 + 2], __int_as_float(i));
     sv.nrm[dst] = make_float4(pnorm[i * 3], pnorm[i * 3 + 1], pnorm[i * 3 + 2], 0.f);
     sv.tv[dst] = make_float4(tverts[i * 3], tverts[i * 3 + 1], tverts[i * 3 + 2], 0.f);
@@ -314,15 +329,18 @@ __device__ __forceinline__ void nb_for_each_run(const GridRef& g, const int* __r
 }
 
 // counts of all levels, one thread per cell: cnt[level * (RA_MAX_CELLS + 1) + cell]
-__global__ void k_nb_count(const FrameConst* fc, const int* __restrict__ cell_start, int* cnt) {
+__global__ void k_nb_count(const FrameConst* fc, const int* __restrict__ cell_start, int* cnt, unsigned char* mask) {
     GridRef g = grid_ref(fc, 0);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.cells; c += gridDim.x * blockDim.x) {
         int cx = c % g.dim[0], cy = (c / g.dim[0]) % g.dim[1], cz = c / (g.dim[0] * g.dim[1]);
+        unsigned m = 0;
         for (int lv = 0; lv < RA_NB_LEVELS; lv++) {
             int n = 0;
             nb_for_each_run(g, cell_start, cx, cy, cz, lv + 1, [&](int s, int e) { n += e - s; });
             cnt[lv * (RA_MAX_CELLS + 1) + c] = n;
+            if (n > 0) m |= 1u << lv;
         }
+        mask[c] = (unsigned char)m;
     }
 }
 
@@ -414,8 +432,9 @@ __global__ void k_nb_fill(const FrameConst* fc, const int* __restrict__ cell_sta
 
 // ------------------------------------------------------------------------------------------ exact 3-NN
 #ifdef RA_KNN_STATS
-__device__ unsigned long long g_knn_stats[8];   // [0] near-path queries, [1] far-path queries, [2] far cells scanned, [3] far verts scanned,
-                                                // [4] near verts scanned, [5] near rings visited, [6] near row scans
+__device__ unsigned long long g_knn_stats[12];   // [0] near-path queries, [1] far-path queries, [2] far cells scanned, [3] far verts scanned,
+                                                // [4] near verts scanned, [5] near rings visited, [6] packets searched, [7] packets refused (too spread out),
+                                                // [8] far lanes served by packets, [9] cells / [10] vertices scanned by packets
 #define KNN_STAT(i, v) atomicAdd(&g_knn_stats[i], (unsigned long long)(v))
 #else
 #define KNN_STAT(i, v)
@@ -464,24 +483,28 @@ __device__ __forceinline__ bool knn3_near(const FrameConst* __restrict__ fc, con
     const int c = cell_of(g, p, cx, cy, cz);
     const int dx_ = g.dim[0], dy_ = g.dim[1], dz_ = g.dim[2];
     const float h = g.h;
+    const unsigned lvmask = __ldg(&sv.nb_mask[c]);
+    if (lvmask == 0) return false;          // nothing within RA_NB_LEVELS cells: nothing to certify, straight to the far phase
 #pragma unroll 1
     for (int lv = 0; lv < RA_NB_LEVELS; lv++) {
         const int r = lv + 1;
-        const int s = __ldg(&sv.nb_start[lv][c]), e = __ldg(&sv.nb_start[lv][c + 1]);
-        const float4* __restrict__ lst = sv.nb_pos[lv];
-        KNN_STAT(4, e - s); KNN_STAT(5, 1);
-        int v = s;
-        for (; v + 4 <= e; v += 4) {          // four independent 16 B loads in flight per lane (the scan is L2-latency bound)
-            const float4 q0 = __ldg(&lst[v]), q1 = __ldg(&lst[v + 1]), q2 = __ldg(&lst[v + 2]), q3 = __ldg(&lst[v + 3]);
-            const float e0 = dist2_ref(p, q0), e1 = dist2_ref(p, q1), e2 = dist2_ref(p, q2), e3 = dist2_ref(p, q3);
-            if (fminf(fminf(e0, e1), fminf(e2, e3)) < o.d2[2]) {
-                knn_insert(o, e0, __float_as_int(q0.w)); knn_insert(o, e1, __float_as_int(q1.w));
-                knn_insert(o, e2, __float_as_int(q2.w)); knn_insert(o, e3, __float_as_int(q3.w));
+        if ((lvmask >> lv) & 1u) {          // (an empty level adds no candidates; the larger explored block may still certify the result)
+            const int s = __ldg(&sv.nb_start[lv][c]), e = __ldg(&sv.nb_start[lv][c + 1]);
+            const float4* __restrict__ lst = sv.nb_pos[lv];
+            KNN_STAT(4, e - s); KNN_STAT(5, 1);
+            int v = s;
+            for (; v + 4 <= e; v += 4) {          // four independent 16 B loads in flight per lane (the scan is L2-latency bound)
+                const float4 q0 = __ldg(&lst[v]), q1 = __ldg(&lst[v + 1]), q2 = __ldg(&lst[v + 2]), q3 = __ldg(&lst[v + 3]);
+                const float e0 = dist2_ref(p, q0), e1 = dist2_ref(p, q1), e2 = dist2_ref(p, q2), e3 = dist2_ref(p, q3);
+                if (fminf(fminf(e0, e1), fminf(e2, e3)) < o.d2[2]) {
+                    knn_insert(o, e0, __float_as_int(q0.w)); knn_insert(o, e1, __float_as_int(q1.w));
+                    knn_insert(o, e2, __float_as_int(q2.w)); knn_insert(o, e3, __float_as_int(q3.w));
+                }
             }
-        }
-        for (; v < e; v++) {
-            float4 q = __ldg(&lst[v]);
-            knn_insert(o, dist2_ref(p, q), __float_as_int(q.w));
+            for (; v < e; v++) {
+                float4 q = __ldg(&lst[v]);
+                knn_insert(o, dist2_ref(p, q), __float_as_int(q.w));
+            }
         }
         // distance from p to the nearest face of the explored block that still has unexplored cells behind it
         float bound = 3.0e38f;
@@ -561,6 +584,114 @@ __device__ __forceinline__ int warp_argmin(float key, int idx) {
     return idx;
 }
 
+// Packet form of the far phase for COHERENT warps (the lanes' points lie close together: parallel rays of neighbouring pixels).
+// The far lanes search together: the box hierarchy is walked ONCE for the packet -- lanes test 32 boxes at a time against the
+// sphere (centre of the packet's points, radius = largest current 3rd-neighbour bound + packet radius) -- and every vertex of a
+// qualifying cell is loaded once (warp-uniform address) and offered to all far lanes, each keeping its own exact top 3 with the
+// same distance arithmetic as the other paths.  Exact: a vertex within lane l's true 3rd distance r_l of p_l is within
+// r_l + |p_l - c| <= sqrt(Bmax) + rho of the centre c, so its cell's box passes the sphere test; bounds only ever shrink towards
+// the true values because they are distances of real vertices.  Against one-query-per-warp this removes the per-query box walk,
+// bootstrap and 5-round shuffle merge (about 4/5 of its instructions).  Returns false (nothing done) when the packet is too
+// spread out to share one sphere; MUST be called by all 32 lanes.
+__device__ __forceinline__ float warp_max_nonneg(float v) { return __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(v))); }
+__device__ int g_pkt_min = RA_PKT_MIN;
+__device__ float g_pkt_rho = RA_PKT_RHO;       // largest packet radius served as one search (env RA_PKT_RHO overrides it for experiments)
+__device__ bool knn3_packet(const FrameConst* __restrict__ fc, const SortedVerts& sv, float3 p, unsigned need, KnnOut& o) {
+    const int lane = threadIdx.x & 31;
+    const int n = fc->n_occ, ns = fc->n_sup;
+    if (n > RA_MAX_OCC) return false;
+    const bool act = (need >> lane) & 1u;
+    float3 lo = act ? p : make3(3e38f, 3e38f, 3e38f), hi = act ? p : make3(-3e38f, -3e38f, -3e38f);
+#pragma unroll
+    for (int m = 16; m; m >>= 1) {
+        lo = make3(fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, m)), fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, m)), fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, m)));
+        hi = make3(fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, m)), fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, m)), fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, m)));
+    }
+    const float3 c = make3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
+    const float ex = hi.x - c.x, ey = hi.y - c.y, ez = hi.z - c.z;
+    const float rho = sqrtf(ex * ex + ey * ey + ez * ez) * 1.0001f + 1e-6f;      // every far point is within rho of c
+    if (rho > g_pkt_rho) { if (lane == 0) KNN_STAT(7, 1); return false; }
+    if (lane == 0) { KNN_STAT(6, 1); KNN_STAT(8, __popc(need)); }
+    const float B = act ? o.d2[2] : 0.f;          // seeds of the near phase are real vertices: upper bound of the true 3rd distance (or 3e38)
+    KnnOut w;
+    w.d2[0] = w.d2[1] = w.d2[2] = 3.0e38f; w.id[0] = w.id[1] = w.id[2] = -1;
+    // one coarse cell: its box and vertex range come in the same two loads; each far lane tests the box against ITS OWN point and
+    // bound (as tight as a single-query search), the cell is scanned if any lane needs it, by the lanes that need it
+    auto scan = [&](int cc, bool all) {
+        const float4 clo = __ldg(&sv.occ_lo[cc]), chi = __ldg(&sv.occ_hi[cc]);
+        const bool mine = act && (all || bbox_dist2(p, clo, chi) * 0.9999f <= fminf(B, w.d2[2]));
+        if (!__any_sync(0xffffffffu, mine)) return;
+        const int s = __float_as_int(clo.w), e = __float_as_int(chi.w);
+        if (lane == 0) { KNN_STAT(9, 1); KNN_STAT(10, e - s); }
+        int v = s;
+        for (; v + 4 <= e; v += 4) {
+            const float4 q0 = __ldg(&sv.pos2[v]), q1 = __ldg(&sv.pos2[v + 1]), q2 = __ldg(&sv.pos2[v + 2]), q3 = __ldg(&sv.pos2[v + 3]);
+            if (mine) {
+                const float e0 = dist2_ref(p, q0), e1 = dist2_ref(p, q1), e2 = dist2_ref(p, q2), e3 = dist2_ref(p, q3);
+                if (fminf(fminf(e0, e1), fminf(e2, e3)) < w.d2[2]) {
+                    knn_insert(w, e0, __float_as_int(q0.w)); knn_insert(w, e1, __float_as_int(q1.w));
+                    knn_insert(w, e2, __float_as_int(q2.w)); knn_insert(w, e3, __float_as_int(q3.w));
+                }
+            }
+        }
+        for (; v < e; v++) {
+            const float4 q = __ldg(&sv.pos2[v]);
+            if (mine) knn_insert(w, dist2_ref(p, q), __float_as_int(q.w));
+        }
+    };
+    auto radius2 = [&]() {                         // squared radius of the packet sphere from the lanes' current bounds
+        const float bm = warp_max_nonneg(act ? fminf(B, w.d2[2]) : 0.f);
+        if (bm >= 3.0e38f) return 3.0e38f;
+        const float R = sqrtf(bm) * 1.0001f + rho;
+        return R * R * 1.0001f;
+    };
+    // bootstrap: the cell nearest to the centre
+    int bc;
+    {
+        float best = 3.0e38f; int bs = 0;
+        for (int s = lane; s < ns; s += 32) {
+            const float lb = bbox_dist2(c, __ldg(&sv.sup_lo[s]), __ldg(&sv.sup_hi[s]));
+            if (lb < best) { best = lb; bs = s; }
+        }
+        bs = warp_argmin(best, bs);
+        const int c0 = __float_as_int(__ldg(&sv.sup_lo[bs]).w), c1 = __float_as_int(__ldg(&sv.sup_hi[bs]).w);
+        best = 3.0e38f; bc = c0;
+        for (int k = c0 + lane; k < c1; k += 32) {
+            const float lb = bbox_dist2(c, __ldg(&sv.occ_lo[k]), __ldg(&sv.occ_hi[k]));
+            if (lb < best) { best = lb; bc = k; }
+        }
+        bc = warp_argmin(best, bc);
+        scan(bc, true);
+    }
+    float R2 = radius2();
+    for (int s0 = 0; s0 < ns; s0 += 32) {               // super cells: one per lane
+        const int si = s0 + lane;
+        bool squal = false;
+        if (si < ns) squal = bbox_dist2(c, __ldg(&sv.sup_lo[si]), __ldg(&sv.sup_hi[si])) * 0.9999f <= R2;
+        unsigned sm = __ballot_sync(0xffffffffu, squal);
+        while (sm) {
+            const int ss = s0 + __ffs(sm) - 1;
+            sm &= sm - 1;
+            const float4 slo = __ldg(&sv.sup_lo[ss]), shi = __ldg(&sv.sup_hi[ss]);
+            if (bbox_dist2(c, slo, shi) * 0.9999f > R2) continue;      // the bound has shrunk since the lane-parallel test
+            const int c0 = __float_as_int(slo.w), c1 = __float_as_int(shi.w);
+            for (int cb = c0; cb < c1; cb += 32) {      // its coarse cells: one per lane
+                const int k = cb + lane;
+                bool qual = false;
+                if (k < c1 && k != bc) qual = bbox_dist2(c, __ldg(&sv.occ_lo[k]), __ldg(&sv.occ_hi[k])) * 0.9999f <= R2;
+                unsigned qm = __ballot_sync(0xffffffffu, qual);
+                while (qm) {
+                    scan(cb + __ffs(qm) - 1, false);
+                    qm &= qm - 1;
+                }
+            }
+            R2 = radius2();
+        }
+    }
+    if (act) o = w;
+    return true;
+}
+
 // Warp-cooperative exact 3-NN.  MUST be called by all 32 lanes (warp-uniform call site).  Every lane first runs the
 // fine-grid search for its own point; the points it cannot finish (farther than 4 fine cells from every vertex) are then
 // processed one at a time by the WHOLE warp over the two-level box hierarchy (super cells -> occupied coarse cells ->
@@ -568,13 +699,15 @@ __device__ __forceinline__ int warp_argmin(float key, int idx) {
 // followed by one shuffle merge of the per-lane triples.  When more than `coop_max` lanes are far (surface rays entering the
 // box: coherent lanes) every lane walks the hierarchy itself instead -- measured on the 512^2 frame: surface stage 2.4 ms
 // per-lane vs 3.4 ms cooperative, shadow stage 18.2 vs 17.9 ms.
-__device__ void knn3_warp(const FrameConst* __restrict__ fc, const SortedVerts& sv, int nverts, float3 p, bool active, KnnOut& o, int coop_max = 12) {
+__device__ void knn3_warp(const FrameConst* __restrict__ fc, const SortedVerts& sv, int nverts, float3 p, bool active, KnnOut& o, int coop_max = 12,
+                          bool packet = false) {
     const int lane = threadIdx.x & 31;
     bool done = true;
     if (active) done = knn3_near(fc, sv, p, o);
     if (active) { if (done) KNN_STAT(0, 1); else KNN_STAT(1, 1); }
     unsigned need = __ballot_sync(0xffffffffu, active && !done);
     if (!need) return;
+    if (packet && __popc(need) >= g_pkt_min && knn3_packet(fc, sv, p, need, o)) return;
     if (__popc(need) > coop_max) {
         if (active && !done) knn3_far(fc, sv, nverts, p, o);
         return;
@@ -680,14 +813,14 @@ __device__ __forceinline__ void inverse3x3_ref(const float* R, float* M) {
 // MUST be called by all 32 lanes of a warp (warp-cooperative 3-NN inside); `active` = this lane has a point.
 template <bool WANT_MATS>
 __device__ void hdq_front(const FrameConst* __restrict__ fc, const SortedVerts& sv, int nverts, float3 x, bool active, float th,
-                          float blend_radius, HdqFront& out, int coop_max = 12) {
+                          float blend_radius, HdqFront& out, int coop_max = 12, bool packet = false) {
     // world -> pose: (x - Th) @ R      blend_utils.py:252-261
     float3 q = make3(x.x - fc->Th[0], x.y - fc->Th[1], x.z - fc->Th[2]);
     float3 p = make3(q.x * fc->R[0] + q.y * fc->R[3] + q.z * fc->R[6],
                      q.x * fc->R[1] + q.y * fc->R[4] + q.z * fc->R[7],
                      q.x * fc->R[2] + q.y * fc->R[5] + q.z * fc->R[8]);
     KnnOut nn;
-    knn3_warp(fc, sv, nverts, p, active, nn, coop_max);
+    knn3_warp(fc, sv, nverts, p, active, nn, coop_max, packet);
     out.in_shell = false;
     out.smpl = 0.f;
     if (!active) return;

@@ -75,7 +75,7 @@ struct ra_handle {
     // ---- frame
     FrameConst* fc = nullptr;
     SortedVerts sv{};
-    int *cell_count = nullptr, *cell_fill = nullptr, *vert_cell = nullptr;
+    int *cell_count = nullptr, *cell_fill = nullptr, *vert_cell = nullptr, *vert_order = nullptr;
     int* nb_cnt = nullptr;           // neighbourhood-list counts, RA_NB_LEVELS x (RA_MAX_CELLS + 1)
     ra_frame frame{};
     // ---- per-render workspace
@@ -89,6 +89,7 @@ struct ra_handle {
     QueryList q{}, q2{};             // q2: second work list for the overlapped half of the shadow rays
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int pkt_order = 1, pkt_search = 1;       // shadow rays generated as packets (same light, 32 neighbouring pixels): bit 0 floor pass, bit 1 human pass; far-field 3-NN per packet (env RA_PKT_ORDER, RA_PKT_SEARCH)
     int overlap = 0;                 // env RA_OVERLAP=1: split the shadow stage over two streams (experiment: -0.3..0.5 ms with k_mlp_tc6, but the co-running
                                      // tracing warps slow the MLP epilogue and blur the per-kernel timing; capping MLP registers for more co-residency lost more than it gained)
     AttrList al{};
@@ -98,6 +99,7 @@ struct ra_handle {
     float *pt_smpl = nullptr; int* pt_slot = nullptr;     // ra_query_sdf scratch
     float* bg_spec = nullptr;
     int* blk_cnt = nullptr; int64_t blk_cap = 0;      // image assembly scratch
+    int g_W = 0, g_H = 0;             // image size of the last ra_ground_begin (the floor's 8 x 4 pixel packets)
     int* pix2ray = nullptr; int64_t pix_cap = 0;      // ground pass: image pixel -> ray (ra_ground_begin)
     float *g_weight = nullptr, *g_light = nullptr;
     KthState* kth = nullptr;          // two order-statistic states (f3: Depth / Shading / Specular / Residual percentiles)
@@ -244,8 +246,9 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
             CK(dalloc(h, &h->sv.nb_pos[lv], (size_t)shell * N));
         }
         CK(dalloc(h, &h->nb_cnt, (size_t)RA_NB_LEVELS * (RA_MAX_CELLS + 1)));
+        CK(dalloc(h, &h->sv.nb_mask, RA_MAX_CELLS));
     }
-    CK(dalloc(h, &h->cell_count, RA_MAX_CELLS + 1)); CK(dalloc(h, &h->cell_fill, RA_MAX_CELLS + 1)); CK(dalloc(h, &h->vert_cell, N));
+    CK(dalloc(h, &h->cell_count, RA_MAX_CELLS + 1)); CK(dalloc(h, &h->cell_fill, RA_MAX_CELLS + 1)); CK(dalloc(h, &h->vert_cell, N)); CK(dalloc(h, &h->vert_order, N));
     float** ssp[] = {&h->ss.t, &h->ss.occ, &h->ss.d0, &h->ss.cd, &h->ss.dt, &h->ss.st, &h->ss.off, &h->ss.rlx, &h->ss.q_smpl};
     for (auto p : ssp) CK(dalloc(h, p, P));
     CK(dalloc(h, &h->ss.q_slot, P));
@@ -263,6 +266,10 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     CK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     if (const char* e = getenv("RA_OVERLAP")) h->overlap = atoi(e);
+    if (const char* e = getenv("RA_PKT_ORDER")) h->pkt_order = atoi(e);
+    if (const char* e = getenv("RA_PKT_SEARCH")) h->pkt_search = atoi(e);
+    if (const char* e = getenv("RA_PKT_MIN")) { int v = atoi(e); CK(cudaMemcpyToSymbol(g_pkt_min, &v, sizeof(int))); }
+    if (const char* e = getenv("RA_PKT_RHO")) { float v = (float)atof(e); CK(cudaMemcpyToSymbol(g_pkt_rho, &v, sizeof(float))); }
     CK(dalloc(h, &h->al.bpts, (size_t)h->attr_cap * 3)); CK(dalloc(h, &h->al.mats, (size_t)h->attr_cap * 18));
     CK(dalloc(h, &h->al.bvds, (size_t)h->attr_cap * 3)); CK(dalloc(h, &h->al.src, (size_t)h->attr_cap));
     CK(dalloc(h, &h->raw, (size_t)h->attr_cap * 17));
@@ -270,7 +277,8 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     h->cnt.n_fg = h->counters_blk; h->cnt.n_shadow = h->counters_blk + 1; h->cnt.n_attr = h->counters_blk + 2;
     h->q.count = h->counters_blk + 3; h->al.count = h->cnt.n_attr;
     h->q2.count = h->counters_blk + 4;
-    h->sr.dropped = h->counters_blk + 6;          // (+5: shadow-ray counter of the floor pass)
+    h->sr.dropped = h->counters_blk + 6;          // (+5: shadow-ray list counter of the floor pass)
+    h->sr.n_rays = h->counters_blk + 7;           // rays appended by the human pass and the floor pass (the list counters count padded packet slots)
     h->cnt.n_queries = (unsigned long long*)(h->counters_blk + 8); h->cnt.n_inshell = (unsigned long long*)(h->counters_blk + 10);
     CK(dalloc(h, &h->pt_smpl, (size_t)h->q_cap)); CK(dalloc(h, &h->pt_slot, (size_t)h->q_cap));
     CK(dalloc(h, &h->bg_spec, 4));
@@ -397,16 +405,18 @@ extern "C" int ra_set_frame(ra_handle* h, const ra_frame* f, void* stream) {
            3 * h->cfg.n_bones, h->resd_w0_raw, h->resd_b0_raw, h->resd_w4_raw, h->resd_b4_raw, h->rend_w3_raw, h->rend_b3_raw, h->cell_count, h->cell_h, h->grid2_ratio);
     LAUNCH(h, k_grid_count, (N + 255) / 256, 256, 0, st, h->fc, 0, f->pverts, (const float4*)nullptr, N, h->cell_count, h->vert_cell);
     LAUNCH(h, k_grid_scan, 1, 1024, 0, st, h->fc, 0, h->cell_count, h->sv.cell_start, h->cell_fill);
+    LAUNCH(h, k_grid_order, (N + 255) / 256, 256, 0, st, N, h->vert_cell, h->sv.cell_start, h->cell_fill, h->vert_order);
     LAUNCH(h, k_grid_fill, (N + 127) / 128, 128, 0, st, h->fc, f->pverts, f->pnorm, f->tverts, f->weights, f->A, f->big_A, N,
-           h->cfg.n_bones, h->vert_cell, h->sv.cell_start, h->cell_fill, h->sv);
+           h->cfg.n_bones, h->vert_cell, h->sv.cell_start, h->vert_order, h->sv);
     // per-cell neighbourhood lists (3x3x3 block + radius-2 / radius-3 shells) for the near phase of the 3-NN search
-    LAUNCH(h, k_nb_count, h->sms * 2, 256, 0, st, h->fc, h->sv.cell_start, h->nb_cnt);
+    LAUNCH(h, k_nb_count, h->sms * 2, 256, 0, st, h->fc, h->sv.cell_start, h->nb_cnt, h->sv.nb_mask);
     LAUNCH(h, k_nb_scan, RA_NB_LEVELS, 1024, 0, st, h->fc, h->nb_cnt, h->sv);
     LAUNCH(h, k_nb_fill, h->sms * 4, 256, 0, st, h->fc, h->sv.cell_start, (const float4*)h->sv.pos, h->sv);
     // coarse second level over the cell-sorted vertices
     LAUNCH(h, k_grid_count, (N + 255) / 256, 256, 0, st, h->fc, 1, f->pverts, (const float4*)h->sv.pos, N, h->cell_count, h->vert_cell);
     LAUNCH(h, k_grid_scan, 1, 1024, 0, st, h->fc, 1, h->cell_count, h->sv.cell_start2, h->cell_fill);
-    LAUNCH(h, k_grid_fill2, (N + 255) / 256, 256, 0, st, (const float4*)h->sv.pos, N, h->vert_cell, h->sv.cell_start2, h->cell_fill, h->sv.pos2);
+    LAUNCH(h, k_grid_order, (N + 255) / 256, 256, 0, st, N, h->vert_cell, h->sv.cell_start2, h->cell_fill, h->vert_order);
+    LAUNCH(h, k_grid_fill2, (N + 255) / 256, 256, 0, st, (const float4*)h->sv.pos, N, h->vert_cell, h->sv.cell_start2, h->vert_order, h->sv.pos2);
     LAUNCH(h, k_grid_occ, 1, 1024, 0, st, h->fc, h->sv.cell_start2, (const float4*)h->sv.pos2, h->sv);
     if (h->cfg.precision == RA_PRECISION_TC) {
         if (h->tc_variant == 2 || h->tc_variant >= 6) tc2_set_frame(h->tc2, h->fc, st, h->launches);
@@ -632,7 +642,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     // light visibility (DFSS)
     int L = c.env_h * c.env_w;
     LAUNCH(h, k_shadow_gen, grid_for(h, P * L / 4, 256, 16), 256, 0, st, h->fc, h->cnt.n_fg, h->fg_ray, h->surf, h->fm.norm, h->ldir, L,
-           c.lv_near, c.bbox_margin, h->chunk_actual, h->lay_block, h->lay_world, h->lay_rank, c.visibility_mode, h->lvis, h->ldot, h->sr, h->cnt.n_shadow);
+           c.lv_near, c.bbox_margin, h->chunk_actual, h->lay_block, h->lay_world, h->lay_rank, c.visibility_mode, h->lvis, h->ldot, h->sr, h->cnt.n_shadow, (h->pkt_order >> 1) & 1);
     TraceCfg sc{c.lv_iter, 1.f, c.lv_relax, c.lv_offset, c.st_eps, c.st_skip, c.lv_dist_th, c.blend_radius};
     const bool split = h->overlap && h->cfg.precision == RA_PRECISION_TC && (h->tc_variant == 1 || h->tc_variant >= 6);
     int64_t n_sh = h->sr.cap;
@@ -644,7 +654,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
         for (int it = 0; it <= c.lv_iter; it++) {
             CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
             LAUNCH(h, k_trace_shadow, gs, h->tb_shadow, 0, st, it, sc, h->fc, h->sv, N, h->cnt.n_shadow, h->fg_ray, h->surf, h->ldir, h->lsharp, L, h->sr,
-                   h->q, h->cnt, h->lvis, 0, 1);
+                   h->q, h->cnt, h->lvis, 0, 1, (h->pkt_search >> 1) & 1);
             if (it < c.lv_iter && distance_pass(h, st, n_sh)) return 1;
         }
     } else {
@@ -659,7 +669,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
                 const QueryList& ql = part ? h->q2 : h->q;
                 CK(cudaMemsetAsync(ql.count, 0, sizeof(int), ps));
                 LAUNCH(h, k_trace_shadow, gs, 128, 0, ps, it, sc, h->fc, h->sv, N, h->cnt.n_shadow, h->fg_ray, h->surf, h->ldir, h->lsharp, L,
-                       h->sr, ql, h->cnt, h->lvis, part, 2);
+                       h->sr, ql, h->cnt, h->lvis, part, 2, (h->pkt_search >> 1) & 1);
                 if (it < c.lv_iter && distance_pass(h, ps, n_sh, &ql)) return 1;
             }
         }
@@ -815,6 +825,7 @@ extern "C" int ra_prepare_rays(ra_handle* h, const float* K, const float* R, con
     for (int i = 0; i < 9; i++) { c.Kinv[i] = (float)(inv[i] / det); c.R[i] = R[i]; }
     for (int a = 0; a < 3; a++) { c.T[a] = T[a]; c.o[a] = -(R[a] * T[0] + R[3 + a] * T[1] + R[6 + a] * T[2]); }       // -R^T T
     int n = H * W, nb = (n + 255) / 256;
+    h->g_W = W; h->g_H = H;
     if (nb > h->blk_cap) { hfree(h, h->blk_cnt); CK(dalloc(h, &h->blk_cnt, (size_t)nb)); h->blk_cap = nb; }
     LAUNCH(h, k_prep_rays_count, nb, 256, 0, st, c, wbounds, H, W, mask_at_box, h->blk_cnt);
     LAUNCH(h, k_scan_blocks, 1, 1024, 0, st, h->blk_cnt, nb);
@@ -835,6 +846,7 @@ static GroundCfg ground_cfg(ra_handle* h, const ra_ground_config* g) {
 extern "C" int ra_ground_begin(ra_handle* h, const unsigned char* mask_at_box, int32_t H, int32_t W, const float* acc_map, float* acc_g, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int n = H * W, nb = (n + 255) / 256;
+    h->g_W = W; h->g_H = H;
     if (nb > h->blk_cap) { hfree(h, h->blk_cnt); CK(dalloc(h, &h->blk_cnt, (size_t)nb)); h->blk_cap = nb; }
     if (n > h->pix_cap) {
         hfree(h, h->pix2ray); hfree(h, h->g_weight);
@@ -871,19 +883,23 @@ extern "C" int ra_render_ground(ra_handle* h, const ra_ground_config* g, const f
     TraceCfg sc{g->iter, 1.f, g->relax, g->offset, c.st_eps, c.st_skip, g->dist_th, c.blend_radius};
     int* n_gshadow = h->counters_blk + 5;
     // processing granularity: as many pixels as the shadow-ray / query workspaces of this handle hold (256 rays per pixel)
-    const int64_t step = std::max<int64_t>(std::min<int64_t>(h->P_cap, h->q_cap / 256), 1);
+    int64_t step = std::max<int64_t>(std::min<int64_t>(h->P_cap, h->q_cap / 256), 1);
+    if (step >= 32) step &= ~(int64_t)31;          // whole 32-pixel packets per batch (k_ground_rays pads the last one)
+    // packets of 8 x 4 pixels (about half the radius of 32 x 1 on the floor) when the batches can be whole groups of 4 image rows
+    int tile_w = 0;
+    if ((int64_t)h->g_W * h->g_H == F && h->g_W % 8 == 0 && h->g_H % 4 == 0 && step >= 4 * h->g_W) { tile_w = h->g_W; step = step / (4 * tile_w) * (4 * tile_w); }
     for (int64_t p0 = 0; p0 < F; p0 += step) {
         const int64_t n = std::min<int64_t>(step, F - p0);
         CK(cudaMemsetAsync(n_gshadow, 0, sizeof(int), st));
         LAUNCH(h, k_ground_rays, grid_for(h, n * L / 4, 256, 16), 256, 0, st, h->fc, gc, out->surf_map, acc_g, (long long)p0, (long long)n, h->ldir, L,
-               human_chunks, chunk_actual, out->lvis_map, h->sr, n_gshadow);
+               human_chunks, chunk_actual, out->lvis_map, h->sr, n_gshadow, h->pkt_order & 1, tile_w);
         const int gs = grid_for(h, n * 64, 256, 8);
         int64_t n_sh = h->sr.cap;
         if (h->cfg.precision == RA_PRECISION_FP32 && read_counter(h, n_gshadow, st, &n_sh)) return 1;
         for (int it = 0; it <= g->iter; it++) {
             CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
             LAUNCH(h, k_trace_shadow, gs, 256, 0, st, it, sc, h->fc, h->sv, N, n_gshadow, (const int*)nullptr, out->surf_map, h->ldir, h->lsharp, L,
-                   h->sr, h->q, h->cnt, out->lvis_map, 0, 1);
+                   h->sr, h->q, h->cnt, out->lvis_map, 0, 1, h->pkt_search & 1);
             if (it < g->iter && distance_pass(h, st, n_sh)) return 1;
         }
     }
@@ -992,11 +1008,12 @@ extern "C" int ra_get_stats(ra_handle* h, ra_stats* out) {
     int c[16];
     CK(cudaMemcpy(c, h->counters_blk, sizeof(c), cudaMemcpyDeviceToHost));
     out->n_rays = h->last_P;
-    out->n_fg = c[0]; out->n_shadow_rays = c[1]; out->n_attr_samples = c[2];
+    out->n_fg = c[0]; out->n_shadow_rays = c[7]; out->n_attr_samples = c[2];
     unsigned long long q[2];
     memcpy(q, &c[8], 16);
     out->n_queries = (int64_t)q[0]; out->n_queries_in_shell = (int64_t)q[1];
     out->n_dropped_shadow_rays = c[6];
+    out->n_shadow_slots = (int64_t)c[1] + c[5];
     return 0;
 }
 
@@ -1030,10 +1047,10 @@ extern "C" int ra_profile_read(ra_handle* h, double* mlp_ms, int64_t* mlp_launch
 }
 
 #ifdef RA_KNN_STATS
-extern "C" int ra_debug_knn_stats(unsigned long long* out8, int reset) {
+extern "C" int ra_debug_knn_stats(unsigned long long* out12, int reset) {
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out8, g_knn_stats, sizeof(unsigned long long) * 8);
-    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_knn_stats, z, sizeof(z)); }
+    cudaMemcpyFromSymbol(out12, g_knn_stats, sizeof(unsigned long long) * 12);
+    if (reset) { unsigned long long z[12] = {0}; cudaMemcpyToSymbol(g_knn_stats, z, sizeof(z)); }
     return 0;
 }
 #endif
@@ -1066,6 +1083,7 @@ extern "C" int ra_assemble_image(ra_handle* h, const float* rgb_map, const float
                                  int32_t W, float bg_brightness, float* out_f, unsigned char* out_u8, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int n = H * W, nb = (n + 255) / 256;
+    h->g_W = W; h->g_H = H;
     if (nb > h->blk_cap) { hfree(h, h->blk_cnt); CK(dalloc(h, &h->blk_cnt, (size_t)nb)); h->blk_cap = nb; }
     LAUNCH(h, k_mask_count, nb, 256, 0, st, mask_at_box, n, h->blk_cnt);
     LAUNCH(h, k_scan_blocks, 1, 1024, 0, st, h->blk_cnt, nb);
@@ -1140,6 +1158,7 @@ extern "C" int ra_assemble_visual(ra_handle* h, const float* map, const float* a
     if (!ic || (ic->channels != 3 && ic->channels != 4)) { h->err = "ra_assemble_visual: channels must be 3 or 4"; return 1; }
     if (ic->probe && (!ic->probe_dirs || ic->uH > H || ic->uW > W)) { h->err = "ra_assemble_visual: probe overlay needs probe_dirs and uH <= H, uW <= W"; return 1; }
     int n = H * W, nb = (n + 255) / 256;
+    h->g_W = W; h->g_H = H;
     if (nb > h->blk_cap) { hfree(h, h->blk_cnt); CK(dalloc(h, &h->blk_cnt, (size_t)nb)); h->blk_cap = nb; }
     LAUNCH(h, k_mask_count, nb, 256, 0, st, mask_at_box, n, h->blk_cnt);
     LAUNCH(h, k_scan_blocks, 1, 1024, 0, st, h->blk_cnt, nb);
@@ -1168,11 +1187,20 @@ extern "C" int ra_set_main_light(ra_handle* h, const float* probe, int32_t ph, i
 
 /* The exact 3-NN of row a4 on its own (pytorch3d.ops.knn_points, K=3; sample_utils.py:122): x (n,3) world points ->
  * ids (n,3) original vertex indices nearest first, d2 (n,3) squared pose-space distances.  Same search the renderers use. */
-extern "C" int ra_query_knn(ra_handle* h, const float* x, int64_t n, int32_t* ids, float* d2, void* stream) {
+static int query_knn(ra_handle* h, const float* x, int64_t n, int32_t* ids, float* d2, int packets, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!h->have_frame) { h->err = "query before ra_set_frame"; return 1; }
     if (n == 0) return 0;
-    LAUNCH(h, k_points_knn, grid_for(h, n, 256, 8), 256, 0, st, h->fc, h->sv, h->cfg.n_verts, x, (int)n, (int*)ids, d2);
+    LAUNCH(h, k_points_knn, grid_for(h, n, 256, 8), 256, 0, st, h->fc, h->sv, h->cfg.n_verts, x, (int)n, (int*)ids, d2, packets);
     CK(cudaGetLastError());
     return 0;
+}
+/* The same with the points taken as packets of 32 consecutive entries (the shadow tracer's warps: parallel rays of neighbouring
+ * pixels): far-field lanes of a packet search the box hierarchy together (hdq.cuh: knn3_packet).  Any input is answered exactly;
+ * the grouping only decides which search runs. */
+extern "C" int ra_query_knn_packets(ra_handle* h, const float* x, int64_t n, int32_t* ids, float* d2, void* stream) {
+    return query_knn(h, x, n, ids, d2, 1, stream);
+}
+extern "C" int ra_query_knn(ra_handle* h, const float* x, int64_t n, int32_t* ids, float* d2, void* stream) {
+    return query_knn(h, x, n, ids, d2, 0, stream);
 }

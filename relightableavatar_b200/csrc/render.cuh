@@ -118,12 +118,30 @@ struct ShadowRays {      // SoA over traced (pixel, light) pairs
     int* q_slot;
     int cap;             // entries the arrays hold (256 per ray of ra_config.max_rays)
     int* dropped;        // device counter: rays that did not fit (reported by ra_get_stats; their light stays 'visible')
+    int* n_rays;         // device counter: rays appended (the list counter itself counts padded packet slots)
 };
 // append guard: a light layout with more than 256 front-facing lights per pixel (not the antipodally symmetric 16x32 grid of
 // gen_light_xyz) could generate more shadow rays than the workspace holds -- drop and count instead of writing out of bounds
 __device__ __forceinline__ bool shadow_slot_ok(const ShadowRays& sr, bool trace, int slot) {
     if (trace && slot >= sr.cap) { atomicAdd(sr.dropped, 1); return false; }
     return trace;
+}
+
+// one warp appends its packet: padded = a whole aligned block of 32 entries (fg = -1 on the lanes without a ray), else compacted
+__device__ __forceinline__ void shadow_append(const ShadowRays& sr, int* n_shadow, bool padded, bool trace, int f, int l, float nr, float fr) {
+    const unsigned any = __ballot_sync(0xffffffffu, trace);
+    if (!any) return;
+    if ((threadIdx.x & 31) == 0) atomicAdd(sr.n_rays, __popc(any));
+    if (padded) {
+        int base = 0;
+        if ((threadIdx.x & 31) == 0) base = atomicAdd(n_shadow, 32);
+        const int slot = __shfl_sync(0xffffffffu, base, 0) + (threadIdx.x & 31);
+        if (slot >= sr.cap) { if (trace) atomicAdd(sr.dropped, 1); return; }
+        sr.fg[slot] = trace ? f : -1; sr.light[slot] = (unsigned short)l; sr.near_[slot] = nr; sr.far_[slot] = fr;
+    } else {
+        const int slot = warp_append(n_shadow, trace);
+        if (shadow_slot_ok(sr, trace, slot)) { sr.fg[slot] = f; sr.light[slot] = (unsigned short)l; sr.near_[slot] = nr; sr.far_[slot] = fr; }
+    }
 }
 
 __device__ __forceinline__ void aabb_near_far(const float* bmin, const float* bmax, float3 o, float3 d, float& near_, float& far_) {
@@ -141,22 +159,32 @@ __device__ __forceinline__ void aabb_near_far(const float* bmin, const float* bm
 }
 
 // light_visibility set-up (:265-329): per (fg pixel, light): ldot, front-facing & box tests, ray append.
+// packets = 0 (the default for the human pass): one warp = 32 lights of one foreground pixel, rays appended compacted.
+// packets = 1: one warp = one PACKET, the same light for 32 consecutive foreground pixels, appended as a whole aligned block of the ray
+// list (lanes without a ray carry fg = -1; compacted instead if the padded list could outgrow the workspace).  That is the floor
+// pass's layout (ground.cuh), where it is worth 2.2x; on the body it measured SLOWER (visibility stage 17.9 -> 19.5 ms at 512^2): the
+// normals of 32 neighbouring pixels sweep most of the hemisphere (a limb is ~30 pixels wide), so nearly every (tile, light) pair holds a
+// ray and the padded list has 1.9x the entries, while rays that leave from ONE pixel share their 3-NN lists during the first iterations.
 __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __restrict__ n_fg, const int* __restrict__ fg_ray,
                              const float* __restrict__ surf /*[P][3] by ray*/, const float* __restrict__ f_norm /*[fg][3]*/,
                              const float* __restrict__ ldir /*[L][3]*/, int L, float lv_near, float bbox_margin, int chunk_actual,
                              int lay_block, int lay_world, int lay_rank,     // tile sharding: local ray -> global ray (identity when world == 1)
                              int vis_mode,       // 0: DFSS tracing; 1: cfg.local_visibility (lvis = ldot > 0); 2: cfg.no_visibility (lvis = 1)   :296-301
-                             float* lvis, float* ldot, ShadowRays sr, int* n_shadow) {
-    int lane = threadIdx.x & 31;
-    long long total = (long long)(*n_fg) * L;
+                             float* lvis, float* ldot, ShadowRays sr, int* n_shadow, int packets /* 0: pixel-major compact list (one warp = 32 lights of a pixel) */) {
+    const int lane = threadIdx.x & 31;
+    const int nfg = *n_fg;
+    const long long ntile = (nfg + 31) >> 5;
+    const long long total = packets ? ntile * L * 32 : (long long)nfg * L;
+    const bool padded = packets && total <= (long long)sr.cap;
     for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += (long long)gridDim.x * blockDim.x) {
-        long long idx = base + lane;
-        bool valid = idx < total;
+        const long long w = base >> 5;
+        const int l = packets ? (int)(w % L) : (int)((base + lane) % L);
+        const int f = packets ? (int)(w / L) * 32 + lane : (int)((base + lane) / L);
+        const bool valid = packets ? f < nfg : base + lane < total;
         bool trace = false;
-        int f = 0, l = 0;
         float nr = 0.f, fr = 0.f;
         if (valid) {
-            f = (int)(idx / L); l = (int)(idx % L);
+            const long long idx = (long long)f * L + l;
             int ray = fg_ray[f];
             float3 n = make3(f_norm[f * 3], f_norm[f * 3 + 1], f_norm[f * 3 + 2]);
             float3 dl = make3(ldir[l * 3], ldir[l * 3 + 1], ldir[l * 3 + 2]);
@@ -178,8 +206,7 @@ __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __res
             }
             lvis[idx] = vis;
         }
-        int slot = warp_append(n_shadow, trace);
-        if (shadow_slot_ok(sr, trace, slot)) { sr.fg[slot] = f; sr.light[slot] = (unsigned short)l; sr.near_[slot] = nr; sr.far_[slot] = fr; }
+        shadow_append(sr, n_shadow, padded, trace, f, l, nr, fr);
     }
 }
 
@@ -187,11 +214,11 @@ __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __res
 __global__ void __launch_bounds__(256, RA_SHADOW_MINBLOCKS) k_trace_shadow(int it, TraceCfg cfg, const FrameConst* __restrict__ fc, SortedVerts sv, int nverts,
                                const int* __restrict__ n_shadow, const int* __restrict__ fg_ray, const float* __restrict__ surf,
                                const float* __restrict__ ldir, const float* __restrict__ lsharp, int L,
-                               ShadowRays sr, QueryList q, Counters cnt, float* lvis, int part, int nparts) {
+                               ShadowRays sr, QueryList q, Counters cnt, float* lvis, int part, int nparts, int packets) {
     // rays [lo, hi) of the list: the host runs the parts on different streams so that one part's CUDA-core work overlaps
     // the other part's tensor-core MLP kernel
     const long long Nall = min(*n_shadow, sr.cap);
-    const int lo = (int)(Nall * part / nparts), N = (int)(Nall * (part + 1) / nparts);
+    const int lo = (int)(Nall * part / nparts) & ~31, N = (part + 1 == nparts) ? (int)Nall : ((int)(Nall * (part + 1) / nparts) & ~31);   // parts cut between packets
     for (int base = lo + blockIdx.x * blockDim.x; base < N; base += gridDim.x * blockDim.x) {      // block-uniform trip count
         int i = base + threadIdx.x;
         bool valid = i < N;
@@ -200,8 +227,9 @@ __global__ void __launch_bounds__(256, RA_SHADOW_MINBLOCKS) k_trace_shadow(int i
         int f = 0, l = 0;
         bool parked = false;        // front did not move (t clamped): same point, same distance -- reuse, no query (exact)
         float d_keep = 0.f;
+        if (valid) { f = sr.fg[i]; valid = f >= 0; }      // padded packets: lanes without a ray
         if (valid) {
-            f = sr.fg[i]; l = sr.light[i];
+            l = sr.light[i];
             int ray = fg_ray ? fg_ray[f] : f;          // floor pass: the ray list indexes image pixels directly
             o = make3(surf[ray * 3], surf[ray * 3 + 1], surf[ray * 3 + 2]);
             d = make3(ldir[l * 3], ldir[l * 3 + 1], ldir[l * 3 + 2]);
@@ -242,7 +270,7 @@ __global__ void __launch_bounds__(256, RA_SHADOW_MINBLOCKS) k_trace_shadow(int i
         if (it < cfg.iters) {
             HdqFront hf; hf.in_shell = false; hf.smpl = 0.f;
             const bool ask = alive && !parked;
-            hdq_front<false>(fc, sv, nverts, o + d * t, ask, cfg.th, cfg.blend_radius, hf, 32);      // shadow rays: far lanes are served by the whole warp
+            hdq_front<false>(fc, sv, nverts, o + d * t, ask, cfg.th, cfg.blend_radius, hf, 32, packets != 0);      // shadow rays: far lanes are served as one packet, stragglers by the whole warp
             bool ins = ask && hf.in_shell;
             count_queries(cnt, ask, ins);
             int slot = warp_append(q.count, ins);
@@ -276,7 +304,8 @@ __global__ void k_points_front(const FrameConst* __restrict__ fc, SortedVerts sv
 
 // The exact 3-NN on its own (row a4: pytorch3d.ops.knn_points K=3 at sample_utils.py:122): world points -> pose space -> the three
 // nearest posed vertices as ORIGINAL vertex indices, nearest first, with their squared distances.
-__global__ void k_points_knn(const FrameConst* __restrict__ fc, SortedVerts sv, int nverts, const float* __restrict__ x, int n, int* ids, float* d2) {
+__global__ void k_points_knn(const FrameConst* __restrict__ fc, SortedVerts sv, int nverts, const float* __restrict__ x, int n, int* ids, float* d2,
+                             int packets /* 1: every 32 consecutive points are one packet (the shadow tracer's search) */) {
     for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {      // block-uniform trip count
         const int i = base + threadIdx.x;
         const bool valid = i < n;
@@ -287,7 +316,7 @@ __global__ void k_points_knn(const FrameConst* __restrict__ fc, SortedVerts sv, 
                       q.x * fc->R[2] + q.y * fc->R[5] + q.z * fc->R[8]);
         }
         KnnOut nn;
-        knn3_warp(fc, sv, nverts, p, valid, nn);
+        knn3_warp(fc, sv, nverts, p, valid, nn, packets ? 32 : 12, packets != 0);
         if (valid)
             for (int k = 0; k < 3; k++) { ids[i * 3 + k] = __float_as_int(__ldg(&sv.pos[nn.id[k]]).w); d2[i * 3 + k] = nn.d2[k]; }
     }

@@ -441,13 +441,15 @@ class Engine:
             self._check(self.lib.ra_query_sdf(self.h, _ptr(x), x.shape[0], th, int(smooth), _ptr(out), self._stream()), 'ra_query_sdf')
         return out
 
-    def query_knn(self, x: torch.Tensor):
-        """Exact 3 nearest posed vertices of world points (sample_utils.py:122): -> ids (n,3) int32 vertex indices, d2 (n,3)."""
+    def query_knn(self, x: torch.Tensor, packets: bool = False):
+        """Exact 3 nearest posed vertices of world points (sample_utils.py:122): -> ids (n,3) int32 vertex indices, d2 (n,3).
+        `packets`: run the search the way the shadow tracer does (every 32 consecutive points = one packet of nearby points)."""
         x = x.to(device=self.device, dtype=torch.float32).reshape(-1, 3).contiguous()
         ids = torch.empty(x.shape[0], 3, device=self.device, dtype=torch.int32)
         d2 = torch.empty(x.shape[0], 3, device=self.device)
         with torch.cuda.device(self.device):
-            self._check(self.lib.ra_query_knn(self.h, _ptr(x), x.shape[0], _ptr(ids), _ptr(d2), self._stream()), 'ra_query_knn')
+            fn = self.lib.ra_query_knn_packets if packets else self.lib.ra_query_knn
+            self._check(fn(self.h, _ptr(x), x.shape[0], _ptr(ids), _ptr(d2), self._stream()), 'ra_query_knn')
         return ids, d2
 
     def query_raw(self, x: torch.Tensor, v: Optional[torch.Tensor] = None) -> torch.Tensor:

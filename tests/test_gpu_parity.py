@@ -721,5 +721,84 @@ def test_knn3_indices_are_exact():
     distinct = (gaps > 4 * tol[:, :1].expand(-1, 3) + 4e-5 * ref_d[:, 3:]).all(dim=1)
     assert distinct.float().mean() > 0.8, float(distinct.float().mean())
     assert torch.equal(ids[distinct].long(), ref_i[distinct, :3])
+    # the same points through the packet search (random grouping: mostly refused as too spread out, answered query by query)
+    ids_p, d2_p = eng.query_knn(x, packets=True)
+    assert torch.equal(d2_p, d2) and torch.equal(ids_p[distinct], ids[distinct])
     eng.close()
 
+
+@pytest.mark.gpu
+def test_knn3_packet_search_is_exact():
+    """The shadow tracer's far-field search (hdq.cuh: knn3_packet): packets of 32 nearby points -- parallel rays of neighbouring pixels --
+    walk the box hierarchy once for all lanes.  Packets of every kind: tight clusters 0.2-3 m from the body, clusters straddling the
+    14 cm near / far limit (mixed near and far lanes), packets with fewer far lanes than the packet threshold, clusters wider than the
+    packet radius (refused, answered query by query) and clusters right at the bounding-box corners -- against brute force."""
+    b = scene.make_batch(32, 32, frame=1, n_frames=3, seed=0, n_env=0)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    eng = Engine(default_config(True, precision=0, max_rays=8192), DEV)
+    eng.upload_weights(sd); eng.set_frame(b)
+    g = torch.Generator().manual_seed(33)
+    wv = torch.as_tensor(b['wverts'][0])
+    lo, hi = wv.min(0)[0], wv.max(0)[0]
+    parts = []
+    for n_pk, dist, width in ((600, 0.2, 0.02), (600, 0.5, 0.05), (400, 1.5, 0.08), (300, 3.0, 0.1), (600, 0.14, 0.05), (300, 0.5, 0.4),
+                              (200, 0.05, 0.15)):
+        anchor = wv[torch.randint(0, wv.shape[0], (n_pk,), generator=g)]
+        dirs = torch.nn.functional.normalize(torch.randn(n_pk, 3, generator=g), dim=-1)
+        centre = anchor + dirs * dist
+        parts.append((centre[:, None] + (torch.rand(n_pk, 32, 3, generator=g) - 0.5) * width).reshape(-1, 3))
+    corners = torch.stack([torch.where(torch.tensor([(k >> a) & 1 for a in range(3)], dtype=torch.bool), hi + 0.25, lo - 0.25) for k in range(8)])
+    parts.append((corners[:, None] + (torch.rand(8, 32, 3, generator=g) - 0.5) * 0.03).reshape(-1, 3))
+    x = torch.cat(parts).float().to(DEV)
+    ids, d2 = eng.query_knn(x, packets=True)
+    ids0, d20 = eng.query_knn(x, packets=False)
+    R = torch.as_tensor(b['R'][0]).to(DEV); Th = torch.as_tensor(b['Th'][0]).reshape(1, 3).to(DEV)
+    pv = torch.as_tensor(b['pverts'][0]).to(DEV)
+    p = (x - Th) @ R
+    ref_d, ref_i = [], []
+    for s in range(0, x.shape[0], 4096):
+        q = p[s:s + 4096]
+        dd = (q[:, None, 0] - pv[None, :, 0]) ** 2
+        dd = dd + (q[:, None, 1] - pv[None, :, 1]) ** 2
+        dd = dd + (q[:, None, 2] - pv[None, :, 2]) ** 2
+        v, i = torch.topk(dd, 4, dim=-1, largest=False, sorted=True)
+        ref_d.append(v); ref_i.append(i)
+    ref_d, ref_i = torch.cat(ref_d), torch.cat(ref_i)
+    tol = 1e-6 * ref_d[:, :3].sqrt() + 1e-5 * ref_d[:, :3] + 1e-9
+    assert bool(((d2 - ref_d[:, :3]).abs() <= tol).all()), float(((d2 - ref_d[:, :3]).abs() - tol).max())
+    assert torch.equal(d2, d20)                         # the two searches see the same pose-space point: identical distances
+    gaps = ref_d[:, 1:] - ref_d[:, :-1]
+    distinct = (gaps > 4 * tol[:, :1].expand(-1, 3) + 4e-5 * ref_d[:, 3:]).all(dim=1)
+    assert distinct.float().mean() > 0.7, float(distinct.float().mean())
+    assert torch.equal(ids[distinct].long(), ref_i[distinct, :3])
+    assert torch.equal(ids[distinct], ids0[distinct])
+    eng.close()
+
+
+
+@pytest.mark.gpu
+def test_shadow_ray_packets_change_nothing(monkeypatch):
+    """Shadow rays are generated as packets (same light, 32 neighbouring pixels) and the far-field 3-NN of a packet runs as one
+    search (hdq.cuh: knn3_packet).  Every ray is still traced on its own with the exact 3-NN, so a frame rendered with the packet
+    order / packet search must equal the frame rendered in the legacy pixel-major order with one search per query BIT FOR BIT --
+    human visibility maps, floor visibility (16 iterations, nearly all far-field queries), pixels and the work counters."""
+    H = 96
+    b = scene.make_batch(H, H, seed=0, n_env=0)
+    sd = scene.make_state_dict(0, relight=True, fitted=True)
+    outs = {}
+    for order, search in ((0, 0), (3, 0), (3, 3), (1, 1)):          # bit 0: floor pass, bit 1: human pass; (1, 1) is the default
+        monkeypatch.setenv('RA_PKT_ORDER', str(order)); monkeypatch.setenv('RA_PKT_SEARCH', str(search))
+        r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='tc', max_rays=16384, test_light=('main',),
+                     return_lvis=True, ground_shading=True, sync_timing=False)
+        r.render(dict(b))
+        out = r.render(dict(b))
+        st = r.engine.stats()
+        outs[(order, search)] = ({k: v.clone() for k, v in out['main'].items() if torch.is_tensor(v)}, st)
+        r.engine.close()
+    ref, st0 = outs[(0, 0)]
+    assert int((ref['lvis_map'] < 0.999).sum()) > 10000
+    for key in ((3, 0), (3, 3), (1, 1)):
+        got, st = outs[key]
+        assert st['n_queries'] == st0['n_queries'] and st['n_queries_in_shell'] == st0['n_queries_in_shell'] and st['n_shadow_rays'] == st0['n_shadow_rays'], (key, st, st0)
+        for k in ('lvis_map', 'ldot_map', 'rgb_map', 'shade_map', 'acc_map'):
+            assert torch.equal(got[k], ref[k]), (key, k, int((got[k] != ref[k]).sum()), float((got[k] - ref[k]).abs().max()))

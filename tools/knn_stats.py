@@ -10,7 +10,7 @@ b = scene.make_batch(512, 512, seed=0, n_env=0)
 sd = scene.make_state_dict(0, True, True)
 r = Renderer(scene.SyntheticNet(sd, True), mode='relight', precision='tc', max_rays=80000, sync_timing=False)
 lib = _lib.load()
-arr = (ctypes.c_ulonglong * 8)()
+arr = (ctypes.c_ulonglong * 12)()
 r.render(b); lib.ra_debug_knn_stats(arr, 1)
 r.render(b); lib.ra_debug_knn_stats(arr, 1)
 n = arr[0] + arr[1]
