@@ -8,8 +8,8 @@
 // (tcgen05.mma kind::f16, M=128, N<=256, K=16): the same compensation scheme as 3xTF32, on the fast tensor path.
 //   smem  : one 4-stage ring, per 16-wide K chunk 16 KB of weights (pre-packed [2][Npad][8] hi image, then the lo image, by TMA)
 //           and 8 KB of activations (hi / lo images [2][128][8] written by the worker warps): 96 KB, two CTAs per SM
-//   warps : 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..9 = workers: load + split X chunk by chunk (4 chunks of
-//           global loads in flight per thread), then the fp32 epilogue (bias, ReLU / Softplus100 / derivative masks of the
+//   warps : 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..9 = workers: load (whole 128 B lines, two groups of four chunks
+//           in flight) + split X, then the fp32 epilogue (bias, ReLU / Softplus100 / derivative masks of the
 //           backward pass) straight to global memory.
 // Persistent: one CTA per SM walks the 128-row tiles (tile = blockIdx.x, + gridDim.x, ...); the row count is read on the device
 // (no host synchronisation), CTAs without a tile exit at once.
@@ -28,7 +28,6 @@
 #define LT_WORKERS 8
 #define LT_THREADS (64 + 32 * LT_WORKERS)
 #define LT_SMEM_BYTES (LT_STAGES * LT_STAGE_BYTES + 256)       // 96.25 KB: two CTAs per SM
-#define LT_PRE 4                                     // chunks whose global loads a worker keeps in flight
 
 struct LinTcArgs {
     const float* X; int ldx;
@@ -69,7 +68,7 @@ __global__ void __launch_bounds__(LT_THREADS, 2) k_lin_tc(const __grid_constant_
     const uint32_t chunk_bytes = (uint32_t)P.Npad * 64u;     // hi + lo of one weight chunk
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < LT_STAGES; s++) { mbar_init(bar_full + 8 * s, 1 + LT_WORKERS); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < LT_STAGES; s++) { mbar_init(bar_full + 8 * s, 1 + LT_WORKERS / 2); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -121,39 +120,67 @@ __global__ void __launch_bounds__(LT_THREADS, 2) k_lin_tc(const __grid_constant_
         }
     } else {
         // ===================== workers: activation chunks, then the epilogue =====================
-        const int e = warp - 2, q = warp & 3, half = e >> 2;          // half: which K-group of a chunk / which column blocks
-        const int row = q * 32 + lane;
-        uint32_t it = 0, tc = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tc++) {
-            const int m = tile * 128 + row;
-            const bool rok = m < M;
-            const float* xr = P.X + (size_t)(rok ? m : 0) * P.ldx + half * 8;
-            for (int c0 = 0; c0 < nch; c0 += LT_PRE) {
-                float v[LT_PRE][8];
+        // Every global access is COALESCED: a load / store instruction of a warp covers 4 rows x 128 contiguous bytes (8 lanes per
+        // row), i.e. 4 cache lines.  (The first version gave every thread its own row: each 16-byte access of a warp touched 32
+        // different lines and the L1TEX tag stage -- 24.5 k line accesses per 128-row tile for X, the saved activations and Y --
+        // bound the kernel at 64-78 % l1tex throughput, 2.2 TB/s of DRAM traffic whatever the row count, tensor pipe 11 %:
+        // profiles/r02_ncu_k_lin_tc_before_coalescing.txt.)
+        //  * X: of every group of four chunks (256 B of a row) the warps of half 0 own the first two chunks, the warps of half 1 the
+        //    last two.  Request j of a warp: lane l reads the float4 `l & 7` of row 4 j + (l >> 3); the values are split into hi / lo
+        //    halves in registers and go to the K-major operand images with 8-byte stores.  The next group's loads are in flight while
+        //    the current group is converted.
+        //  * Y: a 32 x 32 accumulator block is transposed through this warp's 4 KB of the (idle) activation half of the ring --
+        //    XOR-swizzled 16-byte pieces, conflict-free both ways -- and leaves as row segments; bias / activation / derivative masks
+        //    are applied on the way out with the saved activations read in the same coalesced pattern.
+        const int e = warp - 2, q = warp & 3, half = e >> 2;          // half: which chunk pair of a group / which column blocks
+        const int lr = lane >> 3, pc = lane & 7;                      // coalesced pattern: row-in-request, 16-byte piece of the row segment
+        const uint32_t stg = s_base + (uint32_t)(e >> 1) * LT_STAGE_BYTES + LT_W_BYTES + (uint32_t)(e & 1) * 4096u;
+        uint32_t it0 = 0, tc = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tc++, it0 += nch) {
+            const int m0 = tile * 128 + q * 32;                        // first row of this warp's quarter
+            float4 va[8], vb[8];                                       // two groups in flight: request j -> row 4 j + lr, piece pc
+            auto load_group = [&](int c0, float4* dst) {
+                const int c = c0 + 2 * half + (pc >> 2);               // the chunk this lane's piece belongs to
 #pragma unroll
-                for (int u = 0; u < LT_PRE; u++) {              // LT_PRE chunks' loads in flight
-                    if (rok && c0 + u < nch) {
-                        const float4 a = *reinterpret_cast<const float4*>(xr + (c0 + u) * LT_KC), b = *reinterpret_cast<const float4*>(xr + (c0 + u) * LT_KC + 4);
-                        v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = b.x; v[u][5] = b.y; v[u][6] = b.z; v[u][7] = b.w;
-                    } else {
+                for (int j = 0; j < 8; j++) {
+                    const int m = m0 + 4 * j + lr;
+                    dst[j] = (m < M && c < nch) ? *reinterpret_cast<const float4*>(P.X + (size_t)m * P.ldx + (c0 + 2 * half) * LT_KC + pc * 4)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            auto store_group = [&](int c0, const float4* src) {
+                const int cA = c0 + 2 * half;
+                if (cA >= nch) return;
+                const bool two = cA + 1 < nch;
+                const uint32_t itA = it0 + (uint32_t)cA, itB = itA + 1;
+                const uint32_t sA = itA & (LT_STAGES - 1), sB = itB & (LT_STAGES - 1);
+                mbar_wait(bar_empty + 8 * sA, ((itA / LT_STAGES) & 1) ^ 1);
+                if (two) mbar_wait(bar_empty + 8 * sB, ((itB / LT_STAGES) & 1) ^ 1);
+                // piece pc: chunk (pc >> 2), K-group (pc >> 1) & 1, halves 4 (pc & 1) .. + 3 of the 16-byte operand row
+                const uint32_t a_dst = s_base + ((pc >> 2) ? sB : sA) * LT_STAGE_BYTES + LT_W_BYTES + (uint32_t)((pc >> 1) & 1) * 2048u + (uint32_t)(pc & 1) * 8u;
+                if (two || (pc >> 2) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 8; j++) v[u][j] = 0.f;
+                    for (int j = 0; j < 8; j++) {
+                        const float4 x = src[j];
+                        const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+                        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                        const __half2 l0 = __floats2half2_rn(x.x - f0.x, x.y - f0.y), l1 = __floats2half2_rn(x.z - f1.x, x.w - f1.y);
+                        const uint32_t a = a_dst + (uint32_t)(q * 32 + 4 * j + lr) * 16u;
+                        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(a), "r"(*reinterpret_cast<const uint32_t*>(&h0)), "r"(*reinterpret_cast<const uint32_t*>(&h1)) : "memory");
+                        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(a + LT_A_BYTES / 2), "r"(*reinterpret_cast<const uint32_t*>(&l0)), "r"(*reinterpret_cast<const uint32_t*>(&l1)) : "memory");
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < LT_PRE; u++) {
-                    if (c0 + u >= nch) break;
-                    const uint32_t s = it & (LT_STAGES - 1), ph = (it / LT_STAGES) & 1;
-                    it++;
-                    uint32_t hi[4], lo[4];
-                    lt_split8(v[u], hi, lo);
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                    const uint32_t a_hi = s_base + s * LT_STAGE_BYTES + LT_W_BYTES + (uint32_t)half * 2048u + (uint32_t)row * 16u;
-                    st_shared_v4(a_hi, hi[0], hi[1], hi[2], hi[3]);
-                    st_shared_v4(a_hi + LT_A_BYTES / 2, lo[0], lo[1], lo[2], lo[3]);
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_full + 8 * s);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(bar_full + 8 * sA); if (two) mbar_arrive(bar_full + 8 * sB); }
+            };
+            load_group(0, va);
+            for (int c0 = 0; c0 < nch; c0 += 8) {
+                if (c0 + 4 < nch) load_group(c0 + 4, vb);
+                store_group(c0, va);
+                if (c0 + 4 < nch) {
+                    if (c0 + 8 < nch) load_group(c0 + 8, va);
+                    store_group(c0 + 4, vb);
                 }
             }
             // ---- epilogue, 32 accumulator columns at a time (this warp: blocks half, half + 2, ...)
@@ -165,40 +192,51 @@ __global__ void __launch_bounds__(LT_THREADS, 2) k_lin_tc(const __grid_constant_
                 uint32_t r[32];
                 tmem_ld32(t_lane + (uint32_t)(cb * 32), r);
                 tmem_ld_wait();
-                if (!rok) continue;
-                const int n0 = cb * 32;
-                float* yr = P.Y + (size_t)m * P.ldy + n0;
-                const float* ar = (EPI == EPI_MUL_DRELU || EPI == EPI_MUL_DSOFTPLUS) ? P.aux + (size_t)m * P.ldaux + n0 : nullptr;
 #pragma unroll
-                for (int j4 = 0; j4 < 8; j4++) {
-                    float o[4];
-                    const int nb = n0 + j4 * 4;
-                    float4 av = make_float4(0, 0, 0, 0);
-                    const bool full4 = nb + 3 < P.N;
-                    if (ar && full4) av = *reinterpret_cast<const float4*>(ar + j4 * 4);
-                    const float avs[4] = {av.x, av.y, av.z, av.w};
+                for (int j = 0; j < 8; j++)
+                    st_shared_v4(stg + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                __syncwarp();
+                const int nb = cb * 32 + pc * 4;                       // this lane's 4 output columns
+                const bool full4 = nb + 3 < P.N;
+                float bv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (P.bias) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int n = nb + j;
-                        float v = __uint_as_float(r[j4 * 4 + j]);
-                        if (n < P.N) {
-                            if (P.bias) v += __ldg(&P.bias[n]);
-                            float au = 0.f;
-                            if (ar) au = full4 ? avs[j] : ar[j4 * 4 + j];
-                            if (EPI == EPI_RELU) v = fmaxf(v, 0.f);
-                            if (EPI == EPI_SOFTPLUS) v = softplus100(v);
-                            if (EPI == EPI_MUL_DRELU) v = (au > 0.f) ? v : 0.f;
-                            if (EPI == EPI_MUL_DSOFTPLUS) v *= dsoftplus100_from_act(au);
-                        }
-                        o[j] = v;
-                    }
-                    if (full4) *reinterpret_cast<float4*>(yr + j4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
-                    else
-                        for (int j = 0; j < 4; j++)
-                            if (nb + j < P.N) yr[j4 * 4 + j] = o[j];
+                    for (int t = 0; t < 4; t++) if (nb + t < P.N) bv[t] = __ldg(&P.bias[nb + t]);
                 }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int R = 4 * j + lr, m = m0 + R;
+                    uint32_t w0, w1, w2, w3;
+                    ld_shared_v4(stg + (uint32_t)R * 128u + (uint32_t)((pc ^ (R & 7)) << 4), w0, w1, w2, w3);
+                    if (m >= M || nb >= P.N) continue;
+                    float o[4] = {__uint_as_float(w0), __uint_as_float(w1), __uint_as_float(w2), __uint_as_float(w3)};
+                    float au[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (EPI == EPI_MUL_DRELU || EPI == EPI_MUL_DSOFTPLUS) {
+                        const float* ar = P.aux + (size_t)m * P.ldaux + nb;
+                        if (full4) { const float4 a4 = *reinterpret_cast<const float4*>(ar); au[0] = a4.x; au[1] = a4.y; au[2] = a4.z; au[3] = a4.w; }
+                        else
+                            for (int t = 0; t < 4; t++) if (nb + t < P.N) au[t] = ar[t];
+                    }
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        float v = o[t] + bv[t];
+                        if (EPI == EPI_RELU) v = fmaxf(v, 0.f);
+                        if (EPI == EPI_SOFTPLUS) v = softplus100(v);
+                        if (EPI == EPI_MUL_DRELU) v = (au[t] > 0.f) ? v : 0.f;
+                        if (EPI == EPI_MUL_DSOFTPLUS) v *= dsoftplus100_from_act(au[t]);
+                        o[t] = v;
+                    }
+                    float* yr = P.Y + (size_t)m * P.ldy + nb;
+                    if (full4) *reinterpret_cast<float4*>(yr) = make_float4(o[0], o[1], o[2], o[3]);
+                    else
+                        for (int t = 0; t < 4; t++) if (nb + t < P.N) yr[t] = o[t];
+                }
+                __syncwarp();                    // the staging block is reused by the next column block
             }
-            tc_fence_before();                   // accumulator reads done before this warp feeds the next tile's first chunk
+            // all accumulator reads and staging traffic of this tile are done before ANY worker feeds the next tile (the activation
+            // halves of the ring double as staging; the next tile's first MMA overwrites the accumulator)
+            tc_fence_before();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * LT_WORKERS) : "memory");
         }
     }
     tc_fence_before();
