@@ -615,28 +615,39 @@ __device__ bool knn3_packet(const FrameConst* __restrict__ fc, const SortedVerts
     const float B = act ? o.d2[2] : 0.f;          // seeds of the near phase are real vertices: upper bound of the true 3rd distance (or 3e38)
     KnnOut w;
     w.d2[0] = w.d2[1] = w.d2[2] = 3.0e38f; w.id[0] = w.id[1] = w.id[2] = -1;
+    __shared__ float4 pkt_buf[8][32];              // per-warp staging of a cell's vertices (blocks of up to 8 warps)
+    float4* buf = pkt_buf[(threadIdx.x >> 5) & 7];
     // one coarse cell: its box and vertex range come in the same two loads; each far lane tests the box against ITS OWN point and
     // bound (as tight as a single-query search), the cell is scanned if any lane needs it, by the lanes that need it
-    auto scan = [&](int cc, bool all) {
+    auto scan = [&](int cc) {
         const float4 clo = __ldg(&sv.occ_lo[cc]), chi = __ldg(&sv.occ_hi[cc]);
-        const bool mine = act && (all || bbox_dist2(p, clo, chi) * 0.9999f <= fminf(B, w.d2[2]));
+        const bool mine = act && bbox_dist2(p, clo, chi) * 0.9999f <= fminf(B, w.d2[2]);
         if (!__any_sync(0xffffffffu, mine)) return;
         const int s = __float_as_int(clo.w), e = __float_as_int(chi.w);
         if (lane == 0) { KNN_STAT(9, 1); KNN_STAT(10, e - s); }
-        int v = s;
-        for (; v + 4 <= e; v += 4) {
-            const float4 q0 = __ldg(&sv.pos2[v]), q1 = __ldg(&sv.pos2[v + 1]), q2 = __ldg(&sv.pos2[v + 2]), q3 = __ldg(&sv.pos2[v + 3]);
+        // the cell's vertices come in with ONE coalesced load per 32 and are handed to the lanes through shared memory (broadcast
+        // reads: fixed ~25-cycle latency) -- warp-uniform global loads of one vertex at a time left the loop waiting on L1 / L2
+        // (46 % of its stall samples: profiles/r02_ncu_k_trace_shadow_floor.txt)
+        for (int base = s; base < e; base += 32) {
+            const int nv = min(32, e - base);
+            __syncwarp();
+            if (lane < nv) buf[lane] = __ldg(&sv.pos2[base + lane]);
+            __syncwarp();
             if (mine) {
-                const float e0 = dist2_ref(p, q0), e1 = dist2_ref(p, q1), e2 = dist2_ref(p, q2), e3 = dist2_ref(p, q3);
-                if (fminf(fminf(e0, e1), fminf(e2, e3)) < w.d2[2]) {
-                    knn_insert(w, e0, __float_as_int(q0.w)); knn_insert(w, e1, __float_as_int(q1.w));
-                    knn_insert(w, e2, __float_as_int(q2.w)); knn_insert(w, e3, __float_as_int(q3.w));
+                int k = 0;
+                for (; k + 4 <= nv; k += 4) {
+                    const float4 q0 = buf[k], q1 = buf[k + 1], q2 = buf[k + 2], q3 = buf[k + 3];
+                    const float e0 = dist2_ref(p, q0), e1 = dist2_ref(p, q1), e2 = dist2_ref(p, q2), e3 = dist2_ref(p, q3);
+                    if (fminf(fminf(e0, e1), fminf(e2, e3)) < w.d2[2]) {
+                        knn_insert(w, e0, __float_as_int(q0.w)); knn_insert(w, e1, __float_as_int(q1.w));
+                        knn_insert(w, e2, __float_as_int(q2.w)); knn_insert(w, e3, __float_as_int(q3.w));
+                    }
+                }
+                for (; k < nv; k++) {
+                    const float4 q = buf[k];
+                    knn_insert(w, dist2_ref(p, q), __float_as_int(q.w));
                 }
             }
-        }
-        for (; v < e; v++) {
-            const float4 q = __ldg(&sv.pos2[v]);
-            if (mine) knn_insert(w, dist2_ref(p, q), __float_as_int(q.w));
         }
     };
     auto radius2 = [&]() {                         // squared radius of the packet sphere from the lanes' current bounds
@@ -661,7 +672,21 @@ __device__ bool knn3_packet(const FrameConst* __restrict__ fc, const SortedVerts
             if (lb < best) { best = lb; bc = k; }
         }
         bc = warp_argmin(best, bc);
-        scan(bc, true);
+        // (a compact loop of its own: the unrolled scan above is instantiated once, for the main walk)
+        const int s = __float_as_int(__ldg(&sv.occ_lo[bc]).w), e = __float_as_int(__ldg(&sv.occ_hi[bc]).w);
+        if (lane == 0) { KNN_STAT(9, 1); KNN_STAT(10, e - s); }
+        for (int base = s; base < e; base += 32) {
+            const int nv = min(32, e - base);
+            __syncwarp();
+            if (lane < nv) buf[lane] = __ldg(&sv.pos2[base + lane]);
+            __syncwarp();
+            if (act)
+#pragma unroll 1
+                for (int k = 0; k < nv; k++) {
+                    const float4 q = buf[k];
+                    knn_insert(w, dist2_ref(p, q), __float_as_int(q.w));
+                }
+        }
     }
     float R2 = radius2();
     for (int s0 = 0; s0 < ns; s0 += 32) {               // super cells: one per lane
@@ -681,7 +706,7 @@ __device__ bool knn3_packet(const FrameConst* __restrict__ fc, const SortedVerts
                 if (k < c1 && k != bc) qual = bbox_dist2(c, __ldg(&sv.occ_lo[k]), __ldg(&sv.occ_hi[k])) * 0.9999f <= R2;
                 unsigned qm = __ballot_sync(0xffffffffu, qual);
                 while (qm) {
-                    scan(cb + __ffs(qm) - 1, false);
+                    scan(cb + __ffs(qm) - 1);
                     qm &= qm - 1;
                 }
             }
