@@ -332,9 +332,9 @@ __global__ void k_outer_small(const float* __restrict__ U, int ldu, const float*
     int total = *count;
     int M = min(total - row0, rows_cap);
     if (M <= 0) return;
-    size_t n_el = (size_t)M * K;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (size_t)gridDim.x * blockDim.x) {
-        int m = (int)(i / K), k = (int)(i % K);
+    const unsigned n_el = (unsigned)M * (unsigned)K;     // M <= 262 144 rows per chunk, K <= 512: 32-bit index arithmetic
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += gridDim.x * blockDim.x) {
+        int m = (int)(i / (unsigned)K), k = (int)(i % (unsigned)K);
         size_t g = (size_t)m;
         float v = 0.f;
         if (U == nullptr) v = __ldg(&W[k]);
@@ -361,19 +361,26 @@ __device__ __forceinline__ void pe_write(float3 x, int L, float* dst, int width)
 }
 
 // X0[m, 0:64] = PE_L(p[m]);  optionally the same into a second buffer at a column offset (skip input)
+// One thread per (row, feature): the 64-wide rows leave as coalesced segments (a thread per row wrote 63 scattered words
+// through a local-memory buffer: 49 us for the frame's 31 k rows).  Feature values are the same sinf / cosf calls as pe_write.
+__device__ __forceinline__ float pe_feature_ref(const float* __restrict__ x3, int L, int k) {
+    if (k < 3) return x3[k];
+    if (k >= 3 + 6 * L) return 0.f;
+    const int j = k - 3, l = j / 6, r = j % 6;
+    const float a = x3[r % 3] * (float)(1 << l);
+    return (r < 3) ? sinf(a) : cosf(a);
+}
 __global__ void k_encode(const float* __restrict__ pts, int L, float* X0, int ld0, int w0, float* X1, int ld1, int off1,
                          int w1, const int* count, int row0, int rows_cap) {
     int total = *count;
     int M = min(total - row0, rows_cap);
     if (M <= 0) return;
-    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
-        size_t g = (size_t)m;
-        float3 x = make3(pts[g * 3], pts[g * 3 + 1], pts[g * 3 + 2]);
-        float buf[64];
-        pe_write(x, L, buf, 64);
-        for (int k = 0; k < w0; k++) X0[g * ld0 + k] = buf[k];
-        if (X1)
-            for (int k = 0; k < w1; k++) X1[g * ld1 + off1 + k] = buf[k];
+    const unsigned n_el = (unsigned)M * 64u;              // M <= 262 144 rows per chunk
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += gridDim.x * blockDim.x) {
+        const unsigned m = i >> 6, k = i & 63u;
+        const float v = pe_feature_ref(pts + (size_t)m * 3, L, (int)k);
+        if ((int)k < w0) X0[(size_t)m * ld0 + k] = v;
+        if (X1 && (int)k < w1) X1[(size_t)m * ld1 + off1 + k] = v;
     }
 }
 

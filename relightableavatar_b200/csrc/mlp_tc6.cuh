@@ -82,6 +82,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC6_THREADS, 1) k_ml
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int count = *P.count;
+    if (count == 0) return;                      // an empty work list (late tracing iterations, floor batches): every CTA of every cluster leaves before any barrier / TMEM traffic
     const int n_tiles = (count + TC_TILE_M - 1) / TC_TILE_M;
     const int n_quads = (n_tiles + 3) / 4;       // a cluster works on 4 tiles at a time: slot p, rank r -> tile 4 g + 2 p + r
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;

@@ -89,7 +89,7 @@ struct ra_handle {
     QueryList q{}, q2{};             // q2: second work list for the overlapped half of the shadow rays
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int pkt_order = 1, pkt_search = 1;       // shadow rays generated as packets (same light, 32 neighbouring pixels): bit 0 floor pass, bit 1 human pass; far-field 3-NN per packet (env RA_PKT_ORDER, RA_PKT_SEARCH)
+    int pkt_order = 1, pkt_search = 5;       // shadow rays generated as packets (same light, 32 neighbouring pixels): bit 0 floor pass, bit 1 human pass; far-field 3-NN per packet (bit 2: surface rays and volume samples, coherent as they are) (env RA_PKT_ORDER, RA_PKT_SEARCH)
     int overlap = 0;                 // env RA_OVERLAP=1: split the shadow stage over two streams (experiment: -0.3..0.5 ms with k_mlp_tc6, but the co-running
                                      // tracing warps slow the MLP epilogue and blur the per-kernel timing; capping MLP registers for more co-residency lost more than it gained)
     AttrList al{};
@@ -435,7 +435,7 @@ static void mlp_forward_fp32(ra_handle* h, cudaStream_t st, const float* bpts, c
     int g = grid_for(h, rows);
     const float* b0 = &h->fc->resd_b0[0];
     const float* b4 = &h->fc->resd_b4[0];
-    LAUNCH(h, k_encode, g, 256, 0, st, bpts, 10, h->Xr0, 64, 64, h->Xr4, 320, 256, 64, count, row0, rows);
+    LAUNCH(h, k_encode, grid_for(h, (long long)rows * 64), 256, 0, st, bpts, 10, h->Xr0, 64, 64, h->Xr4, 320, 256, 64, count, row0, rows);
     gemm<EPI_RELU>(h, st, h->Xr0, 64, h->resd[0].w, 64, b0, h->ra_[0], 256, nullptr, 0, count, row0, rows, 256, 64);
     gemm<EPI_RELU>(h, st, h->ra_[0], 256, h->resd[1].w, 256, h->resd[1].b, h->ra_[1], 256, nullptr, 0, count, row0, rows, 256, 256);
     gemm<EPI_RELU>(h, st, h->ra_[1], 256, h->resd[2].w, 256, h->resd[2].b, h->ra_[2], 256, nullptr, 0, count, row0, rows, 256, 256);
@@ -445,7 +445,7 @@ static void mlp_forward_fp32(ra_handle* h, cudaStream_t st, const float* bpts, c
         gemm<EPI_RELU>(h, st, h->ra_[l - 1], 256, h->resd[l].w, 256, h->resd[l].b, h->ra_[l], 256, nullptr, 0, count, row0, rows, 256, 256);
     LAUNCH(h, k_skinny, grid_for(h, (long long)rows * 32), 256, 0, st, h->ra_[7], 256, h->resd[8].w, 256, h->resd[8].b, h->z8, 4, count, row0, rows, 3, 256);
     LAUNCH(h, k_resd_finish, g, 256, 0, st, h->z8, 4, bpts, h->cfg.resd_limit, h->resd_o, h->cpts_o, count, row0, rows);
-    LAUNCH(h, k_encode, g, 256, 0, st, h->cpts_o, 8, h->Xs0, 64, 64, h->Xs4, 256, 205, 51, count, row0, rows);
+    LAUNCH(h, k_encode, grid_for(h, (long long)rows * 64), 256, 0, st, h->cpts_o, 8, h->Xs0, 64, 64, h->Xs4, 256, 205, 51, count, row0, rows);
     gemm<EPI_SOFTPLUS>(h, st, h->Xs0, 64, h->sdf[0].w, 64, h->sdf[0].b, h->sb_[0], 256, nullptr, 0, count, row0, rows, 256, 64);
     gemm<EPI_SOFTPLUS>(h, st, h->sb_[0], 256, h->sdf[1].w, 256, h->sdf[1].b, h->sb_[1], 256, nullptr, 0, count, row0, rows, 256, 256);
     gemm<EPI_SOFTPLUS>(h, st, h->sb_[1], 256, h->sdf[2].w, 256, h->sdf[2].b, h->sb_[2], 256, nullptr, 0, count, row0, rows, 256, 256);
@@ -536,7 +536,7 @@ static int attr_pass(ra_handle* h, cudaStream_t st, int64_t max_rows, bool sync_
             LAUNCH(h, k_skinny, grid_for(h, (long long)rows * 32), 256, 0, st, h->hd2, 128, h->rgh[2].w, 128, h->rgh[2].b, h->head_r, 4, count, (int)row0, rows, 1, 128);
         } else {
             if (!h->rend[0].w) { h->err = "render_network weights missing for AniSDF"; return 1; }
-            LAUNCH(h, k_render_input, g, 256, 0, st, h->al.bvds + row0 * 3, h->nrm_o, h->out257, 264, h->Xrn, 288, count, (int)row0, rows);
+            LAUNCH(h, k_render_input, grid_for(h, (long long)rows * 288), 256, 0, st, h->al.bvds + row0 * 3, h->nrm_o, h->out257, 264, h->Xrn, 288, count, (int)row0, rows);
             gemm<EPI_RELU>(h, st, h->Xrn, 288, h->rend[0].w, 288, h->rend[0].b, h->rn1, 256, nullptr, 0, count, (int)row0, rows, 256, 288);
             gemm<EPI_RELU>(h, st, h->rn1, 256, h->rend[1].w, 256, h->rend[1].b, h->rn2, 256, nullptr, 0, count, (int)row0, rows, 256, 256);
             gemm<EPI_RELU>(h, st, h->rn2, 256, h->rend[2].w, 256, h->rend[2].b, h->rn1, 256, nullptr, 0, count, (int)row0, rows, 256, 256);
@@ -622,7 +622,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     for (int it = 0; it <= c.st_iter; it++) {
         CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
         LAUNCH(h, k_trace_surface, g, h->tb_surf, 0, st, it, tc, h->fc, h->sv, N, ray_o, ray_d, near_, far_, (int)P, h->ss, h->q, h->cnt,
-               h->surf, h->acc, h->depth, h->fg_ray);
+               h->surf, h->acc, h->depth, h->fg_ray, (h->pkt_search >> 2) & 1);
         if (it < c.st_iter && distance_pass(h, st, P)) return 1;
     }
     prof_stage(h, st);
@@ -631,7 +631,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
     CK(cudaMemsetAsync(h->raw, 0, (size_t)P * c.n_samples * C * sizeof(float), st));
     LAUNCH(h, k_attr_front, grid_for(h, P * c.n_samples, 256, 8), 256, 0, st, 1, h->fc, h->sv, N, c.dist_th, c.blend_radius,
            (const float*)nullptr, (const float*)nullptr, 0LL, h->cnt.n_fg, h->fg_ray, h->surf, ray_o, ray_d, near_, far_, c.n_samples,
-           c.surf_sample_range, c.clip_near, c.clip_far, 0LL, 0LL, h->al, h->cnt);
+           c.surf_sample_range, c.clip_near, c.clip_far, 0LL, 0LL, h->al, h->cnt, 0);
     if (attr_pass(h, st, P * c.n_samples, h->cfg.precision == RA_PRECISION_FP32)) return 1;
     OutMaps om{out->rgb_map, out->acc_map, out->depth_map, out->surf_map, out->norm_map, out->cpts_map, out->bpts_map, out->resd_map,
                out->albedo_map, out->roughness_map, out->shade_map};
@@ -964,9 +964,9 @@ extern "C" int ra_render_anisdf_volume(ra_handle* h, const float* ray_o, const f
         CK(cudaMemsetAsync(h->raw, 0, (size_t)nr * S * 16 * sizeof(float), st));
         LAUNCH(h, k_attr_front, grid_for(h, nr * S, 256, 8), 256, 0, st, 2, h->fc, h->sv, c.n_verts, c.dist_th, c.blend_radius,
                (const float*)nullptr, (const float*)nullptr, 0LL, h->cnt.n_fg, h->fg_ray, h->surf, ray_o, ray_d, near_, far_, S,
-               c.surf_sample_range, c.clip_near, c.clip_far, (long long)r0, (long long)nr, h->al, h->cnt);
+               c.surf_sample_range, c.clip_near, c.clip_far, (long long)r0, (long long)nr, h->al, h->cnt, (h->pkt_search >> 2) & 1);
         if (attr_pass(h, st, nr * S, true)) return 1;
-        LAUNCH(h, k_volume_blend, grid_for(h, nr), 128, 0, st, h->raw, 16, S, near_, far_, c.clip_near, c.clip_far, (long long)r0, (long long)nr, om);
+        LAUNCH(h, k_volume_blend, grid_for(h, nr * 16, 128, 16), 128, 0, st, h->raw, 16, S, near_, far_, c.clip_near, c.clip_far, (long long)r0, (long long)nr, om);
     }
     CK(cudaGetLastError());
     return 0;
@@ -997,7 +997,7 @@ extern "C" int ra_query_raw(ra_handle* h, const float* x, const float* v, int64_
     CK(cudaMemsetAsync(h->raw, 0, (size_t)n * C * sizeof(float), st));
     LAUNCH(h, k_attr_front, grid_for(h, n, 256, 8), 256, 0, st, 0, h->fc, h->sv, h->cfg.n_verts, h->cfg.dist_th, h->cfg.blend_radius, x, v,
            (long long)n, h->cnt.n_fg, h->fg_ray, h->surf, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr,
-           (const float*)nullptr, 1, 0.f, 0.f, 0.f, 0LL, 0LL, h->al, h->cnt);
+           (const float*)nullptr, 1, 0.f, 0.f, 0.f, 0LL, 0LL, h->al, h->cnt, 0);
     if (attr_pass(h, st, n, true)) return 1;
     CK(cudaMemcpyAsync(raw, h->raw, (size_t)n * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return 0;

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256, RA_TRACE_MINBLOCKS) k_trace_surface(int i
                                 const float* __restrict__ near_, const float* __restrict__ far_, int P,
                                 SurfState s, QueryList q, Counters cnt,
                                 // finalisation outputs (it == iters)
-                                float* surf, float* acc, float* depth, int* fg_ray) {
+                                float* surf, float* acc, float* depth, int* fg_ray, int packets) {
     for (int base = blockIdx.x * blockDim.x; base < P; base += gridDim.x * blockDim.x) {      // block-uniform trip count
         int i = base + threadIdx.x;
         bool valid = i < P;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256, RA_TRACE_MINBLOCKS) k_trace_surface(int i
         if (it < cfg.iters) {
             HdqFront f; f.in_shell = false; f.smpl = 0.f;
             const bool ask = valid && !parked;
-            hdq_front<false>(fc, sv, nverts, o + d * t, ask, cfg.th, cfg.blend_radius, f);
+            hdq_front<false>(fc, sv, nverts, o + d * t, ask, cfg.th, cfg.blend_radius, f, 12, packets != 0);   // a warp = 32 neighbouring pixels of an image row: a packet
             bool ins = ask && f.in_shell;
             count_queries(cnt, ask, ins);
             int slot = warp_append(q.count, ins);
@@ -348,7 +348,7 @@ __global__ void k_attr_front(int mode, const FrameConst* __restrict__ fc, Sorted
                              const float* __restrict__ ray_o, const float* __restrict__ ray_d, const float* __restrict__ near_,
                              const float* __restrict__ far_, int n_samples, float sample_range, float clip_near, float clip_far,
                              long long ray0, long long n_rays,
-                             AttrList al, Counters cnt) {
+                             AttrList al, Counters cnt, int packets) {
     long long total = (mode == 0) ? n_explicit : (mode == 1 ? (long long)(*n_fg) * n_samples : n_rays * n_samples);
     for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {   // block-uniform
         long long i = base + threadIdx.x;
@@ -376,7 +376,7 @@ __global__ void k_attr_front(int mode, const FrameConst* __restrict__ fc, Sorted
             }
         }
         HdqFront f; f.in_shell = false;
-        hdq_front<true>(fc, sv, nverts, px, valid, th, blend_radius, f);
+        hdq_front<true>(fc, sv, nverts, px, valid, th, blend_radius, f, 12, packets != 0);      // volume samples: a warp = 32 consecutive samples of one ray
         bool ins = valid && f.in_shell;
         count_queries(cnt, false, false);
         int slot = warp_append(al.count, ins);
@@ -436,15 +436,15 @@ __global__ void k_render_input(const float* __restrict__ bvds, const float* __re
                                int ldo, float* X, int ldx, const int* count, int row0, int rows_cap) {
     int M = min(*count - row0, rows_cap);
     if (M <= 0) return;
-    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
-        float buf[64];
-        pe_write(make3(bvds[m * 3], bvds[m * 3 + 1], bvds[m * 3 + 2]), 4, buf, 27);
-        float* xr = X + (size_t)m * ldx;
-        for (int k = 0; k < 27; k++) xr[k] = buf[k];
-        xr[27] = nrm[m * 3]; xr[28] = nrm[m * 3 + 1]; xr[29] = nrm[m * 3 + 2];
-        const float* fo = feat + (size_t)m * ldo;
-        for (int k = 0; k < 256; k++) xr[30 + k] = fo[k];
-        xr[286] = 0.f; xr[287] = 0.f;
+    // one thread per (row, column): coalesced copies of the 256 feature columns (a thread per row moved 288 scattered words)
+    const unsigned n_el = (unsigned)M * 288u;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += gridDim.x * blockDim.x) {
+        const unsigned m = i / 288u, k = i % 288u;
+        float v = 0.f;
+        if (k < 27u) v = pe_feature_ref(bvds + (size_t)m * 3, 4, (int)k);
+        else if (k < 30u) v = nrm[(size_t)m * 3 + (k - 27u)];
+        else if (k < 286u) v = feat[(size_t)m * ldo + (k - 30u)];
+        X[(size_t)m * ldx + k] = v;
     }
 }
 
@@ -814,33 +814,37 @@ __global__ void k_scatter_lmaps(const int* __restrict__ n_fg, const int* __restr
 }
 
 // volume rendering over n_samples raw rows per ray (base_renderer.py:72-113; net_utils.py:970-999)
+// Half a warp per ray, one lane per raw channel: a sample's 16 channels are one 64-byte segment, the transmittance product runs in
+// sample order in every lane (the same sequence of roundings as a single thread walking the ray).  C == 16.
 __global__ void k_volume_blend(const float* __restrict__ raw, int C, int n_samples, const float* __restrict__ near_, const float* __restrict__ far_,
                                float clip_near, float clip_far, long long ray0, long long n_rays, OutMaps om) {
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rays; r += (long long)gridDim.x * blockDim.x) {
-        long long ray = ray0 + r;
-        float val[16];
-        for (int c = 0; c < C - 1; c++) val[c] = 0.f;
-        float T = 1.f, wsum = 0.f, dep = 0.f;
-        float nr = fmaxf(near_[ray], clip_near), fr = fminf(far_[ray], clip_far);
+    const int lane = threadIdx.x & 31, c = lane & 15;
+    const long long hw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4, n_hw = ((long long)gridDim.x * blockDim.x) >> 4;
+    const long long n_pad = (n_rays + 1) & ~1LL;          // both halves of a warp iterate together (shuffles below)
+    for (long long r = hw; r < n_pad; r += n_hw) {
+        const bool ok = r < n_rays;
+        const long long ray = ray0 + (ok ? r : 0);
+        float val = 0.f, T = 1.f, wsum = 0.f, dep = 0.f;
+        const float nr = fmaxf(near_[ray], clip_near), fr = fminf(far_[ray], clip_far);
+        const float* rr = raw + (size_t)(ok ? r : 0) * n_samples * C + c;
+#pragma unroll 8
         for (int m = 0; m < n_samples; m++) {
-            const float* rr = raw + ((size_t)r * n_samples + m) * C;
-            float a = rr[C - 1];
-            float w = a * T;
+            const float x = rr[(size_t)m * C];
+            const float a = __shfl_sync(0xffffffffu, x, (lane & 16) | 15);      // the alpha channel of this half's ray
+            const float w = a * T;
             T *= (1.f - a + 1e-8f);
             wsum += w;
-            float tv = (float)m / (float)(n_samples - 1);
+            const float tv = (float)m / (float)(n_samples - 1);
             dep += w * (nr * (1.f - tv) + fr * tv);
-            for (int c = 0; c < C - 1; c++) val[c] += w * rr[c];
+            val += w * x;
         }
-        for (int c = 0; c < 3; c++) {
-            if (om.cpts) om.cpts[ray * 3 + c] = val[c];
-            if (om.bpts) om.bpts[ray * 3 + c] = val[3 + c];
-            if (om.resd) om.resd[ray * 3 + c] = val[6 + c];
-            if (om.norm) om.norm[ray * 3 + c] = val[9 + c];
-            if (om.rgb) om.rgb[ray * 3 + c] = val[12 + c];
+        if (!ok) continue;
+        float* dst = c < 3 ? om.cpts : (c < 6 ? om.bpts : (c < 9 ? om.resd : (c < 12 ? om.norm : (c < 15 ? om.rgb : nullptr))));
+        if (dst) dst[ray * 3 + c % 3] = val;
+        if (c == 15) {
+            if (om.acc) om.acc[ray] = wsum;
+            if (om.depth) om.depth[ray] = dep;
         }
-        if (om.acc) om.acc[ray] = wsum;
-        if (om.depth) om.depth[ray] = dep;
     }
 }
 
