@@ -164,7 +164,8 @@ __device__ __forceinline__ void aabb_near_far(const float* bmin, const float* bm
 // list (lanes without a ray carry fg = -1; compacted instead if the padded list could outgrow the workspace).  That is the floor
 // pass's layout (ground.cuh), where it is worth 2.2x; on the body it measured SLOWER (visibility stage 17.9 -> 19.5 ms at 512^2): the
 // normals of 32 neighbouring pixels sweep most of the hemisphere (a limb is ~30 pixels wide), so nearly every (tile, light) pair holds a
-// ray and the padded list has 1.9x the entries, while rays that leave from ONE pixel share their 3-NN lists during the first iterations.
+// ray and the padded list has 1.9x the entries, while rays that leave from ONE pixel share their 3-NN lists during the first iterations
+// (the same order with a compacted list, packets straddling warps: 18.2 ms -- no better than the pixel-major 18.0).
 __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __restrict__ n_fg, const int* __restrict__ fg_ray,
                              const float* __restrict__ surf /*[P][3] by ray*/, const float* __restrict__ f_norm /*[fg][3]*/,
                              const float* __restrict__ ldir /*[L][3]*/, int L, float lv_near, float bbox_margin, int chunk_actual,

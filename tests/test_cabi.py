@@ -24,7 +24,7 @@ def test_ctypes_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.ra_config) == 39 * 4
     assert ctypes.sizeof(_lib.ra_frame) == 11 * 8
     assert ctypes.sizeof(_lib.ra_outputs) == 14 * 8
-    assert ctypes.sizeof(_lib.ra_stats) == 7 * 8
+    assert ctypes.sizeof(_lib.ra_stats) == 8 * 8
     assert ctypes.sizeof(_lib.ra_ground_config) == 16 * 4
     assert ctypes.sizeof(_lib.ra_ground_outputs) == 10 * 8
     assert ctypes.sizeof(_lib.ra_body) == 7 * 8          # 6 pointers + int32 padded to 8
