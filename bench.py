@@ -397,6 +397,7 @@ def main():
     }
 
     if not args.no_extras:
+        line['frames_in_flight'] = bench_in_flight(args, net, dev, frames_dev, P_max, world, timed, parallel, Renderer, torch)
         line['fp32_mode'] = bench_fp32(args, net, dev, frames_dev, P_max, world, rank, timed, make_steps, Renderer)
         line['configs'] = bench_configs(args, net, dev, eng, world, rank, timed, make_steps, load_frames, Renderer, parallel, scene, torch, dist)
     if gather is not None:
@@ -407,6 +408,28 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_in_flight(args, net, dev, frames_dev, P_max, world, timed, parallel, Renderer, torch, n=2):
+    """Sequence rendering with two frames in flight per GPU (parallel.FramesInFlight: two handles on two streams).  Reported next to
+    `value`, which stays the one-frame-at-a-time number the kernel timings and the roofline refer to."""
+    pool = parallel.FramesInFlight(lambda: Renderer(net, mode='relight', device=dev, precision=args.precision, max_rays=P_max + 1024,
+                                                    test_light=('main',), sync_timing=False), n)
+    tickets = []
+
+    def step(s):
+        tickets.append(pool.submit(frames_dev[s % len(frames_dev)]))
+        if len(tickets) >= n:
+            pool.result(tickets.pop(0))
+
+    def finish():
+        while tickets:
+            pool.result(tickets.pop(0))
+
+    ms, _ = timed(step, args.steps, max(args.warmup, 2 * n), finish)
+    pool.close()
+    return {'in_flight': n, 'value': args.steps * world / (ms / 1e3), 'unit': 'frames/s', 'ms_per_frame': ms / args.steps,
+            'note': 'device-resident inputs, each rank on its own frames (no gather); every frame bit-identical to the one-at-a-time rendering'}
 
 
 def bench_fp32(args, net, dev, frames_dev, P_max, world, rank, timed, make_steps, Renderer):
