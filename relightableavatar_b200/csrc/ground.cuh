@@ -68,6 +68,19 @@ __global__ void k_ground_setup(GroundCfg g, const float* __restrict__ ray_o, con
     }
 }
 
+// visibility of the (pixel, light) pairs before tracing: 1 where the light is in front of the floor and the pixel shows floor (rays that
+// miss the body's box stay at 1, traced rays overwrite theirs), else 0.  Pixel-major, coalesced: k_ground_rays walks the pairs in packet
+// order (32 pixels of one light per warp), where these stores would be 2 KB apart.
+__global__ void k_ground_vis_init(GroundCfg g, const float* __restrict__ acc_g, long long p0, long long n, const float* __restrict__ ldir, int L, float* lvis) {
+    const float3 nn = normalize_ref(make3(g.normal[0], g.normal[1], g.normal[2]));
+    const long long total = n * L;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = p0 + i / L; const int l = (int)(i % L);
+        const float dt = ldir[l * 3] * nn.x + ldir[l * 3 + 1] * nn.y + ldir[l * 3 + 2] * nn.z;
+        lvis[(size_t)pix * L + l] = (dt > 0.f && acc_g[pix] > 0.f) ? 1.f : 0.f;
+    }
+}
+
 // light_visibility set-up for the floor (:265-329): per (pixel, light) front-facing & box tests, shadow-ray append.
 // `pad_chunks0`: how many pixel chunks the human pass already grew wbounds by; the floor's own chunk index comes from the
 // pixel index (`chunk_actual` = the reference's equalised chunk size over the H*W pixels).
@@ -95,7 +108,6 @@ __global__ void k_ground_rays(const FrameConst* __restrict__ fc, GroundCfg g, co
         if (valid) {
             float3 dl = make3(ldir[l * 3], ldir[l * 3 + 1], ldir[l * 3 + 2]);
             float dt = dl.x * nn.x + dl.y * nn.y + dl.z * nn.z;
-            float vis = 0.f;
             if (dt > 0.f && acc_g[pix] > 0.f) {
                 float pad = g.bbox_margin * (float)(pad_chunks0 + 1 + (int)(pix / chunk_actual));
                 float bmin[3] = {fc->wb[0] - pad, fc->wb[1] - pad, fc->wb[2] - pad};
@@ -103,10 +115,8 @@ __global__ void k_ground_rays(const FrameConst* __restrict__ fc, GroundCfg g, co
                 float3 o = make3(surf[pix * 3], surf[pix * 3 + 1], surf[pix * 3 + 2]);
                 aabb_near_far(bmin, bmax, o, dl, nr, fr);
                 nr = fmaxf(nr, g.near_offset); fr = fmaxf(fr, g.near_offset);
-                trace = nr < fr;
-                vis = 1.f;          // misses the box: visible; traced rays overwrite this
+                trace = nr < fr;          // (misses the box: stays visible, k_ground_vis_init)
             }
-            lvis[(size_t)pix * L + l] = vis;
         }
         shadow_append(sr, n_shadow, packets != 0, trace, (int)pix, l, nr, fr);
     }

@@ -279,6 +279,7 @@ static const unsigned char* lin_tc_pack(LinTcWeights& w, const float* W, int ldw
     unsigned char* d = nullptr;
     if (cudaMalloc((void**)&d, blob.size() * 2) != cudaSuccess) return nullptr;
     cudaMemcpy(d, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice);
+    cudaStreamSynchronize(cudaStreamLegacy);      // pageable H2D copies return once staged and run on the legacy stream: a non-blocking caller stream is not ordered behind them
     w.cache[key] = d;
     return d;
 }

@@ -43,6 +43,7 @@
     } while (0)
 
 static const int ATTR_CH = 262144;   // rows per fp32 MLP chunk
+static const int64_t RA_GROUND_SLOTS_MAX = 96ll << 20;      // entries of the floor pass's ray list (x 50 B: 4.7 GB): a whole 512^2 image (67 M); larger images go in batches
 
 struct Lin {            // one fp32 linear layer, K zero-padded to a multiple of 8
     float* w = nullptr; float* b = nullptr; int N = 0, K = 0;     // (N, K) row-major
@@ -99,6 +100,7 @@ struct ra_handle {
     float *pt_smpl = nullptr; int* pt_slot = nullptr;     // ra_query_sdf scratch
     float* bg_spec = nullptr;
     int* blk_cnt = nullptr; int64_t blk_cap = 0;      // image assembly scratch
+    ShadowRays sr_g{}; QueryList q_g{}; int64_t g_slots = 0;      // floor pass: its own ray list / query list, sized for a whole image where that fits (ra_render_ground)
     int g_W = 0, g_H = 0;             // image size of the last ra_ground_begin (the floor's 8 x 4 pixel packets)
     int* pix2ray = nullptr; int64_t pix_cap = 0;      // ground pass: image pixel -> ray (ra_ground_begin)
     float *g_weight = nullptr, *g_light = nullptr;
@@ -129,6 +131,10 @@ template <typename T>
 static cudaError_t dalloc(ra_handle* h, T** p, size_t n) {
     cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
     if (e == cudaSuccess) { h->allocs.insert((void*)*p); e = cudaMemset(*p, 0, n * sizeof(T)); }
+    // cudaMemset of device memory returns before the fill has run, and it runs on the legacy default stream: a caller that works on a
+    // NON-BLOCKING stream (torch side streams: parallel.FramesInFlight) would not be ordered behind it -- the first kernels of a fresh
+    // handle could be overtaken by its own zero-fill.  Allocation happens at creation and on capacity growth only: wait here.
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
     return e;
 }
 template <typename T>
@@ -391,6 +397,10 @@ extern "C" int ra_upload_weights(ra_handle* h, const ra_weights* w, void* stream
     lin_tc_clear(h->lin_tc);         // the packed GEMM images refer to the previous weights
     if (tc_upload(h->tc, w, C, h->err, st)) return 1;
     if (tc2_upload(h->tc2, w, C, h->err, st)) return 1;
+    // the uploads above are pageable host -> device copies on the legacy stream (they return once staged): make them visible to callers
+    // that render on non-blocking streams
+    CK(cudaStreamSynchronize(cudaStreamLegacy));
+    CK(cudaStreamSynchronize(st));
     h->have_weights = true;
     return 0;
 }
@@ -882,8 +892,26 @@ extern "C" int ra_render_ground(ra_handle* h, const ra_ground_config* g, const f
            out->norm_map, out->albedo_map, out->roughness_map, h->g_weight);
     TraceCfg sc{g->iter, 1.f, g->relax, g->offset, c.st_eps, c.st_skip, g->dist_th, c.blend_radius};
     int* n_gshadow = h->counters_blk + 5;
-    // processing granularity: as many pixels as the shadow-ray / query workspaces of this handle hold (256 rays per pixel)
-    int64_t step = std::max<int64_t>(std::min<int64_t>(h->P_cap, h->q_cap / 256), 1);
+    // The floor's rays get a list of their own, sized for the whole image (256 entries of 34 B + a 16 B query slot per pixel: 3.4 GB at
+    // 512^2) up to RA_GROUND_SLOTS_MAX: one batch of 17 tracer + 16 MLP launches instead of one batch per max_rays pixels (at 512^2: four
+    // batches, two of them over the nearly ray-less upper half of the image -- 34 launches of ~0.15 ms and 48 tiny MLP launches for nothing).
+    {
+        const int64_t want = std::max<int64_t>(std::min<int64_t>(256 * F, RA_GROUND_SLOTS_MAX), 256 * 32);
+        if (h->g_slots < want) {
+            ShadowRays& g2 = h->sr_g;
+            hfree(h, g2.fg); hfree(h, g2.light); hfree(h, g2.near_); hfree(h, g2.far_); hfree(h, g2.t); hfree(h, g2.occ); hfree(h, g2.d0); hfree(h, g2.q_smpl);
+            hfree(h, g2.q_slot); hfree(h, h->q_g.bpts); hfree(h, h->q_g.net);
+            h->g_slots = 0;
+            CK(dalloc(h, &g2.fg, want)); CK(dalloc(h, &g2.light, want)); CK(dalloc(h, &g2.near_, want)); CK(dalloc(h, &g2.far_, want));
+            CK(dalloc(h, &g2.t, want)); CK(dalloc(h, &g2.occ, want)); CK(dalloc(h, &g2.d0, want)); CK(dalloc(h, &g2.q_smpl, want)); CK(dalloc(h, &g2.q_slot, want));
+            CK(dalloc(h, &h->q_g.bpts, (size_t)want * 3)); CK(dalloc(h, &h->q_g.net, (size_t)want));
+            g2.cap = (int)want; g2.dropped = h->sr.dropped; g2.n_rays = h->sr.n_rays;
+            h->q_g.count = h->q.count;
+            h->g_slots = want;
+        }
+    }
+    // processing granularity: as many pixels as the floor's ray list holds (256 rays per pixel)
+    int64_t step = std::max<int64_t>(h->g_slots / 256, 1);
     if (step >= 32) step &= ~(int64_t)31;          // whole 32-pixel packets per batch (k_ground_rays pads the last one)
     // packets of 8 x 4 pixels (about half the radius of 32 x 1 on the floor) when the batches can be whole groups of 4 image rows
     int tile_w = 0;
@@ -891,16 +919,17 @@ extern "C" int ra_render_ground(ra_handle* h, const ra_ground_config* g, const f
     for (int64_t p0 = 0; p0 < F; p0 += step) {
         const int64_t n = std::min<int64_t>(step, F - p0);
         CK(cudaMemsetAsync(n_gshadow, 0, sizeof(int), st));
+        LAUNCH(h, k_ground_vis_init, grid_for(h, n * L / 4, 256, 16), 256, 0, st, gc, acc_g, (long long)p0, (long long)n, h->ldir, L, out->lvis_map);
         LAUNCH(h, k_ground_rays, grid_for(h, n * L / 4, 256, 16), 256, 0, st, h->fc, gc, out->surf_map, acc_g, (long long)p0, (long long)n, h->ldir, L,
-               human_chunks, chunk_actual, out->lvis_map, h->sr, n_gshadow, h->pkt_order & 1, tile_w);
+               human_chunks, chunk_actual, out->lvis_map, h->sr_g, n_gshadow, h->pkt_order & 1, tile_w);
         const int gs = grid_for(h, n * 64, 256, 8);
-        int64_t n_sh = h->sr.cap;
+        int64_t n_sh = h->sr_g.cap;
         if (h->cfg.precision == RA_PRECISION_FP32 && read_counter(h, n_gshadow, st, &n_sh)) return 1;
         for (int it = 0; it <= g->iter; it++) {
             CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
             LAUNCH(h, k_trace_shadow, gs, 256, 0, st, it, sc, h->fc, h->sv, N, n_gshadow, (const int*)nullptr, out->surf_map, h->ldir, h->lsharp, L,
-                   h->sr, h->q, h->cnt, out->lvis_map, 0, 1, h->pkt_search & 1);
-            if (it < g->iter && distance_pass(h, st, n_sh)) return 1;
+                   h->sr_g, h->q_g, h->cnt, out->lvis_map, 0, 1, h->pkt_search & 1);
+            if (it < g->iter && distance_pass(h, st, n_sh, &h->q_g)) return 1;
         }
     }
     LAUNCH(h, k_ground_shade, grid_for(h, F * 32, 256, 8), 256, 0, st, gc, 1, 0LL, (long long)F, h->g_weight, h->ldir, h->larea, L, h->g_light,

@@ -87,6 +87,9 @@ vis.encode_frame(out, bb, types=('rendering',), ext='.jpg')
 stage('visualizer')
 ids, d2 = r.engine.query_knn(torch.as_tensor(b['wverts'][0][::5]).float() + 0.3)
 stage('query_knn')
+pts = (torch.as_tensor(b['wverts'][0][::40]).float()[:, None] + 0.4 + torch.rand(1, 32, 3) * 0.05).reshape(-1, 3)
+r.engine.query_knn(pts, packets=True)
+stage('query_knn packets')
 r.engine.close()
 name = next(iter(b['novel_lights']))
 for over in (dict(visibility_mode=1), dict(visibility_mode=2), dict(brdf_mode=1), dict(brdf_mode=2), dict(replace_light=name)):
