@@ -86,24 +86,76 @@ __global__ void k_ground_vis_init(GroundCfg g, const float* __restrict__ acc_g, 
 // pixel index (`chunk_actual` = the reference's equalised chunk size over the H*W pixels).
 __global__ void k_ground_rays(const FrameConst* __restrict__ fc, GroundCfg g, const float* __restrict__ surf, const float* __restrict__ acc_g,
                               long long p0, long long n, const float* __restrict__ ldir, int L, int pad_chunks0, int chunk_actual,
-                              float* lvis, ShadowRays sr, int* n_shadow, int packets,
+                              ShadowRays sr, int* n_shadow, int packets,
                               int tile_w /* image width when a packet is an 8 x 4 pixel tile (batch = whole groups of 4 rows), 0: 32 consecutive pixels */) {
-    // one warp = one packet: the same light for 32 consecutive pixels (see k_shadow_gen); always a whole aligned block of the ray list
-    int lane = threadIdx.x & 31;
-    const long long ntile = (n + 31) >> 5;
-    long long total = packets ? ntile * L * 32 : n * L;
-    float3 nn = normalize_ref(make3(g.normal[0], g.normal[1], g.normal[2]));
-    for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += (long long)gridDim.x * blockDim.x) {
-        const long long w = base >> 5;
-        const int l = packets ? (int)(w % L) : (int)((base + lane) % L);
-        long long k = packets ? (w / L) * 32 + lane : (base + lane) / L;
-        if (packets && tile_w) {
-            const long long tile = w / L, per_row = tile_w >> 3;
-            k = ((tile / per_row) * 4 + (lane >> 3)) * tile_w + (tile % per_row) * 8 + (lane & 7);
+    const int lane = threadIdx.x & 31;
+    const float3 nn = normalize_ref(make3(g.normal[0], g.normal[1], g.normal[2]));
+    if (packets) {
+        // One warp per TILE of 32 pixels (lane = pixel), all lights: a packet = the same light for the tile's pixels, a whole aligned
+        // 32-entry block of the ray list (lanes without a ray carry fg = -1, see k_shadow_gen).  The packets of 32 lights are counted first
+        // and the list grows by one atomic per such group (one atomic per packet -- 0.8 M on one counter at 512^2 -- took 2 ms).  NOT one
+        // atomic per tile: that lays each tile's ~100 packets out contiguously, the tracer's blocks then hold either only expensive packets
+        // (tiles under the body) or only cheap ones, and the floor pass measured 4 ms SLOWER; groups of a few packets from the ~10 k warps
+        // in flight interleave in the list and balance the tracer's blocks.
+        const long long ntile = (n + 31) >> 5;
+        const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+        for (long long tile = warp0; tile < ntile; tile += nwarps) {
+            long long k = tile * 32 + lane;
+            if (tile_w) {
+                const long long per_row = tile_w >> 3;
+                k = ((tile / per_row) * 4 + (lane >> 3)) * tile_w + (tile % per_row) * 8 + (lane & 7);
+            }
+            const long long pix = p0 + k;
+            const bool floor_px = k < n && acc_g[pix] > 0.f;
+            if (!__any_sync(0xffffffffu, floor_px)) continue;
+            float3 o = make3(0.f, 0.f, 0.f);
+            float bmin[3] = {0.f, 0.f, 0.f}, bmax[3] = {0.f, 0.f, 0.f};
+            if (floor_px) {
+                const float pad = g.bbox_margin * (float)(pad_chunks0 + 1 + (int)(pix / chunk_actual));
+                for (int a = 0; a < 3; a++) { bmin[a] = fc->wb[a] - pad; bmax[a] = fc->wb[3 + a] + pad; }
+                o = make3(surf[pix * 3], surf[pix * 3 + 1], surf[pix * 3 + 2]);
+            }
+            auto test = [&](int l, float& nr, float& fr) -> bool {       // this lane's ray towards light l: does it cross the box?
+                const float3 dl = make3(__ldg(&ldir[l * 3]), __ldg(&ldir[l * 3 + 1]), __ldg(&ldir[l * 3 + 2]));
+                if (!(dl.x * nn.x + dl.y * nn.y + dl.z * nn.z > 0.f) || !floor_px) return false;
+                aabb_near_far(bmin, bmax, o, dl, nr, fr);
+                nr = fmaxf(nr, g.near_offset); fr = fmaxf(fr, g.near_offset);
+                return nr < fr;
+            };
+            for (int l0 = 0; l0 < L; l0 += 32) {           // groups of 32 lights: see the note on list order above
+                const int l1 = min(l0 + 32, L);
+                int n_pk = 0;
+                for (int l = l0; l < l1; l++) {
+                    float nr, fr;
+                    if (__any_sync(0xffffffffu, test(l, nr, fr))) n_pk++;
+                }
+                if (n_pk == 0) continue;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(n_shadow, 32 * n_pk);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (int l = l0; l < l1; l++) {
+                    float nr = 0.f, fr = 0.f;
+                    const bool trace = test(l, nr, fr);
+                    const unsigned any = __ballot_sync(0xffffffffu, trace);
+                    if (!any) continue;
+                    if (lane == 0) atomicAdd(sr.n_rays, __popc(any));
+                    const int slot = base + lane;
+                    base += 32;
+                    if (slot >= sr.cap) { if (trace) atomicAdd(sr.dropped, 1); continue; }
+                    sr.fg[slot] = trace ? (int)pix : -1; sr.light[slot] = (unsigned short)l; sr.near_[slot] = nr; sr.far_[slot] = fr;
+                }
+            }
         }
-        bool valid = packets ? k < n : base + lane < total;
+        return;
+    }
+    // legacy order: one warp = 32 lights of one pixel, rays appended compacted
+    const long long total = n * L;
+    for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)((base + lane) % L);
+        const long long k = (base + lane) / L;
+        const bool valid = base + lane < total;
         bool trace = false;
-        long long pix = p0 + k;
+        const long long pix = p0 + k;
         float nr = 0.f, fr = 0.f;
         if (valid) {
             float3 dl = make3(ldir[l * 3], ldir[l * 3 + 1], ldir[l * 3 + 2]);
@@ -118,7 +170,7 @@ __global__ void k_ground_rays(const FrameConst* __restrict__ fc, GroundCfg g, co
                 trace = nr < fr;          // (misses the box: stays visible, k_ground_vis_init)
             }
         }
-        shadow_append(sr, n_shadow, packets != 0, trace, (int)pix, l, nr, fr);
+        shadow_append(sr, n_shadow, false, trace, (int)pix, l, nr, fr);
     }
 }
 

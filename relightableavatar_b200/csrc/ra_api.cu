@@ -920,8 +920,8 @@ extern "C" int ra_render_ground(ra_handle* h, const ra_ground_config* g, const f
         const int64_t n = std::min<int64_t>(step, F - p0);
         CK(cudaMemsetAsync(n_gshadow, 0, sizeof(int), st));
         LAUNCH(h, k_ground_vis_init, grid_for(h, n * L / 4, 256, 16), 256, 0, st, gc, acc_g, (long long)p0, (long long)n, h->ldir, L, out->lvis_map);
-        LAUNCH(h, k_ground_rays, grid_for(h, n * L / 4, 256, 16), 256, 0, st, h->fc, gc, out->surf_map, acc_g, (long long)p0, (long long)n, h->ldir, L,
-               human_chunks, chunk_actual, out->lvis_map, h->sr_g, n_gshadow, h->pkt_order & 1, tile_w);
+        LAUNCH(h, k_ground_rays, (h->pkt_order & 1) ? grid_for(h, n, 128, 16) : grid_for(h, n * L / 4, 256, 16), (h->pkt_order & 1) ? 128 : 256, 0, st, h->fc, gc,
+               out->surf_map, acc_g, (long long)p0, (long long)n, h->ldir, L, human_chunks, chunk_actual, h->sr_g, n_gshadow, h->pkt_order & 1, tile_w);
         const int gs = grid_for(h, n * 64, 256, 8);
         int64_t n_sh = h->sr_g.cap;
         if (h->cfg.precision == RA_PRECISION_FP32 && read_counter(h, n_gshadow, st, &n_sh)) return 1;
