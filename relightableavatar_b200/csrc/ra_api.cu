@@ -91,6 +91,7 @@ struct ra_handle {
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int pkt_order = 1, pkt_search = 5;       // shadow rays generated as packets (same light, 32 neighbouring pixels): bit 0 floor pass, bit 1 human pass; far-field 3-NN per packet (bit 2: surface rays and volume samples, coherent as they are) (env RA_PKT_ORDER, RA_PKT_SEARCH)
+    int final_skip = 1;              // shadow rays whose state is a fixed point are skipped by later tracer launches (env RA_TRACE_FINAL=0: off, for the bit-identity test)
     int overlap = 0;                 // env RA_OVERLAP=1: split the shadow stage over two streams (experiment: -0.3..0.5 ms with k_mlp_tc6, but the co-running
                                      // tracing warps slow the MLP epilogue and blur the per-kernel timing; capping MLP registers for more co-residency lost more than it gained)
     AttrList al{};
@@ -272,6 +273,7 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     CK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     if (const char* e = getenv("RA_OVERLAP")) h->overlap = atoi(e);
+    if (const char* e = getenv("RA_TRACE_FINAL")) h->final_skip = atoi(e);
     if (const char* e = getenv("RA_PKT_ORDER")) h->pkt_order = atoi(e);
     if (const char* e = getenv("RA_PKT_SEARCH")) h->pkt_search = atoi(e);
     if (const char* e = getenv("RA_PKT_MIN")) { int v = atoi(e); CK(cudaMemcpyToSymbol(g_pkt_min, &v, sizeof(int))); }
@@ -664,7 +666,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
         for (int it = 0; it <= c.lv_iter; it++) {
             CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
             LAUNCH(h, k_trace_shadow, gs, h->tb_shadow, 0, st, it, sc, h->fc, h->sv, N, h->cnt.n_shadow, h->fg_ray, h->surf, h->ldir, h->lsharp, L, h->sr,
-                   h->q, h->cnt, h->lvis, 0, 1, (h->pkt_search >> 1) & 1);
+                   h->q, h->cnt, h->lvis, 0, 1, (h->pkt_search >> 1) & 1, h->final_skip);
             if (it < c.lv_iter && distance_pass(h, st, n_sh)) return 1;
         }
     } else {
@@ -679,7 +681,7 @@ static int render_trace(ra_handle* h, const float* ray_o, const float* ray_d, co
                 const QueryList& ql = part ? h->q2 : h->q;
                 CK(cudaMemsetAsync(ql.count, 0, sizeof(int), ps));
                 LAUNCH(h, k_trace_shadow, gs, 128, 0, ps, it, sc, h->fc, h->sv, N, h->cnt.n_shadow, h->fg_ray, h->surf, h->ldir, h->lsharp, L,
-                       h->sr, ql, h->cnt, h->lvis, part, 2, (h->pkt_search >> 1) & 1);
+                       h->sr, ql, h->cnt, h->lvis, part, 2, (h->pkt_search >> 1) & 1, h->final_skip);
                 if (it < c.lv_iter && distance_pass(h, ps, n_sh, &ql)) return 1;
             }
         }
@@ -928,7 +930,7 @@ extern "C" int ra_render_ground(ra_handle* h, const ra_ground_config* g, const f
         for (int it = 0; it <= g->iter; it++) {
             CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
             LAUNCH(h, k_trace_shadow, gs, 256, 0, st, it, sc, h->fc, h->sv, N, n_gshadow, (const int*)nullptr, out->surf_map, h->ldir, h->lsharp, L,
-                   h->sr_g, h->q_g, h->cnt, out->lvis_map, 0, 1, h->pkt_search & 1);
+                   h->sr_g, h->q_g, h->cnt, out->lvis_map, 0, 1, h->pkt_search & 1, h->final_skip);
             if (it < g->iter && distance_pass(h, st, n_sh, &h->q_g)) return 1;
         }
     }

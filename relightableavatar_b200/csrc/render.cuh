@@ -215,7 +215,7 @@ __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __res
 __global__ void __launch_bounds__(256, RA_SHADOW_MINBLOCKS) k_trace_shadow(int it, TraceCfg cfg, const FrameConst* __restrict__ fc, SortedVerts sv, int nverts,
                                const int* __restrict__ n_shadow, const int* __restrict__ fg_ray, const float* __restrict__ surf,
                                const float* __restrict__ ldir, const float* __restrict__ lsharp, int L,
-                               ShadowRays sr, QueryList q, Counters cnt, float* lvis, int part, int nparts, int packets) {
+                               ShadowRays sr, QueryList q, Counters cnt, float* lvis, int part, int nparts, int packets, int final_skip) {
     // rays [lo, hi) of the list: the host runs the parts on different streams so that one part's CUDA-core work overlaps
     // the other part's tensor-core MLP kernel
     const long long Nall = min(*n_shadow, sr.cap);
@@ -229,8 +229,13 @@ __global__ void __launch_bounds__(256, RA_SHADOW_MINBLOCKS) k_trace_shadow(int i
         bool parked = false;        // front did not move (t clamped): same point, same distance -- reuse, no query (exact)
         float d_keep = 0.f;
         if (valid) { f = sr.fg[i]; valid = f >= 0; }      // padded packets: lanes without a ray
-        if (valid) {
-            l = sr.light[i];
+        // A ray whose state can no longer change is FINAL (bit 15 of its light index): fully occluded, or parked for the second iteration
+        // in a row (the first parked iteration still sees a new d0, from the second on every input of the update repeats).  A final ray
+        // costs two loads per launch instead of ten loads, five stores and the update -- most of the floor's 26 M rays in its later iterations.
+        unsigned short lraw = 0;
+        bool fin = false, was_parked = false;
+        if (valid) { lraw = sr.light[i]; l = lraw & 0x7fff; fin = (lraw & 0x8000) != 0; }
+        if (valid && !fin) {
             int ray = fg_ray ? fg_ray[f] : f;          // floor pass: the ray list indexes image pixels directly
             o = make3(surf[ray * 3], surf[ray * 3 + 1], surf[ray * 3 + 2]);
             d = make3(ldir[l * 3], ldir[l * 3 + 1], ldir[l * 3 + 2]);
@@ -242,6 +247,7 @@ __global__ void __launch_bounds__(256, RA_SHADOW_MINBLOCKS) k_trace_shadow(int i
                 // Skipping its remaining queries changes nothing in the result (exact early termination).
                 if (occ > 0.f) {
                     int slot = sr.q_slot[i];
+                    was_parked = slot == -3;
                     float smpl = sr.q_smpl[i];
                     float d1 = (slot >= 0) ? hdq_blend(q.net[slot], smpl, cfg.th, true) : smpl;
                     int pi = it - 1;
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(256, RA_SHADOW_MINBLOCKS) k_trace_shadow(int i
                 }
             }
         }
-        const bool alive = valid && (occ > 0.f);
+        const bool alive = valid && !fin && (occ > 0.f);
         if (it < cfg.iters) {
             HdqFront hf; hf.in_shell = false; hf.smpl = 0.f;
             const bool ask = alive && !parked;
@@ -276,12 +282,13 @@ __global__ void __launch_bounds__(256, RA_SHADOW_MINBLOCKS) k_trace_shadow(int i
             count_queries(cnt, ask, ins);
             int slot = warp_append(q.count, ins);
             if (ins) { q.bpts[(size_t)slot * 3] = hf.bpts.x; q.bpts[(size_t)slot * 3 + 1] = hf.bpts.y; q.bpts[(size_t)slot * 3 + 2] = hf.bpts.z; }
-            if (valid) {
+            if (valid && !fin) {
                 sr.t[i] = t; sr.occ[i] = occ; sr.d0[i] = d0;
-                sr.q_smpl[i] = (alive && parked) ? d_keep : hf.smpl; sr.q_slot[i] = (alive && parked) ? -1 : slot;
+                sr.q_smpl[i] = (alive && parked) ? d_keep : hf.smpl; sr.q_slot[i] = (alive && parked) ? -3 : slot;      // -3: parked, q_smpl is the final distance
+                if (final_skip && (!alive || (parked && was_parked))) sr.light[i] = lraw | 0x8000;
             }
         } else if (valid) {
-            lvis[(size_t)f * L + l] = occ;
+            lvis[(size_t)f * L + l] = fin ? sr.occ[i] : occ;
         }
     }
 }

@@ -786,8 +786,11 @@ def test_shadow_ray_packets_change_nothing(monkeypatch):
     b = scene.make_batch(H, H, seed=0, n_env=0)
     sd = scene.make_state_dict(0, relight=True, fitted=True)
     outs = {}
-    for order, search in ((0, 0), (3, 0), (3, 3), (1, 1)):          # bit 0: floor pass, bit 1: human pass; (1, 1) is the default
+    # bit 0: floor pass, bit 1: human pass, bit 2 (search only): surface rays; (1, 5) is the default.  The legacy run (0, 0) also switches
+    # off the skipping of FINAL shadow rays (k_trace_shadow: rays whose state is a fixed point), another exact shortcut.
+    for order, search in ((0, 0), (3, 0), (3, 7), (1, 5)):
         monkeypatch.setenv('RA_PKT_ORDER', str(order)); monkeypatch.setenv('RA_PKT_SEARCH', str(search))
+        monkeypatch.setenv('RA_TRACE_FINAL', '0' if (order, search) == (0, 0) else '1')
         r = Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='tc', max_rays=16384, test_light=('main',),
                      return_lvis=True, ground_shading=True, sync_timing=False)
         r.render(dict(b))
@@ -797,7 +800,7 @@ def test_shadow_ray_packets_change_nothing(monkeypatch):
         r.engine.close()
     ref, st0 = outs[(0, 0)]
     assert int((ref['lvis_map'] < 0.999).sum()) > 10000
-    for key in ((3, 0), (3, 3), (1, 1)):
+    for key in ((3, 0), (3, 7), (1, 5)):
         got, st = outs[key]
         assert st['n_queries'] == st0['n_queries'] and st['n_queries_in_shell'] == st0['n_queries_in_shell'] and st['n_shadow_rays'] == st0['n_shadow_rays'], (key, st, st0)
         for k in ('lvis_map', 'ldot_map', 'rgb_map', 'shade_map', 'acc_map'):
