@@ -138,7 +138,6 @@ __global__ void k_ground_rays(const FrameConst* __restrict__ fc, GroundCfg g, co
                     const bool trace = test(l, nr, fr);
                     const unsigned any = __ballot_sync(0xffffffffu, trace);
                     if (!any) continue;
-                    if (lane == 0) atomicAdd(sr.n_rays, __popc(any));
                     const int slot = base + lane;
                     base += 32;
                     if (slot >= sr.cap) { if (trace) atomicAdd(sr.dropped, 1); continue; }

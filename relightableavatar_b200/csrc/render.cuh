@@ -118,7 +118,7 @@ struct ShadowRays {      // SoA over traced (pixel, light) pairs
     int* q_slot;
     int cap;             // entries the arrays hold (256 per ray of ra_config.max_rays)
     int* dropped;        // device counter: rays that did not fit (reported by ra_get_stats; their light stays 'visible')
-    int* n_rays;         // device counter: rays appended (the list counter itself counts padded packet slots)
+    int* n_rays;         // device counter: rays traced, counted by the tracer's last launch (the list counter itself counts padded packet slots)
 };
 // append guard: a light layout with more than 256 front-facing lights per pixel (not the antipodally symmetric 16x32 grid of
 // gen_light_xyz) could generate more shadow rays than the workspace holds -- drop and count instead of writing out of bounds
@@ -131,7 +131,6 @@ __device__ __forceinline__ bool shadow_slot_ok(const ShadowRays& sr, bool trace,
 __device__ __forceinline__ void shadow_append(const ShadowRays& sr, int* n_shadow, bool padded, bool trace, int f, int l, float nr, float fr) {
     const unsigned any = __ballot_sync(0xffffffffu, trace);
     if (!any) return;
-    if ((threadIdx.x & 31) == 0) atomicAdd(sr.n_rays, __popc(any));
     if (padded) {
         int base = 0;
         if ((threadIdx.x & 31) == 0) base = atomicAdd(n_shadow, 32);
@@ -287,8 +286,12 @@ __global__ void __launch_bounds__(256, RA_SHADOW_MINBLOCKS) k_trace_shadow(int i
                 sr.q_smpl[i] = (alive && parked) ? d_keep : hf.smpl; sr.q_slot[i] = (alive && parked) ? -3 : slot;      // -3: parked, q_smpl is the final distance
                 if (final_skip && (!alive || (parked && was_parked))) sr.light[i] = lraw | 0x8000;
             }
-        } else if (valid) {
-            lvis[(size_t)f * L + l] = fin ? sr.occ[i] : occ;
+        } else {
+            if (valid) lvis[(size_t)f * L + l] = fin ? sr.occ[i] : occ;
+            // the rays of the list are counted here, once per block and launch (ra_stats.n_shadow_rays; the list counter itself counts
+            // padded packet slots) -- a second same-address atomic per appended warp made k_shadow_gen twice as slow
+            const int c = __syncthreads_count(valid);
+            if (threadIdx.x == 0 && c) atomicAdd(sr.n_rays, c);
         }
     }
 }
