@@ -176,7 +176,7 @@ __device__ __forceinline__ __half2 h2_sp_exp(const __half2 z) {
     return __hfma2(p, e, __hmax2(z, __float2half2_rn(0.f)));
 }
 __device__ __forceinline__ __half2 h2_sp_poly(const __half2 z) {
-    const __half2 w = __hmax2(__hfma2(__habs2(z), __float2half2_rn(-1.f / 0.075f), __float2half2_rn(1.f)), __float2half2_rn(0.f));
+    const __half2 w = __hfma2_relu(__habs2(z), __float2half2_rn(-1.f / 0.075f), __float2half2_rn(1.f));      // max(fma, 0) in one HFMA2.RELU
     __half2 p = __hfma2(w, __float2half2_rn(0.01282501220703125f), __float2half2_rn(-0.006336212158203125f));
     p = __hfma2(p, w, __float2half2_rn(-0.0011892318725585938f));
     p = __hfma2(p, w, __float2half2_rn(0.001796722412109375f));
@@ -190,8 +190,9 @@ __device__ __forceinline__ uint32_t h2_softplus100(float a, float b, bool odd) {
     return *reinterpret_cast<const uint32_t*>(&r);
 }
 __device__ __forceinline__ uint32_t h2_relu(float a, float b) {
-    const __half2 r = __hmax2(__floats2half2_rn(a, b), __float2half2_rn(0.f));
-    return *reinterpret_cast<const uint32_t*>(&r);
+    uint32_t r;                                   // round-to-nearest conversion and ReLU in one instruction (same values as cvt + max)
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
 
 // write 8 consecutive K values (cols k0..k0+7, k0 % 8 == 0) of this thread's row into a K-major buffer
