@@ -84,8 +84,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC6_THREADS, 1) k_ml
     const int count = *P.count;
     if (count == 0) return;                      // an empty work list (late tracing iterations, floor batches): every CTA of every cluster leaves before any barrier / TMEM traffic
     const int n_tiles = (count + TC_TILE_M - 1) / TC_TILE_M;
-    const int n_quads = (n_tiles + 3) / 4;       // a cluster works on 4 tiles at a time: slot p, rank r -> tile 4 g + 2 p + r
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    // A cluster works on 4 tiles at a time: slot p, rank r -> tile 4 g + 2 p + r.  SHORT work lists (the 16 launches of the surface stage,
+    // tile-sharded frames: at most one pair-tile per cluster) use slot 0 only, tile 2 g + r: with nothing to interleave, the second slot
+    // would only put its MMAs between a layer's epilogue and the next layer of the same tile (18 x 4352 instead of 18 x ~3000 clk of chain).
+    const int np = (n_tiles <= 2 * n_clusters) ? 1 : 2;
+    const int n_quads = (np == 2) ? (n_tiles + 3) / 4 : (n_tiles + 1) / 2;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC6_STAGES; s++) { mbar_init(bar_full + 8 * s, rank == 0 ? 2 : 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -116,7 +120,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC6_THREADS, 1) k_ml
                     const unsigned char* src = P.blob + P.layer[l].goff[rank];
                     const unsigned char* bsrc = P.blob + P.layer[l].boff[rank];
                     const int nch = P.layer[l].nchunks / 2;      // 64-wide K chunks (all layer widths are multiples of 64)
-                    for (int p = 0; p < 2; p++)
+                    for (int p = 0; p < np; p++)
                         for (int c = 0; c <= nch; c++, it++) {
                             const uint32_t s = it & (TC6_STAGES - 1), ph = (it / TC6_STAGES) & 1;
                             const uint32_t nb = (c < nch) ? 2 * bytes : bytes / 2;
@@ -134,7 +138,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC6_THREADS, 1) k_ml
             uint32_t it = 0;
             for (int quad = cluster_id; quad < n_quads; quad += n_clusters)
                 for (int l = 0; l < TC_LAYERS; l++) {
-                    const int n = 2 * (P.layer[l].nchunks / 2 + 1);
+                    const int n = np * (P.layer[l].nchunks / 2 + 1);
                     for (int c = 0; c < n; c++, it++) {
                         const uint32_t s = it & (TC6_STAGES - 1), ph = (it / TC6_STAGES) & 1;
                         mbar_wait(bar_full + 8 * s, ph);
@@ -155,7 +159,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC6_THREADS, 1) k_ml
                     const uint32_t lbo_b = (uint32_t)(N / 2) * 16u;
                     const int nch = P.layer[l].nchunks / 2;
                     const int pe_from = P.layer[l].pe_from / 2;      // in 64-wide chunks (0, 4 or "never")
-                    for (int p = 0; p < 2; p++) {
+                    for (int p = 0; p < np; p++) {
                         const uint32_t s_act = s_act0 + p * TC_ACT_BYTES, s_pe = s_pe0 + p * TC_PE_BYTES;
                         const uint32_t tmem_d = tmem_u + (uint32_t)p * 256u;
                         TC_TL(const bool rec = P.dbg && blockIdx.x == 0 && quad == n_clusters && lane == 0;)
@@ -215,7 +219,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC6_THREADS, 1) k_ml
         uint32_t lc = 0;
 
         auto prologue = [&](int quad, int p) {      // PE10(bp) of the slot's new tile -> PE[p]; input of layer R0 ready
-            const int tile = quad * 4 + p * 2 + (int)rank;
+            const int tile = (np == 2) ? quad * 4 + p * 2 + (int)rank : quad * 2 + (int)rank;
             gidx[p] = tile * TC_TILE_M + row;
             bp[p] = make3(0.f, 0.f, 0.f);
             if (gidx[p] < count) bp[p] = make3(P.bpts[(size_t)gidx[p] * 3], P.bpts[(size_t)gidx[p] * 3 + 1], P.bpts[(size_t)gidx[p] * 3 + 2]);
@@ -227,14 +231,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC6_THREADS, 1) k_ml
         };
 
         int quad = cluster_id;
-        if (quad < n_quads) { prologue(quad, 0); prologue(quad, 1); }
+        if (quad < n_quads) { prologue(quad, 0); if (np == 2) prologue(quad, 1); }
         for (; quad < n_quads; quad += n_clusters) {
             const int next = quad + n_clusters;
 #pragma unroll 1
             for (int l = 0; l < TC_LAYERS; l++, lc++) {
                 const int epi = P.layer[l].epi;
 #pragma unroll 1
-                for (int p = 0; p < 2; p++) {
+                for (int p = 0; p < np; p++) {
                     const uint32_t s_act = s_act0 + p * TC_ACT_BYTES, s_pe = s_pe0 + p * TC_PE_BYTES;
                     const uint32_t t_lane = t_lane0 + (uint32_t)p * 256u;
                     TC_TL(const bool rec = P.dbg && blockIdx.x == 0 && quad == n_clusters && warp == 0 && lane == 0;)

@@ -925,13 +925,16 @@ extern "C" int ra_render_ground(ra_handle* h, const ra_ground_config* g, const f
         LAUNCH(h, k_ground_rays, (h->pkt_order & 1) ? grid_for(h, n, 128, 16) : grid_for(h, n * L / 4, 256, 16), (h->pkt_order & 1) ? 128 : 256, 0, st, h->fc, gc,
                out->surf_map, acc_g, (long long)p0, (long long)n, h->ldir, L, human_chunks, chunk_actual, h->sr_g, n_gshadow, h->pkt_order & 1, tile_w);
         const int gs = grid_for(h, n * 64, 256, 8);
-        int64_t n_sh = h->sr_g.cap;
-        if (h->cfg.precision == RA_PRECISION_FP32 && read_counter(h, n_gshadow, st, &n_sh)) return 1;
         for (int it = 0; it <= g->iter; it++) {
             CK(cudaMemsetAsync(h->q.count, 0, sizeof(int), st));
             LAUNCH(h, k_trace_shadow, gs, 256, 0, st, it, sc, h->fc, h->sv, N, n_gshadow, (const int*)nullptr, out->surf_map, h->ldir, h->lsharp, L,
                    h->sr_g, h->q_g, h->cnt, out->lvis_map, 0, 1, h->pkt_search & 1, h->final_skip);
-            if (it < g->iter && distance_pass(h, st, n_sh, &h->q_g)) return 1;
+            // fp32 (reference-precision) mode chunks its GEMM chain on the host: the floor's list has tens of millions of entries of which
+            // a few thousand are in the 5 mm shell, so the bound is the query count itself, read back per iteration (this mode synchronises
+            // anyway; the tensor-core path reads every count on the device)
+            int64_t n_q = h->sr_g.cap;
+            if (it < g->iter && h->cfg.precision == RA_PRECISION_FP32 && read_counter(h, h->q.count, st, &n_q)) return 1;
+            if (it < g->iter && distance_pass(h, st, n_q, &h->q_g)) return 1;
         }
     }
     LAUNCH(h, k_ground_shade, grid_for(h, F * 32, 256, 8), 256, 0, st, gc, 1, 0LL, (long long)F, h->g_weight, h->ldir, h->larea, L, h->g_light,

@@ -229,19 +229,21 @@ def test_empty_rays_are_tolerated(relight_setup):
 
 
 def test_two_cta_kernel_variant_matches_single_cta(relight_setup, monkeypatch):
-    """k_mlp_tc2 / k_mlp_tc6 / k_mlp_tc7 (cta_group::2 pair kernels; tc7, the product kernel, reads the A operand of the two output
-    layers from tensor memory) evaluate the same arithmetic as k_mlp_tc: bit-identical distances."""
+    """k_mlp_tc2 / k_mlp_tc6 / k_mlp_tc7 (cta_group::2 pair kernels; tc6 is the product kernel, tc7 reads the A operand of the two output
+    layers from tensor memory) evaluate the same arithmetic as k_mlp_tc: bit-identical distances -- on a short work list (k_mlp_tc6 runs
+    its single-slot schedule: at most one pair-tile per cluster), on a long one (two slots per CTA) and on one of a single row."""
     b, sd = relight_setup
-    x = _sample_points(b, 20000, seed=3)
-    outs = []
-    for variant in ('1', '2', '6', '7'):
-        monkeypatch.setenv('RA_TC_VARIANT', variant)
-        eng = Engine(default_config(True, precision=1, max_rays=8192), DEV)
-        eng.upload_weights(sd); eng.set_frame(b)
-        outs.append(eng.query_sdf(x, 0.125, True).clone())
-        eng.close()
-    for o in outs[1:]:
-        assert torch.equal(outs[0], o)
+    for n in (12000, 60000, 1):
+        x = _sample_points(b, n, seed=3)
+        outs = []
+        for variant in ('1', '2', '6', '7'):
+            monkeypatch.setenv('RA_TC_VARIANT', variant)
+            eng = Engine(default_config(True, precision=1, max_rays=8192), DEV)
+            eng.upload_weights(sd); eng.set_frame(b)
+            outs.append(eng.query_sdf(x, 0.125, True).clone())
+            eng.close()
+        for o in outs[1:]:
+            assert torch.equal(outs[0], o), n
 
 
 def test_relight_1024_config5_properties():
