@@ -62,7 +62,11 @@ __device__ __forceinline__ void epi_hidden64(uint32_t t_lane, uint32_t s_act, in
                 float a = __uint_as_float(cur[g * 8 + 2 * j]), b = __uint_as_float(cur[g * 8 + 2 * j + 1]);
                 h[j] = SOFTPLUS ? h2_softplus100(a, b, j & 1) : h2_relu(a, b);
             }
+#ifdef RA_TC_NO_ASTORE      // timing experiment only (wrong results): what the hidden layers' A stores cost the co-running MMAs
+            if (h[0] == 0x7fc07fc1u) st_shared_v4(s_act + (uint32_t)((c0 >> 3) + g) * 2048u + (uint32_t)row * 16u, h[0], h[1], h[2], h[3]);
+#else
             st_shared_v4(s_act + (uint32_t)((c0 >> 3) + g) * 2048u + (uint32_t)row * 16u, h[0], h[1], h[2], h[3]);
+#endif
         }
     }
 }

@@ -24,6 +24,7 @@
 #include "mlp_tc2.cuh"
 #include "mlp_tc6.cuh"
 #include "mlp_tc7.cuh"
+#include "mlp_tc8.cuh"
 #include "lin_tc.cuh"
 #include "visual.cuh"
 
@@ -70,9 +71,10 @@ struct ra_handle {
     float *lxyz = nullptr, *larea = nullptr, *lsharp = nullptr, *ldir = nullptr;
     TcWeights tc;                    // fp16 UMMA images for the tcgen05 path
     Tc2Weights tc2;                  // ... and for its 2-CTA (cta_group::2) variant
+    Tc8Weights tc8;                  // ... and for k_mlp_tc8 (A operand in tensor memory: per (layer, half, rank) images)
     int attr_tc = 3;                 // env RA_ATTR_TC: 3 = tcgen05 fp16-split GEMM (lin_tc.cuh), 2 = pipelined 3xTF32 mma.sync GEMM, 1 = first 3xTF32 GEMM, 0 = CUDA-core SGEMM
     LinTcWeights lin_tc;             // packed hi / lo weight images of the attribute-pass GEMMs (built on first use)
-    int tc_variant = 6;              // env RA_TC_VARIANT: 6 = CTA-pair two-slot kernel k_mlp_tc6 (default); 7 = k_mlp_tc7 (tc6 + output layers with A in tensor memory + skewed slots: measured no faster, kept as the tcgen05.st / TS-MMA cross-check); 1 = single-CTA kernel k_mlp_tc; 2 = first CTA-pair kernel k_mlp_tc2 (all bit-identical)
+    int tc_variant = 6;              // env RA_TC_VARIANT: 6 = CTA-pair two-slot kernel k_mlp_tc6 (default); 7 = k_mlp_tc7 (tc6 + output layers with A in tensor memory + skewed slots: measured no faster, kept as the tcgen05.st / TS-MMA cross-check); 8 = k_mlp_tc8 (A of every hidden layer in tensor memory, N in two halves: bit-identical, 41 % slower -- half-width MMAs are A-operand-bound); 1 = single-CTA kernel k_mlp_tc; 2 = first CTA-pair kernel k_mlp_tc2 (all bit-identical)
     // ---- frame
     FrameConst* fc = nullptr;
     SortedVerts sv{};
@@ -303,10 +305,11 @@ extern "C" int ra_create(ra_handle** out, const ra_config* cfg) {
     if (tc2_init(h->tc2, h->err)) return 1;
     if (tc6_init(h->err)) return 1;
     if (tc7_init(h->err)) return 1;
+    if (tc8_init(h->err)) return 1;
     if (gemm_init(h->err)) return 1;
     if (const char* e = getenv("RA_TC_VARIANT")) h->tc_variant = atoi(e);
     if (const char* e = getenv("RA_TC_SKEW")) h->tc2.skew = std::max(0, std::min(17, atoi(e)));
-    if (h->tc_variant != 1 && h->tc_variant != 2 && h->tc_variant != 6 && h->tc_variant != 7) { h->err = "RA_TC_VARIANT must be 1, 2, 6 or 7"; return 1; }
+    if (h->tc_variant != 1 && h->tc_variant != 2 && (h->tc_variant < 6 || h->tc_variant > 8)) { h->err = "RA_TC_VARIANT must be 1, 2, 6, 7 or 8"; return 1; }
     if (const char* e = getenv("RA_ATTR_TC")) h->attr_tc = atoi(e);
     return 0;
 }
@@ -317,6 +320,7 @@ extern "C" void ra_destroy(ra_handle* h) {
     h->allocs.clear();
     tc_free(h->tc);
     tc2_free(h->tc2);
+    tc8_free(h->tc8);
     lin_tc_clear(h->lin_tc);
     if (h->tc.dbg) cudaFree(h->tc.dbg);
     if (h->aux) cudaStreamDestroy(h->aux);
@@ -399,6 +403,7 @@ extern "C" int ra_upload_weights(ra_handle* h, const ra_weights* w, void* stream
     lin_tc_clear(h->lin_tc);         // the packed GEMM images refer to the previous weights
     if (tc_upload(h->tc, w, C, h->err, st)) return 1;
     if (tc2_upload(h->tc2, w, C, h->err, st)) return 1;
+    if (h->tc_variant == 8 && tc8_upload(h->tc8, w, C, h->err, st)) return 1;
     // the uploads above are pageable host -> device copies on the legacy stream (they return once staged): make them visible to callers
     // that render on non-blocking streams
     CK(cudaStreamSynchronize(cudaStreamLegacy));
@@ -432,6 +437,7 @@ extern "C" int ra_set_frame(ra_handle* h, const ra_frame* f, void* stream) {
     LAUNCH(h, k_grid_occ, 1, 1024, 0, st, h->fc, h->sv.cell_start2, (const float4*)h->sv.pos2, h->sv);
     if (h->cfg.precision == RA_PRECISION_TC) {
         if (h->tc_variant == 2 || h->tc_variant >= 6) tc2_set_frame(h->tc2, h->fc, st, h->launches);
+        if (h->tc_variant == 8) tc8_set_frame(h->tc8, h->fc, st, h->launches);
         else tc_set_frame(h->tc, h->fc, st, h->launches);
     }
     CK(cudaGetLastError());
@@ -578,7 +584,8 @@ static int distance_pass(ra_handle* h, cudaStream_t st, int64_t rows_bound, cons
     const QueryList& q = ql ? *ql : h->q;
     if (h->cfg.precision == RA_PRECISION_TC) {
         if (h->prof) cudaEventRecord(prof_event(h->ev_mlp, h->ev_mlp_used), st);
-        if (h->tc_variant == 7) tc7_distance(h->tc2, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
+        if (h->tc_variant == 8) tc8_distance(h->tc8, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
+        else if (h->tc_variant == 7) tc7_distance(h->tc2, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         else if (h->tc_variant == 6) tc6_distance(h->tc2, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         else if (h->tc_variant == 2) tc2_distance(h->tc2, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
         else tc_distance(h->tc, q.bpts, q.net, q.count, h->cfg.resd_limit, h->sms, st, h->launches);
@@ -1092,7 +1099,7 @@ extern "C" int ra_debug_knn_stats(unsigned long long* out12, int reset) {
 // debug: per-layer clock64 timeline of CTA 0 of the fused MLP kernel (tools/tc_timeline.py)
 extern "C" int ra_debug_tc_timeline(ra_handle* h, unsigned long long* out, int enable) {
     if (enable) {
-        if (!h->tc.dbg) { CK(cudaMalloc((void**)&h->tc.dbg, 512 * sizeof(unsigned long long))); h->tc2.dbg = h->tc.dbg; }
+        if (!h->tc.dbg) { CK(cudaMalloc((void**)&h->tc.dbg, 512 * sizeof(unsigned long long))); h->tc2.dbg = h->tc.dbg; h->tc8.dbg = h->tc.dbg; }
         CK(cudaMemset(h->tc.dbg, 0, 512 * sizeof(unsigned long long)));
         return 0;
     }

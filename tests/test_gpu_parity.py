@@ -236,7 +236,7 @@ def test_two_cta_kernel_variant_matches_single_cta(relight_setup, monkeypatch):
     for n in (12000, 60000, 1):
         x = _sample_points(b, n, seed=3)
         outs = []
-        for variant in ('1', '2', '6', '7'):
+        for variant in ('1', '2', '6', '7', '8'):
             monkeypatch.setenv('RA_TC_VARIANT', variant)
             eng = Engine(default_config(True, precision=1, max_rays=8192), DEV)
             eng.upload_weights(sd); eng.set_frame(b)
