@@ -806,8 +806,17 @@ __device__ void knn3_warp(const FrameConst* __restrict__ fc, const SortedVerts& 
                 }
             }
         }
-        for (int m = 16; m; m >>= 1) knn_merge_xor(w, m);
-        if (lane == src) o = w;
+        // global top 3 of the lanes' sorted triples (disjoint vertex sets): three rounds of "smallest head wins, the winner pops" --
+        // ~90 instructions instead of the ~255 of five shuffle-merge rounds with three insertions each (A/B on one box: no measurable
+        // difference in the frame -- the body's far queries are latency-bound, not instruction-bound)
+        KnnOut g;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int win = warp_argmin(w.d2[0], lane);
+            g.d2[r] = __shfl_sync(0xffffffffu, w.d2[0], win); g.id[r] = __shfl_sync(0xffffffffu, w.id[0], win);
+            if (lane == win) { w.d2[0] = w.d2[1]; w.id[0] = w.id[1]; w.d2[1] = w.d2[2]; w.id[1] = w.id[2]; w.d2[2] = 3.0e38f; w.id[2] = -1; }
+        }
+        if (lane == src) o = g;
     }
 }
 
