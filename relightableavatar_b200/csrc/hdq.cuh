@@ -565,12 +565,6 @@ __device__ void knn3_far(const FrameConst* __restrict__ fc, const SortedVerts& s
     }
 }
 
-__device__ __forceinline__ void knn_merge_xor(KnnOut& o, int mask) {
-    // merge this lane's sorted triple with its partner's (disjoint vertex sets)
-    float d0 = __shfl_xor_sync(0xffffffffu, o.d2[0], mask), d1 = __shfl_xor_sync(0xffffffffu, o.d2[1], mask), d2 = __shfl_xor_sync(0xffffffffu, o.d2[2], mask);
-    int i0 = __shfl_xor_sync(0xffffffffu, o.id[0], mask), i1 = __shfl_xor_sync(0xffffffffu, o.id[1], mask), i2 = __shfl_xor_sync(0xffffffffu, o.id[2], mask);
-    knn_insert(o, d0, i0); knn_insert(o, d1, i1); knn_insert(o, d2, i2);
-}
 __device__ __forceinline__ float warp_min_f(float v) {
     for (int m = 16; m; m >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, m));
     return v;
