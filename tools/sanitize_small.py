@@ -103,10 +103,20 @@ bl = dict(b); bl['novel_lights'] = {name: {'probe': b['novel_lights'][name], 'im
 r.render(bl)
 stage('rotation sweep with ground shading')
 r.engine.close()
-os.environ['RA_TC_VARIANT'] = '7'
-eng = Engine(default_config(True, precision=1, max_rays=2048), DEV)
-eng.upload_weights(sd); eng.set_frame(b)
-eng.query_sdf(torch.as_tensor(b['wverts'][0][::3]).float() + 0.01, 0.125, True)
-stage('k_mlp_tc7')
-eng.close()
+for variant in ('7', '8'):
+    os.environ['RA_TC_VARIANT'] = variant
+    eng = Engine(default_config(True, precision=1, max_rays=2048), DEV)
+    eng.upload_weights(sd); eng.set_frame(b)
+    eng.query_sdf(torch.as_tensor(b['wverts'][0][::3]).float() + 0.01, 0.125, True)
+    eng.query_sdf((torch.as_tensor(b['wverts'][0]).float()[:, None] + torch.randn(1, 6, 3) * 0.02).reshape(-1, 3), 0.125, True)      # > 148 tiles: two slots
+    stage(f'k_mlp_tc{variant}')
+    eng.close()
+os.environ.pop('RA_TC_VARIANT')
+from relightableavatar_b200 import parallel
+pool = parallel.FramesInFlight(lambda: Renderer(scene.SyntheticNet(sd, True), mode='relight', device=DEV, precision='tc', max_rays=2048,
+                                                test_light=('main',), sync_timing=False, ground_shading=True), 2)
+for o in pool.render_sequence([b, b, b]):
+    pass
+pool.close()
+stage('frames in flight with ground shading')
 print('SANITIZE_DONE')
