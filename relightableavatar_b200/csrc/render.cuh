@@ -176,11 +176,14 @@ __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __res
     const long long ntile = (nfg + 31) >> 5;
     const long long total = packets ? ntile * L * 32 : (long long)nfg * L;
     const bool padded = packets && total <= (long long)sr.cap;
-    for (long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += (long long)gridDim.x * blockDim.x) {
+    __shared__ int s_wcnt[32], s_base;
+    const int wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (long long bbase = (long long)blockIdx.x * blockDim.x; bbase < total; bbase += (long long)gridDim.x * blockDim.x) {      // block-uniform trip count
+        const long long base = bbase + threadIdx.x - lane;
         const long long w = base >> 5;
         const int l = packets ? (int)(w % L) : (int)((base + lane) % L);
         const int f = packets ? (int)(w / L) * 32 + lane : (int)((base + lane) / L);
-        const bool valid = packets ? f < nfg : base + lane < total;
+        const bool valid = base + lane < total && (!packets || f < nfg);
         bool trace = false;
         float nr = 0.f, fr = 0.f;
         if (valid) {
@@ -206,7 +209,21 @@ __global__ void k_shadow_gen(const FrameConst* __restrict__ fc, const int* __res
             }
             lvis[idx] = vis;
         }
-        shadow_append(sr, n_shadow, padded, trace, f, l, nr, fr);
+        if (packets) { shadow_append(sr, n_shadow, padded, trace, f, l, nr, fr); continue; }
+        // compact list: the block's warps append together with ONE atomic (a warp-level append per 32 (pixel, light) pairs was 167 k
+        // atomics on one counter per frame and bound this kernel: 160 us)
+        const unsigned mask = __ballot_sync(0xffffffffu, trace);
+        if (lane == 0) s_wcnt[wid] = __popc(mask);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int k = 0; k < nwarp; k++) { const int c = s_wcnt[k]; s_wcnt[k] = tot; tot += c; }
+            s_base = tot ? atomicAdd(n_shadow, tot) : 0;
+        }
+        __syncthreads();
+        const int slot = s_base + s_wcnt[wid] + __popc(mask & ((1u << lane) - 1u));
+        if (shadow_slot_ok(sr, trace, slot)) { sr.fg[slot] = f; sr.light[slot] = (unsigned short)l; sr.near_[slot] = nr; sr.far_[slot] = fr; }
+        __syncthreads();          // s_wcnt / s_base are reused by the next iteration
     }
 }
 
